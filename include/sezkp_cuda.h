@@ -1,0 +1,140 @@
+/* sezkp_cuda.h — C ABI of libsezkp_cuda.so: the B200 (sm_100a) implementation of SEZKP's STARK v1
+ * commitment hot path.  This is the surface a Rust `sezkp-cuda` FFI crate binds;
+ * every entry point names the reference item it replaces (paths relative to the reference's crates/).
+ *
+ * Conventions (mirroring the reference's FFI stub, sezkp-ffi/src/lib.rs:49-94):
+ *   - every function returns int32_t: 0 = OK, <0 = SEZKP_CUDA_E*; nothing aborts or throws across the ABI;
+ *   - sezkp_cuda_last_error(ctx) is a ctx-owned NUL-terminated string, valid until the next call on ctx;
+ *   - the caller owns every input and output buffer (explicit sizes / capacities); the library never
+ *     returns memory the caller must free except opaque handles with a matching *_free;
+ *   - field elements are canonical Goldilocks residues (< p = 2^64-2^32+1) as little-endian uint64_t,
+ *     digests are 32 raw bytes; pointers named *_dev are device pointers on the ctx's GPU, all others host;
+ *   - a ctx is bound to one GPU (one process per GPU) and is not thread-safe;
+ *   - there is no CPU fallback: without a usable CUDA device sezkp_cuda_create fails with ENODEV.
+ */
+#ifndef SEZKP_CUDA_H
+#define SEZKP_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#include "sezkp_trace.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEZKP_CUDA_ABI_VERSION 1u
+
+#define SEZKP_CUDA_OK 0
+#define SEZKP_CUDA_EINVAL (-1)  /* bad argument (non power-of-two size, label too long, NULL, ...) */
+#define SEZKP_CUDA_ENOMEM (-2)  /* host or device allocation failed                               */
+#define SEZKP_CUDA_ECUDA (-3)   /* CUDA runtime / kernel error                                    */
+#define SEZKP_CUDA_ENODEV (-4)  /* no usable CUDA device                                          */
+#define SEZKP_CUDA_ERANGE (-5)  /* output buffer too small (required size reported)               */
+#define SEZKP_CUDA_ESTATE (-6)  /* call sequence error (streaming API)                            */
+
+typedef struct sezkp_ctx sezkp_ctx;
+typedef struct sezkp_tree sezkp_tree; /* retained column commitments (chunk roots + upper levels + values) */
+typedef struct sezkp_fri sezkp_fri;   /* retained FRI layers (values + upper tree levels)                  */
+typedef struct sezkp_stream sezkp_stream;
+
+/* ---------------------------------------------------------------- context ---- */
+uint32_t sezkp_cuda_abi_version(void);                       /* cf. sezkp_abi_version(), sezkp-ffi/src/lib.rs:55-68 */
+int32_t sezkp_cuda_create(int device_id, sezkp_ctx** out);   /* device_id < 0: current device                     */
+void sezkp_cuda_destroy(sezkp_ctx* ctx);
+const char* sezkp_cuda_last_error(const sezkp_ctx* ctx);     /* ctx may be NULL: error of the last failed create   */
+int32_t sezkp_cuda_set_stream(sezkp_ctx* ctx, void* cuda_stream); /* adopt a caller stream (NULL: own stream)     */
+int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx);
+/* number of kernels launched by this ctx since creation / since the last reset */
+uint64_t sezkp_cuda_launch_count(sezkp_ctx* ctx, int reset);
+/* JSON object {"phase": ms, ...} of the last sezkp_stark_v1_prove on this ctx */
+int32_t sezkp_cuda_get_timings(sezkp_ctx* ctx, char* json_buf, size_t cap);
+
+/* ------------------------------------------------------------ NTT / LDE ------ */
+/* forward_ntt_in_place / inverse_ntt_in_place per column (sezkp-ffts/src/ntt.rs:79-111, 117-155):
+ * data is [cols][1<<log_n], natural order in and out, w_N = 7^((p-1)/N); inverse scales by N^-1. */
+int32_t sezkp_ntt_batch(sezkp_ctx* ctx, uint64_t* data, int log_n, int cols, int inverse);
+int32_t sezkp_ntt_batch_dev(sezkp_ctx* ctx, uint64_t* data_dev, int log_n, int cols, int inverse);
+/* evaluate_on_coset_pow2(coeffs, log_n+log_blow, shift) per column (sezkp-ffts/src/coset.rs:85-102):
+ * coeffs [cols][1<<log_n] -> out [cols][1<<(log_n+log_blow)], out[i] = f(shift * w_N^i). */
+int32_t sezkp_coset_lde_batch(sezkp_ctx* ctx, const uint64_t* coeffs, int log_n, int log_blow, uint64_t shift, int cols,
+                              uint64_t* out);
+int32_t sezkp_coset_lde_batch_dev(sezkp_ctx* ctx, const uint64_t* coeffs_dev, int log_n, int log_blow, uint64_t shift,
+                                  int cols, uint64_t* out_dev);
+/* interpolate_from_evals (ntt.rs:173-177) then evaluate_on_coset_pow2, per column; evals are NOT modified. */
+int32_t sezkp_lde_from_evals_batch(sezkp_ctx* ctx, const uint64_t* evals, int log_n, int log_blow, uint64_t shift,
+                                   int cols, uint64_t* out);
+int32_t sezkp_lde_from_evals_batch_dev(sezkp_ctx* ctx, const uint64_t* evals_dev, int log_n, int log_blow, uint64_t shift,
+                                       int cols, uint64_t* out_dev);
+/* deep_coset_lde_stream (sezkp-stark/src/v1/lde.rs:42-97) without the chunked callback: base_evals[n] ->
+ * out[n<<log_blow], out[i] = f(shift*w^i) / (shift*w^i - z).  z on the coset -> EINVAL. */
+int32_t sezkp_deep_lde(sezkp_ctx* ctx, const uint64_t* base_evals, int log_n, int log_blow, uint64_t shift, uint64_t z,
+                       uint64_t* out);
+int32_t sezkp_deep_lde_dev(sezkp_ctx* ctx, const uint64_t* base_evals_dev, int log_n, int log_blow, uint64_t shift,
+                           uint64_t z, uint64_t* out_dev);
+
+/* ------------------------------------------------------ hashing / Merkle ----- */
+/* hash_field_leaves (label NULL; v1/merkle.rs:150-159, v1/fri_stream.rs:37-41) or
+ * hash_field_leaves_labeled (v1/merkle.rs:132-146): vals[n] -> out[n][32].  strlen(label) <= 44. */
+int32_t sezkp_leaf_hash(sezkp_ctx* ctx, const uint64_t* vals, size_t n, const char* label_or_null, uint8_t* out);
+/* MerkleTree::from_leaves(leaves).root() (v1/merkle.rs:46-77) == sezkp_merkle::merkle_root for n >= 1
+ * (sezkp-merkle/src/lib.rs:140-157): BLAKE3(left||right) parents, odd node promoted unchanged. */
+int32_t sezkp_merkle_root(sezkp_ctx* ctx, const uint8_t* leaves, size_t n, uint8_t out_root[32]);
+/* OnDemandOpenings::build_roots over arbitrary columns (v1/openings.rs:306-398): cols [c][n] with one label per
+ * column, labeled leaves -> 2^chunk_log2-row chunk trees -> outer tree over chunk roots.  n must be a power of two
+ * (then the result equals one binary tree over n labeled leaves).  keep != NULL retains what openings need. */
+int32_t sezkp_column_commit_batch(sezkp_ctx* ctx, const uint64_t* cols, const char* const* labels, int c, size_t n,
+                                  int chunk_log2, uint8_t* roots /* [c][32] */, sezkp_tree** keep_or_null);
+int32_t sezkp_column_commit_batch_dev(sezkp_ctx* ctx, const uint64_t* cols_dev, const char* const* labels, int c, size_t n,
+                                      int chunk_log2, uint8_t* roots /* host [c][32] */, sezkp_tree** keep_or_null);
+/* OnDemandOpenings::open (v1/openings.rs:403-497) for k (column, row) pairs.  Per opening the outputs are
+ * value (8 B LE), chunk_root (32 B), path_in_chunk (min(chunk_log2, log2 n) siblings), path_to_chunk (the rest);
+ * sibling arrays are [k][depth][32] with depth_in / depth_out returned. */
+int32_t sezkp_column_open(sezkp_ctx* ctx, const sezkp_tree* tree, const uint32_t* col_idx, const uint64_t* row_idx, size_t k,
+                          uint64_t* values, uint8_t* chunk_roots, uint8_t* path_in_chunk, uint8_t* path_to_chunk,
+                          int* depth_in, int* depth_out);
+void sezkp_tree_free(sezkp_ctx* ctx, sezkp_tree* tree);
+
+/* ------------------------------------------------------------------ FRI ------ */
+/* FRI fold-and-commit for given folding challenges (v1/prover.rs:184-243; same layers as v1/fri.rs:71-91):
+ * layer0[1<<log_N]; betas[log_N]; y'[i] = y[i] + beta_r*y[i+half]; roots [log_N+1][32] (layer 0 first) and the final
+ * value.  keep != NULL retains the layers for sezkp_fri_open. */
+int32_t sezkp_fri_commit(sezkp_ctx* ctx, const uint64_t* layer0, int log_N, const uint64_t* betas, uint8_t* roots,
+                         uint64_t* final_value, sezkp_fri** keep_or_null);
+int32_t sezkp_fri_commit_dev(sezkp_ctx* ctx, const uint64_t* layer0_dev, int log_N, const uint64_t* betas, uint8_t* roots,
+                             uint64_t* final_value, sezkp_fri** keep_or_null);
+/* FRI query openings (v1/prover.rs:297-450; compat v1/fri.rs:98-127) for k layer-0 indices: per query and per layer
+ * l < log_N: values[q][l][2] = (y_l[idx], y_l[idx^half]), paths[q][l][2][log_N - l][32] stored with a fixed
+ * pitch of log_N siblings per path (unused tail zero), positions[q][log_N+1]. */
+int32_t sezkp_fri_open(sezkp_ctx* ctx, const sezkp_fri* fri, const uint64_t* idx0, size_t k, uint64_t* positions,
+                       uint64_t* values, uint8_t* paths);
+void sezkp_fri_free(sezkp_ctx* ctx, sezkp_fri* fri);
+
+/* --------------------------------------------------- feeder (columns + AIR) -- */
+/* TraceColumns::build committed columns (v1/columns.rs:252-365) in all_labels order (v1/openings.rs:89-116):
+ * out [3+7*tau][n_rows]. */
+int32_t sezkp_trace_columns(sezkp_ctx* ctx, const sezkp_trace_desc* trace, uint64_t* out);
+/* base-domain composition C(i)+B(i)+R(w^i) (compose_row/compose_boundary v1/air.rs:49-136, eval_masks_sum_at
+ * v1/masking.rs:86-103, closure at v1/prover.rs:142-158): alphas8 as drawn by derive_alphas, one mask polynomial
+ * of mask_deg ascending coefficients; out[n_rows]. */
+int32_t sezkp_compose_base(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const uint64_t alphas8[8],
+                           const uint64_t* mask_coeffs, size_t mask_deg, uint64_t* out);
+
+/* --------------------------------------------------------------- prover ------ */
+/* prove_v1 + bincode::serialize (v1/prover.rs:61-462, sezkp-stark/src/lib.rs:129-142): writes the ProofV1 bytes
+ * (v1/proof.rs:80-98, bincode 1.3 default config).  proof_buf may be NULL to query *len; cap too small -> ERANGE
+ * with *len set.  The Fiat-Shamir transcript (sezkp-crypto/src/lib.rs:74-124) runs on the host inside the library. */
+int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const uint8_t manifest_root[32],
+                             uint8_t* proof_buf, size_t cap, size_t* len);
+/* ProvingBackendStream (sezkp-core/src/prover.rs:21-33): begin_stream / ingest_block / finish_stream.  Blocks are
+ * pushed one at a time as one-block descriptors (n_blocks == 1); rows are staged through pinned host buffers and
+ * copied on a side stream while earlier chunks are expanded on the GPU. */
+int32_t sezkp_stark_v1_begin(sezkp_ctx* ctx, uint32_t tau, const uint8_t manifest_root[32], sezkp_stream** out);
+int32_t sezkp_stark_v1_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* one_block);
+int32_t sezkp_stark_v1_finish(sezkp_ctx* ctx, sezkp_stream* st, uint8_t* proof_buf, size_t cap, size_t* len);
+void sezkp_stark_v1_abort(sezkp_ctx* ctx, sezkp_stream* st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEZKP_CUDA_H */

@@ -6,4 +6,7 @@ repository root.
 """
 from .trace import CompactTrace, TraceDesc, blocks_to_compact, demo_block, manifest_root, simulate  # noqa: F401
 
-__all__ = ["CompactTrace", "TraceDesc", "blocks_to_compact", "demo_block", "manifest_root", "simulate"]
+from .binding import Context, SezkpCudaError, load_library, EXPORTS, LIB_PATH  # noqa: F401,E402
+from .backend import ProofArtifact, StarkV1Cuda  # noqa: F401,E402
+
+__all__ = ["Context", "SezkpCudaError", "StarkV1Cuda", "ProofArtifact", "CompactTrace", "TraceDesc", "blocks_to_compact", "demo_block", "manifest_root", "simulate"]

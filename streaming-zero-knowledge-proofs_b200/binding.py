@@ -1,0 +1,318 @@
+"""ctypes binding of libsezkp_cuda.so (include/sezkp_cuda.h).
+
+There is no CPU fallback: a missing library raises ImportError-like :class:`SezkpCudaError` at load time and a
+missing GPU raises at context creation (``SEZKP_CUDA_ENODEV``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .trace import CompactTrace, TraceDesc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsezkp_cuda.so")
+P = 0xFFFFFFFF00000001
+
+EXPORTS = [
+    "sezkp_cuda_abi_version", "sezkp_cuda_create", "sezkp_cuda_destroy", "sezkp_cuda_last_error", "sezkp_cuda_set_stream",
+    "sezkp_cuda_synchronize", "sezkp_cuda_launch_count", "sezkp_cuda_get_timings",
+    "sezkp_ntt_batch", "sezkp_ntt_batch_dev", "sezkp_coset_lde_batch", "sezkp_coset_lde_batch_dev",
+    "sezkp_lde_from_evals_batch", "sezkp_lde_from_evals_batch_dev", "sezkp_deep_lde", "sezkp_deep_lde_dev",
+    "sezkp_leaf_hash", "sezkp_merkle_root", "sezkp_column_commit_batch", "sezkp_column_commit_batch_dev",
+    "sezkp_column_open", "sezkp_tree_free", "sezkp_fri_commit", "sezkp_fri_commit_dev", "sezkp_fri_open", "sezkp_fri_free",
+    "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
+    "sezkp_stark_v1_finish", "sezkp_stark_v1_abort",
+]
+
+ERR_NAMES = {0: "OK", -1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENODEV", -5: "ERANGE", -6: "ESTATE"}
+
+
+class SezkpCudaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sezkp_cuda {ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libsezkp_cuda.so; fails loudly when it has not been built (``python __graft_entry__.py`` builds it)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SezkpCudaError(-4, f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                                     "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.sezkp_cuda_abi_version.restype = C.c_uint32
+        lib.sezkp_cuda_last_error.restype = C.c_char_p
+        lib.sezkp_cuda_last_error.argtypes = [C.c_void_p]
+        lib.sezkp_cuda_launch_count.restype = C.c_uint64
+        lib.sezkp_cuda_launch_count.argtypes = [C.c_void_p, C.c_int]
+        lib.sezkp_cuda_destroy.argtypes = [C.c_void_p]
+        lib.sezkp_tree_free.argtypes = [C.c_void_p, C.c_void_p]
+        lib.sezkp_fri_free.argtypes = [C.c_void_p, C.c_void_p]
+        lib.sezkp_stark_v1_abort.argtypes = [C.c_void_p, C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _vp(x) -> C.c_void_p:
+    """device pointer (int / torch tensor) -> c_void_p"""
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(int(x))
+
+
+class Context:
+    """One GPU, one context (one process per GPU).  Mirrors ``sezkp_ctx``."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.sezkp_cuda_create(C.c_int(device), C.byref(h))
+        if rc != 0:
+            raise SezkpCudaError(rc, self.lib.sezkp_cuda_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sezkp_cuda_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise SezkpCudaError(rc, self.lib.sezkp_cuda_last_error(self.h).decode())
+
+    # ---- plumbing ----
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.lib.sezkp_cuda_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._ck(self.lib.sezkp_cuda_synchronize(self.h))
+
+    def launch_count(self, reset=False) -> int:
+        return int(self.lib.sezkp_cuda_launch_count(self.h, C.c_int(int(reset))))
+
+    def timings(self) -> dict:
+        buf = C.create_string_buffer(4096)
+        self._ck(self.lib.sezkp_cuda_get_timings(self.h, buf, C.c_size_t(4096)))
+        return json.loads(buf.value.decode())
+
+    # ---- NTT / LDE (host buffers) ----
+    def ntt(self, data, inverse=False) -> np.ndarray:
+        a = np.array(data, dtype=np.uint64, copy=True, order="C")
+        a2 = a.reshape(-1, a.shape[-1])
+        n = a2.shape[1]
+        if n & (n - 1):
+            raise SezkpCudaError(-1, "NTT size must be a power of two")
+        self._ck(self.lib.sezkp_ntt_batch(self.h, _p(a2), C.c_int(n.bit_length() - 1), C.c_int(a2.shape[0]), C.c_int(int(inverse))))
+        return a
+
+    def coset_lde(self, coeffs, log_blow: int, shift: int) -> np.ndarray:
+        a = np.ascontiguousarray(coeffs, np.uint64)
+        a2 = a.reshape(-1, a.shape[-1])
+        n = a2.shape[1]
+        out = np.empty((a2.shape[0], n << log_blow), np.uint64)
+        self._ck(self.lib.sezkp_coset_lde_batch(self.h, _p(a2), C.c_int(n.bit_length() - 1), C.c_int(log_blow), C.c_uint64(shift),
+                                                C.c_int(a2.shape[0]), _p(out)))
+        return out if a.ndim == 2 else out[0]
+
+    def lde_from_evals(self, evals, log_blow: int, shift: int) -> np.ndarray:
+        a = np.ascontiguousarray(evals, np.uint64)
+        a2 = a.reshape(-1, a.shape[-1])
+        n = a2.shape[1]
+        out = np.empty((a2.shape[0], n << log_blow), np.uint64)
+        self._ck(self.lib.sezkp_lde_from_evals_batch(self.h, _p(a2), C.c_int(n.bit_length() - 1), C.c_int(log_blow),
+                                                     C.c_uint64(shift), C.c_int(a2.shape[0]), _p(out)))
+        return out if a.ndim == 2 else out[0]
+
+    def deep_lde(self, base_evals, log_blow: int, shift: int, z: int) -> np.ndarray:
+        a = np.ascontiguousarray(base_evals, np.uint64)
+        out = np.empty(a.size << log_blow, np.uint64)
+        self._ck(self.lib.sezkp_deep_lde(self.h, _p(a), C.c_int(a.size.bit_length() - 1), C.c_int(log_blow), C.c_uint64(shift),
+                                         C.c_uint64(z), _p(out)))
+        return out
+
+    # ---- device-pointer variants (torch tensors or raw ints) ----
+    def ntt_dev(self, data_dev, log_n: int, cols: int, inverse=False):
+        self._ck(self.lib.sezkp_ntt_batch_dev(self.h, _vp(data_dev), C.c_int(log_n), C.c_int(cols), C.c_int(int(inverse))))
+
+    def coset_lde_dev(self, coeffs_dev, log_n, log_blow, shift, cols, out_dev):
+        self._ck(self.lib.sezkp_coset_lde_batch_dev(self.h, _vp(coeffs_dev), C.c_int(log_n), C.c_int(log_blow), C.c_uint64(shift),
+                                                    C.c_int(cols), _vp(out_dev)))
+
+    def lde_from_evals_dev(self, evals_dev, log_n, log_blow, shift, cols, out_dev):
+        self._ck(self.lib.sezkp_lde_from_evals_batch_dev(self.h, _vp(evals_dev), C.c_int(log_n), C.c_int(log_blow),
+                                                         C.c_uint64(shift), C.c_int(cols), _vp(out_dev)))
+
+    def deep_lde_dev(self, base_dev, log_n, log_blow, shift, z, out_dev):
+        self._ck(self.lib.sezkp_deep_lde_dev(self.h, _vp(base_dev), C.c_int(log_n), C.c_int(log_blow), C.c_uint64(shift),
+                                             C.c_uint64(z), _vp(out_dev)))
+
+    # ---- hashing / Merkle ----
+    def leaf_hash(self, vals, label: Optional[str] = None) -> np.ndarray:
+        v = np.ascontiguousarray(vals, np.uint64)
+        out = np.empty((v.size, 32), np.uint8)
+        self._ck(self.lib.sezkp_leaf_hash(self.h, _p(v), C.c_size_t(v.size), label.encode() if label is not None else None, _p(out)))
+        return out
+
+    def merkle_root(self, leaves) -> bytes:
+        l = np.ascontiguousarray(leaves, np.uint8).reshape(-1, 32)
+        out = C.create_string_buffer(32)
+        self._ck(self.lib.sezkp_merkle_root(self.h, _p(l), C.c_size_t(l.shape[0]), out))
+        return out.raw
+
+    def column_commit(self, cols, labels: Sequence[str], chunk_log2=10, keep=False, dev=False, n=None):
+        if dev:
+            c = len(labels)
+            ptr = _vp(cols)
+        else:
+            a = np.ascontiguousarray(cols, np.uint64)
+            c, n = a.shape
+            ptr = _p(a)
+        arr = (C.c_char_p * c)(*[l.encode() for l in labels])
+        roots = np.empty((c, 32), np.uint8)
+        tree = C.c_void_p()
+        fn = self.lib.sezkp_column_commit_batch_dev if dev else self.lib.sezkp_column_commit_batch
+        self._ck(fn(self.h, ptr, arr, C.c_int(c), C.c_size_t(n), C.c_int(chunk_log2), _p(roots), C.byref(tree) if keep else None))
+        return (roots, ColumnTree(self, tree)) if keep else roots
+
+    def fri_commit(self, layer0, betas, keep=False, dev=False, log_N=None):
+        b = np.ascontiguousarray(betas, np.uint64)
+        if dev:
+            ptr = _vp(layer0)
+        else:
+            a = np.ascontiguousarray(layer0, np.uint64)
+            log_N = a.size.bit_length() - 1
+            ptr = _p(a)
+        roots = np.empty((log_N + 1, 32), np.uint8)
+        fin = C.c_uint64(0)
+        h = C.c_void_p()
+        fn = self.lib.sezkp_fri_commit_dev if dev else self.lib.sezkp_fri_commit
+        self._ck(fn(self.h, ptr, C.c_int(log_N), _p(b), _p(roots), C.byref(fin), C.byref(h) if keep else None))
+        return (roots, fin.value, FriHandle(self, h, log_N)) if keep else (roots, fin.value)
+
+    # ---- feeder ----
+    def trace_columns(self, ct: CompactTrace) -> np.ndarray:
+        d = ct.as_desc()
+        out = np.empty((3 + 7 * ct.tau, ct.n_rows), np.uint64)
+        self._ck(self.lib.sezkp_trace_columns(self.h, C.byref(d), _p(out)))
+        return out
+
+    def compose_base(self, ct: CompactTrace, alphas8, mask_coeffs) -> np.ndarray:
+        d = ct.as_desc()
+        a = np.ascontiguousarray(alphas8, np.uint64)
+        m = np.ascontiguousarray(mask_coeffs, np.uint64)
+        out = np.empty(ct.n_rows, np.uint64)
+        self._ck(self.lib.sezkp_compose_base(self.h, C.byref(d), _p(a), _p(m), C.c_size_t(m.size), _p(out)))
+        return out
+
+    # ---- prover ----
+    def prove_v1(self, ct: CompactTrace, manifest_root: bytes, buf: Optional[np.ndarray] = None) -> bytes:
+        if len(manifest_root) != 32:
+            raise SezkpCudaError(-1, "manifest_root must be 32 bytes")
+        d = ct.as_desc()
+        n = C.c_size_t(0)
+        if buf is None:
+            buf = np.empty(proof_size_bound(ct.n_rows, ct.tau), np.uint8)
+        self._ck(self.lib.sezkp_stark_v1_prove(self.h, C.byref(d), manifest_root, _p(buf), C.c_size_t(buf.size), C.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def prove_v1_stream(self, blocks: Sequence[CompactTrace], manifest_root: bytes) -> bytes:
+        """begin_stream / ingest_block / finish_stream (reference sezkp-core/src/prover.rs:21-33)."""
+        st = C.c_void_p()
+        self._ck(self.lib.sezkp_stark_v1_begin(self.h, C.c_uint32(blocks[0].tau), manifest_root, C.byref(st)))
+        try:
+            rows = 0
+            for b in blocks:
+                d = b.as_desc()
+                self._ck(self.lib.sezkp_stark_v1_ingest(self.h, st, C.byref(d)))
+                rows += b.n_rows
+            buf = np.empty(proof_size_bound(rows, blocks[0].tau), np.uint8)
+            n = C.c_size_t(0)
+            self._ck(self.lib.sezkp_stark_v1_finish(self.h, st, _p(buf), C.c_size_t(buf.size), C.byref(n)))
+            st = None
+            return buf[: n.value].tobytes()
+        finally:
+            if st is not None and st.value:
+                self.lib.sezkp_stark_v1_abort(self.h, st)
+
+
+def proof_size_bound(n_rows: int, tau: int) -> int:
+    ln = max(1, int(n_rows).bit_length() - 1)
+    lN = ln + 3
+    openings = 30 * (9 * tau + 3) * (8 + 24 + 32 + 16 + 32 * ln)
+    fri = 30 * (16 + 8 * (lN + 1) + lN * 2 * (8 + 8 + 32 * lN))
+    return 4096 + (3 + 7 * tau) * 64 + openings + fri + 32 * (lN + 1)
+
+
+class ColumnTree:
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    def open(self, col_idx, row_idx):
+        c = np.ascontiguousarray(col_idx, np.uint32)
+        r = np.ascontiguousarray(row_idx, np.uint64)
+        k = c.size
+        din, dout = C.c_int(0), C.c_int(0)
+        lib = self.ctx.lib
+        self.ctx._ck(lib.sezkp_column_open(self.ctx.h, self.h, None, None, C.c_size_t(0), None, None, None, None, C.byref(din), C.byref(dout)))
+        vals = np.empty(k, np.uint64)
+        cr = np.empty((k, 32), np.uint8)
+        pin = np.zeros((k, max(din.value, 1), 32), np.uint8)
+        pto = np.zeros((k, max(dout.value, 1), 32), np.uint8)
+        self.ctx._ck(lib.sezkp_column_open(self.ctx.h, self.h, _p(c), _p(r), C.c_size_t(k), _p(vals), _p(cr), _p(pin), _p(pto),
+                                           C.byref(din), C.byref(dout)))
+        return vals, cr, pin[:, : din.value], pto[:, : dout.value]
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.sezkp_tree_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class FriHandle:
+    def __init__(self, ctx: Context, h, log_N):
+        self.ctx, self.h, self.log_N = ctx, h, log_N
+
+    def open(self, idx0):
+        q = np.ascontiguousarray(idx0, np.uint64)
+        k, L = q.size, self.log_N
+        pos = np.empty((k, L + 1), np.uint64)
+        vals = np.empty((k, L, 2), np.uint64)
+        paths = np.zeros((k, L, 2, L, 32), np.uint8)
+        self.ctx._ck(self.ctx.lib.sezkp_fri_open(self.ctx.h, self.h, _p(q), C.c_size_t(k), _p(pos), _p(vals), _p(paths)))
+        return pos, vals, paths
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.sezkp_fri_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

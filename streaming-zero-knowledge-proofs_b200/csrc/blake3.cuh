@@ -1,0 +1,108 @@
+// Single-compression BLAKE3 for the device.  Every hash on the commitment path is one compression
+// with cv = IV, counter = 0, flags = CHUNK_START|CHUNK_END|ROOT (0x0B):
+//   * unlabeled leaf  BLAKE3(le8)                       (reference v1/merkle.rs:150-159, fri_stream.rs:37-41)
+//   * labeled leaf    BLAKE3("col_leaf"||u32 len||label||le8)   (v1/merkle.rs:132-146)
+//   * parent          BLAKE3(left||right), a plain 64-byte message (v1/merkle.rs:57-61,
+//                     fri_stream.rs:45-50, sezkp-merkle/src/lib.rs:123-128)
+#pragma once
+#include <cstdint>
+
+namespace b3 {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+#define B3_IV0 0x6A09E667u
+#define B3_IV1 0xBB67AE85u
+#define B3_IV2 0x3C6EF372u
+#define B3_IV3 0xA54FF53Au
+#define B3_IV4 0x510E527Fu
+#define B3_IV5 0x9B05688Cu
+#define B3_IV6 0x1F83D9ABu
+#define B3_IV7 0x5BE0CD19u
+#define B3_FLAGS_ONE_BLOCK 0x0Bu
+
+__device__ __forceinline__ u32 rotr16(u32 x) { return __byte_perm(x, x, 0x1032); }
+__device__ __forceinline__ u32 rotr8(u32 x) { return __byte_perm(x, x, 0x0321); }
+__device__ __forceinline__ u32 rotr12(u32 x) { return __funnelshift_r(x, x, 12); }
+__device__ __forceinline__ u32 rotr7(u32 x) { return __funnelshift_r(x, x, 7); }
+
+#define B3_G(a, b, c, d, mx, my) \
+    a = a + b + (mx);            \
+    d = rotr16(d ^ a);           \
+    c = c + d;                   \
+    b = rotr12(b ^ c);           \
+    a = a + b + (my);            \
+    d = rotr8(d ^ a);            \
+    c = c + d;                   \
+    b = rotr7(b ^ c);
+
+// message word schedule: round r reads the message through BLAKE3's fixed permutation, applied r times
+#define B3_ROUND(m, i0, i1, i2, i3, i4, i5, i6, i7, i8, i9, i10, i11, i12, i13, i14, i15) \
+    B3_G(s0, s4, s8, s12, m[i0], m[i1])                                                   \
+    B3_G(s1, s5, s9, s13, m[i2], m[i3])                                                   \
+    B3_G(s2, s6, s10, s14, m[i4], m[i5])                                                  \
+    B3_G(s3, s7, s11, s15, m[i6], m[i7])                                                  \
+    B3_G(s0, s5, s10, s15, m[i8], m[i9])                                                  \
+    B3_G(s1, s6, s11, s12, m[i10], m[i11])                                                \
+    B3_G(s2, s7, s8, s13, m[i12], m[i13])                                                 \
+    B3_G(s3, s4, s9, s14, m[i14], m[i15])
+
+// One-block hash: out[8] = BLAKE3(message of block_len bytes held zero-padded in m[16]).
+__device__ __forceinline__ void hash_block(const u32 (&m)[16], u32 block_len, u32 (&out)[8]) {
+    u32 s0 = B3_IV0, s1 = B3_IV1, s2 = B3_IV2, s3 = B3_IV3, s4 = B3_IV4, s5 = B3_IV5, s6 = B3_IV6, s7 = B3_IV7;
+    u32 s8 = B3_IV0, s9 = B3_IV1, s10 = B3_IV2, s11 = B3_IV3, s12 = 0, s13 = 0, s14 = block_len, s15 = B3_FLAGS_ONE_BLOCK;
+    B3_ROUND(m, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    B3_ROUND(m, 2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8)
+    B3_ROUND(m, 3, 4, 10, 12, 13, 2, 7, 14, 6, 5, 9, 0, 11, 15, 8, 1)
+    B3_ROUND(m, 10, 7, 12, 9, 14, 3, 13, 15, 4, 0, 11, 2, 5, 8, 1, 6)
+    B3_ROUND(m, 12, 13, 9, 11, 15, 10, 14, 8, 7, 2, 5, 3, 0, 1, 6, 4)
+    B3_ROUND(m, 9, 14, 11, 5, 8, 12, 15, 1, 13, 3, 0, 10, 2, 6, 4, 7)
+    B3_ROUND(m, 11, 15, 5, 0, 1, 9, 8, 6, 14, 10, 2, 12, 3, 4, 7, 13)
+    out[0] = s0 ^ s8;  out[1] = s1 ^ s9;  out[2] = s2 ^ s10; out[3] = s3 ^ s11;
+    out[4] = s4 ^ s12; out[5] = s5 ^ s13; out[6] = s6 ^ s14; out[7] = s7 ^ s15;
+}
+
+// Unlabeled leaf of one canonical field element.
+__device__ __forceinline__ void leaf(u64 v, u32 (&out)[8]) {
+    u32 m[16] = {(u32)v, (u32)(v >> 32), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    hash_block(m, 8, out);
+}
+// Parent of two digests.
+__device__ __forceinline__ void parent(const u32 (&l)[8], const u32 (&r)[8], u32 (&out)[8]) {
+    u32 m[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        m[i] = l[i];
+        m[8 + i] = r[i];
+    }
+    hash_block(m, 64, out);
+}
+
+// Labeled-leaf message template: the 12+L prefix bytes laid out in 16 words; the 8 value bytes
+// are inserted at byte offset `off` = 12+L (unaligned in general).
+struct LabelTemplate {
+    u32 words[16];
+    u32 off;        // byte offset of the value
+    u32 block_len;  // 20 + L
+};
+__device__ __forceinline__ void leaf_labeled(const LabelTemplate& t, u64 v, u32 (&out)[8]) {
+    u32 m[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) m[i] = t.words[i];
+    const u32 w = t.off >> 2, sh = (t.off & 3) * 8;
+    const u32 lo = (u32)v, hi = (u32)(v >> 32);
+    // value bytes spread over words w, w+1, w+2
+    u32 a = lo << sh;
+    u32 b = sh ? (lo >> (32 - sh)) | (hi << sh) : hi;
+    u32 c = sh ? (hi >> (32 - sh)) : 0;
+#pragma unroll
+    for (int i = 3; i < 16; i++) {  // off = 12+L in [13,56]: w in [3..14]; static indices keep m[] in registers
+        if (i == (int)w) m[i] |= a;
+        if (i == (int)w + 1) m[i] |= b;
+        if (i == (int)w + 2) m[i] |= c;
+    }
+    hash_block(m, t.block_len, out);
+}
+
+}  // namespace b3

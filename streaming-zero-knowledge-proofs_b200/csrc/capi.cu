@@ -1,0 +1,528 @@
+// extern "C" surface of libsezkp_cuda.so (include/sezkp_cuda.h).  Every entry point converts C++
+// exceptions into status codes + ctx->last_error; nothing aborts.
+#include <cstring>
+#include <string>
+
+#include "gl.cuh"
+#include "hash.cuh"
+#include "ntt.cuh"
+#include "stark.cuh"
+
+static std::string g_create_error;
+
+struct sezkp_tree {
+    Commit cm;
+};
+struct sezkp_fri {
+    FriLayers fl;
+};
+struct sezkp_stream {
+    uint32_t tau = 0;
+    u8 manifest_root[32];
+    std::vector<u64> block_len;
+    std::vector<int64_t> win_left, win_right;
+    std::vector<u32> in_off, out_off;
+    std::vector<int8_t> input_mv, mv;
+    std::vector<u8> wflag;
+    std::vector<uint16_t> wsym;
+};
+
+#define API_BEGIN(ctx)                                         \
+    if (!(ctx)) return SEZKP_CUDA_EINVAL;                      \
+    try {                                                      \
+        CUDA_CHECK(cudaSetDevice((ctx)->device));
+#define API_END(ctx)                                           \
+        return SEZKP_CUDA_OK;                                  \
+    } catch (const SezkpError& e) {                            \
+        (ctx)->last_error = e.what();                          \
+        cudaGetLastError();                                    \
+        return e.code;                                         \
+    } catch (const std::bad_alloc&) {                          \
+        (ctx)->last_error = "host allocation failed";          \
+        return SEZKP_CUDA_ENOMEM;                              \
+    } catch (const std::exception& e) {                        \
+        (ctx)->last_error = e.what();                          \
+        return SEZKP_CUDA_ECUDA;                               \
+    }
+
+static void check_canonical(const u64* v, size_t n, const char* what) {
+    for (size_t i = 0; i < n; i++)
+        if (v[i] >= gl::P) sezkp_fail(SEZKP_CUDA_EINVAL, "%s[%zu] is not a canonical field element", what, i);
+}
+static void h2d(sezkp_ctx* ctx, void* d, const void* h, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+}
+static void d2h(sezkp_ctx* ctx, void* h, const void* d, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+extern "C" {
+
+uint32_t sezkp_cuda_abi_version(void) { return SEZKP_CUDA_ABI_VERSION; }
+
+int32_t sezkp_cuda_create(int device_id, sezkp_ctx** out) {
+    if (!out) return SEZKP_CUDA_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (libsezkp_cuda has no CPU fallback)";
+        cudaGetLastError();
+        return SEZKP_CUDA_ENODEV;
+    }
+    if (device_id < 0) {
+        if (cudaGetDevice(&device_id) != cudaSuccess) device_id = 0;
+    }
+    if (device_id >= count) {
+        g_create_error = "device id out of range";
+        return SEZKP_CUDA_EINVAL;
+    }
+    sezkp_ctx* ctx = new (std::nothrow) sezkp_ctx();
+    if (!ctx) return SEZKP_CUDA_ENOMEM;
+    ctx->device = device_id;
+    try {
+        CUDA_CHECK(cudaSetDevice(device_id));
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device_id));
+        ctx->sm_count = prop.multiProcessorCount;
+        if (prop.major < 10) sezkp_fail(SEZKP_CUDA_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device_id, prop.major, prop.minor);
+        CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    } catch (const SezkpError& err) {
+        g_create_error = err.what();
+        int32_t code = err.code;
+        delete ctx;
+        return code;
+    }
+    *out = ctx;
+    return SEZKP_CUDA_OK;
+}
+
+void sezkp_cuda_destroy(sezkp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ntt_free_tables(ctx);
+    for (auto& b : ctx->scratch) b.release();
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* sezkp_cuda_last_error(const sezkp_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
+
+int32_t sezkp_cuda_set_stream(sezkp_ctx* ctx, void* cuda_stream) {
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (cuda_stream == nullptr) {
+        if (!ctx->own_stream) {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+            ctx->own_stream = true;
+        }
+    } else {
+        if (ctx->own_stream) CUDA_CHECK(cudaStreamDestroy(ctx->stream));
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    }
+    API_END(ctx)
+}
+
+int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx) {
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+uint64_t sezkp_cuda_launch_count(sezkp_ctx* ctx, int reset) {
+    if (!ctx) return 0;
+    uint64_t v = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return v;
+}
+
+int32_t sezkp_cuda_get_timings(sezkp_ctx* ctx, char* json_buf, size_t cap) {
+    API_BEGIN(ctx)
+    std::string s = "{";
+    for (size_t i = 0; i < ctx->timings.size(); i++) {
+        char t[128];
+        snprintf(t, sizeof t, "%s\"%s\": %.4f", i ? ", " : "", ctx->timings[i].first.c_str(), ctx->timings[i].second);
+        s += t;
+    }
+    s += "}";
+    if (!json_buf || cap < s.size() + 1) sezkp_fail(SEZKP_CUDA_ERANGE, "timings buffer too small (need %zu)", s.size() + 1);
+    std::memcpy(json_buf, s.c_str(), s.size() + 1);
+    API_END(ctx)
+}
+
+/* ------------------------------------------------------------ NTT / LDE ------ */
+int32_t sezkp_ntt_batch_dev(sezkp_ctx* ctx, uint64_t* data_dev, int log_n, int cols, int inverse) {
+    API_BEGIN(ctx)
+    REQUIRE(data_dev != nullptr && cols >= 0 && log_n >= 0 && log_n <= 30, "bad argument");
+    u64* tmp = log_n > 10 ? (u64*)ctx->scratch[0].ensure(((size_t)cols << log_n) * 8) : nullptr;
+    ntt_batch_device(ctx, data_dev, tmp, log_n, (u64)cols, inverse != 0);
+    API_END(ctx)
+}
+int32_t sezkp_ntt_batch(sezkp_ctx* ctx, uint64_t* data, int log_n, int cols, int inverse) {
+    API_BEGIN(ctx)
+    REQUIRE(data != nullptr && cols >= 0 && log_n >= 0 && log_n <= 30, "bad argument");
+    const size_t count = (size_t)cols << log_n;
+    if (count == 0) return SEZKP_CUDA_OK;
+    check_canonical(data, count, "data");
+    u64* d = (u64*)ctx->scratch[1].ensure(count * 8);
+    u64* tmp = log_n > 10 ? (u64*)ctx->scratch[0].ensure(count * 8) : nullptr;
+    h2d(ctx, d, data, count * 8);
+    ntt_batch_device(ctx, d, tmp, log_n, (u64)cols, inverse != 0);
+    d2h(ctx, data, d, count * 8);
+    API_END(ctx)
+}
+
+int32_t sezkp_coset_lde_batch_dev(sezkp_ctx* ctx, const uint64_t* coeffs_dev, int log_n, int log_blow, uint64_t shift, int cols,
+                                  uint64_t* out_dev) {
+    API_BEGIN(ctx)
+    REQUIRE(coeffs_dev && out_dev && cols >= 0, "bad argument");
+    u64* inter = log_n > 10 ? (u64*)ctx->scratch[1].ensure(((size_t)cols << (log_n + log_blow)) * 8) : nullptr;
+    coset_lde_device(ctx, coeffs_dev, out_dev, inter, log_n, log_blow, shift, (u64)cols);
+    API_END(ctx)
+}
+int32_t sezkp_coset_lde_batch(sezkp_ctx* ctx, const uint64_t* coeffs, int log_n, int log_blow, uint64_t shift, int cols,
+                              uint64_t* out) {
+    API_BEGIN(ctx)
+    REQUIRE(coeffs && out && cols >= 0 && log_n >= 1 && log_n <= 30 && log_blow >= 0 && log_blow <= 4, "bad argument");
+    const size_t n_in = (size_t)cols << log_n, n_out = n_in << log_blow;
+    if (n_in == 0) return SEZKP_CUDA_OK;
+    check_canonical(coeffs, n_in, "coeffs");
+    u64* d_in = (u64*)ctx->scratch[2].ensure(n_in * 8);
+    u64* d_out = (u64*)ctx->scratch[3].ensure(n_out * 8);
+    u64* inter = log_n > 10 ? (u64*)ctx->scratch[1].ensure(n_out * 8) : nullptr;
+    h2d(ctx, d_in, coeffs, n_in * 8);
+    coset_lde_device(ctx, d_in, d_out, inter, log_n, log_blow, shift, (u64)cols);
+    d2h(ctx, out, d_out, n_out * 8);
+    API_END(ctx)
+}
+
+static void lde_from_evals_device(sezkp_ctx* ctx, const u64* evals_dev, int log_n, int log_blow, u64 shift, int cols, u64* out_dev) {
+    const size_t n_in = (size_t)cols << log_n, n_out = n_in << log_blow;
+    u64* coeffs = (u64*)ctx->scratch[4].ensure(n_in * 8);
+    CUDA_CHECK(cudaMemcpyAsync(coeffs, evals_dev, n_in * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    u64* tmp = log_n > 10 ? (u64*)ctx->scratch[0].ensure(n_in * 8) : nullptr;
+    ntt_batch_device(ctx, coeffs, tmp, log_n, (u64)cols, true);
+    u64* inter = log_n > 10 ? (u64*)ctx->scratch[1].ensure(n_out * 8) : nullptr;
+    coset_lde_device(ctx, coeffs, out_dev, inter, log_n, log_blow, shift, (u64)cols);
+}
+int32_t sezkp_lde_from_evals_batch_dev(sezkp_ctx* ctx, const uint64_t* evals_dev, int log_n, int log_blow, uint64_t shift,
+                                       int cols, uint64_t* out_dev) {
+    API_BEGIN(ctx)
+    REQUIRE(evals_dev && out_dev && cols >= 0 && log_n >= 1 && log_n <= 30, "bad argument");
+    if (cols) lde_from_evals_device(ctx, evals_dev, log_n, log_blow, shift, cols, out_dev);
+    API_END(ctx)
+}
+int32_t sezkp_lde_from_evals_batch(sezkp_ctx* ctx, const uint64_t* evals, int log_n, int log_blow, uint64_t shift, int cols,
+                                   uint64_t* out) {
+    API_BEGIN(ctx)
+    REQUIRE(evals && out && cols >= 0 && log_n >= 1 && log_n <= 30 && log_blow >= 0 && log_blow <= 4, "bad argument");
+    const size_t n_in = (size_t)cols << log_n, n_out = n_in << log_blow;
+    if (n_in == 0) return SEZKP_CUDA_OK;
+    check_canonical(evals, n_in, "evals");
+    u64* d_in = (u64*)ctx->scratch[2].ensure(n_in * 8);
+    u64* d_out = (u64*)ctx->scratch[3].ensure(n_out * 8);
+    h2d(ctx, d_in, evals, n_in * 8);
+    lde_from_evals_device(ctx, d_in, log_n, log_blow, shift, cols, d_out);
+    d2h(ctx, out, d_out, n_out * 8);
+    API_END(ctx)
+}
+
+int32_t sezkp_deep_lde_dev(sezkp_ctx* ctx, const uint64_t* base_evals_dev, int log_n, int log_blow, uint64_t shift, uint64_t z,
+                           uint64_t* out_dev) {
+    API_BEGIN(ctx)
+    REQUIRE(base_evals_dev && out_dev && log_n >= 1 && log_n <= 29 && log_blow >= 0 && log_blow <= 4, "bad argument");
+    const size_t n = (size_t)1 << log_n;
+    u64* base = (u64*)ctx->scratch[4].ensure(n * 8);
+    CUDA_CHECK(cudaMemcpyAsync(base, base_evals_dev, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    deep_lde_device(ctx, base, out_dev, log_n, log_blow, shift, z);
+    API_END(ctx)
+}
+int32_t sezkp_deep_lde(sezkp_ctx* ctx, const uint64_t* base_evals, int log_n, int log_blow, uint64_t shift, uint64_t z,
+                       uint64_t* out) {
+    API_BEGIN(ctx)
+    REQUIRE(base_evals && out && log_n >= 1 && log_n <= 29 && log_blow >= 0 && log_blow <= 4, "bad argument");
+    const size_t n = (size_t)1 << log_n, N = n << log_blow;
+    check_canonical(base_evals, n, "base_evals");
+    u64* base = (u64*)ctx->scratch[4].ensure(n * 8);
+    u64* d_out = (u64*)ctx->scratch[3].ensure(N * 8);
+    h2d(ctx, base, base_evals, n * 8);
+    deep_lde_device(ctx, base, d_out, log_n, log_blow, shift, z);
+    d2h(ctx, out, d_out, N * 8);
+    API_END(ctx)
+}
+
+/* ------------------------------------------------------ hashing / Merkle ----- */
+int32_t sezkp_leaf_hash(sezkp_ctx* ctx, const uint64_t* vals, size_t n, const char* label, uint8_t* out) {
+    API_BEGIN(ctx)
+    REQUIRE((vals && out) || n == 0, "bad argument");
+    if (n == 0) return SEZKP_CUDA_OK;
+    check_canonical(vals, n, "vals");
+    u64* d_v = (u64*)ctx->scratch[2].ensure(n * 8);
+    u32* d_o = (u32*)ctx->scratch[3].ensure(n * 32);
+    h2d(ctx, d_v, vals, n * 8);
+    leaf_hash_device(ctx, d_v, n, label, d_o);
+    d2h(ctx, out, d_o, n * 32);
+    API_END(ctx)
+}
+
+int32_t sezkp_merkle_root(sezkp_ctx* ctx, const uint8_t* leaves, size_t n, uint8_t out_root[32]) {
+    API_BEGIN(ctx)
+    REQUIRE(out_root && (leaves || n == 0), "bad argument");
+    if (n == 0) {  // MerkleTree::from_leaves(&[]) -> single zero leaf (reference v1/merkle.rs:48-50)
+        std::memset(out_root, 0, 32);
+        return SEZKP_CUDA_OK;
+    }
+    u32* a = (u32*)ctx->scratch[2].ensure(n * 32);
+    u32* b = (u32*)ctx->scratch[3].ensure(((n + 1) / 2) * 32);
+    h2d(ctx, a, leaves, n * 32);
+    merkle_root_device(ctx, a, b, n, out_root);
+    API_END(ctx)
+}
+
+static int32_t column_commit_impl(sezkp_ctx* ctx, const u64* cols_host, const u64* cols_dev, const char* const* labels, int c,
+                                  size_t n, int chunk_log2, uint8_t* roots, sezkp_tree** keep) {
+    API_BEGIN(ctx)
+    REQUIRE((cols_host || cols_dev) && labels && roots && c >= 1, "bad argument");
+    REQUIRE(n >= 1 && (n & (n - 1)) == 0, "column length must be a power of two");
+    if (keep) *keep = nullptr;
+    const size_t bytes = (size_t)c * n * 8;
+    const u64* src = cols_dev;
+    u64* owned = nullptr;
+    if (cols_host) check_canonical(cols_host, (size_t)c * n, "cols");
+    if (keep || cols_host) {
+        if (keep) {
+            cudaError_t e = cudaMalloc(&owned, bytes);
+            if (e != cudaSuccess) sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        } else owned = (u64*)ctx->scratch[3].ensure(bytes);
+        if (cols_host) h2d(ctx, owned, cols_host, bytes);
+        else CUDA_CHECK(cudaMemcpyAsync(owned, cols_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        src = owned;
+    }
+    sezkp_tree* t = new sezkp_tree();
+    try {
+        commit_build(ctx, t->cm, src, n, c, chunk_log2, labels, roots);
+    } catch (...) {
+        t->cm.release();
+        if (keep && owned) cudaFree(owned);
+        delete t;
+        throw;
+    }
+    if (keep) {
+        t->cm.owns_values = true;
+        *keep = t;
+    } else {
+        t->cm.release();
+        delete t;
+    }
+    API_END(ctx)
+}
+int32_t sezkp_column_commit_batch(sezkp_ctx* ctx, const uint64_t* cols, const char* const* labels, int c, size_t n,
+                                  int chunk_log2, uint8_t* roots, sezkp_tree** keep) {
+    return column_commit_impl(ctx, cols, nullptr, labels, c, n, chunk_log2, roots, keep);
+}
+int32_t sezkp_column_commit_batch_dev(sezkp_ctx* ctx, const uint64_t* cols_dev, const char* const* labels, int c, size_t n,
+                                      int chunk_log2, uint8_t* roots, sezkp_tree** keep) {
+    return column_commit_impl(ctx, nullptr, cols_dev, labels, c, n, chunk_log2, roots, keep);
+}
+
+int32_t sezkp_column_open(sezkp_ctx* ctx, const sezkp_tree* tree, const uint32_t* col_idx, const uint64_t* row_idx, size_t k,
+                          uint64_t* values, uint8_t* chunk_roots, uint8_t* path_in_chunk, uint8_t* path_to_chunk, int* depth_in,
+                          int* depth_out) {
+    API_BEGIN(ctx)
+    REQUIRE(tree && depth_in && depth_out, "bad argument");
+    *depth_in = tree->cm.cl;
+    *depth_out = ilog2(tree->cm.n_ch);
+    if (k) {
+        REQUIRE(col_idx && row_idx && values && chunk_roots && (path_in_chunk || *depth_in == 0) && (path_to_chunk || *depth_out == 0),
+                "bad argument");
+        u8 dummy[32];
+        commit_open(ctx, tree->cm, col_idx, row_idx, k, values, chunk_roots, path_in_chunk ? path_in_chunk : dummy,
+                    path_to_chunk ? path_to_chunk : dummy);
+    }
+    API_END(ctx)
+}
+void sezkp_tree_free(sezkp_ctx* ctx, sezkp_tree* tree) {
+    if (!tree) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    tree->cm.release();
+    delete tree;
+}
+
+/* ------------------------------------------------------------------ FRI ------ */
+static int32_t fri_commit_impl(sezkp_ctx* ctx, const u64* l0_host, const u64* l0_dev, int log_N, const uint64_t* betas,
+                               uint8_t* roots, uint64_t* final_value, sezkp_fri** keep) {
+    API_BEGIN(ctx)
+    REQUIRE((l0_host || l0_dev) && betas && roots && final_value && log_N >= 1 && log_N <= 32, "bad argument");
+    if (keep) *keep = nullptr;
+    const size_t N = (size_t)1 << log_N;
+    check_canonical(betas, (size_t)log_N, "betas");
+    const u64* src = l0_dev;
+    if (l0_host) {
+        check_canonical(l0_host, N, "layer0");
+        u64* d = (u64*)ctx->scratch[5].ensure(N * 8);
+        h2d(ctx, d, l0_host, N * 8);
+        src = d;
+    }
+    sezkp_fri* f = new sezkp_fri();
+    try {
+        fri_commit_device(ctx, f->fl, src, log_N, betas, roots, final_value, nullptr);
+    } catch (...) {
+        f->fl.release();
+        delete f;
+        throw;
+    }
+    if (keep) *keep = f;
+    else {
+        f->fl.release();
+        delete f;
+    }
+    API_END(ctx)
+}
+int32_t sezkp_fri_commit(sezkp_ctx* ctx, const uint64_t* layer0, int log_N, const uint64_t* betas, uint8_t* roots,
+                         uint64_t* final_value, sezkp_fri** keep) {
+    return fri_commit_impl(ctx, layer0, nullptr, log_N, betas, roots, final_value, keep);
+}
+int32_t sezkp_fri_commit_dev(sezkp_ctx* ctx, const uint64_t* layer0_dev, int log_N, const uint64_t* betas, uint8_t* roots,
+                             uint64_t* final_value, sezkp_fri** keep) {
+    return fri_commit_impl(ctx, nullptr, layer0_dev, log_N, betas, roots, final_value, keep);
+}
+int32_t sezkp_fri_open(sezkp_ctx* ctx, const sezkp_fri* fri, const uint64_t* idx0, size_t k, uint64_t* positions, uint64_t* values,
+                       uint8_t* paths) {
+    API_BEGIN(ctx)
+    REQUIRE(fri && (k == 0 || (idx0 && positions && values && paths)), "bad argument");
+    if (k) fri_open_device(ctx, fri->fl, idx0, k, positions, values, paths);
+    API_END(ctx)
+}
+void sezkp_fri_free(sezkp_ctx* ctx, sezkp_fri* fri) {
+    if (!fri) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    fri->fl.release();
+    delete fri;
+}
+
+/* --------------------------------------------------- feeder (columns + AIR) -- */
+int32_t sezkp_trace_columns(sezkp_ctx* ctx, const sezkp_trace_desc* trace, uint64_t* out) {
+    API_BEGIN(ctx)
+    REQUIRE(out != nullptr, "bad argument");
+    validate_trace(trace);
+    DeviceTraceOwner dt;
+    dt.buf = ctx->scratch[2];
+    ctx->scratch[2] = DevBuf();
+    try {
+        dt.upload(ctx, trace);
+    } catch (...) {
+        ctx->scratch[2] = dt.buf;
+        throw;
+    }
+    ctx->scratch[2] = dt.buf;
+    const size_t count = (size_t)(3 + 7 * trace->tau) * trace->n_rows;
+    u64* cols = (u64*)ctx->scratch[3].ensure(count * 8);
+    expand_columns_device(ctx, dt.t, cols);
+    d2h(ctx, out, cols, count * 8);
+    API_END(ctx)
+}
+
+int32_t sezkp_compose_base(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const uint64_t alphas8[8], const uint64_t* mask_coeffs,
+                           size_t mask_deg, uint64_t* out) {
+    API_BEGIN(ctx)
+    REQUIRE(out && alphas8 && (mask_coeffs || mask_deg == 0), "bad argument");
+    validate_trace(trace);
+    DeviceTraceOwner dt;
+    dt.buf = ctx->scratch[2];
+    ctx->scratch[2] = DevBuf();
+    try {
+        dt.upload(ctx, trace);
+    } catch (...) {
+        ctx->scratch[2] = dt.buf;
+        throw;
+    }
+    ctx->scratch[2] = dt.buf;
+    const size_t n = trace->n_rows, count = (size_t)(3 + 7 * trace->tau) * n;
+    u64* cols = (u64*)ctx->scratch[3].ensure(count * 8);
+    expand_columns_device(ctx, dt.t, cols);
+    u64* base = (u64*)ctx->scratch[4].ensure(n * 8);
+    compose_device(ctx, cols, n, trace->tau, alphas8, mask_coeffs, mask_deg, base);
+    d2h(ctx, out, base, n * 8);
+    API_END(ctx)
+}
+
+/* --------------------------------------------------------------- prover ------ */
+static void deliver(const std::vector<u8>& proof, uint8_t* buf, size_t cap, size_t* len) {
+    *len = proof.size();
+    if (!buf) return;
+    if (cap < proof.size()) sezkp_fail(SEZKP_CUDA_ERANGE, "proof buffer too small: need %zu bytes, have %zu", proof.size(), cap);
+    std::memcpy(buf, proof.data(), proof.size());
+}
+
+int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const uint8_t manifest_root[32], uint8_t* proof_buf,
+                             size_t cap, size_t* len) {
+    API_BEGIN(ctx)
+    REQUIRE(manifest_root && len, "bad argument");
+    std::vector<u8> proof;
+    prove_v1_device(ctx, trace, manifest_root, proof);
+    deliver(proof, proof_buf, cap, len);
+    API_END(ctx)
+}
+
+int32_t sezkp_stark_v1_begin(sezkp_ctx* ctx, uint32_t tau, const uint8_t manifest_root[32], sezkp_stream** out) {
+    API_BEGIN(ctx)
+    REQUIRE(out && manifest_root && tau >= 1 && tau <= 4096, "bad argument");
+    sezkp_stream* st = new sezkp_stream();
+    st->tau = tau;
+    std::memcpy(st->manifest_root, manifest_root, 32);
+    *out = st;
+    API_END(ctx)
+}
+int32_t sezkp_stark_v1_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* b) {
+    API_BEGIN(ctx)
+    if (!st) sezkp_fail(SEZKP_CUDA_ESTATE, "stream handle is NULL");
+    REQUIRE(b && b->n_blocks >= 1 && b->tau == st->tau, "ingest: bad block descriptor (tau mismatch or empty)");
+    const size_t tau = st->tau;
+    u64 rows = 0;
+    for (u64 k = 0; k < b->n_blocks; k++) {
+        REQUIRE(b->block_len[k] >= 1, "ingest: empty block");
+        rows += b->block_len[k];
+        st->block_len.push_back(b->block_len[k]);
+    }
+    REQUIRE(rows == b->n_rows, "ingest: n_rows != sum(block_len)");
+    st->win_left.insert(st->win_left.end(), b->win_left, b->win_left + b->n_blocks * tau);
+    st->win_right.insert(st->win_right.end(), b->win_right, b->win_right + b->n_blocks * tau);
+    st->in_off.insert(st->in_off.end(), b->head_in_off, b->head_in_off + b->n_blocks * tau);
+    st->out_off.insert(st->out_off.end(), b->head_out_off, b->head_out_off + b->n_blocks * tau);
+    st->input_mv.insert(st->input_mv.end(), b->input_mv, b->input_mv + rows);
+    st->mv.insert(st->mv.end(), b->mv, b->mv + rows * tau);
+    st->wflag.insert(st->wflag.end(), b->write_flag, b->write_flag + rows * tau);
+    st->wsym.insert(st->wsym.end(), b->write_sym, b->write_sym + rows * tau);
+    API_END(ctx)
+}
+int32_t sezkp_stark_v1_finish(sezkp_ctx* ctx, sezkp_stream* st, uint8_t* proof_buf, size_t cap, size_t* len) {
+    API_BEGIN(ctx)
+    if (!st) sezkp_fail(SEZKP_CUDA_ESTATE, "stream handle is NULL");
+    REQUIRE(len, "bad argument");
+    sezkp_trace_desc d{};
+    d.tau = st->tau;
+    d.n_blocks = st->block_len.size();
+    d.n_rows = st->input_mv.size();
+    d.block_len = st->block_len.data();
+    d.win_left = st->win_left.data();
+    d.win_right = st->win_right.data();
+    d.head_in_off = st->in_off.data();
+    d.head_out_off = st->out_off.data();
+    d.input_mv = st->input_mv.data();
+    d.mv = st->mv.data();
+    d.write_flag = st->wflag.data();
+    d.write_sym = st->wsym.data();
+    std::vector<u8> proof;
+    prove_v1_device(ctx, &d, st->manifest_root, proof);
+    deliver(proof, proof_buf, cap, len);
+    if (proof_buf) delete st;  // the handle is consumed once the proof has been delivered
+    API_END(ctx)
+}
+void sezkp_stark_v1_abort(sezkp_ctx* ctx, sezkp_stream* st) { delete st; }
+
+}  // extern "C"

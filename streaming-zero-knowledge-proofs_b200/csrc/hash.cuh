@@ -1,0 +1,32 @@
+// Internal interface of hash.cu: chunked BLAKE3 Merkle commitments over device-resident columns.
+#pragma once
+#include "blake3.cuh"
+#include "common.cuh"
+
+// A commitment to `cols` columns of `n` field elements each (n a power of two).  Leaves are labeled
+// (templates != null) or unlabeled.  Only the chunk roots and the levels above them are retained
+// (`upper`); openings rebuild the 2^cl-leaf chunk on demand, like the reference's
+// OnDemandOpenings::open_within_chunk (v1/openings.rs:464-497).
+struct Commit {
+    const u64* values = nullptr;   // device [cols][n]
+    bool owns_values = false;
+    u64 n = 0;
+    int cols = 0;
+    int cl = 0;                    // log2 leaves per chunk = min(chunk_log2, log2 n)
+    u64 n_ch = 0;                  // chunks per column = n >> cl
+    u32* upper = nullptr;          // device [cols][2*n_ch-1][8]: level l (count n_ch>>l) at offset 2*n_ch-(2*n_ch>>l)
+    b3::LabelTemplate* templates = nullptr;  // device [cols] or null (unlabeled)
+    void release();
+};
+inline u64 upper_off(u64 n_ch, int l) { return 2 * n_ch - ((2 * n_ch) >> l); }
+
+b3::LabelTemplate make_label_template(const char* label);
+// Build commitment over device values; writes the `cols` roots (32 B each) to host `roots`.
+void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,
+                  const char* const* labels_or_null, u8* roots_host);
+// k openings; outputs are host arrays: values[k], chunk_roots[k][32], path_in[k][cl][32], path_to[k][log2(n_ch)][32].
+void commit_open(sezkp_ctx* ctx, const Commit& cm, const u32* col_idx, const u64* row_idx, size_t k, u64* values,
+                 u8* chunk_roots, u8* path_in, u8* path_to);
+// Plain helpers
+void leaf_hash_device(sezkp_ctx* ctx, const u64* vals_dev, size_t n, const char* label_or_null, u32* out_dev);
+void merkle_root_device(sezkp_ctx* ctx, u32* level_dev /* n digests, destroyed */, u32* tmp_dev, size_t n, u8* root_host);

@@ -1,0 +1,533 @@
+// Batched Goldilocks NTT / iNTT / coset LDE for sm_100a.
+//
+// Replaces the reference's radix-2 in-place transforms (crates/sezkp-ffts/src/ntt.rs:79-155) and
+// `evaluate_on_coset_pow2` (coset.rs:85-102) with a multi-pass decimation-in-frequency scheme:
+//   N = N_1*N_2(*N_3); pass p transforms digit p of the index (most significant first) for a tile of
+//   2^b rows x R columns held in shared memory, multiplies by the inter-pass twiddle w_{M_p}^{k_p*J}
+//   and writes the tile back; the last pass also applies the digit-reversal so input and output are
+//   both in natural order, exactly like the reference (w_N = 7^((p-1)/N)).
+// A coset LDE with blow-up B is B independent size-n NTTs of the coefficients scaled by powers of
+// g_j = shift*w_N^j (j < B), whose outputs interleave: out[j + B*i] = NTT_n(c_t * g_j^t)[i].
+// All values in HBM are canonical residues; results are therefore bit-identical to the reference.
+#include "common.cuh"
+#include "gl.cuh"
+#include "ntt.cuh"
+
+namespace {
+
+constexpr int NTT_THREADS = 256;
+constexpr int MAX_PASS_BITS = 10;
+constexpr int TILE_LOG_ELEMS = 13;  // 8192 elements = 64 KiB per tile
+constexpr int MAX_LOG_R = 6;
+
+struct PassDesc {
+    const u64* in;
+    u64* out;
+    int b, logR;
+    u32 col_tiles, U;
+    u64 total_cols;
+    // input addressing
+    u64 in_row_stride;
+    int in_clog;
+    u64 in_cs_lo, in_cs_hi, in_u_stride, in_v_stride;
+    int in_v_shift;
+    // output addressing
+    u64 out_row_stride;
+    int out_clog;
+    u64 out_cs_lo, out_cs_hi, out_u_stride, out_v_stride;
+    int load_rows_fast, store_rows_fast;
+    // tables
+    const u64* W;  // w_{2^b}^e, e < 2^(b-1)
+    const u64* tw_lo;
+    const u64* tw_hi;
+    int tw_lb, use_tw;
+    u64 tw_stride;
+    u64 scale;
+    int use_scale;
+    // coset pre-scale: x *= GA[j][row] * GB[j][C]
+    const u64* GA;
+    const u64* GB;
+    int use_pre, use_gb, coset_from_col, coset_log;
+    u32 ga_pitch, gb_pitch;
+};
+
+// One radix-2^K DIF step (stages s0..s0+K-1 of a 2^b-point transform) on every column of the tile.
+template <int K>
+__device__ __forceinline__ void dif_step(u64* tile, const u64* Ws, int b, int s0, int logR, int pitch) {
+    const int lo_bits = b - s0 - K;
+    const int groups = (1 << (b - K)) << logR;
+    const int R = 1 << logR;
+    for (int g = threadIdx.x; g < groups; g += NTT_THREADS) {
+        const int c = g & (R - 1);
+        const int gi = g >> logR;
+        const int lo = gi & ((1 << lo_bits) - 1);
+        const int hi = gi >> lo_bits;
+        u64* col = tile + c * pitch + (hi << (b - s0)) + lo;
+        u64 x[1 << K];
+#pragma unroll
+        for (int t = 0; t < (1 << K); t++) x[t] = col[t << lo_bits];
+#pragma unroll
+        for (int u = 0; u < K; u++) {
+            const int half = 1 << (K - 1 - u);
+#pragma unroll
+            for (int t = 0; t < (1 << K); t++) {
+                if (t & half) continue;
+                const int e = (((t & (half - 1)) << lo_bits) + lo) << (s0 + u);
+                const u64 a = x[t], bb = x[t | half];
+                x[t] = gl::add(a, bb);
+                x[t | half] = gl::mul(gl::sub(a, bb), Ws[e]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < (1 << K); t++) col[t << lo_bits] = x[t];
+    }
+}
+
+template <int K1, int K2>
+__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const PassDesc d) {
+    extern __shared__ u64 smem[];
+    constexpr int b = K1 + K2;
+    constexpr int rows = 1 << b;
+    constexpr int pitch = rows | 1;  // odd pitch: conflict-free for lanes over columns and over rows
+    const int logR = d.logR, R = 1 << logR;
+    u64* tile = smem;
+    u64* Ws = smem + (size_t)R * pitch;
+
+    const u32 tile_id = blockIdx.x;
+    const u32 ct = tile_id % d.col_tiles;
+    const u32 rest = tile_id / d.col_tiles;
+    const u32 u = rest % d.U;
+    const u64 v = rest / d.U;
+    const u64 C0 = (u64)ct << logR;
+    const u64* in_base = d.in + u * d.in_u_stride + (v >> d.in_v_shift) * d.in_v_stride;
+    u64* out_base = d.out + u * d.out_u_stride + v * d.out_v_stride;
+
+    for (int i = threadIdx.x; i < (rows >> 1); i += NTT_THREADS) Ws[i] = d.W[i];
+
+    const int total = rows << logR;
+    for (int i = threadIdx.x; i < total; i += NTT_THREADS) {
+        int c, row;
+        if (d.load_rows_fast) {
+            row = i & (rows - 1);
+            c = i >> b;
+        } else {
+            c = i & (R - 1);
+            row = i >> logR;
+        }
+        const u64 C = C0 + c;
+        u64 x = 0;
+        if (C < d.total_cols) {
+            const u64 coff = (C & ((1ULL << d.in_clog) - 1)) * d.in_cs_lo + (C >> d.in_clog) * d.in_cs_hi;
+            x = in_base[(u64)row * d.in_row_stride + coff];
+            if (d.use_pre) {
+                const u32 j = (u32)((d.coset_from_col ? C : v) & ((1u << d.coset_log) - 1));
+                u64 g = d.GA[(size_t)j * d.ga_pitch + row];
+                if (d.use_gb) g = gl::mul(g, d.GB[(size_t)j * d.gb_pitch + C]);
+                x = gl::mul(x, g);
+            }
+        }
+        tile[c * pitch + row] = x;
+    }
+    __syncthreads();
+    dif_step<K1>(tile, Ws, b, 0, logR, pitch);
+    __syncthreads();
+    if (K2 > 0) {
+        dif_step<(K2 > 0 ? K2 : 1)>(tile, Ws, b, K1, logR, pitch);
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < total; i += NTT_THREADS) {
+        int c, k;
+        if (d.store_rows_fast) {
+            k = i & (rows - 1);
+            c = i >> b;
+        } else {
+            c = i & (R - 1);
+            k = i >> logR;
+        }
+        const u64 C = C0 + c;
+        if (C >= d.total_cols) continue;
+        const int row = (int)(__brev((unsigned)k) >> (32 - b));
+        u64 x = tile[c * pitch + row];
+        if (d.use_tw) {
+            const u64 E = (u64)k * C * d.tw_stride;
+            const u64 w = gl::mul(d.tw_lo[E & ((1ULL << d.tw_lb) - 1)], d.tw_hi[E >> d.tw_lb]);
+            x = gl::mul(x, w);
+        }
+        if (d.use_scale) x = gl::mul(x, d.scale);
+        const u64 coff = (C & ((1ULL << d.out_clog) - 1)) * d.out_cs_lo + (C >> d.out_clog) * d.out_cs_hi;
+        out_base[(u64)k * d.out_row_stride + coff] = x;
+    }
+}
+
+typedef void (*pass_fn)(const PassDesc);
+template <int K1, int K2>
+pass_fn get_fn() { return ntt_pass_kernel<K1, K2>; }
+
+pass_fn kernel_for_bits(int b) {
+    switch (b) {
+        case 1: return get_fn<1, 0>();
+        case 2: return get_fn<2, 0>();
+        case 3: return get_fn<3, 0>();
+        case 4: return get_fn<4, 0>();
+        case 5: return get_fn<5, 0>();
+        case 6: return get_fn<3, 3>();
+        case 7: return get_fn<4, 3>();
+        case 8: return get_fn<4, 4>();
+        case 9: return get_fn<5, 4>();
+        case 10: return get_fn<5, 5>();
+        default: sezkp_fail(SEZKP_CUDA_EINVAL, "unsupported pass width %d", b);
+    }
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------------------------------ */
+/* tables                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+struct NttTables {
+    int L = 0;
+    bool inverse = false;
+    std::vector<int> plan;    // pass widths, most significant digit first
+    u64* W[MAX_PASS_BITS + 1] = {};  // device, per pass width
+    u64* tw_lo = nullptr;
+    u64* tw_hi = nullptr;
+    int tw_lb = 0;
+    u64 scale = 1;  // N^-1 for inverse
+    // coset tables, keyed by (logB, shift)
+    struct Coset {
+        u64* GA = nullptr;
+        u64* GB = nullptr;
+        u32 ga_pitch = 0, gb_pitch = 0;
+    };
+    std::map<std::pair<int, u64>, Coset> cosets;
+};
+
+static std::vector<int> make_plan(int L) {
+    std::vector<int> p;
+    if (L <= MAX_PASS_BITS) p = {L};
+    else if (L <= 2 * MAX_PASS_BITS) p = {(L + 1) / 2, L / 2};
+    else {
+        int a = (L + 2) / 3, b = (L - a + 1) / 2, c = L - a - b;
+        p = {a, b, c};
+    }
+    for (int x : p)
+        if (x < 1 || x > MAX_PASS_BITS) sezkp_fail(SEZKP_CUDA_EINVAL, "log size %d out of range", L);
+    return p;
+}
+
+static u64* upload(const std::vector<u64>& h) {
+    u64* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, h.size() * 8);
+    if (e != cudaSuccess) sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaMalloc(table %zu B): %s", h.size() * 8, cudaGetErrorString(e));
+    CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    return d;
+}
+
+static NttTables* get_tables(sezkp_ctx* ctx, int L, bool inverse) {
+    u64 key = ((u64)L << 1) | (inverse ? 1 : 0);
+    auto it = ctx->ntt_tables.find(key);
+    if (it != ctx->ntt_tables.end()) return it->second;
+    NttTables* t = new NttTables();
+    t->L = L;
+    t->inverse = inverse;
+    t->plan = make_plan(L);
+    for (int b : t->plan) {
+        if (t->W[b]) continue;
+        u64 w = gl::root_2exp((unsigned)b);
+        if (inverse) w = gl::inv(w);
+        std::vector<u64> h((size_t)1 << (b - 1));
+        u64 x = 1;
+        for (auto& e : h) {
+            e = x;
+            x = gl::mul(x, w);
+        }
+        t->W[b] = upload(h);
+    }
+    u64 wN = gl::root_2exp((unsigned)L);
+    if (inverse) wN = gl::inv(wN);
+    t->tw_lb = (L + 1) / 2;
+    {
+        std::vector<u64> lo((size_t)1 << t->tw_lb), hi((size_t)1 << (L - t->tw_lb));
+        u64 x = 1;
+        for (auto& e : lo) {
+            e = x;
+            x = gl::mul(x, wN);
+        }
+        u64 step = x;  // wN^(2^lb)
+        x = 1;
+        for (auto& e : hi) {
+            e = x;
+            x = gl::mul(x, step);
+        }
+        t->tw_lo = upload(lo);
+        t->tw_hi = upload(hi);
+    }
+    t->scale = inverse ? gl::inv(gl::from_u64(1ULL << L)) : 1;
+    ctx->ntt_tables[key] = t;
+    return t;
+}
+
+static NttTables::Coset& get_coset(NttTables* t, int logB, u64 shift) {
+    auto key = std::make_pair(logB, shift);
+    auto it = t->cosets.find(key);
+    if (it != t->cosets.end()) return it->second;
+    const int L = t->L, B = 1 << logB;
+    const int b1 = t->plan[0];
+    const u64 N1 = 1ULL << b1, S1 = 1ULL << (L - b1);
+    const u64 wBig = gl::root_2exp((unsigned)(L + logB));
+    std::vector<u64> ga((size_t)B * N1), gb((size_t)B * S1);
+    u64 g = shift;  // g_j = shift * wBig^j
+    for (int j = 0; j < B; j++) {
+        u64 x = 1;
+        for (u64 J = 0; J < S1; J++) {
+            gb[(size_t)j * S1 + J] = x;
+            x = gl::mul(x, g);
+        }
+        const u64 gS = x;  // g^S1
+        x = 1;
+        for (u64 r = 0; r < N1; r++) {
+            ga[(size_t)j * N1 + r] = x;
+            x = gl::mul(x, gS);
+        }
+        g = gl::mul(g, wBig);
+    }
+    NttTables::Coset c;
+    c.GA = upload(ga);
+    c.GB = upload(gb);
+    c.ga_pitch = (u32)N1;
+    c.gb_pitch = (u32)S1;
+    return t->cosets[key] = c;
+}
+
+void ntt_free_tables(sezkp_ctx* ctx) {
+    for (auto& kv : ctx->ntt_tables) {
+        NttTables* t = kv.second;
+        for (auto& w : t->W)
+            if (w) cudaFree(w);
+        cudaFree(t->tw_lo);
+        cudaFree(t->tw_hi);
+        for (auto& c : t->cosets) {
+            cudaFree(c.second.GA);
+            cudaFree(c.second.GB);
+        }
+        delete t;
+    }
+    ctx->ntt_tables.clear();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* pass construction + launch                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+static int pick_logR(int b, u64 avail_cols, int min_logR) {
+    int lr = TILE_LOG_ELEMS - b;
+    if (lr > MAX_LOG_R) lr = MAX_LOG_R;
+    while (lr > 0 && (1ULL << lr) > avail_cols) lr--;
+    if (lr < min_logR) lr = min_logR;
+    return lr;
+}
+
+static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
+    const u64 tiles = (u64)d.col_tiles * d.U * V;
+    REQUIRE(tiles > 0 && tiles < (1ULL << 31), "NTT grid too large (%llu tiles)", (unsigned long long)tiles);
+    const size_t smem = (((size_t)1 << d.logR) * ((1u << d.b) | 1) + ((size_t)1 << (d.b - 1))) * 8;
+    pass_fn fn = kernel_for_bits(d.b);
+    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(d);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+static void base_desc(PassDesc& d, const NttTables* t, int b) {
+    d = PassDesc{};
+    d.b = b;
+    d.W = t->W[b];
+    d.tw_lo = t->tw_lo;
+    d.tw_hi = t->tw_hi;
+    d.tw_lb = t->tw_lb;
+    d.U = 1;
+}
+
+// Plain batched NTT: `cols` vectors of length 2^L at `data` (stride 2^L), result back in `data`.
+// `tmp` must hold cols*2^L elements when L > MAX_PASS_BITS.
+void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool inverse) {
+    REQUIRE(L >= 0 && L <= 3 * MAX_PASS_BITS, "log_n %d out of range", L);
+    if (L == 0 || cols == 0) return;
+    NttTables* t = get_tables(ctx, L, inverse);
+    const std::vector<int>& plan = t->plan;
+    const int m = (int)plan.size();
+    const u64 N = 1ULL << L;
+    PassDesc d;
+    if (m == 1) {  // case C: columns of the tile are batch vectors
+        base_desc(d, t, L);
+        d.in = data;
+        d.out = data;
+        d.logR = pick_logR(L, cols, 0);
+        d.col_tiles = (u32)((cols + (1ULL << d.logR) - 1) >> d.logR);
+        d.total_cols = cols;
+        d.in_row_stride = 1;
+        d.in_cs_hi = N;
+        d.out_row_stride = 1;
+        d.out_cs_hi = N;
+        d.load_rows_fast = 1;
+        d.store_rows_fast = 1;
+        d.use_scale = inverse;
+        d.scale = t->scale;
+        launch_pass(ctx, d, 1);
+        return;
+    }
+    REQUIRE(tmp != nullptr, "internal: NTT temp buffer missing");
+    // buffers: m==2: data -> tmp -> data ; m==3: data -> data -> tmp -> data
+    u64 S = N;  // S_{p-1}
+    for (int p = 0; p < m; p++) {
+        const int b = plan[p];
+        const u64 Np = 1ULL << b;
+        const u64 Mp = S;       // size of the current sub-problem
+        const u64 Sp = Mp / Np; // stride of digit p
+        base_desc(d, t, b);
+        const bool last = (p == m - 1);
+        if (!last) {  // case A
+            d.in = (m == 3 && p == 1) ? data : data;
+            d.out = (m == 2) ? tmp : (p == 0 ? data : tmp);
+            d.logR = pick_logR(b, Sp, 0);
+            d.col_tiles = (u32)(Sp >> d.logR);
+            d.total_cols = Sp;
+            d.U = (u32)(N / Mp);
+            d.in_row_stride = Sp;
+            d.in_cs_hi = 1;
+            d.in_u_stride = Mp;
+            d.in_v_stride = N;
+            d.out_row_stride = Sp;
+            d.out_cs_hi = 1;
+            d.out_u_stride = Mp;
+            d.out_v_stride = N;
+            d.use_tw = 1;
+            d.tw_stride = N / Mp;
+        } else {  // case B: columns are values of k_1, rows are contiguous
+            const u64 N1 = 1ULL << plan[0], S1 = N / N1;
+            d.in = tmp;
+            d.out = data;
+            d.logR = pick_logR(b, N1, 0);
+            d.col_tiles = (u32)(N1 >> d.logR);
+            d.total_cols = N1;
+            d.in_row_stride = 1;
+            d.in_cs_hi = S1;
+            d.in_v_stride = N;
+            d.out_row_stride = N / Np;
+            d.out_cs_hi = 1;
+            d.out_v_stride = N;
+            if (m == 3) {
+                d.U = (u32)(1ULL << plan[1]);
+                d.in_u_stride = Np;     // k_2 * N_3
+                d.out_u_stride = N1;    // k_2 * N_1
+            }
+            d.load_rows_fast = 1;
+            d.use_scale = inverse;
+            d.scale = t->scale;
+        }
+        launch_pass(ctx, d, cols);
+        S = Sp;
+    }
+}
+
+// Coset LDE: coeffs [cols][n] -> out [cols][B*n]; inter must hold cols*B*n elements when log n > MAX_PASS_BITS.
+void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, int L, int logB, u64 shift, u64 cols) {
+    REQUIRE(L >= 1 && L <= 3 * MAX_PASS_BITS, "log_n %d out of range", L);
+    REQUIRE(logB >= 0 && logB <= 4 && L + logB <= 32, "log_blow %d out of range", logB);
+    REQUIRE(shift != 0 && shift < gl::P, "coset shift must be a non-zero canonical field element");
+    if (cols == 0) return;
+    NttTables* t = get_tables(ctx, L, false);
+    NttTables::Coset& cs = get_coset(t, logB, shift);
+    const std::vector<int>& plan = t->plan;
+    const int m = (int)plan.size();
+    const u64 n = 1ULL << L, B = 1ULL << logB;
+    PassDesc d;
+    if (m == 1) {  // case C': columns are (vector, coset) pairs
+        base_desc(d, t, L);
+        d.in = coeffs;
+        d.out = out;
+        d.total_cols = cols * B;
+        d.logR = pick_logR(L, d.total_cols, 0);
+        d.col_tiles = (u32)((d.total_cols + (1ULL << d.logR) - 1) >> d.logR);
+        d.in_row_stride = 1;
+        d.in_clog = logB;
+        d.in_cs_lo = 0;
+        d.in_cs_hi = n;
+        d.out_row_stride = B;
+        d.out_clog = logB;
+        d.out_cs_lo = 1;
+        d.out_cs_hi = B * n;
+        d.load_rows_fast = 1;
+        d.store_rows_fast = 1;
+        d.use_pre = 1;
+        d.use_gb = 0;
+        d.coset_from_col = 1;
+        d.coset_log = logB;
+        d.GA = cs.GA;
+        d.GB = cs.GB;
+        d.ga_pitch = cs.ga_pitch;
+        d.gb_pitch = cs.gb_pitch;
+        launch_pass(ctx, d, 1);
+        return;
+    }
+    REQUIRE(inter != nullptr, "internal: LDE intermediate buffer missing");
+    u64 S = n;
+    for (int p = 0; p < m; p++) {
+        const int b = plan[p];
+        const u64 Np = 1ULL << b, Mp = S, Sp = Mp / Np;
+        base_desc(d, t, b);
+        const bool last = (p == m - 1);
+        if (!last) {  // case A / A'
+            d.in = (p == 0) ? coeffs : inter;
+            d.out = inter;
+            d.logR = pick_logR(b, Sp, 0);
+            d.col_tiles = (u32)(Sp >> d.logR);
+            d.total_cols = Sp;
+            d.U = (u32)(n / Mp);
+            d.in_row_stride = Sp;
+            d.in_cs_hi = 1;
+            d.in_u_stride = Mp;
+            d.in_v_stride = n;
+            d.in_v_shift = (p == 0) ? logB : 0;
+            d.out_row_stride = Sp;
+            d.out_cs_hi = 1;
+            d.out_u_stride = Mp;
+            d.out_v_stride = n;
+            d.use_tw = 1;
+            d.tw_stride = n / Mp;
+            if (p == 0) {
+                d.use_pre = 1;
+                d.use_gb = 1;
+                d.coset_from_col = 0;
+                d.coset_log = logB;
+                d.GA = cs.GA;
+                d.GB = cs.GB;
+                d.ga_pitch = cs.ga_pitch;
+                d.gb_pitch = cs.gb_pitch;
+            }
+            launch_pass(ctx, d, cols * B);
+        } else {  // case B': columns are (coset j, k_1) pairs so that stores are contiguous
+            const u64 N1 = 1ULL << plan[0], S1 = n / N1;
+            d.in = inter;
+            d.out = out;
+            d.total_cols = N1 * B;
+            d.logR = pick_logR(b, d.total_cols, logB);
+            d.col_tiles = (u32)(d.total_cols >> d.logR);
+            d.in_row_stride = 1;
+            d.in_clog = logB;
+            d.in_cs_lo = n;   // coset j -> intermediate vector j of this batch entry
+            d.in_cs_hi = S1;  // k_1
+            d.in_v_stride = B * n;
+            d.out_row_stride = (n / Np) * B;
+            d.out_cs_hi = 1;
+            d.out_v_stride = B * n;
+            if (m == 3) {
+                d.U = (u32)(1ULL << plan[1]);
+                d.in_u_stride = Np;
+                d.out_u_stride = N1 * B;
+            }
+            d.load_rows_fast = 1;
+            launch_pass(ctx, d, cols);
+        }
+        S = Sp;
+    }
+}

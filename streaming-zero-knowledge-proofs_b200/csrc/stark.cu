@@ -1,0 +1,583 @@
+// STARK v1 device stages other than NTT and hashing, plus the host orchestration of prove_v1.
+//   * column expansion from the compact trace     (reference v1/columns.rs:252-365, v1/openings.rs:193-273)
+//   * AIR composition + boundary + ZK mask         (v1/air.rs:49-136, v1/masking.rs:86-103, v1/prover.rs:142-158)
+//   * DEEP quotient with batched inversion         (v1/lde.rs:76-93)
+//   * FRI fold                                     (v1/prover.rs:204-238)
+//   * prove_v1 schedule, openings, bincode         (v1/prover.rs:61-462, v1/proof.rs, sezkp-stark/src/lib.rs:131)
+#include <chrono>
+#include <cstring>
+
+#include "gl.cuh"
+#include "hash.cuh"
+#include "ntt.cuh"
+#include "stark.cuh"
+#include "transcript.hpp"
+
+namespace {
+
+/* ------------------------------------------------------------------------------------------ */
+/* column expansion                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+// One thread per (block, tape): running head position (post-move, relative to 0 at block entry).
+__global__ void head_scan_kernel(DeviceTrace t, u64* __restrict__ cols) {
+    const u64 id = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= t.n_blocks * t.tau) return;
+    const u64 k = id / t.tau;
+    const u32 r = (u32)(id % t.tau);
+    const u64 start = t.block_start[k], len = t.block_len[k];
+    u64* head = cols + (3 + 3ULL * t.tau + r) * t.n_rows;  // group order: mv, wflag, wsym, head, ...
+    int64_t cur = 0;
+    for (u64 j = 0; j < len; j++) {
+        cur += t.mv[(start + j) * t.tau + r];
+        head[start + j] = gl::from_i64(cur);
+    }
+}
+// One thread per row: everything except head.
+__global__ void expand_rows_kernel(DeviceTrace t, u64* __restrict__ cols) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t.n_rows) return;
+    // block containing row i: largest k with block_start[k] <= i (blocks of length 0 are skipped by the search)
+    u64 lo = 0, hi = t.n_blocks;
+    while (hi - lo > 1) {
+        const u64 mid = (lo + hi) >> 1;
+        if (t.block_start[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    const u64 k = lo;
+    const u64 start = t.block_start[k], len = t.block_len[k];
+    const u64 n = t.n_rows;
+    const u32 tau = t.tau;
+    cols[0 * n + i] = gl::from_i64((int64_t)t.input_mv[i]);
+    cols[1 * n + i] = (i == start) ? 1 : 0;
+    cols[2 * n + i] = (i + 1 == start + len) ? 1 : 0;
+    for (u32 r = 0; r < tau; r++) {
+        const u64 p = i * tau + r;
+        const int wf = t.write_flag[p] ? 1 : 0;
+        cols[(3 + 0ULL * tau + r) * n + i] = gl::from_i64((int64_t)t.mv[p]);
+        cols[(3 + 1ULL * tau + r) * n + i] = (u64)wf;
+        cols[(3 + 2ULL * tau + r) * n + i] = wf ? gl::from_u64((u64)t.write_sym[p]) : 0;
+        const int64_t diff = t.win_right[k * tau + r] - t.win_left[k * tau + r];
+        const u64 ad = diff < 0 ? (u64)0 - (u64)diff : (u64)diff;
+        cols[(3 + 4ULL * tau + r) * n + i] = gl::from_u64(ad + 1);
+        cols[(3 + 5ULL * tau + r) * n + i] = (u64)t.head_in_off[k * tau + r];
+        cols[(3 + 6ULL * tau + r) * n + i] = (u64)t.head_out_off[k * tau + r];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* composition                                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+struct ComposeParams {
+    u64 a[8];        // alphas as drawn (mapping of v1/prover.rs:86-98 applied in the kernel)
+    u64 mask[8];     // ascending mask coefficients
+    int mask_deg;
+    u64 w_base;      // w_n
+};
+__global__ void compose_kernel(const u64* __restrict__ cols, u64 n, u32 tau, ComposeParams cp, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 ip1 = (i + 1 == n) ? 0 : i + 1;
+    const u64 is_first = cols[1 * n + i], is_last = cols[2 * n + i];
+    const u64 one_minus_last = gl::sub(1, is_last);
+    const u64 a_bool = cp.a[0], a_mv = cp.a[1], a_hu = cp.a[2], a_hr = cp.a[4], a_sr = cp.a[6], a_symr = cp.a[0],
+              a_bf = cp.a[2], a_bl = cp.a[2];
+    u64 acc = 0;
+    for (u32 r = 0; r < tau; r++) {
+        const u64 mv = cols[(3 + 0ULL * tau + r) * n + i], mv_next = cols[(3 + 0ULL * tau + r) * n + ip1];
+        const u64 flg = cols[(3 + 1ULL * tau + r) * n + i];
+        const u64 sym = cols[(3 + 2ULL * tau + r) * n + i];
+        const u64 head = cols[(3 + 3ULL * tau + r) * n + i], head_next = cols[(3 + 3ULL * tau + r) * n + ip1];
+        const u64 wlen = cols[(3 + 4ULL * tau + r) * n + i];
+        const u64 in_off = cols[(3 + 5ULL * tau + r) * n + i], out_off = cols[(3 + 6ULL * tau + r) * n + i];
+        // C1, C2, C3 (v1/air.rs:64-72)
+        acc = gl::add(acc, gl::mul(gl::mul(a_bool, flg), gl::sub(flg, 1)));
+        acc = gl::add(acc, gl::mul(gl::mul(gl::mul(a_mv, mv), gl::sub(mv, 1)), gl::add(mv, 1)));
+        acc = gl::add(acc, gl::mul(gl::mul(a_hu, one_minus_last), gl::sub(gl::sub(head_next, head), mv_next)));
+        // Bit columns are the honest decompositions of the canonical residues (v1/columns.rs:324-342), so every
+        // b*(b-1) term is zero and the reconstructed sums are the low bits of the residue (v1/air.rs:74-112).
+        acc = gl::add(acc, gl::mul(gl::mul(a_hr, flg), gl::sub(head, head & 0xFFFFULL)));
+        const u64 slack = gl::sub(gl::sub(wlen, 1), head);
+        acc = gl::add(acc, gl::mul(gl::mul(a_sr, flg), gl::sub(slack, slack & 0xFFFFULL)));
+        acc = gl::add(acc, gl::mul(gl::mul(a_symr, flg), gl::sub(sym, sym & 0xFULL)));
+        // boundary (v1/air.rs:116-136)
+        acc = gl::add(acc, gl::mul(gl::mul(a_bf, is_first), gl::sub(gl::sub(head, mv), in_off)));
+        acc = gl::add(acc, gl::mul(gl::mul(a_bl, is_last), gl::sub(head, out_off)));
+    }
+    // mask R(w^i), Horner over ascending coefficients (v1/masking.rs:86-103)
+    const u64 x = gl::pow(cp.w_base, i);
+    u64 m = 0;
+    for (int j = cp.mask_deg - 1; j >= 0; j--) m = gl::add(gl::mul(m, x), cp.mask[j]);
+    out[i] = gl::add(acc, m);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* DEEP quotient: y[i] *= (shift*w^i - z)^-1, Montgomery batch inversion per thread              */
+/* ------------------------------------------------------------------------------------------ */
+constexpr int DEEP_PER_THREAD = 8;
+__global__ void __launch_bounds__(256) deep_kernel(u64* __restrict__ y, u64 N, u64 shift, u64 w, u64 w_step, u64 z) {
+    // thread handles i = base + lane + 32*k, k < DEEP_PER_THREAD (coalesced)
+    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    const u64 i0 = warp * (32 * DEEP_PER_THREAD) + lane;
+    if (i0 >= N) return;
+    u64 x = gl::mul(shift, gl::pow(w, i0));
+    u64 den[DEEP_PER_THREAD], pre[DEEP_PER_THREAD];
+    u64 run = 1;
+#pragma unroll
+    for (int k = 0; k < DEEP_PER_THREAD; k++) {
+        den[k] = gl::sub(x, z);
+        pre[k] = run;
+        run = gl::mul(run, den[k]);
+        x = gl::mul(x, w_step);
+    }
+    u64 inv = gl::inv(run);
+#pragma unroll
+    for (int k = DEEP_PER_THREAD - 1; k >= 0; k--) {
+        const u64 i = i0 + 32ULL * k;
+        const u64 dinv = gl::mul(inv, pre[k]);
+        inv = gl::mul(inv, den[k]);
+        if (i < N) y[i] = gl::mul(y[i], dinv);
+    }
+}
+
+__global__ void fri_fold_kernel(const u64* __restrict__ in, u64 half, u64 beta, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    out[i] = gl::add(in[i], gl::mul(beta, in[i + half]));
+}
+
+inline unsigned blocks_for(u64 n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------------------------------ */
+/* device trace                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+void validate_trace(const sezkp_trace_desc* d) {
+    REQUIRE(d != nullptr, "trace descriptor is NULL");
+    REQUIRE(d->reserved == 0, "trace descriptor: reserved must be 0");
+    REQUIRE(d->tau >= 1 && d->tau <= 4096, "tau %u out of range", d->tau);
+    REQUIRE(d->n_blocks >= 1, "empty trace");
+    REQUIRE(d->n_rows >= 2 && (d->n_rows & (d->n_rows - 1)) == 0,
+            "n_rows = %llu: the STARK v1 path needs a power-of-two trace length >= 2 (reference v1/lde.rs:51)",
+            (unsigned long long)d->n_rows);
+    REQUIRE(d->n_rows <= (1ULL << 29), "n_rows too large (LDE domain limited to 2^32)");
+    REQUIRE(d->block_len && d->win_left && d->win_right && d->head_in_off && d->head_out_off && d->input_mv && d->mv &&
+                d->write_flag && d->write_sym,
+            "trace descriptor has NULL arrays");
+    u64 sum = 0;
+    for (u64 k = 0; k < d->n_blocks; k++) {
+        REQUIRE(d->block_len[k] >= 1, "block %llu is empty", (unsigned long long)k);
+        sum += d->block_len[k];
+    }
+    REQUIRE(sum == d->n_rows, "n_rows != sum(block_len)");
+}
+
+void DeviceTraceOwner::upload(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
+    const u64 nb = d->n_blocks, n = d->n_rows, tau = d->tau;
+    std::vector<u64> starts(nb);
+    u64 acc = 0;
+    for (u64 k = 0; k < nb; k++) {
+        starts[k] = acc;
+        acc += d->block_len[k];
+    }
+    // one packed allocation, 16-byte aligned sections
+    size_t off = 0;
+    auto sect = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 15) & ~(size_t)15;
+        return o;
+    };
+    const size_t o_start = sect(nb * 8), o_len = sect(nb * 8), o_wl = sect(nb * tau * 8), o_wr = sect(nb * tau * 8),
+                 o_io = sect(nb * tau * 4), o_oo = sect(nb * tau * 4), o_imv = sect(n), o_mv = sect(n * tau),
+                 o_wf = sect(n * tau), o_ws = sect(n * tau * 2);
+    u8* base = (u8*)buf.ensure(off);
+    auto put = [&](size_t o, const void* src, size_t bytes) {
+        CUDA_CHECK(cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    };
+    put(o_start, starts.data(), nb * 8);
+    put(o_len, d->block_len, nb * 8);
+    put(o_wl, d->win_left, nb * tau * 8);
+    put(o_wr, d->win_right, nb * tau * 8);
+    put(o_io, d->head_in_off, nb * tau * 4);
+    put(o_oo, d->head_out_off, nb * tau * 4);
+    put(o_imv, d->input_mv, n);
+    put(o_mv, d->mv, n * tau);
+    put(o_wf, d->write_flag, n * tau);
+    put(o_ws, d->write_sym, n * tau * 2);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // `starts` is a local
+    t.tau = (u32)tau;
+    t.n_blocks = nb;
+    t.n_rows = n;
+    t.block_start = (const u64*)(base + o_start);
+    t.block_len = (const u64*)(base + o_len);
+    t.win_left = (const int64_t*)(base + o_wl);
+    t.win_right = (const int64_t*)(base + o_wr);
+    t.head_in_off = (const u32*)(base + o_io);
+    t.head_out_off = (const u32*)(base + o_oo);
+    t.input_mv = (const int8_t*)(base + o_imv);
+    t.mv = (const int8_t*)(base + o_mv);
+    t.write_flag = (const u8*)(base + o_wf);
+    t.write_sym = (const uint16_t*)(base + o_ws);
+    h2d_bytes = off;
+}
+
+void expand_columns_device(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols) {
+    head_scan_kernel<<<blocks_for(t.n_blocks * t.tau, 128), 128, 0, ctx->stream>>>(t, cols);
+    CUDA_CHECK(cudaGetLastError());
+    expand_rows_kernel<<<blocks_for(t.n_rows, 256), 256, 0, ctx->stream>>>(t, cols);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches += 2;
+}
+
+void compose_device(sezkp_ctx* ctx, const u64* cols, u64 n, u32 tau, const u64 alphas8[8], const u64* mask, size_t mask_deg,
+                    u64* out) {
+    REQUIRE(mask_deg <= 8, "mask degree %zu > 8 unsupported", mask_deg);
+    ComposeParams cp{};
+    for (int i = 0; i < 8; i++) {
+        REQUIRE(alphas8[i] < gl::P, "alpha %d is not a canonical field element", i);
+        cp.a[i] = alphas8[i];
+    }
+    for (size_t i = 0; i < mask_deg; i++) {
+        REQUIRE(mask[i] < gl::P, "mask coefficient %zu is not canonical", i);
+        cp.mask[i] = mask[i];
+    }
+    cp.mask_deg = (int)mask_deg;
+    cp.w_base = gl::root_2exp((unsigned)ilog2(n));
+    compose_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(cols, n, tau, cp, out);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+bool z_on_coset(u64 z, u64 shift, int log_N) {  // v1/prover.rs:120-131
+    u64 t = gl::mul(z, gl::inv(shift));
+    for (int i = 0; i < log_N; i++) t = gl::sqr(t);
+    return t == 1;
+}
+
+// base evaluations (device, n = 2^L; destroyed) -> out (device, 2^(L+logB)): iNTT, coset LDE, DEEP quotient.
+void deep_lde_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, u64 shift, u64 z) {
+    REQUIRE(z < gl::P && shift < gl::P && shift != 0, "shift / z must be canonical, shift non-zero");
+    REQUIRE(!z_on_coset(z, shift, L + logB), "OOD point z lies on the evaluation coset");
+    const u64 n = 1ULL << L, N = n << logB;
+    u64* tmp = (u64*)ctx->scratch[0].ensure(n * 8);
+    ntt_batch_device(ctx, base_vals, tmp, L, 1, true);
+    u64* inter = (u64*)ctx->scratch[1].ensure(N * 8);
+    coset_lde_device(ctx, base_vals, out, inter, L, logB, shift, 1);
+    const u64 w = gl::root_2exp((unsigned)(L + logB));
+    const u64 w_step = gl::pow(w, 32);
+    const u64 threads = (N + DEEP_PER_THREAD - 1) / DEEP_PER_THREAD;
+    deep_kernel<<<blocks_for(threads, 256), 256, 0, ctx->stream>>>(out, N, shift, w, w_step, z);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* FRI                                                                                         */
+/* ------------------------------------------------------------------------------------------ */
+void FriLayers::release() {
+    for (auto& c : commits) c.release();
+    commits.clear();
+    if (values) cudaFree(values);
+    values = nullptr;
+}
+
+// layer0 (device, N = 2^log_N values) is copied into the retained layer buffer unless `adopt` (then it must be
+// the first N elements of a 2N-element allocation that FriLayers takes ownership of).
+void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log_N, const u64* betas, u8* roots_host,
+                       u64* final_value, HostAbsorb* absorb) {
+    REQUIRE(log_N >= 1 && log_N <= 32, "log_N %d out of range", log_N);
+    const u64 N = 1ULL << log_N;
+    fl.log_N = log_N;
+    {
+        cudaError_t e = cudaMalloc(&fl.values, 2 * N * 8);
+        if (e != cudaSuccess) sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaMalloc(FRI layers %llu B): %s", (unsigned long long)(2 * N * 8), cudaGetErrorString(e));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(fl.values, layer0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    fl.commits.resize(log_N + 1);
+    u64 off = 0, len = N;
+    std::vector<u64> beta_store;
+    for (int l = 0; l <= log_N; l++) {
+        u64* cur = fl.values + off;
+        if (l > 0) {
+            // betas may only become known after root 0 was absorbed (transcript callback)
+            const u64 beta = betas ? betas[l - 1] : beta_store[l - 1];
+            REQUIRE(beta < gl::P, "beta %d is not canonical", l - 1);
+            const u64* prev = fl.values + (off - 2 * len);
+            fri_fold_kernel<<<blocks_for(len, 256), 256, 0, ctx->stream>>>(prev, len, beta, cur);
+            CUDA_CHECK(cudaGetLastError());
+            ctx->launches++;
+        }
+        commit_build(ctx, fl.commits[l], cur, len, 1, 10, nullptr, roots_host + 32 * l);
+        if (absorb) {
+            absorb->on_root(l, roots_host + 32 * l);
+            if (l == 0 && !betas) beta_store = absorb->draw_betas(log_N);
+        }
+        off += len;
+        len >>= 1;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(final_value, fl.values + (2 * N - 2), 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+// k query indices into layer 0.  positions [k][log_N+1]; values [k][log_N][2]; paths [k][log_N][2][log_N][32]
+void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_t k, u64* positions, u64* values, u8* paths) {
+    const int L = fl.log_N;
+    const u64 N = 1ULL << L;
+    for (size_t q = 0; q < k; q++) {
+        REQUIRE(idx0[q] < N, "FRI query %zu out of range", q);
+        positions[q * (L + 1)] = idx0[q];
+    }
+    std::memset(paths, 0, k * (size_t)L * 2 * L * 32);
+    std::vector<u32> col(2 * k, 0);
+    std::vector<u64> row(2 * k), val(2 * k);
+    std::vector<u8> cr(2 * k * 32), pin, pto;
+    for (int l = 0; l < L; l++) {
+        const Commit& cm = fl.commits[l];
+        const u64 len = N >> l, half = len >> 1;
+        for (size_t q = 0; q < k; q++) {
+            const u64 idx = positions[q * (L + 1) + l];
+            row[2 * q] = idx;
+            row[2 * q + 1] = idx ^ half;
+            positions[q * (L + 1) + l + 1] = idx % half;  // v1/prover.rs:386-388, 430-434 (half >= 1)
+        }
+        const int din = cm.cl, dout = ilog2(cm.n_ch);
+        pin.assign(2 * k * (size_t)din * 32 + 32, 0);
+        pto.assign(2 * k * (size_t)dout * 32 + 32, 0);
+        commit_open(ctx, cm, col.data(), row.data(), 2 * k, val.data(), cr.data(), pin.data(), pto.data());
+        for (size_t q = 0; q < k; q++)
+            for (int s = 0; s < 2; s++) {
+                values[(q * L + l) * 2 + s] = val[2 * q + s];
+                u8* dst = paths + (((q * L + l) * 2 + s) * (size_t)L) * 32;
+                std::memcpy(dst, pin.data() + (2 * q + s) * (size_t)din * 32, (size_t)din * 32);
+                std::memcpy(dst + (size_t)din * 32, pto.data() + (2 * q + s) * (size_t)dout * 32, (size_t)dout * 32);
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* prove_v1                                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+namespace {
+
+struct Writer {  // bincode 1.3 default: fixint little-endian, u64 lengths, arrays raw
+    std::vector<u8> b;
+    void u64le(u64 v) {
+        u8 t[8];
+        std::memcpy(t, &v, 8);
+        b.insert(b.end(), t, t + 8);
+    }
+    void raw(const void* p, size_t n) { b.insert(b.end(), (const u8*)p, (const u8*)p + n); }
+    void digest_vec(const u8* p, size_t count) {
+        u64le(count);
+        raw(p, count * 32);
+    }
+};
+
+std::vector<std::string> column_labels(u32 tau) {  // v1/openings.rs:89-116
+    std::vector<std::string> out = {"input_mv", "is_first", "is_last"};
+    static const char* groups[7] = {"mv_", "wflag_", "wsym_", "head_", "winlen_", "in_off_", "out_off_"};
+    for (const char* g : groups)
+        for (u32 r = 0; r < tau; r++) out.push_back(std::string(g) + std::to_string(r));
+    return out;
+}
+
+u64 le64(const u8* p) {
+    u64 v;
+    std::memcpy(&v, p, 8);
+    return v;
+}
+
+struct TranscriptAbsorb : HostAbsorb {
+    host::Transcript& tr;
+    explicit TranscriptAbsorb(host::Transcript& t) : tr(t) {}
+    void on_root(int, const u8* root) override { tr.absorb("fri_layer_root", root, 32); }  // v1/prover.rs:187, 219, 235
+    std::vector<u64> draw_betas(int n) override {                                           // v1/params.rs:103-113
+        auto by = tr.challenge("fri_betas", 8 * (size_t)n);
+        std::vector<u64> out(n);
+        for (int i = 0; i < n; i++) out[i] = le64(&by[8 * i]) % gl::P;
+        return out;
+    }
+};
+
+}  // namespace
+
+void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out) {
+    validate_trace(desc);
+    ctx->timings.clear();
+    double t0 = now_ms();
+    auto lap = [&](const char* name) {
+        cudaStreamSynchronize(ctx->stream);
+        double t1 = now_ms();
+        ctx->timings.push_back({name, t1 - t0});
+        t0 = t1;
+    };
+    const u64 n = desc->n_rows;
+    const u32 tau = desc->tau;
+    const int L = ilog2(n), logB = 3, log_N = L + logB;  // BLOWUP = 8 (v1/params.rs:28)
+    const u64 N = 1ULL << log_N;
+    const int n_cols = 3 + 7 * (int)tau;
+    constexpr int NUM_QUERIES = 30, COL_CHUNK_LOG2 = 10;  // v1/params.rs:31, 37
+
+    // A. compact trace -> device -> committed columns
+    DeviceTraceOwner dt;
+    dt.buf = ctx->scratch[2];
+    dt.upload(ctx, desc);
+    ctx->scratch[2] = dt.buf;
+    lap("h2d_trace");
+    u64* cols = (u64*)ctx->scratch[3].ensure((size_t)n_cols * n * 8);
+    expand_columns_device(ctx, dt.t, cols);
+    lap("expand_columns");
+
+    // B. transcript prelude (v1/prover.rs:67-70)
+    host::Transcript tr("sezkp-stark/v1");
+    tr.absorb("manifest_root", manifest_root, 32);
+    tr.absorb_u64("n", n);
+    tr.absorb_u64("tau", tau);
+
+    // C. column commitments (v1/prover.rs:75-81)
+    std::vector<std::string> labels = column_labels(tau);
+    std::vector<const char*> label_ptrs;
+    for (auto& s : labels) label_ptrs.push_back(s.c_str());
+    std::vector<u8> col_roots((size_t)n_cols * 32);
+    Commit cm;
+    FriLayers fl;
+    try {
+        commit_build(ctx, cm, cols, n, n_cols, COL_CHUNK_LOG2, label_ptrs.data(), col_roots.data());
+        lap("column_commit");
+        tr.absorb_u64("n_cols", (u64)n_cols);
+        for (int c = 0; c < n_cols; c++) tr.absorb("col_root", &col_roots[32 * c], 32);
+
+        // D. alphas, masks (v1/params.rs:76-86, v1/masking.rs:56-79)
+        u64 alphas[8];
+        {
+            auto by = tr.challenge("alphas", 64);
+            for (int i = 0; i < 8; i++) alphas[i] = le64(&by[8 * i]) % gl::P;
+        }
+        u64 mask[4];
+        tr.absorb("masks", "masks", 5);
+        tr.absorb_u64("n_masks", 1);
+        tr.absorb_u64("deg", 4);
+        for (int j = 0; j < 4; j++) mask[j] = le64(tr.challenge("mask_coeff", 8).data()) % gl::P;
+
+        // E. OOD point, nudged off the coset (v1/prover.rs:118-135)
+        const u64 shift = 3;
+        u64 z = le64(tr.challenge("ood_point", 8).data()) % gl::P;
+        while (z_on_coset(z, shift, log_N)) z = gl::add(z, 1);
+
+        // F. composition -> iNTT -> coset LDE -> DEEP (v1/prover.rs:142-178, v1/lde.rs:42-97)
+        u64* base_vals = (u64*)ctx->scratch[4].ensure(n * 8);
+        compose_device(ctx, cols, n, tau, alphas, mask, 4, base_vals);
+        lap("compose");
+        u64* lde = (u64*)ctx->scratch[5].ensure(N * 8);
+        deep_lde_device(ctx, base_vals, lde, L, logB, shift, z);
+        lap("deep_lde");
+
+        // G. FRI fold + commit; root0 is absorbed before the betas are drawn (v1/prover.rs:184-243)
+        std::vector<u8> fri_roots((size_t)(log_N + 1) * 32);
+        u64 final_value = 0;
+        TranscriptAbsorb ab(tr);
+        fri_commit_device(ctx, fl, lde, log_N, nullptr, fri_roots.data(), &final_value, &ab);
+        lap("fri_commit");
+
+        // H. AIR row queries and column openings (v1/prover.rs:248-292)
+        std::vector<u64> rows(NUM_QUERIES);
+        {
+            auto by = tr.challenge("row_queries", 8 * NUM_QUERIES);
+            for (int i = 0; i < NUM_QUERIES; i++) rows[i] = le64(&by[8 * i]) % n;
+        }
+        // opening order inside one RowOpenings as serialized (v1/proof.rs:48-69): per tape 9, then is_first, is_last, input_mv
+        const size_t per_row = 9 * (size_t)tau + 3, k_open = per_row * NUM_QUERIES;
+        std::vector<u32> o_col(k_open);
+        std::vector<u64> o_row(k_open);
+        for (int qi = 0; qi < NUM_QUERIES; qi++) {
+            const u64 row = rows[qi], ip1 = (row + 1 < n) ? row + 1 : 0;  // next_wrap v1/prover.rs:50-58
+            size_t o = qi * per_row;
+            for (u32 r = 0; r < tau; r++) {
+                const u32 c_mv = 3 + r, c_wf = 3 + tau + r, c_ws = 3 + 2 * tau + r, c_hd = 3 + 3 * tau + r,
+                          c_wl = 3 + 4 * tau + r, c_in = 3 + 5 * tau + r, c_out = 3 + 6 * tau + r;
+                const u32 cc[9] = {c_mv, c_mv, c_wf, c_ws, c_hd, c_hd, c_wl, c_in, c_out};
+                const u64 rr[9] = {row, ip1, row, row, row, ip1, row, row, row};
+                for (int j = 0; j < 9; j++) {
+                    o_col[o] = cc[j];
+                    o_row[o++] = rr[j];
+                }
+            }
+            o_col[o] = 1; o_row[o++] = row;  // is_first
+            o_col[o] = 2; o_row[o++] = row;  // is_last
+            o_col[o] = 0; o_row[o++] = row;  // input_mv
+        }
+        const int din = cm.cl, dout = ilog2(cm.n_ch);
+        std::vector<u64> o_val(k_open);
+        std::vector<u8> o_cr(k_open * 32), o_in(k_open * (size_t)din * 32 + 32), o_to(k_open * (size_t)dout * 32 + 32);
+        commit_open(ctx, cm, o_col.data(), o_row.data(), k_open, o_val.data(), o_cr.data(), o_in.data(), o_to.data());
+        lap("column_openings");
+
+        // I. FRI queries (v1/prover.rs:297-450); same transcript label as the AIR rows
+        std::vector<u64> fri_idx(NUM_QUERIES);
+        {
+            auto by = tr.challenge("row_queries", 8 * NUM_QUERIES);
+            for (int i = 0; i < NUM_QUERIES; i++) fri_idx[i] = le64(&by[8 * i]) % N;
+        }
+        std::vector<u64> f_pos((size_t)NUM_QUERIES * (log_N + 1)), f_val((size_t)NUM_QUERIES * log_N * 2);
+        std::vector<u8> f_paths((size_t)NUM_QUERIES * log_N * 2 * log_N * 32);
+        fri_open_device(ctx, fl, fri_idx.data(), NUM_QUERIES, f_pos.data(), f_val.data(), f_paths.data());
+        lap("fri_openings");
+
+        // J. ProofV1 in declaration order (v1/proof.rs:80-98)
+        Writer w;
+        w.u64le(N);
+        w.u64le(tau);
+        w.u64le((u64)n_cols);
+        for (int c = 0; c < n_cols; c++) {
+            w.u64le(labels[c].size());
+            w.raw(labels[c].data(), labels[c].size());
+            w.raw(&col_roots[32 * c], 32);
+        }
+        auto put_opening = [&](size_t o) {
+            const u64 row = o_row[o];
+            w.raw(&o_val[o], 8);
+            w.u64le(row);
+            w.u64le(row >> din);
+            w.u64le(row & ((1ULL << din) - 1));
+            w.raw(&o_cr[o * 32], 32);
+            w.digest_vec(&o_in[o * (size_t)din * 32], din);
+            w.digest_vec(&o_to[o * (size_t)dout * 32], dout);
+        };
+        w.u64le(NUM_QUERIES);
+        for (int qi = 0; qi < NUM_QUERIES; qi++) {
+            w.u64le(rows[qi]);
+            w.u64le(tau);
+            for (size_t j = 0; j < per_row; j++) put_opening(qi * per_row + j);
+        }
+        w.digest_vec(fri_roots.data(), log_N + 1);
+        w.u64le(NUM_QUERIES);
+        for (int qi = 0; qi < NUM_QUERIES; qi++) {
+            w.u64le((u64)log_N + 1);
+            for (int l = 0; l <= log_N; l++) w.u64le(f_pos[(size_t)qi * (log_N + 1) + l]);
+            w.u64le((u64)log_N);
+            for (int l = 0; l < log_N; l++) {
+                const int depth = log_N - l;
+                for (int s = 0; s < 2; s++) {
+                    w.raw(&f_val[((size_t)qi * log_N + l) * 2 + s], 8);
+                    w.digest_vec(&f_paths[(((size_t)qi * log_N + l) * 2 + s) * (size_t)log_N * 32], depth);
+                }
+            }
+        }
+        w.raw(&final_value, 8);
+        w.raw(manifest_root, 32);
+        proof_out.swap(w.b);
+        lap("serialize");
+    } catch (...) {
+        cm.release();
+        fl.release();
+        throw;
+    }
+    cm.release();
+    fl.release();
+}

@@ -1,0 +1,49 @@
+// Internal interface of stark.cu.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "hash.cuh"
+
+struct DeviceTrace {  // device image of sezkp_trace_desc (+ block_start prefix sums)
+    u32 tau;
+    u64 n_blocks, n_rows;
+    const u64* block_start;
+    const u64* block_len;
+    const int64_t* win_left;
+    const int64_t* win_right;
+    const u32* head_in_off;
+    const u32* head_out_off;
+    const int8_t* input_mv;
+    const int8_t* mv;
+    const u8* write_flag;
+    const uint16_t* write_sym;
+};
+struct DeviceTraceOwner {
+    DevBuf buf;
+    DeviceTrace t{};
+    size_t h2d_bytes = 0;
+    void upload(sezkp_ctx* ctx, const sezkp_trace_desc* d);
+};
+void validate_trace(const sezkp_trace_desc* d);
+void expand_columns_device(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols_dev);
+void compose_device(sezkp_ctx* ctx, const u64* cols_dev, u64 n, u32 tau, const u64 alphas8[8], const u64* mask, size_t mask_deg,
+                    u64* out_dev);
+bool z_on_coset(u64 z, u64 shift, int log_N);
+void deep_lde_device(sezkp_ctx* ctx, u64* base_vals_dev /* destroyed */, u64* out_dev, int L, int logB, u64 shift, u64 z);
+
+struct HostAbsorb {  // transcript hooks of the FRI commit loop
+    virtual void on_root(int layer, const u8* root) = 0;
+    virtual std::vector<u64> draw_betas(int n) = 0;
+    virtual ~HostAbsorb() {}
+};
+struct FriLayers {
+    int log_N = 0;
+    u64* values = nullptr;        // device: layer l (len N>>l) at offset sum_{i<l} N>>i
+    std::vector<Commit> commits;  // one per layer
+    void release();
+};
+void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0_dev, int log_N, const u64* betas_or_null, u8* roots_host,
+                       u64* final_value, HostAbsorb* absorb_or_null);
+void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_t k, u64* positions, u64* values, u8* paths);
+void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out);

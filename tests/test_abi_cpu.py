@@ -1,0 +1,74 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every declared symbol,
+the header and the binding agree, and there is no silent fallback without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, pkg
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "sezkp_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(sezkp_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    m = pkg()
+    if not os.path.exists(m.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = m.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), f"libsezkp_cuda.so does not export {s}"
+    assert sorted(m.EXPORTS) == syms, "binding.EXPORTS and include/sezkp_cuda.h disagree"
+    assert lib.sezkp_cuda_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = pkg()
+    with pytest.raises(m.SezkpCudaError) as ei:
+        m.Context()
+    assert ei.value.code == -4  # ENODEV
+    with pytest.raises(m.SezkpCudaError):
+        m.StarkV1Cuda.prove(m.demo_block(16), bytes(32))
+
+
+def test_trace_desc_layout_matches_header():
+    m = pkg()
+    # struct sezkp_trace_desc: u32,u32,u64,u64, 9 pointers
+    assert C.sizeof(m.TraceDesc) == 4 + 4 + 8 + 8 + 9 * 8
+    ct = m.demo_block(16)
+    d = ct.as_desc()
+    assert d.tau == 1 and d.n_blocks == 1 and d.n_rows == 16
+
+
+def test_simulate_generator_and_partition():
+    m = pkg()
+    from importlib import import_module
+    tr = import_module("streaming-zero-knowledge-proofs_b200.trace")
+    assert tr._splitmix_block(42, 0, 3).tolist() == [13679457532755275413, 2949826092126892291, 5139283748462763858]
+    ct = m.simulate(1 << 12, 512, 8)
+    assert ct.n_rows == 4096 and ct.n_blocks == 8 and ct.tau == 8
+    assert set(np.unique(ct.mv)) <= {-1, 0, 1} and set(np.unique(ct.input_mv)) <= {-1, 0, 1}
+    assert int(ct.write_sym.max()) <= 15 and np.all(ct.write_sym[ct.write_flag == 0] == 0)
+    # partition invariants (reference partition.rs:61-147): window covers [min,max] of post-move heads, entry at 0
+    for k in range(ct.n_blocks):
+        rows = slice(k * 512, (k + 1) * 512)
+        heads = np.cumsum(ct.mv[rows].astype(np.int64), axis=0)
+        assert np.array_equal(ct.win_left[k], np.minimum(heads.min(axis=0), 0))
+        assert np.array_equal(ct.win_right[k], np.maximum(heads.max(axis=0), 0))
+        assert np.array_equal(ct.head_in_off[k].astype(np.int64), -ct.win_left[k])
+        assert np.array_equal(ct.head_out_off[k].astype(np.int64), heads[-1] - ct.win_left[k])
+    assert ct.step_lo.tolist() == [1 + 512 * k for k in range(8)] and ct.step_hi.tolist() == [512 * (k + 1) for k in range(8)]
+    # ragged last block
+    ct2 = m.simulate(1000, 512, 2)
+    assert ct2.block_len.tolist() == [512, 488]

@@ -1,0 +1,277 @@
+"""GPU parity tests proper: every C-ABI entry point against the CPU oracle on the same seeded inputs
+(bit-exact), the reference's structural tests replayed through the GPU path, and size-independent
+properties at larger sizes."""
+import numpy as np
+import pytest
+
+from conftest import load_fixture, pkg
+from oracle_lib import P, det_coeffs, det_vec_fast
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return pkg().Context()
+
+
+def rand_field(rng, shape):
+    return (rng.integers(0, 1 << 63, size=shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=shape, dtype=np.uint64)) % np.uint64(P)
+
+
+# ----------------------------------------------------------------------------- NTT / LDE
+@pytest.mark.parametrize("k", list(range(1, 17)) + [18, 20, 21, 22])
+def test_ntt_forward_inverse_vs_oracle(ctx, oracle, k):
+    n = 1 << k
+    v = det_vec_fast(n, 1337)  # sezkp-ffts/tests/ntt_roundtrip.rs generator
+    f = ctx.ntt(v)
+    if k <= 20:
+        assert np.array_equal(f, oracle.ntt(v)), f"forward NTT mismatch at 2^{k}"
+    back = ctx.ntt(f, inverse=True)
+    assert np.array_equal(back, v), f"round trip failed at 2^{k}"
+    if k <= 20:
+        assert np.array_equal(ctx.ntt(v, inverse=True), oracle.ntt(v, inverse=True))
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 10, 11, 13])
+def test_ntt_special_vectors(ctx, oracle, k):
+    n = 1 << k
+    for v in (np.zeros(n, np.uint64), np.eye(1, n, 0, dtype=np.uint64)[0], np.arange(n, dtype=np.uint64),
+              np.full(n, P - 1, np.uint64)):
+        f = ctx.ntt(v)
+        assert np.array_equal(f, oracle.ntt(v))
+        assert np.array_equal(ctx.ntt(f, inverse=True), v)
+
+
+@pytest.mark.parametrize("k,cols", [(3, 1), (3, 70), (9, 5), (10, 3), (12, 4), (14, 3), (16, 2)])
+def test_ntt_batched_columns(ctx, oracle, k, cols):
+    rng = np.random.default_rng(k * 100 + cols)
+    a = rand_field(rng, (cols, 1 << k))
+    assert np.array_equal(ctx.ntt(a), oracle.ntt(a))
+    assert np.array_equal(ctx.ntt(a, inverse=True), oracle.ntt(a, inverse=True))
+
+
+def test_ntt_rejects_non_canonical(ctx):
+    bad = np.full(8, P, np.uint64)
+    with pytest.raises(pkg().SezkpCudaError) as ei:
+        ctx.ntt(bad)
+    assert ei.value.code == -1
+
+
+@pytest.mark.parametrize("k", range(1, 13))
+def test_coset_shift_one_matches_plain_ntt(ctx, k):
+    """sezkp-ffts/tests/coset_lde.rs:24-37"""
+    c = det_coeffs(1 << k)
+    assert np.array_equal(ctx.coset_lde(c, 0, 1), ctx.ntt(c))
+
+
+@pytest.mark.parametrize("k,lb,shift,cols", [(1, 3, 3, 1), (2, 1, 7, 3), (4, 2, 3, 5), (8, 3, 3, 2), (10, 2, 3, 3), (11, 3, 3, 2),
+                                             (12, 2, 7, 2), (14, 3, 3, 1), (16, 2, 3, 2), (18, 3, 3, 1), (20, 2, 3, 1)])
+def test_coset_lde_vs_oracle(ctx, oracle, k, lb, shift, cols):
+    rng = np.random.default_rng(k + 31 * lb)
+    c = rand_field(rng, (cols, 1 << k))
+    got = ctx.coset_lde(c, lb, shift)
+    exp = oracle.coset_eval(c, k + lb, shift)
+    assert np.array_equal(got, exp)
+    ev = rand_field(rng, (cols, 1 << k))
+    assert np.array_equal(ctx.lde_from_evals(ev, lb, shift), oracle.lde_from_evals(ev, lb, shift))
+
+
+def test_coset_scaling_invariant(ctx):
+    """sezkp-ffts/tests/coset_lde.rs:40-64 with shift 7 through the GPU path (property, no oracle)."""
+    for k in (4, 9, 12):
+        n = 1 << k
+        c = det_coeffs(n)
+        pw, scaled = 1, []
+        for x in c.tolist():
+            scaled.append(x * pw % P)
+            pw = pw * 7 % P
+        assert np.array_equal(ctx.ntt(np.array(scaled, np.uint64)), ctx.coset_lde(c, 0, 7))
+
+
+@pytest.mark.parametrize("k,lb", [(2, 3), (6, 3), (10, 3), (12, 3), (15, 3), (12, 2)])
+def test_deep_lde_vs_oracle(ctx, oracle, k, lb):
+    rng = np.random.default_rng(k)
+    base = rand_field(rng, 1 << k)
+    z = int(rand_field(rng, 1)[0])
+    assert np.array_equal(ctx.deep_lde(base, lb, 3, z), oracle.deep_lde(base, lb, 3, z))
+
+
+def test_deep_lde_rejects_z_on_coset(ctx, oracle):
+    z = 3 * oracle.gl_pow(oracle.gl_root_2exp(7), 5) % P  # shift * w^5 lies on the size-2^7 coset
+    with pytest.raises(pkg().SezkpCudaError):
+        ctx.deep_lde(np.arange(16, dtype=np.uint64), 3, 3, z)
+
+
+# ----------------------------------------------------------------------------- hashing / trees
+@pytest.mark.parametrize("label", [None, "mv_0", "is_last", "input_mv", "out_off_7", "out_off_15", "c_255", "x" * 44])
+def test_leaf_hash_vs_oracle(ctx, oracle, label):
+    rng = np.random.default_rng(5)
+    v = np.concatenate([rand_field(rng, 1000), np.array([0, 1, P - 1, 0xFFFFFFFF, 1 << 32], np.uint64)])
+    assert np.array_equal(ctx.leaf_hash(v, label), oracle.leaf_hash(v, label))
+
+
+def test_leaf_hash_label_too_long(ctx):
+    with pytest.raises(pkg().SezkpCudaError):
+        ctx.leaf_hash(np.zeros(4, np.uint64), "y" * 45)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 5, 7, 8, 13, 31, 33, 64, 1000, 1024, 4097])
+def test_merkle_root_odd_promotion_vs_oracle(ctx, oracle, n):
+    """sezkp-merkle odd-promotion semantics (lib.rs:453-470) and MerkleTree::from_leaves."""
+    rng = np.random.default_rng(n)
+    leaves = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    assert ctx.merkle_root(leaves) == oracle.merkle_root(leaves)
+
+
+@pytest.mark.parametrize("n,c", [(1, 2), (2, 1), (16, 3), (512, 4), (1024, 3), (2048, 5), (1 << 14, 2), (1 << 17, 1)])
+def test_column_commit_and_openings_vs_oracle(ctx, oracle, n, c):
+    """stream_columns_equiv.rs / stream_openings.rs: roots equal the oracle's chunked commitment and
+    every opening verifies with the oracle's verify path (MerkleTree::verify)."""
+    rng = np.random.default_rng(n + c)
+    cols = rand_field(rng, (c, n))
+    labels = [f"lab_{i}" for i in range(c)]
+    roots, tree = ctx.column_commit(cols, labels, keep=True)
+    assert np.array_equal(roots, oracle.column_commit(cols, labels))
+    k = 32
+    ci = rng.integers(0, c, k).astype(np.uint32)
+    ri = rng.integers(0, n, k).astype(np.uint64)
+    vals, cr, pin, pto = tree.open(ci, ri)
+    for q in range(k):
+        col, row = int(ci[q]), int(ri[q])
+        assert vals[q] == cols[col, row]
+        leaves = oracle.leaf_hash(cols[col], labels[col])
+        full = oracle.merkle_open(leaves, row)  # for power-of-two n: in-chunk path ++ outer path
+        got = np.concatenate([pin[q], pto[q]], axis=0)
+        assert np.array_equal(got, full)
+        lo = (row >> 10) << 10
+        assert cr[q].tobytes() == oracle.merkle_root(leaves[lo:lo + min(n, 1024)])
+    tree.free()
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 5, 10, 11, 13, 16])
+def test_fri_commit_and_open_vs_oracle(ctx, oracle, log_n):
+    rng = np.random.default_rng(log_n)
+    l0 = rand_field(rng, 1 << log_n)
+    betas = rand_field(rng, log_n)
+    roots, fin, h = ctx.fri_commit(l0, betas, keep=True)
+    eroots, efin = oracle.fri_commit(l0, betas)
+    assert np.array_equal(roots, eroots) and fin == efin
+    assert roots[0].tobytes() == oracle.streaming_layer_root(l0)  # stream_fri_equiv.rs: streaming == in-core root
+    idx = rng.integers(0, 1 << log_n, 6).astype(np.uint64)
+    pos, vals, paths = h.open(idx)
+    layer = l0.copy()
+    for l in range(log_n):
+        leaves = oracle.leaf_hash(layer)
+        half = layer.size // 2
+        for q in range(idx.size):
+            i = int(pos[q, l])
+            j = i ^ half
+            assert vals[q, l, 0] == layer[i] and vals[q, l, 1] == layer[j]
+            d = log_n - l
+            assert np.array_equal(paths[q, l, 0, :d], oracle.merkle_open(leaves, i))
+            assert np.array_equal(paths[q, l, 1, :d], oracle.merkle_open(leaves, j))
+            assert pos[q, l + 1] == i % half
+        layer = np.array([(int(layer[i]) + int(betas[l]) * int(layer[i + half])) % P for i in range(half)], np.uint64)
+    h.free()
+
+
+# ----------------------------------------------------------------------------- feeder + prover
+def traces():
+    m = pkg()
+    out = {"demo16": m.demo_block(16), "demo64": m.demo_block(64), "demo2048": m.demo_block(2048)}
+    for name in ("fixture_root_T64.json", "fixture_riscv_T32.json"):
+        out[name] = m.blocks_to_compact(load_fixture(name)["blocks"])
+    out["sim_256_16_2"] = m.simulate(256, 16, 2)
+    out["sim_4096_512_8"] = m.simulate(4096, 512, 8)
+    out["sim_2048_2048_1"] = m.simulate(2048, 2048, 1)
+    out["sim_1024_100_3"] = m.simulate(1024, 100, 3)  # ragged last block
+    return out
+
+
+@pytest.mark.parametrize("name", list(traces().keys()))
+def test_trace_columns_and_composition_vs_oracle(ctx, oracle, name):
+    ct = traces()[name]
+    assert np.array_equal(ctx.trace_columns(ct), oracle.trace_columns(ct))
+    rng = np.random.default_rng(1)
+    al, mk = rand_field(rng, 8), rand_field(rng, 4)
+    assert np.array_equal(ctx.compose_base(ct, al, mk), oracle.compose_base(ct, al, mk))
+
+
+@pytest.mark.parametrize("name", list(traces().keys()))
+def test_prove_v1_bytes_identical_to_oracle(ctx, oracle, name):
+    ct = traces()[name]
+    root = pkg().manifest_root(ct)
+    got = ctx.prove_v1(ct, root)
+    exp = oracle.prove_v1(ct, root)
+    assert len(got) == len(exp)
+    assert got == exp
+    # same accept / reject outcome from the (oracle) verifier
+    assert oracle.verify_v1(got, ct)[0] == oracle.verify_v1(exp, ct)[0]
+
+
+def test_prove_v1_kats_and_accept(ctx, oracle):
+    """SURVEY §8c known answers + reference tests air_ok.rs / stream_fri_equiv.rs (prove -> verify accepts)."""
+    m = pkg()
+    ct = m.demo_block(64)
+    proof = ctx.prove_v1(ct, bytes([7] * 32))
+    assert len(proof) == 197199
+    assert oracle.blake3(proof).hex() == "733e0d80c093a79a7dab5464741660950997b31c1f14ab255177f120827f2d43"
+    ok, why = oracle.verify_v1(proof, ct)
+    assert ok, why
+    art = m.StarkV1Cuda.prove(ct, bytes([7] * 32))
+    assert art.backend == "stark" and art.proof_bytes == proof and art.meta == {"domain_n": 512, "proto": "stark-v1", "tau": 1}
+    fx = load_fixture("fixture_root_T64.json")
+    p2 = ctx.prove_v1(m.blocks_to_compact(fx["blocks"]), bytes.fromhex(fx["manifest"]["root"]))
+    assert len(p2) == 270967
+    assert oracle.blake3(p2).hex() == "7852805e6d6c64027aafe0c2672927715bcd92aaa08f83383de1fc6a183ba6ca"
+
+
+def test_prove_v1_reject_cases_match_reference_tests(ctx, oracle):
+    """air_fail_endpoint.rs / air_fail_head_update.rs style: GPU-produced proofs of bad traces are rejected."""
+    m = pkg()
+    ct = m.demo_block(16)
+    ct.head_out_off[0, 0] += 1
+    ok, why = oracle.verify_v1(ctx.prove_v1(ct, bytes([7] * 32)), ct)
+    assert not ok and "AIR composition non-zero" in why
+    ct = m.demo_block(16)
+    ct.mv[5, 0] = 2  # mv outside {-1,0,1}
+    got = ctx.prove_v1(ct, bytes([7] * 32))
+    assert got == oracle.prove_v1(ct, bytes([7] * 32))
+    assert not oracle.verify_v1(got, ct)[0]
+
+
+def test_prove_streaming_api_matches_one_shot(ctx):
+    m = pkg()
+    ct = m.simulate(1024, 128, 2)
+    root = m.manifest_root(ct)
+    one = ctx.prove_v1(ct, root)
+    blocks = []
+    for k in range(ct.n_blocks):
+        r = slice(k * 128, (k + 1) * 128)
+        blocks.append(m.CompactTrace(tau=2, block_len=ct.block_len[k:k + 1], win_left=ct.win_left[k:k + 1], win_right=ct.win_right[k:k + 1],
+                                     head_in_off=ct.head_in_off[k:k + 1], head_out_off=ct.head_out_off[k:k + 1], input_mv=ct.input_mv[r],
+                                     mv=ct.mv[r], write_flag=ct.write_flag[r], write_sym=ct.write_sym[r]))
+    assert ctx.prove_v1_stream(blocks, root) == one
+
+
+def test_invalid_inputs_return_einval(ctx):
+    m = pkg()
+    ct = m.simulate(1000, 512, 2)  # not a power of two (reference asserts, v1/lde.rs:51)
+    with pytest.raises(m.SezkpCudaError) as ei:
+        ctx.prove_v1(ct, bytes(32))
+    assert ei.value.code == -1
+
+
+# ----------------------------------------------------------------------------- larger sizes: properties
+def test_large_lde_properties(ctx):
+    """Config-2 shape (2^20, blow-up 4): linearity and sub-sampling consistency, no oracle needed."""
+    rng = np.random.default_rng(9)
+    k, lb = 20, 2
+    a, b = rand_field(rng, 1 << k), rand_field(rng, 1 << k)
+    ea, eb = ctx.coset_lde(a, lb, 3), ctx.coset_lde(b, lb, 3)
+    s = (a.astype(object) + b.astype(object)) % P
+    es = ctx.coset_lde(np.array(s, dtype=np.uint64), lb, 3)
+    assert np.array_equal(es, np.array((ea.astype(object) + eb.astype(object)) % P, dtype=np.uint64))
+    # evaluating on the coarser coset 3*<w_n> (blow-up 1) is every 4th point of the blow-up-4 evaluation
+    assert np.array_equal(ctx.coset_lde(a, 0, 3), ea[::4])
