@@ -37,6 +37,7 @@ typedef struct sezkp_ctx sezkp_ctx;
 typedef struct sezkp_tree sezkp_tree; /* retained column commitments (chunk roots + upper levels + values) */
 typedef struct sezkp_fri sezkp_fri;   /* retained FRI layers (values + upper tree levels)                  */
 typedef struct sezkp_stream sezkp_stream;
+typedef struct sezkp_trace_dev sezkp_trace_dev; /* compact trace resident in HBM */
 
 /* ---------------------------------------------------------------- context ---- */
 uint32_t sezkp_cuda_abi_version(void);                       /* cf. sezkp_abi_version(), sezkp-ffi/src/lib.rs:55-68 */
@@ -126,6 +127,12 @@ int32_t sezkp_compose_base(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const 
  * with *len set.  The Fiat-Shamir transcript (sezkp-crypto/src/lib.rs:74-124) runs on the host inside the library. */
 int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const uint8_t manifest_root[32],
                              uint8_t* proof_buf, size_t cap, size_t* len);
+/* Same prover over a compact trace that is already resident in HBM (upload once, prove many times: lets a caller
+ * overlap the next trace's H2D copy with the current proof, and separates copy time from kernel time). */
+int32_t sezkp_trace_upload(sezkp_ctx* ctx, const sezkp_trace_desc* trace, sezkp_trace_dev** out);
+void sezkp_trace_free(sezkp_ctx* ctx, sezkp_trace_dev* trace);
+int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* trace, const uint8_t manifest_root[32],
+                                      uint8_t* proof_buf, size_t cap, size_t* len);
 /* ProvingBackendStream (sezkp-core/src/prover.rs:21-33): begin_stream / ingest_block / finish_stream.  Blocks are
  * pushed one at a time as one-block descriptors (n_blocks == 1); rows are staged through pinned host buffers and
  * copied on a side stream while earlier chunks are expanded on the GPU. */

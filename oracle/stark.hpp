@@ -700,6 +700,7 @@ struct ColumnOracle {
     const TraceColumns& tc;
     size_t chunk_log2, chunk_size;
     std::vector<std::string> labels;
+    mutable std::vector<std::pair<bool, MerkleTree>> outer_cache;  // per label, like OnDemandOpenings::outer_cache (openings.rs:285)
     ColumnOracle(const TraceColumns& t, size_t cl2) : tc(t), chunk_log2(cl2), chunk_size((size_t)1 << cl2), labels(all_labels(t.tau)) {}
 
     std::vector<Digest> chunk_roots(size_t ci) const {  // openings.rs:436-460 / :306-398
@@ -739,7 +740,9 @@ struct ColumnOracle {
         o.index = row; o.chunk_index = chunk_idx; o.index_in_chunk = idx_in;
         o.chunk_root = ct.root();
         o.path_in_chunk = ct.open(idx_in);
-        o.path_to_chunk = MerkleTree::from_leaves(chunk_roots(ci)).open(chunk_idx);
+        if (outer_cache.empty()) outer_cache.resize(labels.size());
+        if (!outer_cache[ci].first) outer_cache[ci] = {true, MerkleTree::from_leaves(chunk_roots(ci))};  // openings.rs:415-419
+        o.path_to_chunk = outer_cache[ci].second.open(chunk_idx);
         return o;
     }
 };

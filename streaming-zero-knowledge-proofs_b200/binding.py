@@ -26,7 +26,8 @@ EXPORTS = [
     "sezkp_leaf_hash", "sezkp_merkle_root", "sezkp_column_commit_batch", "sezkp_column_commit_batch_dev",
     "sezkp_column_open", "sezkp_tree_free", "sezkp_fri_commit", "sezkp_fri_commit_dev", "sezkp_fri_open", "sezkp_fri_free",
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
-    "sezkp_stark_v1_finish", "sezkp_stark_v1_abort",
+    "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_trace_upload", "sezkp_trace_free",
+    "sezkp_stark_v1_prove_resident",
 ]
 
 ERR_NAMES = {0: "OK", -1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENODEV", -5: "ERANGE", -6: "ESTATE"}
@@ -58,6 +59,7 @@ def load_library() -> C.CDLL:
         lib.sezkp_tree_free.argtypes = [C.c_void_p, C.c_void_p]
         lib.sezkp_fri_free.argtypes = [C.c_void_p, C.c_void_p]
         lib.sezkp_stark_v1_abort.argtypes = [C.c_void_p, C.c_void_p]
+        lib.sezkp_trace_free.argtypes = [C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -234,6 +236,19 @@ class Context:
         self._ck(self.lib.sezkp_stark_v1_prove(self.h, C.byref(d), manifest_root, _p(buf), C.c_size_t(buf.size), C.byref(n)))
         return buf[: n.value].tobytes()
 
+    def upload_trace(self, ct: CompactTrace) -> "ResidentTrace":
+        d = ct.as_desc()
+        h = C.c_void_p()
+        self._ck(self.lib.sezkp_trace_upload(self.h, C.byref(d), C.byref(h)))
+        return ResidentTrace(self, h, ct.n_rows, ct.tau)
+
+    def prove_v1_resident(self, rt: "ResidentTrace", manifest_root: bytes, buf: Optional[np.ndarray] = None) -> bytes:
+        n = C.c_size_t(0)
+        if buf is None:
+            buf = np.empty(proof_size_bound(rt.n_rows, rt.tau), np.uint8)
+        self._ck(self.lib.sezkp_stark_v1_prove_resident(self.h, rt.h, manifest_root, _p(buf), C.c_size_t(buf.size), C.byref(n)))
+        return buf[: n.value].tobytes()
+
     def prove_v1_stream(self, blocks: Sequence[CompactTrace], manifest_root: bytes) -> bytes:
         """begin_stream / ingest_block / finish_stream (reference sezkp-core/src/prover.rs:21-33)."""
         st = C.c_void_p()
@@ -260,6 +275,22 @@ def proof_size_bound(n_rows: int, tau: int) -> int:
     openings = 30 * (9 * tau + 3) * (8 + 24 + 32 + 16 + 32 * ln)
     fri = 30 * (16 + 8 * (lN + 1) + lN * 2 * (8 + 8 + 32 * lN))
     return 4096 + (3 + 7 * tau) * 64 + openings + fri + 32 * (lN + 1)
+
+
+class ResidentTrace:
+    def __init__(self, ctx: Context, h, n_rows, tau):
+        self.ctx, self.h, self.n_rows, self.tau = ctx, h, n_rows, tau
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.sezkp_trace_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class ColumnTree:

@@ -16,6 +16,9 @@ struct sezkp_tree {
 struct sezkp_fri {
     FriLayers fl;
 };
+struct sezkp_trace_dev {
+    DeviceTraceOwner owner;
+};
 struct sezkp_stream {
     uint32_t tau = 0;
     u8 manifest_root[32];
@@ -465,6 +468,38 @@ int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, cons
     REQUIRE(manifest_root && len, "bad argument");
     std::vector<u8> proof;
     prove_v1_device(ctx, trace, manifest_root, proof);
+    deliver(proof, proof_buf, cap, len);
+    API_END(ctx)
+}
+
+int32_t sezkp_trace_upload(sezkp_ctx* ctx, const sezkp_trace_desc* trace, sezkp_trace_dev** out) {
+    API_BEGIN(ctx)
+    REQUIRE(out != nullptr, "bad argument");
+    *out = nullptr;
+    validate_trace(trace);
+    sezkp_trace_dev* t = new sezkp_trace_dev();
+    try {
+        t->owner.upload(ctx, trace);
+    } catch (...) {
+        t->owner.buf.release();
+        delete t;
+        throw;
+    }
+    *out = t;
+    API_END(ctx)
+}
+void sezkp_trace_free(sezkp_ctx* ctx, sezkp_trace_dev* t) {
+    if (!t) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    t->owner.buf.release();
+    delete t;
+}
+int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* trace, const uint8_t manifest_root[32],
+                                      uint8_t* proof_buf, size_t cap, size_t* len) {
+    API_BEGIN(ctx)
+    REQUIRE(trace && manifest_root && len, "bad argument");
+    std::vector<u8> proof;
+    prove_v1_resident(ctx, trace->owner.t, manifest_root, proof);
     deliver(proof, proof_buf, cap, len);
     API_END(ctx)
 }

@@ -410,6 +410,25 @@ struct TranscriptAbsorb : HostAbsorb {
 void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out) {
     validate_trace(desc);
     ctx->timings.clear();
+    const double t0 = now_ms();
+    DeviceTraceOwner dt;
+    dt.buf = ctx->scratch[2];
+    ctx->scratch[2] = DevBuf();
+    try {
+        dt.upload(ctx, desc);
+    } catch (...) {
+        ctx->scratch[2] = dt.buf;
+        throw;
+    }
+    ctx->scratch[2] = dt.buf;
+    const double t1 = now_ms();
+    prove_v1_resident(ctx, dt.t, manifest_root, proof_out);
+    ctx->timings.insert(ctx->timings.begin(), {"h2d_trace", t1 - t0});
+}
+
+// The whole prover from a device-resident compact trace.
+void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out) {
+    ctx->timings.clear();
     double t0 = now_ms();
     auto lap = [&](const char* name) {
         cudaStreamSynchronize(ctx->stream);
@@ -417,21 +436,16 @@ void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 mani
         ctx->timings.push_back({name, t1 - t0});
         t0 = t1;
     };
-    const u64 n = desc->n_rows;
-    const u32 tau = desc->tau;
+    const u64 n = trace.n_rows;
+    const u32 tau = trace.tau;
     const int L = ilog2(n), logB = 3, log_N = L + logB;  // BLOWUP = 8 (v1/params.rs:28)
     const u64 N = 1ULL << log_N;
     const int n_cols = 3 + 7 * (int)tau;
     constexpr int NUM_QUERIES = 30, COL_CHUNK_LOG2 = 10;  // v1/params.rs:31, 37
 
-    // A. compact trace -> device -> committed columns
-    DeviceTraceOwner dt;
-    dt.buf = ctx->scratch[2];
-    dt.upload(ctx, desc);
-    ctx->scratch[2] = dt.buf;
-    lap("h2d_trace");
+    // A. compact trace -> committed columns
     u64* cols = (u64*)ctx->scratch[3].ensure((size_t)n_cols * n * 8);
-    expand_columns_device(ctx, dt.t, cols);
+    expand_columns_device(ctx, trace, cols);
     lap("expand_columns");
 
     // B. transcript prelude (v1/prover.rs:67-70)

@@ -96,7 +96,7 @@ class CompactTrace:
         d.n_rows = self.n_rows
         for name, arr in a.items():
             setattr(d, name, arr.ctypes.data if arr.size else None)
-        self._keep = list(a.values())
+        self._desc_arrays = list(a.values())
         return d
 
 
