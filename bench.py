@@ -187,7 +187,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m = importlib.import_module(PKG)
     ctx = m.Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()  # the library launches on torch's current stream so torch events bracket its work
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     hbm_peak, peak_src = peaks()
 
     wl = workload()

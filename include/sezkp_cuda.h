@@ -44,7 +44,9 @@ uint32_t sezkp_cuda_abi_version(void);                       /* cf. sezkp_abi_ve
 int32_t sezkp_cuda_create(int device_id, sezkp_ctx** out);   /* device_id < 0: current device                     */
 void sezkp_cuda_destroy(sezkp_ctx* ctx);
 const char* sezkp_cuda_last_error(const sezkp_ctx* ctx);     /* ctx may be NULL: error of the last failed create   */
-int32_t sezkp_cuda_set_stream(sezkp_ctx* ctx, void* cuda_stream); /* adopt a caller stream (NULL: own stream)     */
+/* use_own != 0: (re)create a private non-blocking stream; else adopt the caller's cudaStream_t (NULL = legacy default
+ * stream), e.g. torch.cuda.current_stream().cuda_stream, so that the caller's events bracket the library's work */
+int32_t sezkp_cuda_set_stream(sezkp_ctx* ctx, void* cuda_stream, int use_own);
 int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx);
 /* number of kernels launched by this ctx since creation / since the last reset */
 uint64_t sezkp_cuda_launch_count(sezkp_ctx* ctx, int reset);

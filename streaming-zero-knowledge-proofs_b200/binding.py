@@ -102,8 +102,12 @@ class Context:
             raise SezkpCudaError(rc, self.lib.sezkp_cuda_last_error(self.h).decode())
 
     # ---- plumbing ----
-    def set_stream(self, cuda_stream: int):
-        self._ck(self.lib.sezkp_cuda_set_stream(self.h, C.c_void_p(cuda_stream)))
+    def set_stream(self, cuda_stream: Optional[int]):
+        """adopt a caller stream handle (0 = legacy default stream); None -> private stream"""
+        if cuda_stream is None:
+            self._ck(self.lib.sezkp_cuda_set_stream(self.h, None, C.c_int(1)))
+        else:
+            self._ck(self.lib.sezkp_cuda_set_stream(self.h, C.c_void_p(cuda_stream), C.c_int(0)))
 
     def synchronize(self):
         self._ck(self.lib.sezkp_cuda_synchronize(self.h))

@@ -86,23 +86,34 @@ struct LabelTemplate {
     u32 off;        // byte offset of the value
     u32 block_len;  // 20 + L
 };
-__device__ __forceinline__ void leaf_labeled(const LabelTemplate& t, u64 v, u32 (&out)[8]) {
+// W = word index of the first value byte (static so that the 16 message words stay in registers).
+template <int W>
+__device__ __forceinline__ void leaf_labeled_w(const LabelTemplate& t, u64 v, u32 (&out)[8]) {
     u32 m[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) m[i] = t.words[i];
-    const u32 w = t.off >> 2, sh = (t.off & 3) * 8;
+    const u32 sh = (t.off & 3) * 8;
     const u32 lo = (u32)v, hi = (u32)(v >> 32);
-    // value bytes spread over words w, w+1, w+2
-    u32 a = lo << sh;
-    u32 b = sh ? (lo >> (32 - sh)) | (hi << sh) : hi;
-    u32 c = sh ? (hi >> (32 - sh)) : 0;
-#pragma unroll
-    for (int i = 3; i < 16; i++) {  // off = 12+L in [13,56]: w in [3..14]; static indices keep m[] in registers
-        if (i == (int)w) m[i] |= a;
-        if (i == (int)w + 1) m[i] |= b;
-        if (i == (int)w + 2) m[i] |= c;
-    }
+    m[W] |= lo << sh;
+    if (W + 1 < 16) m[W + 1] |= __funnelshift_l(lo, hi, sh);
+    if (W + 2 < 16) m[W + 2] |= __funnelshift_l(hi, 0u, sh);
     hash_block(m, t.block_len, out);
 }
+// Runs BODY with a compile-time W matching the (block-uniform) template; BODY uses LEAF(v, out).
+#define B3_DISPATCH_LABELED(t, BODY)                                       \
+    switch ((t).off >> 2) {                                                \
+        case 3: { constexpr int B3W = 3; BODY } break;                     \
+        case 4: { constexpr int B3W = 4; BODY } break;                     \
+        case 5: { constexpr int B3W = 5; BODY } break;                     \
+        case 6: { constexpr int B3W = 6; BODY } break;                     \
+        case 7: { constexpr int B3W = 7; BODY } break;                     \
+        case 8: { constexpr int B3W = 8; BODY } break;                     \
+        case 9: { constexpr int B3W = 9; BODY } break;                     \
+        case 10: { constexpr int B3W = 10; BODY } break;                   \
+        case 11: { constexpr int B3W = 11; BODY } break;                   \
+        case 12: { constexpr int B3W = 12; BODY } break;                   \
+        case 13: { constexpr int B3W = 13; BODY } break;                   \
+        default: { constexpr int B3W = 14; BODY } break;                   \
+    }
 
 }  // namespace b3

@@ -109,21 +109,24 @@ void sezkp_cuda_destroy(sezkp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ntt_free_tables(ctx);
     for (auto& b : ctx->scratch) b.release();
+    for (auto& kv : ctx->pool.live) cudaFree(kv.first);
+    ctx->pool.live.clear();
+    ctx->pool.trim();
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 const char* sezkp_cuda_last_error(const sezkp_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_create_error.c_str(); }
 
-int32_t sezkp_cuda_set_stream(sezkp_ctx* ctx, void* cuda_stream) {
+int32_t sezkp_cuda_set_stream(sezkp_ctx* ctx, void* cuda_stream, int use_own) {
     API_BEGIN(ctx)
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    if (cuda_stream == nullptr) {
+    if (use_own) {
         if (!ctx->own_stream) {
             CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
             ctx->own_stream = true;
         }
-    } else {
+    } else {  // NULL is the legacy default stream
         if (ctx->own_stream) CUDA_CHECK(cudaStreamDestroy(ctx->stream));
         ctx->stream = (cudaStream_t)cuda_stream;
         ctx->own_stream = false;
@@ -298,10 +301,8 @@ static int32_t column_commit_impl(sezkp_ctx* ctx, const u64* cols_host, const u6
     u64* owned = nullptr;
     if (cols_host) check_canonical(cols_host, (size_t)c * n, "cols");
     if (keep || cols_host) {
-        if (keep) {
-            cudaError_t e = cudaMalloc(&owned, bytes);
-            if (e != cudaSuccess) sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
-        } else owned = (u64*)ctx->scratch[3].ensure(bytes);
+        if (keep) owned = (u64*)ctx->pool.alloc(bytes);
+        else owned = (u64*)ctx->scratch[3].ensure(bytes);
         if (cols_host) h2d(ctx, owned, cols_host, bytes);
         else CUDA_CHECK(cudaMemcpyAsync(owned, cols_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         src = owned;
@@ -310,8 +311,8 @@ static int32_t column_commit_impl(sezkp_ctx* ctx, const u64* cols_host, const u6
     try {
         commit_build(ctx, t->cm, src, n, c, chunk_log2, labels, roots);
     } catch (...) {
-        t->cm.release();
-        if (keep && owned) cudaFree(owned);
+        t->cm.release(ctx);
+        if (keep && owned) ctx->pool.free(owned);
         delete t;
         throw;
     }
@@ -319,7 +320,7 @@ static int32_t column_commit_impl(sezkp_ctx* ctx, const u64* cols_host, const u6
         t->cm.owns_values = true;
         *keep = t;
     } else {
-        t->cm.release();
+        t->cm.release(ctx);
         delete t;
     }
     API_END(ctx)
@@ -351,8 +352,10 @@ int32_t sezkp_column_open(sezkp_ctx* ctx, const sezkp_tree* tree, const uint32_t
 }
 void sezkp_tree_free(sezkp_ctx* ctx, sezkp_tree* tree) {
     if (!tree) return;
-    if (ctx) cudaSetDevice(ctx->device);
-    tree->cm.release();
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    tree->cm.release(ctx);
     delete tree;
 }
 
@@ -375,13 +378,13 @@ static int32_t fri_commit_impl(sezkp_ctx* ctx, const u64* l0_host, const u64* l0
     try {
         fri_commit_device(ctx, f->fl, src, log_N, betas, roots, final_value, nullptr);
     } catch (...) {
-        f->fl.release();
+        f->fl.release(ctx);
         delete f;
         throw;
     }
     if (keep) *keep = f;
     else {
-        f->fl.release();
+        f->fl.release(ctx);
         delete f;
     }
     API_END(ctx)
@@ -403,8 +406,10 @@ int32_t sezkp_fri_open(sezkp_ctx* ctx, const sezkp_fri* fri, const uint64_t* idx
 }
 void sezkp_fri_free(sezkp_ctx* ctx, sezkp_fri* fri) {
     if (!fri) return;
-    if (ctx) cudaSetDevice(ctx->device);
-    fri->fl.release();
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    fri->fl.release(ctx);
     delete fri;
 }
 

@@ -68,6 +68,55 @@ struct DevBuf {
 
 struct NttTables;  // ntt.cu
 
+// Size-keyed caching device allocator: repeated proofs reuse their buffers instead of paying
+// cudaMalloc / cudaFree (which synchronises the device) on every call.
+struct DevPool {
+    std::map<size_t, std::vector<void*>> free_lists;
+    std::map<void*, size_t> live;
+    size_t cached_bytes = 0;
+    void* alloc(size_t bytes) {
+        if (bytes == 0) bytes = 256;
+        bytes = (bytes + 255) & ~(size_t)255;
+        auto it = free_lists.find(bytes);
+        void* p = nullptr;
+        if (it != free_lists.end() && !it->second.empty()) {
+            p = it->second.back();
+            it->second.pop_back();
+            cached_bytes -= bytes;
+        } else {
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) {
+                trim();  // give cached blocks back and retry once
+                cudaGetLastError();
+                e = cudaMalloc(&p, bytes);
+            }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            }
+        }
+        live[p] = bytes;
+        return p;
+    }
+    void free(void* p) {
+        if (!p) return;
+        auto it = live.find(p);
+        if (it == live.end()) {
+            cudaFree(p);
+            return;
+        }
+        free_lists[it->second].push_back(p);
+        cached_bytes += it->second;
+        live.erase(it);
+    }
+    void trim() {
+        for (auto& kv : free_lists)
+            for (void* p : kv.second) cudaFree(p);
+        free_lists.clear();
+        cached_bytes = 0;
+    }
+};
+
 struct sezkp_ctx {
     int device = 0;
     int sm_count = 148;
@@ -75,6 +124,7 @@ struct sezkp_ctx {
     bool own_stream = false;
     std::string last_error;
     std::map<u64, NttTables*> ntt_tables;  // key: (log_n, inverse, coset params)
+    DevPool pool;
     DevBuf scratch[8];                      // reusable work buffers (per purpose, see users)
     std::vector<std::pair<std::string, double>> timings;  // phase -> ms (last prove)
     u64 launches = 0;                       // kernels launched since last reset

@@ -76,12 +76,22 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(const u64* _
     const u64* v = values + (u64)col * n + (chunk << cl);
     b3::LabelTemplate t;
     if (templates) t = templates[col];
-    for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
-        u32 d[8];
-        if (templates) b3::leaf_labeled(t, v[i], d);
-        else b3::leaf(v[i], d);
+    if (templates) {
+        B3_DISPATCH_LABELED(t, {
+            for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
+                u32 d[8];
+                b3::leaf_labeled_w<B3W>(t, v[i], d);
 #pragma unroll
-        for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
+                for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
+            }
+        })
+    } else {
+        for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
+            u32 d[8];
+            b3::leaf(v[i], d);
+#pragma unroll
+            for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
+        }
     }
     __syncthreads();
     reduce_levels_smem(s, pitch, leaves, nullptr, 0, 0, 0, nullptr, 0);
@@ -124,12 +134,22 @@ __global__ void __launch_bounds__(HASH_THREADS) open_kernel(const u64* __restric
     const u64* v = values + (u64)rq.col * n + (chunk << cl);
     b3::LabelTemplate t;
     if (templates) t = templates[rq.col];
-    for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
-        u32 d[8];
-        if (templates) b3::leaf_labeled(t, v[i], d);
-        else b3::leaf(v[i], d);
+    if (templates) {
+        B3_DISPATCH_LABELED(t, {
+            for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
+                u32 d[8];
+                b3::leaf_labeled_w<B3W>(t, v[i], d);
 #pragma unroll
-        for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
+                for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
+            }
+        })
+    } else {
+        for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
+            u32 d[8];
+            b3::leaf(v[i], d);
+#pragma unroll
+            for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
+        }
     }
     if (threadIdx.x == 0) out_values[q] = v[idx_in];
     __syncthreads();
@@ -150,7 +170,7 @@ __global__ void leaf_hash_kernel(const u64* __restrict__ vals, size_t n, const b
     u32 d[8];
     if (tpl) {
         b3::LabelTemplate t = *tpl;
-        b3::leaf_labeled(t, vals[i], d);
+        B3_DISPATCH_LABELED(t, { b3::leaf_labeled_w<B3W>(t, vals[i], d); })
     } else b3::leaf(vals[i], d);
     uint4* o = reinterpret_cast<uint4*>(out + i * 8);
     o[0] = make_uint4(d[0], d[1], d[2], d[3]);
@@ -196,10 +216,10 @@ b3::LabelTemplate make_label_template(const char* label) {
     return t;
 }
 
-void Commit::release() {
-    if (owns_values && values) cudaFree((void*)values);
-    if (upper) cudaFree(upper);
-    if (templates) cudaFree(templates);
+void Commit::release(sezkp_ctx* ctx) {
+    if (owns_values && values) ctx->pool.free((void*)values);
+    ctx->pool.free(upper);
+    ctx->pool.free(templates);
     values = nullptr;
     upper = nullptr;
     templates = nullptr;
@@ -223,16 +243,12 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
             REQUIRE(labels[c] != nullptr, "label %d is NULL", c);
             h[c] = make_label_template(labels[c]);
         }
-        cudaError_t e = cudaMalloc(&cm.templates, sizeof(b3::LabelTemplate) * cols);
-        if (e != cudaSuccess) sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaMalloc(templates): %s", cudaGetErrorString(e));
+        cm.templates = (b3::LabelTemplate*)ctx->pool.alloc(sizeof(b3::LabelTemplate) * cols);
         CUDA_CHECK(cudaMemcpyAsync(cm.templates, h.data(), sizeof(b3::LabelTemplate) * cols, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // h goes out of scope
     }
     const size_t upper_bytes = (size_t)cols * (2 * cm.n_ch - 1) * 32;
-    {
-        cudaError_t e = cudaMalloc(&cm.upper, upper_bytes);
-        if (e != cudaSuccess) sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaMalloc(upper %zu B): %s", upper_bytes, cudaGetErrorString(e));
-    }
+    cm.upper = (u32*)ctx->pool.alloc(upper_bytes);
     dim3 grid((unsigned)cm.n_ch, (unsigned)cols);
     chunk_commit_kernel<<<grid, HASH_THREADS, 0, ctx->stream>>>(values_dev, n, cm.cl, cm.templates, cm.upper, cm.n_ch);
     CUDA_CHECK(cudaGetLastError());

@@ -16,7 +16,7 @@ struct Commit {
     u64 n_ch = 0;                  // chunks per column = n >> cl
     u32* upper = nullptr;          // device [cols][2*n_ch-1][8]: level l (count n_ch>>l) at offset 2*n_ch-(2*n_ch>>l)
     b3::LabelTemplate* templates = nullptr;  // device [cols] or null (unlabeled)
-    void release();
+    void release(sezkp_ctx* ctx);
 };
 inline u64 upper_off(u64 n_ch, int l) { return 2 * n_ch - ((2 * n_ch) >> l); }
 

@@ -331,7 +331,11 @@ static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
     REQUIRE(tiles > 0 && tiles < (1ULL << 31), "NTT grid too large (%llu tiles)", (unsigned long long)tiles);
     const size_t smem = (((size_t)1 << d.logR) * ((1u << d.b) | 1) + ((size_t)1 << (d.b - 1))) * 8;
     pass_fn fn = kernel_for_bits(d.b);
-    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static std::map<pass_fn, size_t> configured;  // max dynamic smem already granted per kernel
+    if (smem > 48 * 1024 && configured[fn] < smem) {
+        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[fn] = smem;
+    }
     fn<<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(d);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;

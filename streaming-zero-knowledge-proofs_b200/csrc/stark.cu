@@ -280,10 +280,10 @@ void deep_lde_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, 
 /* ------------------------------------------------------------------------------------------ */
 /* FRI                                                                                         */
 /* ------------------------------------------------------------------------------------------ */
-void FriLayers::release() {
-    for (auto& c : commits) c.release();
+void FriLayers::release(sezkp_ctx* ctx) {
+    for (auto& c : commits) c.release(ctx);
     commits.clear();
-    if (values) cudaFree(values);
+    ctx->pool.free(values);
     values = nullptr;
 }
 
@@ -294,10 +294,7 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     REQUIRE(log_N >= 1 && log_N <= 32, "log_N %d out of range", log_N);
     const u64 N = 1ULL << log_N;
     fl.log_N = log_N;
-    {
-        cudaError_t e = cudaMalloc(&fl.values, 2 * N * 8);
-        if (e != cudaSuccess) sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaMalloc(FRI layers %llu B): %s", (unsigned long long)(2 * N * 8), cudaGetErrorString(e));
-    }
+    fl.values = (u64*)ctx->pool.alloc(2 * N * 8);
     CUDA_CHECK(cudaMemcpyAsync(fl.values, layer0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     fl.commits.resize(log_N + 1);
     u64 off = 0, len = N;
@@ -588,10 +585,10 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         proof_out.swap(w.b);
         lap("serialize");
     } catch (...) {
-        cm.release();
-        fl.release();
+        cm.release(ctx);
+        fl.release(ctx);
         throw;
     }
-    cm.release();
-    fl.release();
+    cm.release(ctx);
+    fl.release(ctx);
 }

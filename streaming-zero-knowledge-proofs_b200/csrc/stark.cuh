@@ -41,7 +41,7 @@ struct FriLayers {
     int log_N = 0;
     u64* values = nullptr;        // device: layer l (len N>>l) at offset sum_{i<l} N>>i
     std::vector<Commit> commits;  // one per layer
-    void release();
+    void release(sezkp_ctx* ctx);
 };
 void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0_dev, int log_N, const u64* betas_or_null, u8* roots_host,
                        u64* final_value, HostAbsorb* absorb_or_null);
