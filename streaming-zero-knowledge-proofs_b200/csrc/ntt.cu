@@ -52,9 +52,9 @@ struct PassDesc {
 };
 
 // One radix-2^K DIF step (stages s0..s0+K-1 of a 2^b-point transform) on every column of the tile.
-template <int K>
+template <int K, bool LAST>
 __device__ __forceinline__ void dif_step(u64* tile, const u64* Ws, int b, int s0, int logR, int pitch) {
-    const int lo_bits = b - s0 - K;
+    const int lo_bits = LAST ? 0 : b - s0 - K;
     const int groups = (1 << (b - K)) << logR;
     const int R = 1 << logR;
     for (int g = threadIdx.x; g < groups; g += NTT_THREADS) {
@@ -74,8 +74,10 @@ __device__ __forceinline__ void dif_step(u64* tile, const u64* Ws, int b, int s0
                 if (t & half) continue;
                 const int e = (((t & (half - 1)) << lo_bits) + lo) << (s0 + u);
                 const u64 a = x[t], bb = x[t | half];
-                x[t] = gl::add(a, bb);
-                x[t | half] = gl::mul(gl::sub(a, bb), Ws[e]);
+                x[t] = gl::lazy::add(a, bb);
+                const u64 df = gl::lazy::sub(a, bb);
+                // in the last step of a pass (lo_bits == 0) the exponent is a compile-time constant: skip w^0
+                x[t | half] = (LAST && (t & (half - 1)) == 0) ? df : gl::lazy::mul(df, Ws[e]);
             }
         }
 #pragma unroll
@@ -122,17 +124,17 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const PassDesc d)
             if (d.use_pre) {
                 const u32 j = (u32)((d.coset_from_col ? C : v) & ((1u << d.coset_log) - 1));
                 u64 g = d.GA[(size_t)j * d.ga_pitch + row];
-                if (d.use_gb) g = gl::mul(g, d.GB[(size_t)j * d.gb_pitch + C]);
-                x = gl::mul(x, g);
+                if (d.use_gb) g = gl::lazy::mul(g, d.GB[(size_t)j * d.gb_pitch + C]);
+                x = gl::lazy::mul(x, g);
             }
         }
         tile[c * pitch + row] = x;
     }
     __syncthreads();
-    dif_step<K1>(tile, Ws, b, 0, logR, pitch);
+    dif_step<K1, K2 == 0>(tile, Ws, b, 0, logR, pitch);
     __syncthreads();
     if (K2 > 0) {
-        dif_step<(K2 > 0 ? K2 : 1)>(tile, Ws, b, K1, logR, pitch);
+        dif_step<(K2 > 0 ? K2 : 1), true>(tile, Ws, b, K1, logR, pitch);
         __syncthreads();
     }
     for (int i = threadIdx.x; i < total; i += NTT_THREADS) {
@@ -150,10 +152,11 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const PassDesc d)
         u64 x = tile[c * pitch + row];
         if (d.use_tw) {
             const u64 E = (u64)k * C * d.tw_stride;
-            const u64 w = gl::mul(d.tw_lo[E & ((1ULL << d.tw_lb) - 1)], d.tw_hi[E >> d.tw_lb]);
-            x = gl::mul(x, w);
+            const u64 w = gl::lazy::mul(d.tw_lo[E & ((1ULL << d.tw_lb) - 1)], d.tw_hi[E >> d.tw_lb]);
+            x = gl::lazy::mul(x, w);
         }
-        if (d.use_scale) x = gl::mul(x, d.scale);
+        if (d.use_scale) x = gl::lazy::mul(x, d.scale);
+        x = gl::lazy::canon(x);  // values in HBM are canonical
         const u64 coff = (C & ((1ULL << d.out_clog) - 1)) * d.out_cs_lo + (C >> d.out_clog) * d.out_cs_hi;
         out_base[(u64)k * d.out_row_stride + coff] = x;
     }
