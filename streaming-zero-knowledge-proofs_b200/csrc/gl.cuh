@@ -94,10 +94,12 @@ __device__ __forceinline__ u64 add(u64 a, u64 b) {
         "mov.b64 {b0, b1}, %2;\n\t"
         "add.cc.u32 a0, a0, b0;\n\t"
         "addc.cc.u32 a1, a1, b1;\n\t"
-        "subc.u32 m, 0, 0;\n\t"          // m = carry ? 0xffffffff : 0  (= EPS * carry)
+        "addc.u32 m, 0, 0;\n\t"         // carry (0/1); NB: `subc` after an add chain sees the inverted flag in hardware
+        "neg.s32 m, m;\n\t"             // EPS * carry
         "add.cc.u32 a0, a0, m;\n\t"
         "addc.cc.u32 a1, a1, 0;\n\t"
-        "subc.u32 m, 0, 0;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "neg.s32 m, m;\n\t"
         "add.cc.u32 a0, a0, m;\n\t"
         "addc.u32 a1, a1, 0;\n\t"
         "mov.b64 %0, {a0, a1};\n\t"
@@ -142,7 +144,8 @@ __device__ __forceinline__ u64 reduce_words(u32 w0, u32 w1, u32 w2, u32 w3) {
         "subc.u32 y1, %3, 0;\n\t"
         "add.cc.u32 x0, x0, y0;\n\t"
         "addc.cc.u32 x1, x1, y1;\n\t"
-        "subc.u32 m, 0, 0;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "neg.s32 m, m;\n\t"
         "add.cc.u32 x0, x0, m;\n\t"       // carry: +EPS (cannot carry again: y <= 2^64 - 2^33 + 1)
         "addc.u32 x1, x1, 0;\n\t"
         "mov.b64 %0, {x0, x1};\n\t"

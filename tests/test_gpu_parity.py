@@ -19,6 +19,20 @@ def rand_field(rng, shape):
     return (rng.integers(0, 1 << 63, size=shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=shape, dtype=np.uint64)) % np.uint64(P)
 
 
+def test_device_arithmetic_selftest():
+    """Lazy PTX Goldilocks add/sub/mul (csrc/gl.cuh) against canonical host arithmetic on 1M edge + random operands."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tools", "arith_test")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "bad add=0 sub=0 mul=0" in r.stdout
+
+
 # ----------------------------------------------------------------------------- NTT / LDE
 @pytest.mark.parametrize("k", list(range(1, 17)) + [18, 20, 21, 22])
 def test_ntt_forward_inverse_vs_oracle(ctx, oracle, k):
