@@ -1,5 +1,6 @@
 // extern "C" surface of libsezkp_cuda.so (include/sezkp_cuda.h).  Every entry point converts C++
 // exceptions into status codes + ctx->last_error; nothing aborts.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -93,6 +94,8 @@ int32_t sezkp_cuda_create(int device_id, sezkp_ctx** out) {
         if (prop.major < 10) sezkp_fail(SEZKP_CUDA_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a only", device_id, prop.major, prop.minor);
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         ctx->own_stream = true;
+        const char* nd = getenv("SEZKP_NO_DEDUP");
+        if (nd && nd[0] == '1') ctx->dedup_enabled = false;
     } catch (const SezkpError& err) {
         g_create_error = err.what();
         int32_t code = err.code;
@@ -137,6 +140,14 @@ int32_t sezkp_cuda_set_stream(sezkp_ctx* ctx, void* cuda_stream, int use_own) {
 int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx) {
     API_BEGIN(ctx)
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value) {
+    API_BEGIN(ctx)
+    REQUIRE(name != nullptr, "bad argument");
+    if (std::strcmp(name, "dedup") == 0) ctx->dedup_enabled = value != 0;
+    else sezkp_fail(SEZKP_CUDA_EINVAL, "unknown option '%s'", name);
     API_END(ctx)
 }
 
@@ -309,7 +320,10 @@ static int32_t column_commit_impl(sezkp_ctx* ctx, const u64* cols_host, const u6
     }
     sezkp_tree* t = new sezkp_tree();
     try {
-        commit_build(ctx, t->cm, src, n, c, chunk_log2, labels, roots);
+        CommitOpts o;
+        o.dedup = true;
+        o.roots_host = roots;
+        commit_build(ctx, t->cm, src, n, c, chunk_log2, labels, o);
     } catch (...) {
         t->cm.release(ctx);
         if (keep && owned) ctx->pool.free(owned);

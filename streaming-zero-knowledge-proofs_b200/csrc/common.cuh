@@ -127,6 +127,7 @@ struct sezkp_ctx {
     DevPool pool;
     DevBuf scratch[8];                      // reusable work buffers (per purpose, see users)
     std::vector<std::pair<std::string, double>> timings;  // phase -> ms (last prove)
+    bool dedup_enabled = true;              // value-aware column commit (SEZKP_NO_DEDUP=1 or sezkp_cuda_set_option disables)
     u64 launches = 0;                       // kernels launched since last reset
 };
 

@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "hash.cuh"
+#include "gl.cuh"
 
 namespace {
 
@@ -64,38 +65,266 @@ __device__ __forceinline__ void reduce_levels_smem(u32* s, int pitch, int count,
     }
 }
 
+// Leaf hashing of a chunk into the word-major digest array (block-uniform label template or unlabeled).
+#define HASH_LEAVES_INTO(s, pitch, leaves, VALUE_EXPR, templates_nonnull, t)          \
+    if (templates_nonnull) {                                                          \
+        B3_DISPATCH_LABELED(t, {                                                      \
+            for (int i = threadIdx.x; i < (leaves); i += HASH_THREADS) {              \
+                u32 d[8];                                                             \
+                b3::leaf_labeled_w<B3W>(t, (VALUE_EXPR), d);                          \
+                _Pragma("unroll") for (int w = 0; w < 8; w++) s[w * (pitch) + i] = d[w]; \
+            }                                                                         \
+        })                                                                            \
+    } else {                                                                          \
+        for (int i = threadIdx.x; i < (leaves); i += HASH_THREADS) {                  \
+            u32 d[8];                                                                 \
+            b3::leaf((VALUE_EXPR), d);                                                \
+            _Pragma("unroll") for (int w = 0; w < 8; w++) s[w * (pitch) + i] = d[w];  \
+        }                                                                             \
+    }
+
 // values -> leaf hashes -> chunk root.  grid (n_ch, cols).  Writes chunk roots into level 0 of `upper`.
-__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(const u64* __restrict__ values, u64 n, int cl,
+// FOLD: the values are produced on the fly as the FRI fold of the previous layer,
+//   y'[i] = y[i] + beta*y[i+half]  (reference v1/prover.rs:204-238), written to `values` and hashed in one pass.
+template <bool FOLD>
+__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(u64* __restrict__ values, u64 n, int cl,
                                                                     const b3::LabelTemplate* __restrict__ templates,
-                                                                    u32* __restrict__ upper, u64 n_ch) {
+                                                                    u32* __restrict__ upper, u64 n_ch,
+                                                                    const u64* __restrict__ fold_src, u64 beta) {
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
     const int pitch = (1 << MAX_CL) + 2;
     const u64 chunk = blockIdx.x;
     const int col = blockIdx.y;
     const int leaves = 1 << cl;
-    const u64* v = values + (u64)col * n + (chunk << cl);
+    u64* v = values + (u64)col * n + (chunk << cl);
     b3::LabelTemplate t;
     if (templates) t = templates[col];
-    if (templates) {
-        B3_DISPATCH_LABELED(t, {
-            for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
-                u32 d[8];
-                b3::leaf_labeled_w<B3W>(t, v[i], d);
-#pragma unroll
-                for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
-            }
-        })
-    } else {
+    if (FOLD) {
+        const u64* lo = fold_src + (chunk << cl);
         for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
+            const u64 y = gl::add(lo[i], gl::mul(beta, lo[i + n]));
+            v[i] = y;
             u32 d[8];
-            b3::leaf(v[i], d);
+            b3::leaf(y, d);
 #pragma unroll
             for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
         }
+    } else {
+        HASH_LEAVES_INTO(s, pitch, leaves, v[i], templates != nullptr, t)
     }
     __syncthreads();
     reduce_levels_smem(s, pitch, leaves, nullptr, 0, 0, 0, nullptr, 0);
     if (threadIdx.x < 8) upper[((u64)col * (2 * n_ch - 1) + chunk) * 8 + threadIdx.x] = s[threadIdx.x * pitch];
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* value-aware chunk commit: identical leaves / identical sibling pairs are hashed once         */
+/* ------------------------------------------------------------------------------------------ */
+// Trace columns take few distinct values per 1024-row chunk (flags, moves in {-1,0,1}, 4-bit symbols, block
+// constants, a slowly moving head).  BLAKE3 is a function: equal inputs give equal digests, so the kernel assigns
+// every node a small id per distinct digest, hashes each distinct leaf value and each distinct (left id, right id)
+// pair once, and falls back to the plain reduction as soon as ids stop repeating.  Outputs are bit-identical to
+// the plain kernel; only redundant compressions are skipped.
+constexpr int DD_PA = (1 << MAX_CL) + 2;       // pitch of buffer A (1024 entries)
+constexpr int DD_PB = (1 << (MAX_CL - 1)) + 2; // pitch of buffer B (512 entries)
+constexpr int DD_PAIR_CAP = 4096;              // dedup a level while D*D <= cap
+struct DedupSmem {
+    u32 A[8 * DD_PA];
+    u32 B[8 * DD_PB];
+    u32 bitmap[DD_PAIR_CAP / 32];
+    u32 wprefix[DD_PAIR_CAP / 32];
+    unsigned short idA[1 << MAX_CL];
+    unsigned short idB[1 << (MAX_CL - 1)];
+    unsigned short list[DD_PAIR_CAP];
+    u64 red[2 * (HASH_THREADS / 32)];
+    u32 total;
+};
+
+// exclusive prefix of popcounts over `words` bitmap words (<= 128); leaves the total in sm.total
+__device__ __forceinline__ void bitmap_prefix(DedupSmem& sm, int words) {
+    if (threadIdx.x < 32) {
+        const int per = (words + 31) >> 5;  // <= 4
+        u32 cnt[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int w = threadIdx.x * per + j;
+            cnt[j] = (j < per && w < words) ? __popc(sm.bitmap[w]) : 0;
+            sum += cnt[j];
+        }
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += y;
+        }
+        u32 run = incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int w = threadIdx.x * per + j;
+            if (j < per && w < words) sm.wprefix[w] = run;
+            run += cnt[j];
+        }
+        if (threadIdx.x == 31) sm.total = incl;
+    }
+}
+__device__ __forceinline__ u32 bitmap_rank(const DedupSmem& sm, u32 key) {
+    return sm.wprefix[key >> 5] + __popc(sm.bitmap[key >> 5] & ((1u << (key & 31)) - 1u));
+}
+
+__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, int cl,
+                                                                          const b3::LabelTemplate* __restrict__ templates,
+                                                                          u32* __restrict__ upper, u64 n_ch) {
+    extern __shared__ __align__(16) unsigned char dd_raw[];
+    DedupSmem& sm = *reinterpret_cast<DedupSmem*>(dd_raw);
+    const u64 chunk = blockIdx.x;
+    const int col = blockIdx.y;
+    const int leaves = 1 << cl;
+    const u64* v = values + (u64)col * n + (chunk << cl);
+    const int tid = threadIdx.x;
+    b3::LabelTemplate t;
+    if (templates) t = templates[col];
+    u32* out_root = upper + ((u64)col * (2 * n_ch - 1) + chunk) * 8;
+
+    // ---- keys: value + 2^31 (mod p) so that small negative residues sit next to small positive ones ----
+    constexpr u64 HALF = 1ULL << 31;
+    u64 key[4];
+    u64 mn = ~0ULL, mx = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = tid + k * HASH_THREADS;
+        if (i < leaves) {
+            key[k] = gl::add(v[i], HALF);
+            mn = key[k] < mn ? key[k] : mn;
+            mx = key[k] > mx ? key[k] : mx;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u64 a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((tid & 31) == 0) {
+        sm.red[tid >> 5] = mn;
+        sm.red[HASH_THREADS / 32 + (tid >> 5)] = mx;
+    }
+    if (tid < DD_PAIR_CAP / 32) sm.bitmap[tid] = 0;
+    __syncthreads();
+    mn = sm.red[0];
+    mx = sm.red[HASH_THREADS / 32];
+#pragma unroll
+    for (int w = 1; w < HASH_THREADS / 32; w++) {
+        mn = sm.red[w] < mn ? sm.red[w] : mn;
+        mx = sm.red[HASH_THREADS / 32 + w] > mx ? sm.red[HASH_THREADS / 32 + w] : mx;
+    }
+    if (mx - mn >= (u64)(1 << MAX_CL)) {  // values too spread out: plain path
+        HASH_LEAVES_INTO(sm.A, DD_PA, leaves, v[i], templates != nullptr, t)
+        __syncthreads();
+        reduce_levels_smem(sm.A, DD_PA, leaves, nullptr, 0, 0, 0, nullptr, 0);
+        if (tid < 8) out_root[tid] = sm.A[tid * DD_PA];
+        return;
+    }
+
+    // ---- level 0: ids of distinct values, one leaf hash per distinct value ----
+    const int range = (int)(mx - mn) + 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = tid + k * HASH_THREADS;
+        if (i < leaves) {
+            const u32 kk = (u32)(key[k] - mn);
+            atomicOr(&sm.bitmap[kk >> 5], 1u << (kk & 31));
+        }
+    }
+    __syncthreads();
+    bitmap_prefix(sm, (range + 31) >> 5);
+    __syncthreads();
+    int D = (int)sm.total;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = tid + k * HASH_THREADS;
+        if (i < leaves) sm.idA[i] = (unsigned short)bitmap_rank(sm, (u32)(key[k] - mn));
+    }
+    for (int j = tid; j < range; j += HASH_THREADS)
+        if (sm.bitmap[j >> 5] & (1u << (j & 31))) sm.list[bitmap_rank(sm, (u32)j)] = (unsigned short)j;
+    __syncthreads();
+    HASH_LEAVES_INTO(sm.A, DD_PA, D, gl::sub(mn + (u64)sm.list[i], HALF), templates != nullptr, t)
+    __syncthreads();
+
+    // ---- levels: dedup while the pair space is small, then one indirect level into the other buffer, then plain ----
+    u32* Tcur = sm.A;
+    u32* Tnext = sm.B;
+    int Pcur = DD_PA, Pnext = DD_PB;
+    unsigned short* idcur = sm.idA;
+    unsigned short* idnext = sm.idB;
+    int nodes = leaves;
+    while (nodes > 1) {
+        const int half = nodes >> 1;
+        const int i0 = tid, i1 = tid + HASH_THREADS;
+        if (D * D <= DD_PAIR_CAP) {
+            const int space = D * D;
+            for (int w = tid; w < ((space + 31) >> 5); w += HASH_THREADS) sm.bitmap[w] = 0;
+            __syncthreads();
+            u32 k0 = 0, k1 = 0;
+            if (i0 < half) {
+                k0 = (u32)idcur[2 * i0] * D + idcur[2 * i0 + 1];
+                atomicOr(&sm.bitmap[k0 >> 5], 1u << (k0 & 31));
+            }
+            if (i1 < half) {
+                k1 = (u32)idcur[2 * i1] * D + idcur[2 * i1 + 1];
+                atomicOr(&sm.bitmap[k1 >> 5], 1u << (k1 & 31));
+            }
+            __syncthreads();
+            bitmap_prefix(sm, (space + 31) >> 5);
+            __syncthreads();
+            const int Dn = (int)sm.total;
+            if (i0 < half) idnext[i0] = (unsigned short)bitmap_rank(sm, k0);
+            if (i1 < half) idnext[i1] = (unsigned short)bitmap_rank(sm, k1);
+            for (int j = tid; j < space; j += HASH_THREADS)
+                if (sm.bitmap[j >> 5] & (1u << (j & 31))) sm.list[bitmap_rank(sm, (u32)j)] = (unsigned short)j;
+            __syncthreads();
+            for (int r = tid; r < Dn; r += HASH_THREADS) {
+                const int kk = sm.list[r], a = kk / D, b = kk - a * D;
+                u32 l[8], rr[8], d[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    l[w] = Tcur[w * Pcur + a];
+                    rr[w] = Tcur[w * Pcur + b];
+                }
+                b3::parent(l, rr, d);
+#pragma unroll
+                for (int w = 0; w < 8; w++) Tnext[w * Pnext + r] = d[w];
+            }
+            __syncthreads();
+            D = Dn;
+            nodes = half;
+            u32* tp = Tcur; Tcur = Tnext; Tnext = tp;
+            int pp = Pcur; Pcur = Pnext; Pnext = pp;
+            unsigned short* ip = idcur; idcur = idnext; idnext = ip;
+            // buffer B holds at most 512 entries: after an odd number of levels nodes <= 512 and D <= nodes
+        } else {
+            // too many distinct digests: compute the next level through the ids into the other buffer, then plain
+            u32 d0[8], d1[8];
+            auto indirect_parent = [&](int i, u32 (&d)[8]) {
+                const int a = idcur[2 * i], b = idcur[2 * i + 1];
+                u32 l[8], rr[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    l[w] = Tcur[w * Pcur + a];
+                    rr[w] = Tcur[w * Pcur + b];
+                }
+                b3::parent(l, rr, d);
+            };
+            if (i0 < half) indirect_parent(i0, d0);
+            if (i1 < half) indirect_parent(i1, d1);
+            if (i0 < half) put_digest(Tnext, Pnext, i0, d0, nullptr);
+            if (i1 < half) put_digest(Tnext, Pnext, i1, d1, nullptr);
+            __syncthreads();
+            reduce_levels_smem(Tnext, Pnext, half, nullptr, 0, 0, 0, nullptr, 0);
+            if (tid < 8) out_root[tid] = Tnext[tid * Pnext];
+            return;
+        }
+    }
+    if (tid < 8) out_root[tid] = Tcur[tid * Pcur];  // single node left: id 0
 }
 
 // digests at level l0 of `upper` -> reduce groups of 2^k -> levels l0+1..l0+k stored.  grid (count>>k, cols)
@@ -112,54 +341,33 @@ __global__ void __launch_bounds__(HASH_THREADS) upper_reduce_kernel(u32* __restr
     reduce_levels_smem(s, pitch, cnt, base, grp, l0, n_ch, nullptr, 0);
 }
 
-struct OpenReq {
-    u32 col;
-    u32 pad;
-    u64 row;
-};
 // One CTA per opening: rebuild the chunk, record the in-chunk sibling path and chunk root, gather the upper path.
-__global__ void __launch_bounds__(HASH_THREADS) open_kernel(const u64* __restrict__ values, u64 n, int cl,
-                                                            const b3::LabelTemplate* __restrict__ templates,
-                                                            const u32* __restrict__ upper, u64 n_ch, int depth_out,
-                                                            const OpenReq* __restrict__ reqs, u64* __restrict__ out_values,
-                                                            u32* __restrict__ out_chunk_roots, u32* __restrict__ out_path_in,
-                                                            u32* __restrict__ out_path_to) {
+// Requests carry their own commitment pointers so that openings into many commitments (all FRI layers, all
+// columns) go out in ONE launch.
+__global__ void __launch_bounds__(HASH_THREADS) open_kernel(const OpenReq* __restrict__ reqs, u64* __restrict__ out_values,
+                                                            u32* __restrict__ out_chunk_roots, u32* __restrict__ out_paths) {
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
     const int pitch = (1 << MAX_CL) + 2;
     const u64 q = blockIdx.x;
     const OpenReq rq = reqs[q];
+    const int cl = (int)rq.cl;
     const u64 chunk = rq.row >> cl;
     const int idx_in = (int)(rq.row & ((1ULL << cl) - 1));
     const int leaves = 1 << cl;
-    const u64* v = values + (u64)rq.col * n + (chunk << cl);
+    const u64* v = rq.values + (chunk << cl);
     b3::LabelTemplate t;
-    if (templates) t = templates[rq.col];
-    if (templates) {
-        B3_DISPATCH_LABELED(t, {
-            for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
-                u32 d[8];
-                b3::leaf_labeled_w<B3W>(t, v[i], d);
-#pragma unroll
-                for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
-            }
-        })
-    } else {
-        for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
-            u32 d[8];
-            b3::leaf(v[i], d);
-#pragma unroll
-            for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
-        }
-    }
+    if (rq.tpl) t = *rq.tpl;
+    HASH_LEAVES_INTO(s, pitch, leaves, v[i], rq.tpl != nullptr, t)
     if (threadIdx.x == 0) out_values[q] = v[idx_in];
     __syncthreads();
-    reduce_levels_smem(s, pitch, leaves, nullptr, 0, 0, 0, out_path_in + q * (u64)cl * 8, idx_in);
+    u32* path = out_paths + (u64)rq.out_off * 8;
+    reduce_levels_smem(s, pitch, leaves, nullptr, 0, 0, 0, path, idx_in);
     if (threadIdx.x < 8) out_chunk_roots[q * 8 + threadIdx.x] = s[threadIdx.x * pitch];
-    const u32* base = upper + (u64)rq.col * (2 * n_ch - 1) * 8;
-    for (int i = threadIdx.x; i < depth_out * 8; i += HASH_THREADS) {
+    const u64 n_ch = rq.n_ch;
+    for (int i = threadIdx.x; i < (int)rq.depth_out * 8; i += HASH_THREADS) {
         const int l = i >> 3, w = i & 7;
         const u64 sib = (chunk >> l) ^ 1;
-        out_path_to[q * (u64)depth_out * 8 + i] = base[((2 * n_ch - ((2 * n_ch) >> l)) + sib) * 8 + w];
+        path[(u64)cl * 8 + i] = rq.upper[((2 * n_ch - ((2 * n_ch) >> l)) + sib) * 8 + w];
     }
 }
 
@@ -226,7 +434,7 @@ void Commit::release(sezkp_ctx* ctx) {
 }
 
 void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,
-                  const char* const* labels, u8* roots_host) {
+                  const char* const* labels, const CommitOpts& opt) {
     REQUIRE(n >= 1 && (n & (n - 1)) == 0, "column length %llu is not a power of two", (unsigned long long)n);
     REQUIRE(cols >= 1 && cols <= 65535, "column count %d out of range", cols);
     REQUIRE(chunk_log2 >= 0 && chunk_log2 <= MAX_CL, "chunk_log2 %d out of range (0..10)", chunk_log2);
@@ -250,7 +458,22 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
     const size_t upper_bytes = (size_t)cols * (2 * cm.n_ch - 1) * 32;
     cm.upper = (u32*)ctx->pool.alloc(upper_bytes);
     dim3 grid((unsigned)cm.n_ch, (unsigned)cols);
-    chunk_commit_kernel<<<grid, HASH_THREADS, 0, ctx->stream>>>(values_dev, n, cm.cl, cm.templates, cm.upper, cm.n_ch);
+    if (opt.fold_src) {
+        REQUIRE(cols == 1 && !labels, "internal: fused fold needs a single unlabeled column");
+        chunk_commit_kernel<true><<<grid, HASH_THREADS, 0, ctx->stream>>>((u64*)values_dev, n, cm.cl, nullptr, cm.upper, cm.n_ch,
+                                                                           opt.fold_src, opt.fold_beta);
+    } else if (opt.dedup && ctx->dedup_enabled) {
+        static bool configured = false;
+        if (!configured) {
+            CUDA_CHECK(cudaFuncSetAttribute(chunk_commit_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem)));
+            configured = true;
+        }
+        chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(values_dev, n, cm.cl, cm.templates, cm.upper,
+                                                                                           cm.n_ch);
+    } else {
+        chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>((u64*)values_dev, n, cm.cl, cm.templates, cm.upper, cm.n_ch,
+                                                                            nullptr, 0);
+    }
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     const int depth = ilog2(cm.n_ch);
@@ -263,41 +486,63 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
         ctx->launches++;
         l0 += k;
     }
-    if (roots_host) {
-        CUDA_CHECK(cudaMemcpy2DAsync(roots_host, 32, (const u8*)cm.upper + (2 * cm.n_ch - 2) * 32, (2 * cm.n_ch - 1) * 32, 32, cols,
-                                     cudaMemcpyDeviceToHost, ctx->stream));
+    const u8* root0 = (const u8*)cm.upper + (2 * cm.n_ch - 2) * 32;
+    const size_t col_pitch = (2 * cm.n_ch - 1) * 32;
+    if (opt.roots_dev) CUDA_CHECK(cudaMemcpy2DAsync(opt.roots_dev, 32, root0, col_pitch, 32, cols, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (opt.roots_host) {
+        CUDA_CHECK(cudaMemcpy2DAsync(opt.roots_host, 32, root0, col_pitch, 32, cols, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
+}
+
+OpenReq make_open_req(const Commit& cm, u32 col, u64 row, u32 out_off) {
+    REQUIRE(col < (u32)cm.cols, "opening: column %u out of range", col);
+    REQUIRE(row < cm.n, "opening: row %llu out of range", (unsigned long long)row);
+    OpenReq r;
+    r.values = cm.values + (u64)col * cm.n;
+    r.upper = cm.upper + (u64)col * (2 * cm.n_ch - 1) * 8;
+    r.tpl = cm.templates ? cm.templates + col : nullptr;
+    r.n_ch = cm.n_ch;
+    r.row = row;
+    r.cl = (u32)cm.cl;
+    r.depth_out = (u32)ilog2(cm.n_ch);
+    r.out_off = out_off;
+    r.pad = 0;
+    return r;
+}
+
+// One launch for any mix of openings.  paths_host receives, per request, cl + depth_out digests at out_off (32 B units).
+void open_batch(sezkp_ctx* ctx, const std::vector<OpenReq>& reqs, size_t path_digests, u64* values, u8* chunk_roots, u8* paths_host) {
+    const size_t k = reqs.size();
+    if (k == 0) return;
+    const size_t b_req = k * sizeof(OpenReq), b_val = k * 8, b_cr = k * 32, b_path = path_digests * 32;
+    u8* d = (u8*)ctx->scratch[7].ensure(b_req + b_val + b_cr + b_path + 64);
+    OpenReq* d_req = (OpenReq*)d;
+    u64* d_val = (u64*)(d + b_req);
+    u32* d_cr = (u32*)(d + b_req + b_val);
+    u32* d_path = (u32*)(d + b_req + b_val + b_cr);
+    CUDA_CHECK(cudaMemcpyAsync(d_req, reqs.data(), b_req, cudaMemcpyHostToDevice, ctx->stream));
+    open_kernel<<<(unsigned)k, HASH_THREADS, 0, ctx->stream>>>(d_req, d_val, d_cr, d_path);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    CUDA_CHECK(cudaMemcpyAsync(values, d_val, b_val, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(chunk_roots, d_cr, b_cr, cudaMemcpyDeviceToHost, ctx->stream));
+    if (b_path) CUDA_CHECK(cudaMemcpyAsync(paths_host, d_path, b_path, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
 void commit_open(sezkp_ctx* ctx, const Commit& cm, const u32* col_idx, const u64* row_idx, size_t k, u64* values,
                  u8* chunk_roots, u8* path_in, u8* path_to) {
     if (k == 0) return;
-    const int depth_out = ilog2(cm.n_ch);
+    const int din = cm.cl, dout = ilog2(cm.n_ch), depth = din + dout;
     std::vector<OpenReq> reqs(k);
+    for (size_t i = 0; i < k; i++) reqs[i] = make_open_req(cm, col_idx[i], row_idx[i], (u32)(i * depth));
+    std::vector<u8> paths(k * (size_t)depth * 32 + 32);
+    open_batch(ctx, reqs, k * (size_t)depth, values, chunk_roots, paths.data());
     for (size_t i = 0; i < k; i++) {
-        REQUIRE(col_idx[i] < (u32)cm.cols, "opening %zu: column %u out of range", i, col_idx[i]);
-        REQUIRE(row_idx[i] < cm.n, "opening %zu: row %llu out of range", i, (unsigned long long)row_idx[i]);
-        reqs[i] = OpenReq{col_idx[i], 0, row_idx[i]};
+        if (din) std::memcpy(path_in + i * (size_t)din * 32, &paths[i * (size_t)depth * 32], (size_t)din * 32);
+        if (dout) std::memcpy(path_to + i * (size_t)dout * 32, &paths[(i * (size_t)depth + din) * 32], (size_t)dout * 32);
     }
-    const size_t b_req = k * sizeof(OpenReq), b_val = k * 8, b_cr = k * 32, b_in = k * (size_t)cm.cl * 32,
-                 b_to = k * (size_t)depth_out * 32;
-    u8* d = (u8*)ctx->scratch[7].ensure(b_req + b_val + b_cr + b_in + b_to + 64);
-    OpenReq* d_req = (OpenReq*)d;
-    u64* d_val = (u64*)(d + b_req);
-    u32* d_cr = (u32*)(d + b_req + b_val);
-    u32* d_in = (u32*)(d + b_req + b_val + b_cr);
-    u32* d_to = (u32*)(d + b_req + b_val + b_cr + b_in);
-    CUDA_CHECK(cudaMemcpyAsync(d_req, reqs.data(), b_req, cudaMemcpyHostToDevice, ctx->stream));
-    open_kernel<<<(unsigned)k, HASH_THREADS, 0, ctx->stream>>>(cm.values, cm.n, cm.cl, cm.templates, cm.upper, cm.n_ch, depth_out,
-                                                               d_req, d_val, d_cr, d_in, d_to);
-    CUDA_CHECK(cudaGetLastError());
-    ctx->launches++;
-    CUDA_CHECK(cudaMemcpyAsync(values, d_val, b_val, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(chunk_roots, d_cr, b_cr, cudaMemcpyDeviceToHost, ctx->stream));
-    if (b_in) CUDA_CHECK(cudaMemcpyAsync(path_in, d_in, b_in, cudaMemcpyDeviceToHost, ctx->stream));
-    if (b_to) CUDA_CHECK(cudaMemcpyAsync(path_to, d_to, b_to, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
 void leaf_hash_device(sezkp_ctx* ctx, const u64* vals_dev, size_t n, const char* label, u32* out_dev) {

@@ -1,6 +1,8 @@
 // Internal interface of hash.cu: chunked BLAKE3 Merkle commitments over device-resident columns.
 #pragma once
 #include "blake3.cuh"
+#include <vector>
+
 #include "common.cuh"
 
 // A commitment to `cols` columns of `n` field elements each (n a power of two).  Leaves are labeled
@@ -21,9 +23,27 @@ struct Commit {
 inline u64 upper_off(u64 n_ch, int l) { return 2 * n_ch - ((2 * n_ch) >> l); }
 
 b3::LabelTemplate make_label_template(const char* label);
-// Build commitment over device values; writes the `cols` roots (32 B each) to host `roots`.
+struct CommitOpts {
+    bool dedup = false;             // value-aware kernel (identical leaves / sibling pairs hashed once); same outputs
+    const u64* fold_src = nullptr;  // fused FRI fold: values[i] = fold_src[i] + fold_beta*fold_src[i+n], written + hashed
+    u64 fold_beta = 0;
+    u8* roots_host = nullptr;       // [cols][32]; copying to the host synchronises the stream
+    u8* roots_dev = nullptr;        // [cols][32] device copy (no synchronisation)
+};
+// Build a commitment over device values (all launches on ctx->stream).
 void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,
-                  const char* const* labels_or_null, u8* roots_host);
+                  const char* const* labels_or_null, const CommitOpts& opt);
+// Generic opening request: one CTA rebuilds the chunk containing `row` of one committed column.
+struct OpenReq {
+    const u64* values;             // the column
+    const u32* upper;              // its retained upper levels
+    const b3::LabelTemplate* tpl;  // null = unlabeled
+    u64 n_ch, row;
+    u32 cl, depth_out;
+    u32 out_off, pad;              // path position in the output (32 B units): cl in-chunk siblings then depth_out upper siblings
+};
+OpenReq make_open_req(const Commit& cm, u32 col, u64 row, u32 out_off);
+void open_batch(sezkp_ctx* ctx, const std::vector<OpenReq>& reqs, size_t path_digests, u64* values, u8* chunk_roots, u8* paths_host);
 // k openings; outputs are host arrays: values[k], chunk_roots[k][32], path_in[k][cl][32], path_to[k][log2(n_ch)][32].
 void commit_open(sezkp_ctx* ctx, const Commit& cm, const u32* col_idx, const u64* row_idx, size_t k, u64* values,
                  u8* chunk_roots, u8* path_in, u8* path_to);

@@ -287,74 +287,78 @@ void FriLayers::release(sezkp_ctx* ctx) {
     values = nullptr;
 }
 
-// layer0 (device, N = 2^log_N values) is copied into the retained layer buffer unless `adopt` (then it must be
-// the first N elements of a 2N-element allocation that FriLayers takes ownership of).
+// layer0 (device, N = 2^log_N values) is copied into the retained layer buffer; every further layer is folded and
+// hashed by one fused kernel.  Only root 0 is needed on the host before the betas exist (v1/prover.rs:187-198); the
+// other roots are collected on the device and copied back once, then absorbed in order (v1/prover.rs:219, 235).
 void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log_N, const u64* betas, u8* roots_host,
                        u64* final_value, HostAbsorb* absorb) {
     REQUIRE(log_N >= 1 && log_N <= 32, "log_N %d out of range", log_N);
     const u64 N = 1ULL << log_N;
     fl.log_N = log_N;
     fl.values = (u64*)ctx->pool.alloc(2 * N * 8);
+    u8* d_roots = (u8*)ctx->scratch[6].ensure((size_t)(log_N + 1) * 32 + 64);
     CUDA_CHECK(cudaMemcpyAsync(fl.values, layer0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     fl.commits.resize(log_N + 1);
-    u64 off = 0, len = N;
     std::vector<u64> beta_store;
-    for (int l = 0; l <= log_N; l++) {
-        u64* cur = fl.values + off;
-        if (l > 0) {
-            // betas may only become known after root 0 was absorbed (transcript callback)
-            const u64 beta = betas ? betas[l - 1] : beta_store[l - 1];
-            REQUIRE(beta < gl::P, "beta %d is not canonical", l - 1);
-            const u64* prev = fl.values + (off - 2 * len);
-            fri_fold_kernel<<<blocks_for(len, 256), 256, 0, ctx->stream>>>(prev, len, beta, cur);
-            CUDA_CHECK(cudaGetLastError());
-            ctx->launches++;
-        }
-        commit_build(ctx, fl.commits[l], cur, len, 1, 10, nullptr, roots_host + 32 * l);
+    {
+        CommitOpts o;
+        o.roots_host = roots_host;
+        commit_build(ctx, fl.commits[0], fl.values, N, 1, 10, nullptr, o);
         if (absorb) {
-            absorb->on_root(l, roots_host + 32 * l);
-            if (l == 0 && !betas) beta_store = absorb->draw_betas(log_N);
+            absorb->on_root(0, roots_host);
+            if (!betas) {
+                beta_store = absorb->draw_betas(log_N);
+                betas = beta_store.data();
+            }
         }
+    }
+    REQUIRE(betas != nullptr, "internal: FRI betas missing");
+    u64 off = N, len = N >> 1;
+    for (int l = 1; l <= log_N; l++) {
+        REQUIRE(betas[l - 1] < gl::P, "beta %d is not canonical", l - 1);
+        CommitOpts o;
+        o.fold_src = fl.values + (off - 2 * len);
+        o.fold_beta = betas[l - 1];
+        o.roots_dev = d_roots + 32 * l;
+        commit_build(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
         off += len;
         len >>= 1;
     }
+    CUDA_CHECK(cudaMemcpyAsync(roots_host + 32, d_roots + 32, (size_t)log_N * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(final_value, fl.values + (2 * N - 2), 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (absorb)
+        for (int l = 1; l <= log_N; l++) absorb->on_root(l, roots_host + 32 * l);
+}
+
+// Requests for k query indices into layer 0 (two openings per layer per query), appended to `reqs`.
+// positions [k][log_N+1] is filled; request (q, l, s) gets path offset base_off + ((q*log_N + l)*2 + s)*log_N.
+void fri_open_requests(const FriLayers& fl, const u64* idx0, size_t k, u64* positions, std::vector<OpenReq>& reqs, u32 base_off) {
+    const int L = fl.log_N;
+    const u64 N = 1ULL << L;
+    for (size_t q = 0; q < k; q++) {
+        REQUIRE(idx0[q] < N, "FRI query %zu out of range", q);
+        u64 idx = idx0[q];
+        for (int l = 0; l < L; l++) {
+            const u64 half = (N >> l) >> 1;
+            positions[q * (L + 1) + l] = idx;
+            for (int s = 0; s < 2; s++)
+                reqs.push_back(make_open_req(fl.commits[l], 0, s ? (idx ^ half) : idx, base_off + (u32)(((q * L + l) * 2 + s) * L)));
+            idx %= half;  // v1/prover.rs:386-388, 430-434 (half >= 1)
+        }
+        positions[q * (L + 1) + L] = idx;
+    }
 }
 
 // k query indices into layer 0.  positions [k][log_N+1]; values [k][log_N][2]; paths [k][log_N][2][log_N][32]
 void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_t k, u64* positions, u64* values, u8* paths) {
     const int L = fl.log_N;
-    const u64 N = 1ULL << L;
-    for (size_t q = 0; q < k; q++) {
-        REQUIRE(idx0[q] < N, "FRI query %zu out of range", q);
-        positions[q * (L + 1)] = idx0[q];
-    }
+    std::vector<OpenReq> reqs;
+    reqs.reserve(k * L * 2);
+    fri_open_requests(fl, idx0, k, positions, reqs, 0);
     std::memset(paths, 0, k * (size_t)L * 2 * L * 32);
-    std::vector<u32> col(2 * k, 0);
-    std::vector<u64> row(2 * k), val(2 * k);
-    std::vector<u8> cr(2 * k * 32), pin, pto;
-    for (int l = 0; l < L; l++) {
-        const Commit& cm = fl.commits[l];
-        const u64 len = N >> l, half = len >> 1;
-        for (size_t q = 0; q < k; q++) {
-            const u64 idx = positions[q * (L + 1) + l];
-            row[2 * q] = idx;
-            row[2 * q + 1] = idx ^ half;
-            positions[q * (L + 1) + l + 1] = idx % half;  // v1/prover.rs:386-388, 430-434 (half >= 1)
-        }
-        const int din = cm.cl, dout = ilog2(cm.n_ch);
-        pin.assign(2 * k * (size_t)din * 32 + 32, 0);
-        pto.assign(2 * k * (size_t)dout * 32 + 32, 0);
-        commit_open(ctx, cm, col.data(), row.data(), 2 * k, val.data(), cr.data(), pin.data(), pto.data());
-        for (size_t q = 0; q < k; q++)
-            for (int s = 0; s < 2; s++) {
-                values[(q * L + l) * 2 + s] = val[2 * q + s];
-                u8* dst = paths + (((q * L + l) * 2 + s) * (size_t)L) * 32;
-                std::memcpy(dst, pin.data() + (2 * q + s) * (size_t)din * 32, (size_t)din * 32);
-                std::memcpy(dst + (size_t)din * 32, pto.data() + (2 * q + s) * (size_t)dout * 32, (size_t)dout * 32);
-            }
-    }
+    std::vector<u8> cr(reqs.size() * 32);
+    open_batch(ctx, reqs, k * (size_t)L * 2 * L, values, cr.data(), paths);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -459,7 +463,10 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
     Commit cm;
     FriLayers fl;
     try {
-        commit_build(ctx, cm, cols, n, n_cols, COL_CHUNK_LOG2, label_ptrs.data(), col_roots.data());
+        CommitOpts copt;
+        copt.dedup = true;
+        copt.roots_host = col_roots.data();
+        commit_build(ctx, cm, cols, n, n_cols, COL_CHUNK_LOG2, label_ptrs.data(), copt);
         lap("column_commit");
         tr.absorb_u64("n_cols", (u64)n_cols);
         for (int c = 0; c < n_cols; c++) tr.absorb("col_root", &col_roots[32 * c], 32);
@@ -523,22 +530,29 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             o_col[o] = 2; o_row[o++] = row;  // is_last
             o_col[o] = 0; o_row[o++] = row;  // input_mv
         }
-        const int din = cm.cl, dout = ilog2(cm.n_ch);
-        std::vector<u64> o_val(k_open);
-        std::vector<u8> o_cr(k_open * 32), o_in(k_open * (size_t)din * 32 + 32), o_to(k_open * (size_t)dout * 32 + 32);
-        commit_open(ctx, cm, o_col.data(), o_row.data(), k_open, o_val.data(), o_cr.data(), o_in.data(), o_to.data());
-        lap("column_openings");
-
-        // I. FRI queries (v1/prover.rs:297-450); same transcript label as the AIR rows
+        // I. FRI query indices (v1/prover.rs:297; same transcript label as the AIR rows; nothing is absorbed in between,
+        //    so all openings of the proof go out in one launch)
         std::vector<u64> fri_idx(NUM_QUERIES);
         {
             auto by = tr.challenge("row_queries", 8 * NUM_QUERIES);
             for (int i = 0; i < NUM_QUERIES; i++) fri_idx[i] = le64(&by[8 * i]) % N;
         }
-        std::vector<u64> f_pos((size_t)NUM_QUERIES * (log_N + 1)), f_val((size_t)NUM_QUERIES * log_N * 2);
-        std::vector<u8> f_paths((size_t)NUM_QUERIES * log_N * 2 * log_N * 32);
-        fri_open_device(ctx, fl, fri_idx.data(), NUM_QUERIES, f_pos.data(), f_val.data(), f_paths.data());
-        lap("fri_openings");
+        const int din = cm.cl, dout = ilog2(cm.n_ch), cdepth = din + dout;
+        std::vector<OpenReq> reqs;
+        reqs.reserve(k_open + (size_t)NUM_QUERIES * log_N * 2);
+        for (size_t o = 0; o < k_open; o++) reqs.push_back(make_open_req(cm, o_col[o], o_row[o], (u32)(o * cdepth)));
+        const size_t fri_base = k_open * (size_t)cdepth, fri_digests = (size_t)NUM_QUERIES * log_N * 2 * log_N;
+        std::vector<u64> f_pos((size_t)NUM_QUERIES * (log_N + 1));
+        fri_open_requests(fl, fri_idx.data(), NUM_QUERIES, f_pos.data(), reqs, (u32)fri_base);
+        std::vector<u64> all_val(reqs.size());
+        std::vector<u8> all_cr(reqs.size() * 32), all_paths((fri_base + fri_digests) * 32 + 32);
+        open_batch(ctx, reqs, fri_base + fri_digests, all_val.data(), all_cr.data(), all_paths.data());
+        const u64* o_val = all_val.data();
+        const u8* o_cr = all_cr.data();
+        const u8* o_paths = all_paths.data();
+        const u64* f_val = all_val.data() + k_open;
+        const u8* f_paths = all_paths.data() + fri_base * 32;
+        lap("openings");
 
         // J. ProofV1 in declaration order (v1/proof.rs:80-98)
         Writer w;
@@ -557,8 +571,8 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             w.u64le(row >> din);
             w.u64le(row & ((1ULL << din) - 1));
             w.raw(&o_cr[o * 32], 32);
-            w.digest_vec(&o_in[o * (size_t)din * 32], din);
-            w.digest_vec(&o_to[o * (size_t)dout * 32], dout);
+            w.digest_vec(&o_paths[o * (size_t)cdepth * 32], din);
+            w.digest_vec(&o_paths[(o * (size_t)cdepth + din) * 32], dout);
         };
         w.u64le(NUM_QUERIES);
         for (int qi = 0; qi < NUM_QUERIES; qi++) {

@@ -45,6 +45,7 @@ struct FriLayers {
 };
 void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0_dev, int log_N, const u64* betas_or_null, u8* roots_host,
                        u64* final_value, HostAbsorb* absorb_or_null);
+void fri_open_requests(const FriLayers& fl, const u64* idx0, size_t k, u64* positions, std::vector<OpenReq>& reqs, u32 base_off);
 void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_t k, u64* positions, u64* values, u8* paths);
 void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out);
 void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out);

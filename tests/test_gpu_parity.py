@@ -163,6 +163,39 @@ def test_column_commit_and_openings_vs_oracle(ctx, oracle, n, c):
     tree.free()
 
 
+@pytest.mark.parametrize("kind", ["const", "flags", "moves", "sym16", "walk", "counter", "wide_small", "mixed_sign", "random"])
+@pytest.mark.parametrize("n", [4, 256, 1024, 8192])
+def test_value_aware_commit_matches_plain_and_oracle(ctx, oracle, kind, n):
+    """The dedup kernel (identical leaves / sibling pairs hashed once) must give the same roots and openings as one
+    compression per node, for every value distribution that steers it through a different branch."""
+    rng = np.random.default_rng(n)
+    i = np.arange(n)
+    col = {
+        "const": np.full(n, 7),
+        "flags": (rng.random(n) < 0.4).astype(np.int64),
+        "moves": rng.integers(-1, 2, n),
+        "sym16": np.where(rng.random(n) < 0.4, rng.integers(0, 16, n), 0),
+        "walk": np.cumsum(rng.integers(-1, 2, n)),
+        "counter": i % 1024,                       # 1024 distinct values in range 1024
+        "wide_small": (i * 37) % 1000,             # many distinct, still inside the key range
+        "mixed_sign": np.where(i % 2 == 0, -(i % 50), i % 60),
+        "random": None,
+    }[kind]
+    if col is None:
+        vals = rand_field(rng, n)
+    else:
+        vals = np.array([int(x) % P for x in col], dtype=np.uint64)
+    cols = np.stack([vals, vals[::-1].copy()])
+    labels = ["head_3", "wsym_11"]
+    exp = oracle.column_commit(cols, labels)
+    ctx.set_option("dedup", 1)
+    got = ctx.column_commit(cols, labels)
+    ctx.set_option("dedup", 0)
+    plain = ctx.column_commit(cols, labels)
+    ctx.set_option("dedup", 1)
+    assert np.array_equal(got, exp) and np.array_equal(plain, exp)
+
+
 @pytest.mark.parametrize("log_n", [1, 2, 5, 10, 11, 13, 16])
 def test_fri_commit_and_open_vs_oracle(ctx, oracle, log_n):
     rng = np.random.default_rng(log_n)

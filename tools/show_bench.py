@@ -7,7 +7,7 @@ d = json.load(open(sys.argv[1]))
 print(f"value {d['value']:.4g} {d['unit']}  ms/step {d['ms_per_step']:.2f}  e2e {d['e2e']['value']:.4g} ({d['e2e']['ms_per_step']:.2f} ms)  launches {d['gpu_launches']}")
 print("phases", {k: round(v, 2) for k, v in d["phases_ms"].items()})
 r = d["roofline"]
-print(f"roofline {r['kernel']}: {r['ms_per_launch']:.2f} ms, {r['achieved']:.1f} GB/s, frac {r['frac']:.4f}, compressions/s {r['int_alu']['compressions_per_s']:.3g}")
+print(f"roofline {r['kernel']}: {r['ms_per_launch']:.2f} ms, {r['achieved']:.1f} GB/s, frac {r['frac']:.4f}, plain {r['int_alu']['plain_ms_per_launch']:.2f} ms ({r['int_alu']['plain_frac_of_alu_pipe_bound']:.3f} of ALU-pipe bound)")
 if d.get("micro"):
     print("micro", {k: (round(v["ms"], 3), round(v["GBps"], 1), round(v["frac_of_hbm_peak"], 4)) for k, v in d["micro"].items()})
 print("cpu", d["cpu_baseline"]["value"], d["cpu_baseline"].get("gpu_proof_identical"), "clocks", d["clocks"])
