@@ -125,12 +125,11 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(u64* __restr
 // every node a small id per distinct digest, hashes each distinct leaf value and each distinct (left id, right id)
 // pair once, and falls back to the plain reduction as soon as ids stop repeating.  Outputs are bit-identical to
 // the plain kernel; only redundant compressions are skipped.
-constexpr int DD_PA = (1 << MAX_CL) + 2;       // pitch of buffer A (1024 entries)
-constexpr int DD_PB = (1 << (MAX_CL - 1)) + 2; // pitch of buffer B (512 entries)
-constexpr int DD_PAIR_CAP = 4096;              // dedup a level while D*D <= cap
+constexpr int DD_PA = (1 << MAX_CL) + 2;       // pitch of the digest array (1024 entries); tables live in its two halves
+constexpr int DD_HALF = 1 << (MAX_CL - 1);     // 512 entries per half
+constexpr int DD_PAIR_CAP = 2048;              // dedup a level while D*D <= cap
 struct DedupSmem {
     u32 A[8 * DD_PA];
-    u32 B[8 * DD_PB];
     u32 bitmap[DD_PAIR_CAP / 32];
     u32 wprefix[DD_PAIR_CAP / 32];
     unsigned short idA[1 << MAX_CL];
@@ -140,13 +139,13 @@ struct DedupSmem {
     u32 total;
 };
 
-// exclusive prefix of popcounts over `words` bitmap words (<= 128); leaves the total in sm.total
+// exclusive prefix of popcounts over `words` bitmap words (<= 64); leaves the total in sm.total
 __device__ __forceinline__ void bitmap_prefix(DedupSmem& sm, int words) {
     if (threadIdx.x < 32) {
-        const int per = (words + 31) >> 5;  // <= 4
-        u32 cnt[4], sum = 0;
+        const int per = (words + 31) >> 5;  // <= 2
+        u32 cnt[2], sum = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 2; j++) {
             const int w = threadIdx.x * per + j;
             cnt[j] = (j < per && w < words) ? __popc(sm.bitmap[w]) : 0;
             sum += cnt[j];
@@ -159,7 +158,7 @@ __device__ __forceinline__ void bitmap_prefix(DedupSmem& sm, int words) {
         }
         u32 run = incl - sum;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 2; j++) {
             const int w = threadIdx.x * per + j;
             if (j < per && w < words) sm.wprefix[w] = run;
             run += cnt[j];
@@ -169,6 +168,20 @@ __device__ __forceinline__ void bitmap_prefix(DedupSmem& sm, int words) {
 }
 __device__ __forceinline__ u32 bitmap_rank(const DedupSmem& sm, u32 key) {
     return sm.wprefix[key >> 5] + __popc(sm.bitmap[key >> 5] & ((1u << (key & 31)) - 1u));
+}
+// Set bit `key` for every valid lane with one shared-memory atomic per distinct bitmap word per warp
+// (all lanes of a low-entropy chunk hit the same word; unaggregated atomics would serialise).  Whole warp must call.
+__device__ __forceinline__ void bitmap_set_warp(u32* bitmap, u32 key, bool valid) {
+    unsigned todo = __ballot_sync(0xffffffffu, valid);
+    const u32 word = key >> 5, bit = 1u << (key & 31);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const u32 w = __shfl_sync(0xffffffffu, word, leader);
+        const unsigned peers = __ballot_sync(0xffffffffu, valid && word == w);
+        const u32 bits = __reduce_or_sync(0xffffffffu, (valid && word == w) ? bit : 0u);
+        if ((int)(threadIdx.x & 31) == leader) atomicOr(&bitmap[w], bits);
+        todo &= ~peers;
+    }
 }
 
 __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, int cl,
@@ -192,6 +205,7 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int i = tid + k * HASH_THREADS;
+        key[k] = 0;
         if (i < leaves) {
             key[k] = gl::add(v[i], HALF);
             mn = key[k] < mn ? key[k] : mn;
@@ -217,7 +231,18 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
         mn = sm.red[w] < mn ? sm.red[w] : mn;
         mx = sm.red[HASH_THREADS / 32 + w] > mx ? sm.red[HASH_THREADS / 32 + w] : mx;
     }
-    if (mx - mn >= (u64)(1 << MAX_CL)) {  // values too spread out: plain path
+    int D = 0;
+    bool dedup = (mx - mn) < (u64)(1 << MAX_CL);
+    if (dedup) {  // ids of the distinct values
+#pragma unroll
+        for (int k = 0; k < 4; k++) bitmap_set_warp(sm.bitmap, (u32)(key[k] - mn), tid + k * HASH_THREADS < leaves);
+        __syncthreads();
+        bitmap_prefix(sm, ((int)(mx - mn) + 32) >> 5);
+        __syncthreads();
+        D = (int)sm.total;
+        dedup = D <= DD_HALF;
+    }
+    if (!dedup) {  // values too spread out / too many distinct values: plain path
         HASH_LEAVES_INTO(sm.A, DD_PA, leaves, v[i], templates != nullptr, t)
         __syncthreads();
         reduce_levels_smem(sm.A, DD_PA, leaves, nullptr, 0, 0, 0, nullptr, 0);
@@ -225,20 +250,8 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
         return;
     }
 
-    // ---- level 0: ids of distinct values, one leaf hash per distinct value ----
+    // ---- level 0: one leaf hash per distinct value (table in the low half of A) ----
     const int range = (int)(mx - mn) + 1;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int i = tid + k * HASH_THREADS;
-        if (i < leaves) {
-            const u32 kk = (u32)(key[k] - mn);
-            atomicOr(&sm.bitmap[kk >> 5], 1u << (kk & 31));
-        }
-    }
-    __syncthreads();
-    bitmap_prefix(sm, (range + 31) >> 5);
-    __syncthreads();
-    int D = (int)sm.total;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int i = tid + k * HASH_THREADS;
@@ -250,29 +263,39 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
     HASH_LEAVES_INTO(sm.A, DD_PA, D, gl::sub(mn + (u64)sm.list[i], HALF), templates != nullptr, t)
     __syncthreads();
 
-    // ---- levels: dedup while the pair space is small, then one indirect level into the other buffer, then plain ----
+    // ---- levels: dedup while the pair space is small, then one indirect level into the other half, then plain ----
     u32* Tcur = sm.A;
-    u32* Tnext = sm.B;
-    int Pcur = DD_PA, Pnext = DD_PB;
+    u32* Tnext = sm.A + DD_HALF;
     unsigned short* idcur = sm.idA;
     unsigned short* idnext = sm.idB;
     int nodes = leaves;
     while (nodes > 1) {
         const int half = nodes >> 1;
         const int i0 = tid, i1 = tid + HASH_THREADS;
+        if (D == 1) {
+            // every node of this level carries the same digest: the rest of the tree is a chain x -> H(x, x)
+            if (tid == 0) {
+                u32 d[8], e[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) d[w] = Tcur[w * DD_PA];
+                for (int m2 = nodes; m2 > 1; m2 >>= 1) {
+                    b3::parent(d, d, e);
+#pragma unroll
+                    for (int w = 0; w < 8; w++) d[w] = e[w];
+                }
+#pragma unroll
+                for (int w = 0; w < 8; w++) out_root[w] = d[w];
+            }
+            return;
+        }
         if (D * D <= DD_PAIR_CAP) {
             const int space = D * D;
             for (int w = tid; w < ((space + 31) >> 5); w += HASH_THREADS) sm.bitmap[w] = 0;
             __syncthreads();
-            u32 k0 = 0, k1 = 0;
-            if (i0 < half) {
-                k0 = (u32)idcur[2 * i0] * D + idcur[2 * i0 + 1];
-                atomicOr(&sm.bitmap[k0 >> 5], 1u << (k0 & 31));
-            }
-            if (i1 < half) {
-                k1 = (u32)idcur[2 * i1] * D + idcur[2 * i1 + 1];
-                atomicOr(&sm.bitmap[k1 >> 5], 1u << (k1 & 31));
-            }
+            const u32 k0 = (i0 < half) ? (u32)idcur[2 * i0] * D + idcur[2 * i0 + 1] : 0u;
+            const u32 k1 = (i1 < half) ? (u32)idcur[2 * i1] * D + idcur[2 * i1 + 1] : 0u;
+            bitmap_set_warp(sm.bitmap, k0, i0 < half);
+            bitmap_set_warp(sm.bitmap, k1, i1 < half);
             __syncthreads();
             bitmap_prefix(sm, (space + 31) >> 5);
             __syncthreads();
@@ -287,44 +310,42 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
                 u32 l[8], rr[8], d[8];
 #pragma unroll
                 for (int w = 0; w < 8; w++) {
-                    l[w] = Tcur[w * Pcur + a];
-                    rr[w] = Tcur[w * Pcur + b];
+                    l[w] = Tcur[w * DD_PA + a];
+                    rr[w] = Tcur[w * DD_PA + b];
                 }
                 b3::parent(l, rr, d);
 #pragma unroll
-                for (int w = 0; w < 8; w++) Tnext[w * Pnext + r] = d[w];
+                for (int w = 0; w < 8; w++) Tnext[w * DD_PA + r] = d[w];
             }
             __syncthreads();
             D = Dn;
             nodes = half;
             u32* tp = Tcur; Tcur = Tnext; Tnext = tp;
-            int pp = Pcur; Pcur = Pnext; Pnext = pp;
             unsigned short* ip = idcur; idcur = idnext; idnext = ip;
-            // buffer B holds at most 512 entries: after an odd number of levels nodes <= 512 and D <= nodes
         } else {
-            // too many distinct digests: compute the next level through the ids into the other buffer, then plain
+            // too many distinct digests: compute the next level through the ids into the other half, then plain
             u32 d0[8], d1[8];
             auto indirect_parent = [&](int i, u32 (&d)[8]) {
                 const int a = idcur[2 * i], b = idcur[2 * i + 1];
                 u32 l[8], rr[8];
 #pragma unroll
                 for (int w = 0; w < 8; w++) {
-                    l[w] = Tcur[w * Pcur + a];
-                    rr[w] = Tcur[w * Pcur + b];
+                    l[w] = Tcur[w * DD_PA + a];
+                    rr[w] = Tcur[w * DD_PA + b];
                 }
                 b3::parent(l, rr, d);
             };
             if (i0 < half) indirect_parent(i0, d0);
             if (i1 < half) indirect_parent(i1, d1);
-            if (i0 < half) put_digest(Tnext, Pnext, i0, d0, nullptr);
-            if (i1 < half) put_digest(Tnext, Pnext, i1, d1, nullptr);
+            if (i0 < half) put_digest(Tnext, DD_PA, i0, d0, nullptr);
+            if (i1 < half) put_digest(Tnext, DD_PA, i1, d1, nullptr);
             __syncthreads();
-            reduce_levels_smem(Tnext, Pnext, half, nullptr, 0, 0, 0, nullptr, 0);
-            if (tid < 8) out_root[tid] = Tnext[tid * Pnext];
+            reduce_levels_smem(Tnext, DD_PA, half, nullptr, 0, 0, 0, nullptr, 0);
+            if (tid < 8) out_root[tid] = Tnext[tid * DD_PA];
             return;
         }
     }
-    if (tid < 8) out_root[tid] = Tcur[tid * Pcur];  // single node left: id 0
+    if (tid < 8) out_root[tid] = Tcur[tid * DD_PA];  // single node left: id 0
 }
 
 // digests at level l0 of `upper` -> reduce groups of 2^k -> levels l0+1..l0+k stored.  grid (count>>k, cols)
