@@ -125,7 +125,7 @@ struct sezkp_ctx {
     std::string last_error;
     std::map<u64, NttTables*> ntt_tables;  // key: (log_n, inverse, coset params)
     DevPool pool;
-    DevBuf scratch[8];                      // reusable work buffers (per purpose, see users)
+    DevBuf scratch[12];                      // reusable work buffers (per purpose, see users)
     std::vector<std::pair<std::string, double>> timings;  // phase -> ms (last prove)
     bool dedup_enabled = true;              // value-aware column commit (SEZKP_NO_DEDUP=1 or sezkp_cuda_set_option disables)
     u64 launches = 0;                       // kernels launched since last reset

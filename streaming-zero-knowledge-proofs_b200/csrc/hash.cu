@@ -184,9 +184,20 @@ __device__ __forceinline__ void bitmap_set_warp(u32* bitmap, u32 key, bool valid
     }
 }
 
+constexpr int MEMO_SLOTS = 4096;  // power of two
+constexpr int MEMO_WORDS = 18;    // state, height, x[8], root[8]
+__device__ __forceinline__ u32 ld_acquire_u32(const u32* p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(u32* p, u32 v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, int cl,
                                                                           const b3::LabelTemplate* __restrict__ templates,
-                                                                          u32* __restrict__ upper, u64 n_ch) {
+                                                                          u32* __restrict__ upper, u64 n_ch, u32* memo) {
     extern __shared__ __align__(16) unsigned char dd_raw[];
     DedupSmem& sm = *reinterpret_cast<DedupSmem*>(dd_raw);
     const u64 chunk = blockIdx.x;
@@ -273,18 +284,47 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
         const int half = nodes >> 1;
         const int i0 = tid, i1 = tid + HASH_THREADS;
         if (D == 1) {
-            // every node of this level carries the same digest: the rest of the tree is a chain x -> H(x, x)
+            // every node of this level carries the same digest x: the rest of the tree is the chain x -> H(x, x).
+            // Block-constant columns repeat the same x in most chunks, so finished chains are shared through a small
+            // direct-mapped memo in global memory keyed by (x, height); a miss just computes the chain.
             if (tid == 0) {
                 u32 d[8], e[8];
 #pragma unroll
                 for (int w = 0; w < 8; w++) d[w] = Tcur[w * DD_PA];
-                for (int m2 = nodes; m2 > 1; m2 >>= 1) {
-                    b3::parent(d, d, e);
+                const u32 height = (u32)nodes;
+                u32* ent = memo + (size_t)((d[0] ^ (d[1] * 0x9E3779B1u) ^ height) & (MEMO_SLOTS - 1)) * MEMO_WORDS;
+                bool hit = false;
+                if (ld_acquire_u32(ent) == 2u && ent[1] == height) {
+                    hit = true;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) d[w] = e[w];
+                    for (int w = 0; w < 8; w++) hit = hit && (ent[2 + w] == d[w]);
+                    if (hit) {
+#pragma unroll
+                        for (int w = 0; w < 8; w++) out_root[w] = ent[10 + w];
+                    }
                 }
+                if (!hit) {
+                    u32 x[8];
 #pragma unroll
-                for (int w = 0; w < 8; w++) out_root[w] = d[w];
+                    for (int w = 0; w < 8; w++) x[w] = d[w];
+                    for (int m2 = nodes; m2 > 1; m2 >>= 1) {
+                        b3::parent(d, d, e);
+#pragma unroll
+                        for (int w = 0; w < 8; w++) d[w] = e[w];
+                    }
+#pragma unroll
+                    for (int w = 0; w < 8; w++) out_root[w] = d[w];
+                    if (atomicCAS(ent, 0u, 1u) == 0u) {  // claim an empty slot; busy or occupied slots are left alone
+                        ent[1] = height;
+#pragma unroll
+                        for (int w = 0; w < 8; w++) {
+                            ent[2 + w] = x[w];
+                            ent[10 + w] = d[w];
+                        }
+                        __threadfence();
+                        st_release_u32(ent, 2u);
+                    }
+                }
             }
             return;
         }
@@ -489,8 +529,10 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
             CUDA_CHECK(cudaFuncSetAttribute(chunk_commit_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem)));
             configured = true;
         }
+        u32* memo = (u32*)ctx->scratch[8].ensure((size_t)MEMO_SLOTS * MEMO_WORDS * 4);
+        CUDA_CHECK(cudaMemsetAsync(memo, 0, (size_t)MEMO_SLOTS * MEMO_WORDS * 4, ctx->stream));
         chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(values_dev, n, cm.cl, cm.templates, cm.upper,
-                                                                                           cm.n_ch);
+                                                                                           cm.n_ch, memo);
     } else {
         chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>((u64*)values_dev, n, cm.cl, cm.templates, cm.upper, cm.n_ch,
                                                                             nullptr, 0);
@@ -571,7 +613,7 @@ void leaf_hash_device(sezkp_ctx* ctx, const u64* vals_dev, size_t n, const char*
     b3::LabelTemplate* d_t = nullptr;
     if (label) {
         b3::LabelTemplate t = make_label_template(label);
-        d_t = (b3::LabelTemplate*)ctx->scratch[6].ensure(sizeof t);
+        d_t = (b3::LabelTemplate*)ctx->scratch[9].ensure(sizeof t);
         CUDA_CHECK(cudaMemcpyAsync(d_t, &t, sizeof t, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }

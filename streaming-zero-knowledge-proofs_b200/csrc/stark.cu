@@ -296,7 +296,7 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     const u64 N = 1ULL << log_N;
     fl.log_N = log_N;
     fl.values = (u64*)ctx->pool.alloc(2 * N * 8);
-    u8* d_roots = (u8*)ctx->scratch[6].ensure((size_t)(log_N + 1) * 32 + 64);
+    u8* d_roots = (u8*)ctx->scratch[10].ensure((size_t)(log_N + 1) * 32 + 64);
     CUDA_CHECK(cudaMemcpyAsync(fl.values, layer0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     fl.commits.resize(log_N + 1);
     std::vector<u64> beta_store;
