@@ -100,41 +100,34 @@ struct LabelTemplate {
     u32 off;        // byte offset of the value
     u32 block_len;  // 20 + L
 };
-// Message of a labeled leaf: the template with the 8 value bytes spliced in at byte offset t.off.  The word index
-// is block-uniform; the switch keeps every m[] index static (registers) while the compression itself stays one
-// shared code site after it (instruction-cache footprint matters: one compression is ~12 KB of SASS).
-__device__ __forceinline__ void labeled_message(const LabelTemplate& t, u64 v, u32 (&m)[16]) {
+// W = word index of the first value byte (static so that the 16 message words stay in registers).
+template <int W>
+__device__ __forceinline__ void leaf_labeled_w(const LabelTemplate& t, u64 v, u32 (&out)[8]) {
+    u32 m[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) m[i] = t.words[i];
     const u32 sh = (t.off & 3) * 8;
     const u32 lo = (u32)v, hi = (u32)(v >> 32);
-    const u32 a = lo << sh, b = __funnelshift_l(lo, hi, sh), c = __funnelshift_l(hi, 0u, sh);
-    switch (t.off >> 2) {
-        case 3: m[3] |= a; m[4] |= b; m[5] |= c; break;
-        case 4: m[4] |= a; m[5] |= b; m[6] |= c; break;
-        case 5: m[5] |= a; m[6] |= b; m[7] |= c; break;
-        case 6: m[6] |= a; m[7] |= b; m[8] |= c; break;
-        case 7: m[7] |= a; m[8] |= b; m[9] |= c; break;
-        case 8: m[8] |= a; m[9] |= b; m[10] |= c; break;
-        case 9: m[9] |= a; m[10] |= b; m[11] |= c; break;
-        case 10: m[10] |= a; m[11] |= b; m[12] |= c; break;
-        case 11: m[11] |= a; m[12] |= b; m[13] |= c; break;
-        case 12: m[12] |= a; m[13] |= b; m[14] |= c; break;
-        case 13: m[13] |= a; m[14] |= b; m[15] |= c; break;
-        default: m[14] |= a; m[15] |= b; break;  // off = 56: the value ends the block
-    }
+    m[W] |= lo << sh;
+    if (W + 1 < 16) m[W + 1] |= __funnelshift_l(lo, hi, sh);
+    if (W + 2 < 16) m[W + 2] |= __funnelshift_l(hi, 0u, sh);
+    hash_block(m, t.block_len, out);
 }
-__device__ __forceinline__ void leaf_message(const LabelTemplate* t_or_null, const LabelTemplate& t, u64 v, u32 (&m)[16], u32& block_len) {
-    if (t_or_null) {
-        labeled_message(t, v, m);
-        block_len = t.block_len;
-    } else {
-#pragma unroll
-        for (int i = 2; i < 16; i++) m[i] = 0;
-        m[0] = (u32)v;
-        m[1] = (u32)(v >> 32);
-        block_len = 8;
+// Runs BODY with a compile-time W matching the (block-uniform) template; BODY uses LEAF(v, out).
+#define B3_DISPATCH_LABELED(t, BODY)                                       \
+    switch ((t).off >> 2) {                                                \
+        case 3: { constexpr int B3W = 3; BODY } break;                     \
+        case 4: { constexpr int B3W = 4; BODY } break;                     \
+        case 5: { constexpr int B3W = 5; BODY } break;                     \
+        case 6: { constexpr int B3W = 6; BODY } break;                     \
+        case 7: { constexpr int B3W = 7; BODY } break;                     \
+        case 8: { constexpr int B3W = 8; BODY } break;                     \
+        case 9: { constexpr int B3W = 9; BODY } break;                     \
+        case 10: { constexpr int B3W = 10; BODY } break;                   \
+        case 11: { constexpr int B3W = 11; BODY } break;                   \
+        case 12: { constexpr int B3W = 12; BODY } break;                   \
+        case 13: { constexpr int B3W = 13; BODY } break;                   \
+        default: { constexpr int B3W = 14; BODY } break;                   \
     }
-}
 
 }  // namespace b3

@@ -66,12 +66,21 @@ __device__ __forceinline__ void reduce_levels_smem(u32* s, int pitch, int count,
 }
 
 // Leaf hashing of a chunk into the word-major digest array (block-uniform label template or unlabeled).
-#define HASH_LEAVES_INTO(s, pitch, leaves, VALUE_EXPR, templates_nonnull, t)      \
-    for (int i = threadIdx.x; i < (leaves); i += HASH_THREADS) {                  \
-        u32 m_[16], bl_, d_[8];                                                   \
-        b3::leaf_message((templates_nonnull) ? &(t) : nullptr, t, (VALUE_EXPR), m_, bl_); \
-        b3::hash_block(m_, bl_, d_);                                              \
-        _Pragma("unroll") for (int w = 0; w < 8; w++) s[w * (pitch) + i] = d_[w]; \
+#define HASH_LEAVES_INTO(s, pitch, leaves, VALUE_EXPR, templates_nonnull, t)          \
+    if (templates_nonnull) {                                                          \
+        B3_DISPATCH_LABELED(t, {                                                      \
+            for (int i = threadIdx.x; i < (leaves); i += HASH_THREADS) {              \
+                u32 d[8];                                                             \
+                b3::leaf_labeled_w<B3W>(t, (VALUE_EXPR), d);                          \
+                _Pragma("unroll") for (int w = 0; w < 8; w++) s[w * (pitch) + i] = d[w]; \
+            }                                                                         \
+        })                                                                            \
+    } else {                                                                          \
+        for (int i = threadIdx.x; i < (leaves); i += HASH_THREADS) {                  \
+            u32 d[8];                                                                 \
+            b3::leaf((VALUE_EXPR), d);                                                \
+            _Pragma("unroll") for (int w = 0; w < 8; w++) s[w * (pitch) + i] = d[w];  \
+        }                                                                             \
     }
 
 // values -> leaf hashes -> chunk root.  grid (n_ch, cols).  Writes chunk roots into level 0 of `upper`.
@@ -186,7 +195,7 @@ __device__ __forceinline__ void st_release_u32(u32* p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(HASH_THREADS, 4) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, int cl,
+__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, int cl,
                                                                           const b3::LabelTemplate* __restrict__ templates,
                                                                           u32* __restrict__ upper, u64 n_ch, u32* memo) {
     extern __shared__ __align__(16) unsigned char dd_raw[];
@@ -252,7 +261,7 @@ __global__ void __launch_bounds__(HASH_THREADS, 4) chunk_commit_dedup_kernel(con
         return;
     }
 
-    // ---- ids of the leaves and the list of distinct keys ----
+    // ---- level 0: one leaf hash per distinct value (table in the low half of A) ----
     const int range = (int)(mx - mn) + 1;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -262,122 +271,65 @@ __global__ void __launch_bounds__(HASH_THREADS, 4) chunk_commit_dedup_kernel(con
     for (int j = tid; j < range; j += HASH_THREADS)
         if (sm.bitmap[j >> 5] & (1u << (j & 31))) sm.list[bitmap_rank(sm, (u32)j)] = (unsigned short)j;
     __syncthreads();
+    HASH_LEAVES_INTO(sm.A, DD_PA, D, gl::sub(mn + (u64)sm.list[i], HALF), templates != nullptr, t)
+    __syncthreads();
 
-    // ---- one generic phase loop with a single compression site (instruction-cache footprint) ----
-    //  LEAF      item r: leaf of distinct value r                         -> table[r]
-    //  PAIR      item r: parent of the r-th distinct (left id, right id)  -> next table[r]
-    //  INDIRECT  item i: parent of node pair i looked up through the ids  -> next[i]   (ids are the identity afterwards)
-    //  PLAIN     item i: parent of entries 2i, 2i+1                       -> next[i]
-    //  CHAIN     one item: x -> H(x,x) repeated over the remaining levels (all nodes equal), memoised across chunks
-    enum { LEAF, PAIR, INDIRECT, PLAIN, CHAIN };
-    u32* Tcur = sm.A + DD_HALF;  // unused during LEAF
-    u32* Tnext = sm.A;           // the leaf table goes to the low half
+    // ---- levels: dedup while the pair space is small, then one indirect level into the other half, then plain ----
+    u32* Tcur = sm.A;
+    u32* Tnext = sm.A + DD_HALF;
     unsigned short* idcur = sm.idA;
     unsigned short* idnext = sm.idB;
-    int mode = LEAF, count = D, nodes = leaves, Dn = D;
-    bool identity = false;
-    u32* memo_ent = nullptr;
-    for (;;) {
-        for (int r = tid; r < count; r += HASH_THREADS) {
-            u32 m[16], blen, d[8];
-            int chain = 1;
-            if (mode == LEAF) {
-                b3::leaf_message(templates ? &t : nullptr, t, gl::sub(mn + (u64)sm.list[r], HALF), m, blen);
-            } else {
-                int a, b;
-                if (mode == PAIR) {
-                    const int kk = sm.list[r];
-                    a = kk / D;
-                    b = kk - a * D;
-                } else if (mode == INDIRECT) {
-                    a = idcur[2 * r];
-                    b = idcur[2 * r + 1];
-                } else if (mode == PLAIN) {
-                    a = 2 * r;
-                    b = 2 * r + 1;
-                } else {
-                    a = b = 0;
-                    chain = 31 - __clz(nodes);  // log2(nodes) levels left
-                }
-#pragma unroll
-                for (int w = 0; w < 8; w++) {
-                    m[w] = Tcur[w * DD_PA + a];
-                    m[8 + w] = Tcur[w * DD_PA + b];
-                }
-                blen = 64;
-            }
-            for (;;) {
-                b3::hash_block(m, blen, d);
-                if (--chain <= 0) break;
-#pragma unroll
-                for (int w = 0; w < 8; w++) m[w] = m[8 + w] = d[w];
-            }
-            if (mode == CHAIN) {
-#pragma unroll
-                for (int w = 0; w < 8; w++) out_root[w] = d[w];
-                if (atomicCAS(memo_ent, 0u, 1u) == 0u) {  // claim an empty slot; busy or occupied slots are left alone
-                    memo_ent[1] = (u32)nodes;
-#pragma unroll
-                    for (int w = 0; w < 8; w++) {
-                        memo_ent[2 + w] = Tcur[w * DD_PA];
-                        memo_ent[10 + w] = d[w];
-                    }
-                    __threadfence();
-                    st_release_u32(memo_ent, 2u);
-                }
-            } else {
-#pragma unroll
-                for (int w = 0; w < 8; w++) Tnext[w * DD_PA + r] = d[w];
-            }
-        }
-        if (mode == CHAIN) return;
-        __syncthreads();
-        // ---- the phase just finished produced the table / level in Tnext ----
-        if (mode == LEAF) {
-            Tcur = sm.A;
-            Tnext = sm.A + DD_HALF;
-        } else {
-            u32* tp = Tcur; Tcur = Tnext; Tnext = tp;
-            nodes >>= 1;
-            if (mode == PAIR) {
-                D = Dn;
-                unsigned short* ip = idcur; idcur = idnext; idnext = ip;
-            } else identity = true;
-        }
-        if (nodes == 1) break;
-        // ---- choose the next phase ----
+    int nodes = leaves;
+    while (nodes > 1) {
         const int half = nodes >> 1;
-        if (identity) {
-            mode = PLAIN;
-            count = half;
-        } else if (D == 1) {
-            // every node carries the same digest x: the rest of the tree is the chain x -> H(x,x).  Block-constant
-            // columns repeat the same x in most chunks: finished chains are shared through a small direct-mapped memo.
+        const int i0 = tid, i1 = tid + HASH_THREADS;
+        if (D == 1) {
+            // every node of this level carries the same digest x: the rest of the tree is the chain x -> H(x, x).
+            // Block-constant columns repeat the same x in most chunks, so finished chains are shared through a small
+            // direct-mapped memo in global memory keyed by (x, height); a miss just computes the chain.
             if (tid == 0) {
-                u32 x[8];
+                u32 d[8], e[8];
 #pragma unroll
-                for (int w = 0; w < 8; w++) x[w] = Tcur[w * DD_PA];
-                u32* ent = memo + (size_t)((x[0] ^ (x[1] * 0x9E3779B1u) ^ (u32)nodes) & (MEMO_SLOTS - 1)) * MEMO_WORDS;
+                for (int w = 0; w < 8; w++) d[w] = Tcur[w * DD_PA];
+                const u32 height = (u32)nodes;
+                u32* ent = memo + (size_t)((d[0] ^ (d[1] * 0x9E3779B1u) ^ height) & (MEMO_SLOTS - 1)) * MEMO_WORDS;
                 bool hit = false;
-                if (ld_acquire_u32(ent) == 2u && ent[1] == (u32)nodes) {
+                if (ld_acquire_u32(ent) == 2u && ent[1] == height) {
                     hit = true;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) hit = hit && (ent[2 + w] == x[w]);
+                    for (int w = 0; w < 8; w++) hit = hit && (ent[2 + w] == d[w]);
                     if (hit) {
 #pragma unroll
                         for (int w = 0; w < 8; w++) out_root[w] = ent[10 + w];
                     }
                 }
-                sm.total = hit ? 1u : 0u;
-                sm.red[0] = (u64)(uintptr_t)ent;
+                if (!hit) {
+                    u32 x[8];
+#pragma unroll
+                    for (int w = 0; w < 8; w++) x[w] = d[w];
+                    for (int m2 = nodes; m2 > 1; m2 >>= 1) {
+                        b3::parent(d, d, e);
+#pragma unroll
+                        for (int w = 0; w < 8; w++) d[w] = e[w];
+                    }
+#pragma unroll
+                    for (int w = 0; w < 8; w++) out_root[w] = d[w];
+                    if (atomicCAS(ent, 0u, 1u) == 0u) {  // claim an empty slot; busy or occupied slots are left alone
+                        ent[1] = height;
+#pragma unroll
+                        for (int w = 0; w < 8; w++) {
+                            ent[2 + w] = x[w];
+                            ent[10 + w] = d[w];
+                        }
+                        __threadfence();
+                        st_release_u32(ent, 2u);
+                    }
+                }
             }
-            __syncthreads();
-            if (sm.total) return;
-            memo_ent = (u32*)(uintptr_t)sm.red[0];
-            mode = CHAIN;
-            count = 1;
-        } else if (D * D <= DD_PAIR_CAP) {
-            const int space = D * D, i0 = tid, i1 = tid + HASH_THREADS;
+            return;
+        }
+        if (D * D <= DD_PAIR_CAP) {
+            const int space = D * D;
             for (int w = tid; w < ((space + 31) >> 5); w += HASH_THREADS) sm.bitmap[w] = 0;
             __syncthreads();
             const u32 k0 = (i0 < half) ? (u32)idcur[2 * i0] * D + idcur[2 * i0 + 1] : 0u;
@@ -387,20 +339,53 @@ __global__ void __launch_bounds__(HASH_THREADS, 4) chunk_commit_dedup_kernel(con
             __syncthreads();
             bitmap_prefix(sm, (space + 31) >> 5);
             __syncthreads();
-            Dn = (int)sm.total;
+            const int Dn = (int)sm.total;
             if (i0 < half) idnext[i0] = (unsigned short)bitmap_rank(sm, k0);
             if (i1 < half) idnext[i1] = (unsigned short)bitmap_rank(sm, k1);
             for (int j = tid; j < space; j += HASH_THREADS)
                 if (sm.bitmap[j >> 5] & (1u << (j & 31))) sm.list[bitmap_rank(sm, (u32)j)] = (unsigned short)j;
             __syncthreads();
-            mode = PAIR;
-            count = Dn;
+            for (int r = tid; r < Dn; r += HASH_THREADS) {
+                const int kk = sm.list[r], a = kk / D, b = kk - a * D;
+                u32 l[8], rr[8], d[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    l[w] = Tcur[w * DD_PA + a];
+                    rr[w] = Tcur[w * DD_PA + b];
+                }
+                b3::parent(l, rr, d);
+#pragma unroll
+                for (int w = 0; w < 8; w++) Tnext[w * DD_PA + r] = d[w];
+            }
+            __syncthreads();
+            D = Dn;
+            nodes = half;
+            u32* tp = Tcur; Tcur = Tnext; Tnext = tp;
+            unsigned short* ip = idcur; idcur = idnext; idnext = ip;
         } else {
-            mode = INDIRECT;
-            count = half;
+            // too many distinct digests: compute the next level through the ids into the other half, then plain
+            u32 d0[8], d1[8];
+            auto indirect_parent = [&](int i, u32 (&d)[8]) {
+                const int a = idcur[2 * i], b = idcur[2 * i + 1];
+                u32 l[8], rr[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    l[w] = Tcur[w * DD_PA + a];
+                    rr[w] = Tcur[w * DD_PA + b];
+                }
+                b3::parent(l, rr, d);
+            };
+            if (i0 < half) indirect_parent(i0, d0);
+            if (i1 < half) indirect_parent(i1, d1);
+            if (i0 < half) put_digest(Tnext, DD_PA, i0, d0, nullptr);
+            if (i1 < half) put_digest(Tnext, DD_PA, i1, d1, nullptr);
+            __syncthreads();
+            reduce_levels_smem(Tnext, DD_PA, half, nullptr, 0, 0, 0, nullptr, 0);
+            if (tid < 8) out_root[tid] = Tnext[tid * DD_PA];
+            return;
         }
     }
-    if (tid < 8) out_root[tid] = Tcur[tid * DD_PA];  // single node left
+    if (tid < 8) out_root[tid] = Tcur[tid * DD_PA];  // single node left: id 0
 }
 
 // digests at level l0 of `upper` -> reduce groups of 2^k -> levels l0+1..l0+k stored.  grid (count>>k, cols)
@@ -451,11 +436,11 @@ __global__ void leaf_hash_kernel(const u64* __restrict__ vals, size_t n, const b
                                  u32* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    u32 d[8], m[16], bl;
-    b3::LabelTemplate t;
-    if (tpl) t = *tpl;
-    b3::leaf_message(tpl, t, vals[i], m, bl);
-    b3::hash_block(m, bl, d);
+    u32 d[8];
+    if (tpl) {
+        b3::LabelTemplate t = *tpl;
+        B3_DISPATCH_LABELED(t, { b3::leaf_labeled_w<B3W>(t, vals[i], d); })
+    } else b3::leaf(vals[i], d);
     uint4* o = reinterpret_cast<uint4*>(out + i * 8);
     o[0] = make_uint4(d[0], d[1], d[2], d[3]);
     o[1] = make_uint4(d[4], d[5], d[6], d[7]);
