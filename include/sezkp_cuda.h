@@ -32,6 +32,7 @@ extern "C" {
 #define SEZKP_CUDA_ENODEV (-4)  /* no usable CUDA device                                          */
 #define SEZKP_CUDA_ERANGE (-5)  /* output buffer too small (required size reported)               */
 #define SEZKP_CUDA_ESTATE (-6)  /* call sequence error (streaming API)                            */
+#define SEZKP_CUDA_ECOMM (-7)   /* the caller-supplied collective callback failed                 */
 
 typedef struct sezkp_ctx sezkp_ctx;
 typedef struct sezkp_tree sezkp_tree; /* retained column commitments (chunk roots + upper levels + values) */
@@ -132,6 +133,16 @@ int32_t sezkp_compose_base(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const 
  * with *len set.  The Fiat-Shamir transcript (sezkp-crypto/src/lib.rs:74-124) runs on the host inside the library. */
 int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const uint8_t manifest_root[32],
                              uint8_t* proof_buf, size_t cap, size_t* len);
+/* Column-sharded prover for the GPUs of one box, one process (and one ctx) per GPU: rank r commits and
+ * opens only the columns c with c % world == r; everything that depends on all columns (composition, LDE, FRI) is
+ * replicated.  The only exchange steps are two all-gathers of small host buffers — the 32-byte column roots and the
+ * opening records — done through `allgather`, which the host binding implements over NCCL (or any collective):
+ * it must fill recv_all[world][bytes] with every rank's `send`, rank-major, and return 0.  Every rank returns the
+ * identical proof, byte-equal to sezkp_stark_v1_prove. */
+typedef int32_t (*sezkp_allgather_fn)(void* user, const void* send, size_t bytes, void* recv_all);
+int32_t sezkp_stark_v1_prove_sharded(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const uint8_t manifest_root[32], int rank,
+                                     int world, sezkp_allgather_fn allgather, void* user, uint8_t* proof_buf, size_t cap,
+                                     size_t* len);
 /* Same prover over a compact trace that is already resident in HBM (upload once, prove many times: lets a caller
  * overlap the next trace's H2D copy with the current proof, and separates copy time from kernel time). */
 int32_t sezkp_trace_upload(sezkp_ctx* ctx, const sezkp_trace_desc* trace, sezkp_trace_dev** out);

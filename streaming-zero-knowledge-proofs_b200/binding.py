@@ -27,7 +27,7 @@ EXPORTS = [
     "sezkp_column_open", "sezkp_tree_free", "sezkp_fri_commit", "sezkp_fri_commit_dev", "sezkp_fri_open", "sezkp_fri_free",
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
     "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_trace_upload", "sezkp_trace_free",
-    "sezkp_stark_v1_prove_resident",
+    "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded",
 ]
 
 ERR_NAMES = {0: "OK", -1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENODEV", -5: "ERANGE", -6: "ESTATE"}
@@ -241,6 +241,17 @@ class Context:
         if buf is None:
             buf = np.empty(proof_size_bound(ct.n_rows, ct.tau), np.uint8)
         self._ck(self.lib.sezkp_stark_v1_prove(self.h, C.byref(d), manifest_root, _p(buf), C.c_size_t(buf.size), C.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def prove_v1_sharded(self, ct: CompactTrace, manifest_root: bytes, rank: int, world: int, allgather_cb,
+                         buf: Optional[np.ndarray] = None) -> bytes:
+        """Column-sharded prove: `allgather_cb` is a parallel.ALLGATHER_FN (see parallel.dist_allgather_callback)."""
+        d = ct.as_desc()
+        n = C.c_size_t(0)
+        if buf is None:
+            buf = np.empty(proof_size_bound(ct.n_rows, ct.tau), np.uint8)
+        self._ck(self.lib.sezkp_stark_v1_prove_sharded(self.h, C.byref(d), manifest_root, C.c_int(rank), C.c_int(world), allgather_cb,
+                                                        None, _p(buf), C.c_size_t(buf.size), C.byref(n)))
         return buf[: n.value].tobytes()
 
     def upload_trace(self, ct: CompactTrace) -> "ResidentTrace":

@@ -491,6 +491,18 @@ int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, cons
     API_END(ctx)
 }
 
+int32_t sezkp_stark_v1_prove_sharded(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const uint8_t manifest_root[32], int rank, int world,
+                                     sezkp_allgather_fn allgather, void* user, uint8_t* proof_buf, size_t cap, size_t* len) {
+    API_BEGIN(ctx)
+    REQUIRE(manifest_root && len && world >= 1 && rank >= 0 && rank < world, "bad argument");
+    REQUIRE(world == 1 || allgather != nullptr, "allgather callback is NULL");
+    ShardInfo sh{rank, world, allgather, user};
+    std::vector<u8> proof;
+    prove_v1_device(ctx, trace, manifest_root, proof, world > 1 ? &sh : nullptr);
+    deliver(proof, proof_buf, cap, len);
+    API_END(ctx)
+}
+
 int32_t sezkp_trace_upload(sezkp_ctx* ctx, const sezkp_trace_desc* trace, sezkp_trace_dev** out) {
     API_BEGIN(ctx)
     REQUIRE(out != nullptr, "bad argument");

@@ -87,7 +87,7 @@ __device__ __forceinline__ void reduce_levels_smem(u32* s, int pitch, int count,
 // FOLD: the values are produced on the fly as the FRI fold of the previous layer,
 //   y'[i] = y[i] + beta*y[i+half]  (reference v1/prover.rs:204-238), written to `values` and hashed in one pass.
 template <bool FOLD>
-__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(u64* __restrict__ values, u64 n, int cl,
+__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(u64* __restrict__ values, u64 n, u64 col_stride, int cl,
                                                                     const b3::LabelTemplate* __restrict__ templates,
                                                                     u32* __restrict__ upper, u64 n_ch,
                                                                     const u64* __restrict__ fold_src, u64 beta) {
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(u64* __restr
     const u64 chunk = blockIdx.x;
     const int col = blockIdx.y;
     const int leaves = 1 << cl;
-    u64* v = values + (u64)col * n + (chunk << cl);
+    u64* v = values + (u64)col * col_stride + (chunk << cl);
     b3::LabelTemplate t;
     if (templates) t = templates[col];
     if (FOLD) {
@@ -195,7 +195,7 @@ __device__ __forceinline__ void st_release_u32(u32* p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, int cl,
+__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, u64 col_stride, int cl,
                                                                           const b3::LabelTemplate* __restrict__ templates,
                                                                           u32* __restrict__ upper, u64 n_ch, u32* memo) {
     extern __shared__ __align__(16) unsigned char dd_raw[];
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
     const u64 chunk = blockIdx.x;
     const int col = blockIdx.y;
     const int leaves = 1 << cl;
-    const u64* v = values + (u64)col * n + (chunk << cl);
+    const u64* v = values + (u64)col * col_stride + (chunk << cl);
     const int tid = threadIdx.x;
     b3::LabelTemplate t;
     if (templates) t = templates[col];
@@ -502,6 +502,7 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
     const int ln = ilog2(n);
     cm.values = values_dev;
     cm.n = n;
+    cm.col_stride = opt.col_stride ? opt.col_stride : n;
     cm.cols = cols;
     cm.cl = ln < chunk_log2 ? ln : chunk_log2;
     cm.n_ch = n >> cm.cl;
@@ -521,7 +522,7 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
     dim3 grid((unsigned)cm.n_ch, (unsigned)cols);
     if (opt.fold_src) {
         REQUIRE(cols == 1 && !labels, "internal: fused fold needs a single unlabeled column");
-        chunk_commit_kernel<true><<<grid, HASH_THREADS, 0, ctx->stream>>>((u64*)values_dev, n, cm.cl, nullptr, cm.upper, cm.n_ch,
+        chunk_commit_kernel<true><<<grid, HASH_THREADS, 0, ctx->stream>>>((u64*)values_dev, n, cm.col_stride, cm.cl, nullptr, cm.upper, cm.n_ch,
                                                                            opt.fold_src, opt.fold_beta);
     } else if (opt.dedup && ctx->dedup_enabled) {
         static bool configured = false;
@@ -531,10 +532,10 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
         }
         u32* memo = (u32*)ctx->scratch[8].ensure((size_t)MEMO_SLOTS * MEMO_WORDS * 4);
         CUDA_CHECK(cudaMemsetAsync(memo, 0, (size_t)MEMO_SLOTS * MEMO_WORDS * 4, ctx->stream));
-        chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(values_dev, n, cm.cl, cm.templates, cm.upper,
+        chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(values_dev, n, cm.col_stride, cm.cl, cm.templates, cm.upper,
                                                                                            cm.n_ch, memo);
     } else {
-        chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>((u64*)values_dev, n, cm.cl, cm.templates, cm.upper, cm.n_ch,
+        chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>((u64*)values_dev, n, cm.col_stride, cm.cl, cm.templates, cm.upper, cm.n_ch,
                                                                             nullptr, 0);
     }
     CUDA_CHECK(cudaGetLastError());
@@ -562,7 +563,7 @@ OpenReq make_open_req(const Commit& cm, u32 col, u64 row, u32 out_off) {
     REQUIRE(col < (u32)cm.cols, "opening: column %u out of range", col);
     REQUIRE(row < cm.n, "opening: row %llu out of range", (unsigned long long)row);
     OpenReq r;
-    r.values = cm.values + (u64)col * cm.n;
+    r.values = cm.values + (u64)col * cm.col_stride;
     r.upper = cm.upper + (u64)col * (2 * cm.n_ch - 1) * 8;
     r.tpl = cm.templates ? cm.templates + col : nullptr;
     r.n_ch = cm.n_ch;

@@ -13,6 +13,7 @@ struct Commit {
     const u64* values = nullptr;   // device [cols][n]
     bool owns_values = false;
     u64 n = 0;
+    u64 col_stride = 0;            // elements between consecutive committed columns (n when dense)
     int cols = 0;
     int cl = 0;                    // log2 leaves per chunk = min(chunk_log2, log2 n)
     u64 n_ch = 0;                  // chunks per column = n >> cl
@@ -29,6 +30,7 @@ struct CommitOpts {
     u64 fold_beta = 0;
     u8* roots_host = nullptr;       // [cols][32]; copying to the host synchronises the stream
     u8* roots_dev = nullptr;        // [cols][32] device copy (no synchronisation)
+    u64 col_stride = 0;             // 0 = dense (n); column sharding commits every world-th column of a dense array
 };
 // Build a commitment over device values (all launches on ctx->stream).
 void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,

@@ -408,7 +408,8 @@ struct TranscriptAbsorb : HostAbsorb {
 
 }  // namespace
 
-void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out) {
+void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out,
+                     const ShardInfo* shard) {
     validate_trace(desc);
     ctx->timings.clear();
     const double t0 = now_ms();
@@ -423,12 +424,18 @@ void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 mani
     }
     ctx->scratch[2] = dt.buf;
     const double t1 = now_ms();
-    prove_v1_resident(ctx, dt.t, manifest_root, proof_out);
+    prove_v1_resident(ctx, dt.t, manifest_root, proof_out, shard);
     ctx->timings.insert(ctx->timings.begin(), {"h2d_trace", t1 - t0});
 }
 
 // The whole prover from a device-resident compact trace.
-void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out) {
+void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out,
+                       const ShardInfo* shard) {
+    const int world = shard ? shard->world : 1, rank = shard ? shard->rank : 0;
+    auto exchange = [&](const void* send, size_t bytes, void* recv) {  // all-gather through the host callback
+        const int32_t rc = shard->allgather(shard->user, send, bytes, recv);
+        if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "allgather callback failed with status %d", rc);
+    };
     ctx->timings.clear();
     double t0 = now_ms();
     auto lap = [&](const char* name) {
@@ -463,10 +470,25 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
     Commit cm;
     FriLayers fl;
     try {
-        CommitOpts copt;
-        copt.dedup = true;
-        copt.roots_host = col_roots.data();
-        commit_build(ctx, cm, cols, n, n_cols, COL_CHUNK_LOG2, label_ptrs.data(), copt);
+        // column c is committed (and later opened) by rank c % world; local column j of rank r is global r + j*world
+        const int n_local = (n_cols - rank + world - 1) / world, max_local = (n_cols + world - 1) / world;
+        {
+            std::vector<const char*> local_labels;
+            for (int j = 0; j < n_local; j++) local_labels.push_back(label_ptrs[rank + j * world]);
+            std::vector<u8> local_roots((size_t)max_local * 32, 0);
+            CommitOpts copt;
+            copt.dedup = true;
+            copt.roots_host = local_roots.data();
+            copt.col_stride = (u64)world * n;
+            commit_build(ctx, cm, cols + (u64)rank * n, n, n_local, COL_CHUNK_LOG2, local_labels.data(), copt);
+            if (world == 1) col_roots = local_roots;
+            else {  // C1 of SURVEY §2b: all-gather of 32-byte column roots
+                std::vector<u8> all((size_t)world * max_local * 32);
+                exchange(local_roots.data(), local_roots.size(), all.data());
+                for (int c = 0; c < n_cols; c++)
+                    std::memcpy(&col_roots[32 * c], &all[((size_t)(c % world) * max_local + c / world) * 32], 32);
+            }
+        }
         lap("column_commit");
         tr.absorb_u64("n_cols", (u64)n_cols);
         for (int c = 0; c < n_cols; c++) tr.absorb("col_root", &col_roots[32 * c], 32);
@@ -540,17 +562,46 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         const int din = cm.cl, dout = ilog2(cm.n_ch), cdepth = din + dout;
         std::vector<OpenReq> reqs;
         reqs.reserve(k_open + (size_t)NUM_QUERIES * log_N * 2);
-        for (size_t o = 0; o < k_open; o++) reqs.push_back(make_open_req(cm, o_col[o], o_row[o], (u32)(o * cdepth)));
+        // column openings: only the locally committed columns; slots of the other ranks are filled by the exchange
+        std::vector<u32> req_slot;  // request index -> opening slot
+        for (size_t o = 0; o < k_open; o++)
+            if ((int)(o_col[o] % world) == rank) {
+                reqs.push_back(make_open_req(cm, o_col[o] / world, o_row[o], (u32)(o * cdepth)));
+                req_slot.push_back((u32)o);
+            }
+        const size_t n_col_reqs = reqs.size();
         const size_t fri_base = k_open * (size_t)cdepth, fri_digests = (size_t)NUM_QUERIES * log_N * 2 * log_N;
         std::vector<u64> f_pos((size_t)NUM_QUERIES * (log_N + 1));
         fri_open_requests(fl, fri_idx.data(), NUM_QUERIES, f_pos.data(), reqs, (u32)fri_base);
-        std::vector<u64> all_val(reqs.size());
-        std::vector<u8> all_cr(reqs.size() * 32), all_paths((fri_base + fri_digests) * 32 + 32);
-        open_batch(ctx, reqs, fri_base + fri_digests, all_val.data(), all_cr.data(), all_paths.data());
-        const u64* o_val = all_val.data();
-        const u8* o_cr = all_cr.data();
+        std::vector<u64> req_val(reqs.size());
+        std::vector<u8> req_cr(reqs.size() * 32), all_paths((fri_base + fri_digests) * 32 + 32, 0);
+        open_batch(ctx, reqs, fri_base + fri_digests, req_val.data(), req_cr.data(), all_paths.data());
+        std::vector<u64> col_val(k_open, 0);
+        std::vector<u8> col_cr(k_open * 32, 0);
+        for (size_t i = 0; i < n_col_reqs; i++) {
+            col_val[req_slot[i]] = req_val[i];
+            std::memcpy(&col_cr[(size_t)req_slot[i] * 32], &req_cr[i * 32], 32);
+        }
+        if (world > 1) {  // gather the opening records (value, chunk root, path) of every rank and keep each owner's
+            const size_t rec = 8 + 32 + (size_t)cdepth * 32, bytes = k_open * rec;
+            std::vector<u8> mine(bytes, 0), all((size_t)world * bytes);
+            for (size_t o = 0; o < k_open; o++) {
+                std::memcpy(&mine[o * rec], &col_val[o], 8);
+                std::memcpy(&mine[o * rec + 8], &col_cr[o * 32], 32);
+                std::memcpy(&mine[o * rec + 40], &all_paths[o * (size_t)cdepth * 32], (size_t)cdepth * 32);
+            }
+            exchange(mine.data(), bytes, all.data());
+            for (size_t o = 0; o < k_open; o++) {
+                const u8* src = &all[(size_t)(o_col[o] % world) * bytes + o * rec];
+                std::memcpy(&col_val[o], src, 8);
+                std::memcpy(&col_cr[o * 32], src + 8, 32);
+                std::memcpy(&all_paths[o * (size_t)cdepth * 32], src + 40, (size_t)cdepth * 32);
+            }
+        }
+        const u64* o_val = col_val.data();
+        const u8* o_cr = col_cr.data();
         const u8* o_paths = all_paths.data();
-        const u64* f_val = all_val.data() + k_open;
+        const u64* f_val = req_val.data() + n_col_reqs;
         const u8* f_paths = all_paths.data() + fri_base * 32;
         lap("openings");
 

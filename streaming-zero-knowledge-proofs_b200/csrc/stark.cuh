@@ -47,5 +47,12 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0_dev, int
                        u64* final_value, HostAbsorb* absorb_or_null);
 void fri_open_requests(const FriLayers& fl, const u64* idx0, size_t k, u64* positions, std::vector<OpenReq>& reqs, u32 base_off);
 void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_t k, u64* positions, u64* values, u8* paths);
-void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out);
-void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out);
+struct ShardInfo {  // column sharding across the GPUs of one box (one process per GPU)
+    int rank, world;
+    sezkp_allgather_fn allgather;
+    void* user;
+};
+void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out,
+                       const ShardInfo* shard = nullptr);
+void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out,
+                     const ShardInfo* shard = nullptr);

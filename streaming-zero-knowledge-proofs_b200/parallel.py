@@ -1,0 +1,119 @@
+"""Multi-GPU plumbing for the column-sharded prover (one process per GPU).
+
+The C ABI (`sezkp_stark_v1_prove_sharded`) asks the host for exactly one collective: an all-gather of a small host
+buffer (32-byte column roots, then the opening records).  This module provides that callback
+
+  * over ``torch.distributed`` — NCCL over NVLink on the GPU box (the bytes are staged through a device tensor), or
+    gloo on CPU-only machines (used by the CPU tests), and
+  * over threads of one process (``ThreadGroup``), which lets a single-GPU box exercise world sizes > 1,
+
+plus the pure index helpers that define the sharding contract (which rank owns which column, where a rank's roots sit
+in the gathered buffer).  No data-path collective exists: field columns never cross GPUs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Callable, List, Sequence
+
+import numpy as np
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+# ---------------------------------------------------------------------------------------------- sharding contract
+def owner_of_column(c: int, world: int) -> int:
+    return c % world
+
+
+def local_columns(n_cols: int, rank: int, world: int) -> List[int]:
+    """global column indices committed by `rank`, in local order"""
+    return list(range(rank, n_cols, world))
+
+
+def max_local(n_cols: int, world: int) -> int:
+    return (n_cols + world - 1) // world
+
+
+def merge_roots(gathered: np.ndarray, n_cols: int, world: int) -> np.ndarray:
+    """gathered: [world][max_local][32] (rank-major, zero padded) -> [n_cols][32] in canonical column order"""
+    g = np.asarray(gathered, np.uint8).reshape(world, max_local(n_cols, world), 32)
+    return np.stack([g[c % world, c // world] for c in range(n_cols)])
+
+
+def merge_records(gathered: np.ndarray, owner: Sequence[int], world: int) -> np.ndarray:
+    """gathered: [world][k][rec] -> [k][rec] taking record o from rank owner[o]"""
+    k = len(owner)
+    g = np.asarray(gathered, np.uint8).reshape(world, k, -1)
+    return np.stack([g[owner[o], o] for o in range(k)])
+
+
+# ---------------------------------------------------------------------------------------------- collectives
+def dist_allgather_callback(device=None):
+    """All-gather callback over torch.distributed's default group (nccl: staged through `device`; gloo: CPU)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+
+    def _cb(user, send, nbytes, recv):
+        try:
+            src = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(nbytes,))
+            t = torch.from_numpy(src.copy())
+            if device is not None:
+                t = t.to(device)
+            outs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(outs, t)
+            dst = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), shape=(world * nbytes,))
+            dst[:] = torch.cat(outs).cpu().numpy()
+            return 0
+        except Exception as e:  # never raise through the C frame
+            print("sezkp allgather callback failed:", repr(e))
+            return -1
+
+    return ALLGATHER_FN(_cb)
+
+
+class ThreadGroup:
+    """`world` ranks as threads of one process; all-gather through a barrier (test / single-GPU emulation)."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots: List[bytes] = [b""] * world
+
+    def callback(self, rank: int):
+        def _cb(user, send, nbytes, recv):
+            try:
+                self.slots[rank] = C.string_at(send, nbytes)
+                self.barrier.wait(timeout=120)
+                C.memmove(recv, b"".join(self.slots), self.world * nbytes)
+                self.barrier.wait(timeout=120)
+                return 0
+            except Exception as e:
+                print("sezkp thread allgather failed:", repr(e))
+                return -1
+
+        return ALLGATHER_FN(_cb)
+
+    def run(self, fn: Callable[[int], object]) -> list:
+        """run fn(rank) on `world` threads, return the results in rank order (exceptions re-raised)"""
+        out: list = [None] * self.world
+        err: list = [None] * self.world
+
+        def _t(r):
+            try:
+                out[r] = fn(r)
+            except BaseException as e:
+                err[r] = e
+                self.barrier.abort()
+
+        ts = [threading.Thread(target=_t, args=(r,)) for r in range(self.world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        for e in err:
+            if e is not None:
+                raise e
+        return out

@@ -302,6 +302,20 @@ def test_prove_streaming_api_matches_one_shot(ctx):
     assert ctx.prove_v1_stream(blocks, root) == one
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_column_sharded_prove_identical_on_every_rank(oracle, world):
+    """sezkp_stark_v1_prove_sharded: `world` ranks (threads with their own ctx on this GPU) exchange column roots and
+    opening records through the all-gather callback; every rank must return the single-GPU proof bytes."""
+    m = pkg()
+    ct = m.simulate(2048, 256, 2) if world < 8 else m.simulate(1024, 128, 1)
+    root = m.manifest_root(ct)
+    ref = oracle.prove_v1(ct, root)
+    tg = m.parallel.ThreadGroup(world)
+    ctxs = [m.Context() for _ in range(world)]
+    proofs = tg.run(lambda r: ctxs[r].prove_v1_sharded(ct, root, r, world, tg.callback(r)))
+    assert all(p == ref for p in proofs)
+
+
 def test_invalid_inputs_return_einval(ctx):
     m = pkg()
     ct = m.simulate(1000, 512, 2)  # not a power of two (reference asserts, v1/lde.rs:51)
