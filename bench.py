@@ -184,6 +184,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("SEZKP_NCCL_DEBUG", "NONE")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     m = importlib.import_module(PKG)
     ctx = m.Context(local)

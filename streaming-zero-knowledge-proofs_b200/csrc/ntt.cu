@@ -42,6 +42,8 @@ struct PassDesc {
     const u64* tw_hi;
     int tw_lb, use_tw;
     u64 tw_stride;
+    const u64* tw_full;  // optional full twiddle matrix of this pass (null: two-level tables)
+    u64 tw_pitch;
     u64 scale;
     int use_scale;
     // coset pre-scale: x *= GA[j][row] * GB[j][C]
@@ -86,7 +88,7 @@ __device__ __forceinline__ void dif_step(u64* tile, const u64* Ws, int b, int s0
 }
 
 template <int K1, int K2>
-__global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const PassDesc d) {
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const PassDesc d) {
     extern __shared__ u64 smem[];
     constexpr int b = K1 + K2;
     constexpr int rows = 1 << b;
@@ -106,29 +108,36 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const PassDesc d)
 
     for (int i = threadIdx.x; i < (rows >> 1); i += NTT_THREADS) Ws[i] = d.W[i];
 
-    const int total = rows << logR;
-    for (int i = threadIdx.x; i < total; i += NTT_THREADS) {
-        int c, row;
-        if (d.load_rows_fast) {
-            row = i & (rows - 1);
-            c = i >> b;
-        } else {
-            c = i & (R - 1);
-            row = i >> logR;
-        }
+    // ---- load (optionally pre-scaled by the coset powers); per-thread invariants hoisted out of the loops ----
+    const int tid = threadIdx.x;
+    auto load_column = [&](int c, int row0, int rstep) {
         const u64 C = C0 + c;
-        u64 x = 0;
-        if (C < d.total_cols) {
-            const u64 coff = (C & ((1ULL << d.in_clog) - 1)) * d.in_cs_lo + (C >> d.in_clog) * d.in_cs_hi;
-            x = in_base[(u64)row * d.in_row_stride + coff];
-            if (d.use_pre) {
-                const u32 j = (u32)((d.coset_from_col ? C : v) & ((1u << d.coset_log) - 1));
-                u64 g = d.GA[(size_t)j * d.ga_pitch + row];
-                if (d.use_gb) g = gl::lazy::mul(g, d.GB[(size_t)j * d.gb_pitch + C]);
-                x = gl::lazy::mul(x, g);
-            }
+        u64* dst = tile + c * pitch;
+        if (C >= d.total_cols) {
+            for (int row = row0; row < rows; row += rstep) dst[row] = 0;
+            return;
         }
-        tile[c * pitch + row] = x;
+        const u64* src = in_base + (C & ((1ULL << d.in_clog) - 1)) * d.in_cs_lo + (C >> d.in_clog) * d.in_cs_hi;
+        const u64 rs = d.in_row_stride;
+        if (d.use_pre) {
+            const u32 j = (u32)((d.coset_from_col ? C : v) & ((1u << d.coset_log) - 1));
+            const u64* ga = d.GA + (size_t)j * d.ga_pitch;
+            const u64 gbc = d.use_gb ? d.GB[(size_t)j * d.gb_pitch + C] : 1;
+#pragma unroll 4
+            for (int row = row0; row < rows; row += rstep) {
+                u64 g = ga[row];
+                if (d.use_gb) g = gl::lazy::mul(g, gbc);
+                dst[row] = gl::lazy::mul(src[(u64)row * rs], g);
+            }
+        } else {
+#pragma unroll 8
+            for (int row = row0; row < rows; row += rstep) dst[row] = src[(u64)row * rs];
+        }
+    };
+    if (d.load_rows_fast) {
+        for (int c = 0; c < R; c++) load_column(c, tid, NTT_THREADS);
+    } else {
+        load_column(tid & (R - 1), tid >> logR, NTT_THREADS >> logR);
     }
     __syncthreads();
     dif_step<K1, K2 == 0>(tile, Ws, b, 0, logR, pitch);
@@ -137,29 +146,47 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(const PassDesc d)
         dif_step<(K2 > 0 ? K2 : 1), true>(tile, Ws, b, K1, logR, pitch);
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < total; i += NTT_THREADS) {
-        int c, k;
-        if (d.store_rows_fast) {
-            k = i & (rows - 1);
-            c = i >> b;
-        } else {
-            c = i & (R - 1);
-            k = i >> logR;
-        }
+    // ---- store: bit-reversed row -> output index k, inter-pass twiddle, optional scale, canonicalise ----
+    auto store_column = [&](int c, int k0, int kstep) {
         const u64 C = C0 + c;
-        if (C >= d.total_cols) continue;
-        const int row = (int)(__brev((unsigned)k) >> (32 - b));
-        u64 x = tile[c * pitch + row];
-        if (d.use_tw) {
-            const u64 E = (u64)k * C * d.tw_stride;
-            const u64 w = gl::lazy::mul(d.tw_lo[E & ((1ULL << d.tw_lb) - 1)], d.tw_hi[E >> d.tw_lb]);
-            x = gl::lazy::mul(x, w);
+        if (C >= d.total_cols) return;
+        const u64* src = tile + c * pitch;
+        u64* dst = out_base + (C & ((1ULL << d.out_clog) - 1)) * d.out_cs_lo + (C >> d.out_clog) * d.out_cs_hi;
+        const u64 rs = d.out_row_stride;
+        const u64* twf = d.tw_full ? d.tw_full + C : nullptr;
+        const u64 Cs = C * d.tw_stride;
+#pragma unroll 4
+        for (int k = k0; k < rows; k += kstep) {
+            u64 x = src[__brev((unsigned)k) >> (32 - b)];
+            if (d.use_tw) {
+                u64 w;
+                if (twf) w = twf[(u64)k * d.tw_pitch];
+                else {
+                    const u64 E = (u64)k * Cs;
+                    w = gl::lazy::mul(d.tw_lo[E & ((1ULL << d.tw_lb) - 1)], d.tw_hi[E >> d.tw_lb]);
+                }
+                x = gl::lazy::mul(x, w);
+            }
+            if (d.use_scale) x = gl::lazy::mul(x, d.scale);
+            dst[(u64)k * rs] = gl::lazy::canon(x);  // values in HBM are canonical
         }
-        if (d.use_scale) x = gl::lazy::mul(x, d.scale);
-        x = gl::lazy::canon(x);  // values in HBM are canonical
-        const u64 coff = (C & ((1ULL << d.out_clog) - 1)) * d.out_cs_lo + (C >> d.out_clog) * d.out_cs_hi;
-        out_base[(u64)k * d.out_row_stride + coff] = x;
+    };
+    if (d.store_rows_fast) {
+        for (int c = 0; c < R; c++) store_column(c, tid, NTT_THREADS);
+    } else {
+        store_column(tid & (R - 1), tid >> logR, NTT_THREADS >> logR);
     }
+}
+
+// Full inter-pass twiddle matrix T[k][J] = w^(k*J*stride) (k < rows, J < pitch): same shape as the data block, so the
+// store loop reads it with the data's own coalescing; it stays in L2 across the columns of a batch.
+__global__ void tw_fill_kernel(u64* __restrict__ out, u64 count, u64 pitch, u64 stride, const u64* __restrict__ lo,
+                               const u64* __restrict__ hi, int lb) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const u64 k = i / pitch, J = i - k * pitch;
+    const u64 E = k * J * stride;
+    out[i] = gl::mul(lo[E & ((1ULL << lb) - 1)], hi[E >> lb]);
 }
 
 typedef void (*pass_fn)(const PassDesc);
@@ -194,6 +221,7 @@ struct NttTables {
     u64* W[MAX_PASS_BITS + 1] = {};  // device, per pass width
     u64* tw_lo = nullptr;
     u64* tw_hi = nullptr;
+    u64* tw_full[3] = {nullptr, nullptr, nullptr};  // per non-last pass, built on first use when the transform is small enough
     int tw_lb = 0;
     u64 scale = 1;  // N^-1 for inverse
     // coset tables, keyed by (logB, shift)
@@ -309,6 +337,8 @@ void ntt_free_tables(sezkp_ctx* ctx) {
             if (w) cudaFree(w);
         cudaFree(t->tw_lo);
         cudaFree(t->tw_hi);
+        for (auto& f : t->tw_full)
+            if (f) cudaFree(f);
         for (auto& c : t->cosets) {
             cudaFree(c.second.GA);
             cudaFree(c.second.GB);
@@ -342,6 +372,24 @@ static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
     fn<<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(d);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
+}
+
+constexpr int FULL_TW_MAX_LOG = 23;  // full twiddle matrices up to 2^23 entries (64 MiB) per pass
+static void attach_full_twiddles(sezkp_ctx* ctx, NttTables* t, PassDesc& d, int p, u64 rows, u64 Sp, u64 stride) {
+    const u64 count = rows * Sp;
+    if (count > (1ULL << FULL_TW_MAX_LOG)) return;
+    if (!t->tw_full[p]) {
+        u64* buf = nullptr;
+        if (cudaMalloc(&buf, count * 8) != cudaSuccess) {
+            cudaGetLastError();
+            return;  // fall back to the two-level tables
+        }
+        tw_fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(buf, count, Sp, stride, t->tw_lo, t->tw_hi, t->tw_lb);
+        ctx->launches++;
+        t->tw_full[p] = buf;
+    }
+    d.tw_full = t->tw_full[p];
+    d.tw_pitch = Sp;
 }
 
 static void base_desc(PassDesc& d, const NttTables* t, int b) {
@@ -409,6 +457,7 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
             d.out_v_stride = N;
             d.use_tw = 1;
             d.tw_stride = N / Mp;
+            attach_full_twiddles(ctx, t, d, p, Np, Sp, N / Mp);
         } else {  // case B: columns are values of k_1, rows are contiguous
             const u64 N1 = 1ULL << plan[0], S1 = N / N1;
             d.in = tmp;
@@ -501,6 +550,7 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
             d.out_v_stride = n;
             d.use_tw = 1;
             d.tw_stride = n / Mp;
+            attach_full_twiddles(ctx, t, d, p, Np, Sp, n / Mp);
             if (p == 0) {
                 d.use_pre = 1;
                 d.use_gb = 1;

@@ -3,7 +3,7 @@
 import json
 import sys
 
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
 print(f"value {d['value']:.4g} {d['unit']}  ms/step {d['ms_per_step']:.2f}  e2e {d['e2e']['value']:.4g} ({d['e2e']['ms_per_step']:.2f} ms)  launches {d['gpu_launches']}")
 print("phases", {k: round(v, 2) for k, v in d["phases_ms"].items()})
 r = d["roofline"]
@@ -11,3 +11,6 @@ print(f"roofline {r['kernel']}: {r['ms_per_launch']:.2f} ms, {r['achieved']:.1f}
 if d.get("micro"):
     print("micro", {k: (round(v["ms"], 3), round(v["GBps"], 1), round(v["frac_of_hbm_peak"], 4)) for k, v in d["micro"].items()})
 print("cpu", d["cpu_baseline"]["value"], d["cpu_baseline"].get("gpu_proof_identical"), "clocks", d["clocks"])
+if d.get("sharded_single_proof"):
+    sh = d["sharded_single_proof"]
+    print("sharded", round(sh["ms_per_proof"], 2), "ms/proof", f"{sh['rows_per_s']:.4g} rows/s", "identical", sh["identical_on_all_ranks"], {k: round(v, 2) for k, v in sh["phases_ms_rank0"].items()})
