@@ -164,6 +164,47 @@ def micro_bench(torch, ctx, hbm_peak):
     return res
 
 
+def lde_commit_bench(torch, dist, ctx, rank, world, hbm_peak, steps):
+    """BASELINE configs[3] shape family (LDE + labeled BLAKE3 column commit), columns sharded c % world, roots all-gathered
+    with NCCL.  Default 64 columns x 2^22 rows, blow-up 8 (SEZKP_W_COLS / SEZKP_W_LOG_N select e.g. the full 256 x 2^24)."""
+    cols, k, lb = env_int("SEZKP_W_COLS", 64), env_int("SEZKP_W_LOG_N", 22), 3
+    n = 1 << k
+    mine = list(range(rank, cols, world))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0x5EED + rank)
+    ev = torch.randint(0, (1 << 62), (max(len(mine), 1), n), dtype=torch.int64, device="cuda", generator=g)  # < 2^62 < p: canonical
+    labels = [f"c_{c}" for c in mine]
+
+    def step():
+        roots = ctx.lde_commit(ev, labels, lb, 3, dev=True, log_n=k) if mine else np.zeros((0, 32), np.uint8)
+        if world > 1:  # C1: all-gather of 32-byte column roots (padded to the per-rank maximum)
+            pad = torch.zeros(((cols + world - 1) // world) * 32, dtype=torch.uint8, device="cuda")
+            pad[: roots.size] = torch.from_numpy(roots.reshape(-1)).cuda()
+            out = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(out, pad)
+        return roots
+
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    alg = cols * (8 * n * (1 + (1 << lb)) + 8 * (n << lb))  # LDE (read n, write B*n) + commit (read B*n)
+    del ev
+    return {"workload": f"{cols} columns x 2^{k} rows, blow-up 8: iNTT + coset LDE + labeled BLAKE3 commit, columns sharded over {world} GPU(s)",
+            "ms_per_step": ms, "rows_per_s": n / (ms / 1e3), "algorithmic_GB": alg / 1e9, "GBps": alg / ms / 1e6,
+            "GBps_per_gpu": alg / ms / 1e6 / world, "frac_of_hbm_peak_per_gpu": alg / ms / 1e6 / world / hbm_peak,
+            "leaf_compressions_per_s": cols * (2 * (n << lb) - 1) / (ms / 1e3)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -278,6 +319,8 @@ def main():
         sharded = {"ms_per_proof": sh_ms, "rows_per_s": T / (sh_ms / 1e3), "identical_on_all_ranks": bool(lo.item() == hi.item()),
                    "phases_ms_rank0": ctx.timings(), "note": "one T-row proof, columns sharded c % world, host pinned input (e2e)"}
 
+    lde_commit = None if args.no_micro else lde_commit_bench(torch, dist, ctx, rank, world, hbm_peak, max(2, min(args.steps, 3)))
+
     out = None
     if rank == 0:
         # ---- dominant kernel alone: column commit (chunk_commit_kernel + upper levels) over resident columns ----
@@ -334,7 +377,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h_bytes), "api": "sezkp_stark_v1_prove (host pinned buffers)"},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "phases_ms": phases, "e2e_phases_ms": e2e_phases, "proof_bytes": len(proof), "micro": micro, "sharded_single_proof": sharded,
+            "phases_ms": phases, "e2e_phases_ms": e2e_phases, "proof_bytes": len(proof), "micro": micro, "lde_commit": lde_commit, "sharded_single_proof": sharded,
         }
     if world > 1:
         dist.barrier()

@@ -94,6 +94,13 @@ int32_t sezkp_column_commit_batch(sezkp_ctx* ctx, const uint64_t* cols, const ch
                                   int chunk_log2, uint8_t* roots /* [c][32] */, sezkp_tree** keep_or_null);
 int32_t sezkp_column_commit_batch_dev(sezkp_ctx* ctx, const uint64_t* cols_dev, const char* const* labels, int c, size_t n,
                                       int chunk_log2, uint8_t* roots /* host [c][32] */, sezkp_tree** keep_or_null);
+/* LDE + commitment of extended columns (BASELINE.json configs[3]): per column interpolate_from_evals
+ * (ntt.rs:173-177) -> evaluate_on_coset_pow2 (coset.rs:85-102) -> hash_field_leaves_labeled over the extended column ->
+ * chunked tree root, processed in column groups so the extended columns are never all resident.  evals [c][1<<log_n]. */
+int32_t sezkp_lde_commit_batch(sezkp_ctx* ctx, const uint64_t* evals, const char* const* labels, int c, int log_n, int log_blow,
+                               uint64_t shift, int chunk_log2, uint8_t* roots /* [c][32] */);
+int32_t sezkp_lde_commit_batch_dev(sezkp_ctx* ctx, const uint64_t* evals_dev, const char* const* labels, int c, int log_n,
+                                   int log_blow, uint64_t shift, int chunk_log2, uint8_t* roots /* host [c][32] */);
 /* OnDemandOpenings::open (v1/openings.rs:403-497) for k (column, row) pairs.  Per opening the outputs are
  * value (8 B LE), chunk_root (32 B), path_in_chunk (min(chunk_log2, log2 n) siblings), path_to_chunk (the rest);
  * sibling arrays are [k][depth][32] with depth_in / depth_out returned. */

@@ -24,7 +24,7 @@ EXPORTS = [
     "sezkp_ntt_batch", "sezkp_ntt_batch_dev", "sezkp_coset_lde_batch", "sezkp_coset_lde_batch_dev",
     "sezkp_lde_from_evals_batch", "sezkp_lde_from_evals_batch_dev", "sezkp_deep_lde", "sezkp_deep_lde_dev",
     "sezkp_leaf_hash", "sezkp_merkle_root", "sezkp_column_commit_batch", "sezkp_column_commit_batch_dev",
-    "sezkp_column_open", "sezkp_tree_free", "sezkp_fri_commit", "sezkp_fri_commit_dev", "sezkp_fri_open", "sezkp_fri_free",
+    "sezkp_lde_commit_batch", "sezkp_lde_commit_batch_dev", "sezkp_column_open", "sezkp_tree_free", "sezkp_fri_commit", "sezkp_fri_commit_dev", "sezkp_fri_open", "sezkp_fri_free",
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
     "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_trace_upload", "sezkp_trace_free",
     "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded",
@@ -201,6 +201,22 @@ class Context:
         fn = self.lib.sezkp_column_commit_batch_dev if dev else self.lib.sezkp_column_commit_batch
         self._ck(fn(self.h, ptr, arr, C.c_int(c), C.c_size_t(n), C.c_int(chunk_log2), _p(roots), C.byref(tree) if keep else None))
         return (roots, ColumnTree(self, tree)) if keep else roots
+
+    def lde_commit(self, evals, labels: Sequence[str], log_blow: int, shift: int = 3, chunk_log2=10, dev=False, log_n=None) -> np.ndarray:
+        """iNTT -> coset LDE -> labeled leaf hash -> root per column (extended columns never all resident)."""
+        c = len(labels)
+        if dev:
+            ptr = _vp(evals)
+        else:
+            a = np.ascontiguousarray(evals, np.uint64)
+            assert a.shape[0] == c
+            log_n = a.shape[1].bit_length() - 1
+            ptr = _p(a)
+        arr = (C.c_char_p * c)(*[l.encode() for l in labels])
+        roots = np.empty((c, 32), np.uint8)
+        fn = self.lib.sezkp_lde_commit_batch_dev if dev else self.lib.sezkp_lde_commit_batch
+        self._ck(fn(self.h, ptr, arr, C.c_int(c), C.c_int(log_n), C.c_int(log_blow), C.c_uint64(shift), C.c_int(chunk_log2), _p(roots)))
+        return roots
 
     def fri_commit(self, layer0, betas, keep=False, dev=False, log_N=None):
         b = np.ascontiguousarray(betas, np.uint64)

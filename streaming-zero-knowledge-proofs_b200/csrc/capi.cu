@@ -249,6 +249,61 @@ int32_t sezkp_lde_from_evals_batch(sezkp_ctx* ctx, const uint64_t* evals, int lo
     API_END(ctx)
 }
 
+// LDE + commit pipeline (BASELINE config 4 / SURVEY K7): per column group iNTT -> coset LDE -> labeled leaves -> tree.
+// The extended columns live only in a scratch buffer that is reused group by group (never all resident): at blow-up 8 a
+// 2^24-row column is 1 GiB extended.  The leaf hash is NOT fused into the LDE's last pass: BLAKE3 is ALU-bound at ~32 ps
+// per leaf while the extra HBM round trip of the extended value costs 16 B / 6.5 TB/s = 2.5 ps, and the pass's tile
+// (strided rows) does not cover whole 1024-leaf chunks.
+static void lde_commit_device(sezkp_ctx* ctx, const u64* evals_dev, const char* const* labels, int c, int log_n, int log_blow, u64 shift,
+                              int chunk_log2, u8* roots_host) {
+    const size_t n = (size_t)1 << log_n, N = n << log_blow;
+    size_t group = ((size_t)2 << 30) / (N * 8);  // ~2 GiB of extended values per group
+    if (group < 1) group = 1;
+    if (group > (size_t)c) group = (size_t)c;
+    u64* coeffs = (u64*)ctx->scratch[4].ensure(group * n * 8);
+    u64* tmp = log_n > 10 ? (u64*)ctx->scratch[0].ensure(group * n * 8) : nullptr;
+    u64* inter = log_n > 10 ? (u64*)ctx->scratch[1].ensure(group * N * 8) : nullptr;
+    u64* ext = (u64*)ctx->scratch[5].ensure(group * N * 8);
+    u8* d_roots = (u8*)ctx->scratch[10].ensure((size_t)c * 32 + 64);
+    for (size_t c0 = 0; c0 < (size_t)c; c0 += group) {
+        const size_t g = (c0 + group <= (size_t)c) ? group : (size_t)c - c0;
+        CUDA_CHECK(cudaMemcpyAsync(coeffs, evals_dev + c0 * n, g * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        ntt_batch_device(ctx, coeffs, tmp, log_n, g, true);
+        coset_lde_device(ctx, coeffs, ext, inter, log_n, log_blow, shift, g);
+        Commit cm;
+        CommitOpts o;
+        o.dedup = false;  // extended values are high-entropy
+        o.roots_dev = d_roots + c0 * 32;
+        try {
+            commit_build(ctx, cm, ext, N, (int)g, chunk_log2, labels + c0, o);
+        } catch (...) {
+            cm.release(ctx);
+            throw;
+        }
+        cm.release(ctx);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(roots_host, d_roots, (size_t)c * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+int32_t sezkp_lde_commit_batch_dev(sezkp_ctx* ctx, const uint64_t* evals_dev, const char* const* labels, int c, int log_n, int log_blow,
+                                   uint64_t shift, int chunk_log2, uint8_t* roots) {
+    API_BEGIN(ctx)
+    REQUIRE(evals_dev && labels && roots && c >= 1 && log_n >= 1 && log_n <= 29 && log_blow >= 0 && log_blow <= 4, "bad argument");
+    lde_commit_device(ctx, evals_dev, labels, c, log_n, log_blow, shift, chunk_log2, roots);
+    API_END(ctx)
+}
+int32_t sezkp_lde_commit_batch(sezkp_ctx* ctx, const uint64_t* evals, const char* const* labels, int c, int log_n, int log_blow,
+                               uint64_t shift, int chunk_log2, uint8_t* roots) {
+    API_BEGIN(ctx)
+    REQUIRE(evals && labels && roots && c >= 1 && log_n >= 1 && log_n <= 29 && log_blow >= 0 && log_blow <= 4, "bad argument");
+    const size_t count = (size_t)c << log_n;
+    check_canonical(evals, count, "evals");
+    u64* d = (u64*)ctx->scratch[2].ensure(count * 8);
+    h2d(ctx, d, evals, count * 8);
+    lde_commit_device(ctx, d, labels, c, log_n, log_blow, shift, chunk_log2, roots);
+    API_END(ctx)
+}
+
 int32_t sezkp_deep_lde_dev(sezkp_ctx* ctx, const uint64_t* base_evals_dev, int log_n, int log_blow, uint64_t shift, uint64_t z,
                            uint64_t* out_dev) {
     API_BEGIN(ctx)

@@ -196,6 +196,16 @@ def test_value_aware_commit_matches_plain_and_oracle(ctx, oracle, kind, n):
     assert np.array_equal(got, exp) and np.array_equal(plain, exp)
 
 
+@pytest.mark.parametrize("k,lb,c", [(1, 3, 2), (6, 3, 3), (10, 2, 2), (12, 3, 5), (14, 3, 2)])
+def test_lde_commit_pipeline_vs_oracle(ctx, oracle, k, lb, c):
+    """config-4 pipeline: iNTT -> coset LDE -> labeled commit of the extended column == oracle composition of the same steps"""
+    rng = np.random.default_rng(k * 7 + c)
+    ev = rand_field(rng, (c, 1 << k))
+    labels = [f"c_{i}" for i in range(c)]
+    ext = oracle.lde_from_evals(ev, lb, 3)
+    assert np.array_equal(ctx.lde_commit(ev, labels, lb, 3), oracle.column_commit(ext, labels))
+
+
 @pytest.mark.parametrize("log_n", [1, 2, 5, 10, 11, 13, 16])
 def test_fri_commit_and_open_vs_oracle(ctx, oracle, log_n):
     rng = np.random.default_rng(log_n)
