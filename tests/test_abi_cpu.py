@@ -72,3 +72,23 @@ def test_simulate_generator_and_partition():
     # ragged last block
     ct2 = m.simulate(1000, 512, 2)
     assert ct2.block_len.tolist() == [512, 488]
+
+
+def test_artifact_envelope_matches_reference_fixture_shape(tmp_path):
+    """CBOR/JSON envelope round trip; same map shape as the reference's shipped proof_stark.cbor (v0 artifact)."""
+    import cbor2
+    from conftest import load_fixture
+    m = pkg()
+    fx = load_fixture("fixture_root_T64.json")["proof_v0"]
+    art = m.ProofArtifact("stark", bytes.fromhex(fx["manifest_root"]), bytes.fromhex(fx["proof_bytes"]),
+                          {"tau": 2, "proto": "stark-v1", "domain_n": 512})
+    for ext in ("cbor", "json"):
+        p = str(tmp_path / f"proof.{ext}")
+        m.artifact.write_proof_auto(p, art)
+        back = m.artifact.read_proof_auto(p)
+        assert back == art
+    obj = cbor2.load(open(str(tmp_path / "proof.cbor"), "rb"))
+    assert list(obj.keys()) == ["backend", "manifest_root", "proof_bytes", "meta"]
+    assert isinstance(obj["proof_bytes"], list) and all(isinstance(x, int) for x in obj["proof_bytes"][:8])  # Vec<u8> without serde_bytes
+    assert list(obj["meta"].keys()) == ["domain_n", "proto", "tau"]  # serde_json map: alphabetical
+    assert len(obj["manifest_root"]) == 32
