@@ -156,13 +156,19 @@ int32_t sezkp_trace_upload(sezkp_ctx* ctx, const sezkp_trace_desc* trace, sezkp_
 void sezkp_trace_free(sezkp_ctx* ctx, sezkp_trace_dev* trace);
 int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* trace, const uint8_t manifest_root[32],
                                       uint8_t* proof_buf, size_t cap, size_t* len);
-/* ProvingBackendStream (sezkp-core/src/prover.rs:21-33): begin_stream / ingest_block / finish_stream.  Blocks are
- * pushed one at a time as one-block descriptors (n_blocks == 1); rows are staged through pinned host buffers and
- * copied on a side stream while earlier chunks are expanded on the GPU. */
-int32_t sezkp_stark_v1_begin(sezkp_ctx* ctx, uint32_t tau, const uint8_t manifest_root[32], sezkp_stream** out);
-int32_t sezkp_stark_v1_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* one_block);
+/* ProvingBackendStream (sezkp-core/src/prover.rs:21-33): begin_stream / ingest_block / finish_stream, driven like
+ * StreamingProver::prove_stream_iter (prover.rs:104-150) over a block iterator (core/io.rs:111-139).  Each ingest pushes
+ * one or more blocks (a descriptor whose arrays cover just those blocks); rows are packed into pinned staging buffers
+ * and copied to the GPU on a side stream every 2^20 rows while the host keeps parsing, so at finish only the tail is
+ * still in flight.  expected_rows (0 = unknown) pre-sizes the device trace.  finish consumes the handle on success;
+ * sezkp_cuda_get_timings then also reports stream_h2d_copy_ms, stream_copy_exposed_ms and stream_copy_hidden_frac. */
+int32_t sezkp_stark_v1_begin(sezkp_ctx* ctx, uint32_t tau, const uint8_t manifest_root[32], uint64_t expected_rows,
+                             sezkp_stream** out);
+int32_t sezkp_stark_v1_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* blocks);
 int32_t sezkp_stark_v1_finish(sezkp_ctx* ctx, sezkp_stream* st, uint8_t* proof_buf, size_t cap, size_t* len);
 void sezkp_stark_v1_abort(sezkp_ctx* ctx, sezkp_stream* st);
+/* upper bound of the serialized ProofV1 size for n_rows rows and tau tapes (for sizing proof_buf) */
+size_t sezkp_stark_v1_proof_bound(uint64_t n_rows, uint32_t tau);
 
 #ifdef __cplusplus
 }

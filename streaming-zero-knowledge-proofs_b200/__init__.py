@@ -8,6 +8,6 @@ from .trace import CompactTrace, TraceDesc, blocks_to_compact, demo_block, manif
 
 from .binding import Context, SezkpCudaError, load_library, EXPORTS, LIB_PATH  # noqa: F401,E402
 from .backend import ProofArtifact, StarkV1Cuda  # noqa: F401,E402
-from . import artifact, parallel  # noqa: F401,E402
+from . import artifact, io_jsonl, parallel  # noqa: F401,E402
 
 __all__ = ["Context", "SezkpCudaError", "StarkV1Cuda", "ProofArtifact", "CompactTrace", "TraceDesc", "blocks_to_compact", "demo_block", "manifest_root", "simulate"]

@@ -26,7 +26,7 @@ EXPORTS = [
     "sezkp_leaf_hash", "sezkp_merkle_root", "sezkp_column_commit_batch", "sezkp_column_commit_batch_dev",
     "sezkp_lde_commit_batch", "sezkp_lde_commit_batch_dev", "sezkp_column_open", "sezkp_tree_free", "sezkp_fri_commit", "sezkp_fri_commit_dev", "sezkp_fri_open", "sezkp_fri_free",
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
-    "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_trace_upload", "sezkp_trace_free",
+    "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_stark_v1_proof_bound", "sezkp_trace_upload", "sezkp_trace_free",
     "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded",
 ]
 
@@ -60,6 +60,8 @@ def load_library() -> C.CDLL:
         lib.sezkp_fri_free.argtypes = [C.c_void_p, C.c_void_p]
         lib.sezkp_stark_v1_abort.argtypes = [C.c_void_p, C.c_void_p]
         lib.sezkp_trace_free.argtypes = [C.c_void_p, C.c_void_p]
+        lib.sezkp_stark_v1_proof_bound.restype = C.c_size_t
+        lib.sezkp_stark_v1_proof_bound.argtypes = [C.c_uint64, C.c_uint32]
         _lib = lib
     return _lib
 
@@ -283,17 +285,22 @@ class Context:
         self._ck(self.lib.sezkp_stark_v1_prove_resident(self.h, rt.h, manifest_root, _p(buf), C.c_size_t(buf.size), C.byref(n)))
         return buf[: n.value].tobytes()
 
-    def prove_v1_stream(self, blocks: Sequence[CompactTrace], manifest_root: bytes) -> bytes:
-        """begin_stream / ingest_block / finish_stream (reference sezkp-core/src/prover.rs:21-33)."""
+    def prove_v1_stream(self, blocks, manifest_root: bytes, tau: Optional[int] = None, expected_rows: int = 0) -> bytes:
+        """begin_stream / ingest_block / finish_stream (reference sezkp-core/src/prover.rs:21-33).  `blocks` is any
+        iterable of CompactTrace pieces (one or more blocks each), e.g. a generator parsing JSONL lines."""
+        it = iter(blocks)
+        first = next(it)
+        tau = tau or first.tau
         st = C.c_void_p()
-        self._ck(self.lib.sezkp_stark_v1_begin(self.h, C.c_uint32(blocks[0].tau), manifest_root, C.byref(st)))
+        self._ck(self.lib.sezkp_stark_v1_begin(self.h, C.c_uint32(tau), manifest_root, C.c_uint64(expected_rows), C.byref(st)))
         try:
             rows = 0
-            for b in blocks:
+            import itertools
+            for b in itertools.chain([first], it):
                 d = b.as_desc()
                 self._ck(self.lib.sezkp_stark_v1_ingest(self.h, st, C.byref(d)))
                 rows += b.n_rows
-            buf = np.empty(proof_size_bound(rows, blocks[0].tau), np.uint8)
+            buf = np.empty(proof_size_bound(rows, tau), np.uint8)
             n = C.c_size_t(0)
             self._ck(self.lib.sezkp_stark_v1_finish(self.h, st, _p(buf), C.c_size_t(buf.size), C.byref(n)))
             st = None

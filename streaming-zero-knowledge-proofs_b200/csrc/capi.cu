@@ -20,17 +20,6 @@ struct sezkp_fri {
 struct sezkp_trace_dev {
     DeviceTraceOwner owner;
 };
-struct sezkp_stream {
-    uint32_t tau = 0;
-    u8 manifest_root[32];
-    std::vector<u64> block_len;
-    std::vector<int64_t> win_left, win_right;
-    std::vector<u32> in_off, out_off;
-    std::vector<int8_t> input_mv, mv;
-    std::vector<u8> wflag;
-    std::vector<uint16_t> wsym;
-};
-
 #define API_BEGIN(ctx)                                         \
     if (!(ctx)) return SEZKP_CUDA_EINVAL;                      \
     try {                                                      \
@@ -590,60 +579,41 @@ int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* tra
     API_END(ctx)
 }
 
-int32_t sezkp_stark_v1_begin(sezkp_ctx* ctx, uint32_t tau, const uint8_t manifest_root[32], sezkp_stream** out) {
+int32_t sezkp_stark_v1_begin(sezkp_ctx* ctx, uint32_t tau, const uint8_t manifest_root[32], uint64_t expected_rows, sezkp_stream** out) {
     API_BEGIN(ctx)
-    REQUIRE(out && manifest_root && tau >= 1 && tau <= 4096, "bad argument");
-    sezkp_stream* st = new sezkp_stream();
-    st->tau = tau;
-    std::memcpy(st->manifest_root, manifest_root, 32);
-    *out = st;
+    REQUIRE(out && manifest_root && tau >= 1 && tau <= 4096 && expected_rows <= (1ULL << 29), "bad argument");
+    *out = stream_begin(ctx, tau, manifest_root, expected_rows);
     API_END(ctx)
 }
-int32_t sezkp_stark_v1_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* b) {
+int32_t sezkp_stark_v1_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* blocks) {
     API_BEGIN(ctx)
     if (!st) sezkp_fail(SEZKP_CUDA_ESTATE, "stream handle is NULL");
-    REQUIRE(b && b->n_blocks >= 1 && b->tau == st->tau, "ingest: bad block descriptor (tau mismatch or empty)");
-    const size_t tau = st->tau;
-    u64 rows = 0;
-    for (u64 k = 0; k < b->n_blocks; k++) {
-        REQUIRE(b->block_len[k] >= 1, "ingest: empty block");
-        rows += b->block_len[k];
-        st->block_len.push_back(b->block_len[k]);
-    }
-    REQUIRE(rows == b->n_rows, "ingest: n_rows != sum(block_len)");
-    st->win_left.insert(st->win_left.end(), b->win_left, b->win_left + b->n_blocks * tau);
-    st->win_right.insert(st->win_right.end(), b->win_right, b->win_right + b->n_blocks * tau);
-    st->in_off.insert(st->in_off.end(), b->head_in_off, b->head_in_off + b->n_blocks * tau);
-    st->out_off.insert(st->out_off.end(), b->head_out_off, b->head_out_off + b->n_blocks * tau);
-    st->input_mv.insert(st->input_mv.end(), b->input_mv, b->input_mv + rows);
-    st->mv.insert(st->mv.end(), b->mv, b->mv + rows * tau);
-    st->wflag.insert(st->wflag.end(), b->write_flag, b->write_flag + rows * tau);
-    st->wsym.insert(st->wsym.end(), b->write_sym, b->write_sym + rows * tau);
+    stream_ingest(ctx, st, blocks);
     API_END(ctx)
 }
 int32_t sezkp_stark_v1_finish(sezkp_ctx* ctx, sezkp_stream* st, uint8_t* proof_buf, size_t cap, size_t* len) {
     API_BEGIN(ctx)
     if (!st) sezkp_fail(SEZKP_CUDA_ESTATE, "stream handle is NULL");
-    REQUIRE(len, "bad argument");
-    sezkp_trace_desc d{};
-    d.tau = st->tau;
-    d.n_blocks = st->block_len.size();
-    d.n_rows = st->input_mv.size();
-    d.block_len = st->block_len.data();
-    d.win_left = st->win_left.data();
-    d.win_right = st->win_right.data();
-    d.head_in_off = st->in_off.data();
-    d.head_out_off = st->out_off.data();
-    d.input_mv = st->input_mv.data();
-    d.mv = st->mv.data();
-    d.write_flag = st->wflag.data();
-    d.write_sym = st->wsym.data();
+    REQUIRE(proof_buf && len, "finish needs a proof buffer (use sezkp_stark_v1_proof_bound for its size)");
     std::vector<u8> proof;
-    prove_v1_device(ctx, &d, st->manifest_root, proof);
+    stream_finish(ctx, st, proof);
     deliver(proof, proof_buf, cap, len);
-    if (proof_buf) delete st;  // the handle is consumed once the proof has been delivered
+    stream_free(ctx, st);  // the handle is consumed once the proof has been delivered
     API_END(ctx)
 }
-void sezkp_stark_v1_abort(sezkp_ctx* ctx, sezkp_stream* st) { delete st; }
+void sezkp_stark_v1_abort(sezkp_ctx* ctx, sezkp_stream* st) {
+    if (!ctx || !st) return;
+    cudaSetDevice(ctx->device);
+    stream_free(ctx, st);
+}
+/* upper bound of the ProofV1 size for a trace of n_rows rows and tau tapes */
+size_t sezkp_stark_v1_proof_bound(uint64_t n_rows, uint32_t tau) {
+    size_t ln = 1;
+    while ((1ULL << ln) < n_rows) ln++;
+    const size_t lN = ln + 3;
+    const size_t openings = 30 * (9 * (size_t)tau + 3) * (8 + 24 + 32 + 16 + 32 * ln);
+    const size_t fri = 30 * (16 + 8 * (lN + 1) + lN * 2 * (8 + 8 + 32 * lN));
+    return 4096 + (3 + 7 * (size_t)tau) * 64 + openings + fri + 32 * (lN + 1);
+}
 
 }  // extern "C"

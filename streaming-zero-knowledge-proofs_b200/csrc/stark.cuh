@@ -56,3 +56,10 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
                        const ShardInfo* shard = nullptr);
 void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out,
                      const ShardInfo* shard = nullptr);
+
+// stream.cu
+struct sezkp_stream;
+sezkp_stream* stream_begin(sezkp_ctx* ctx, u32 tau, const u8 manifest_root[32], u64 expected_rows);
+void stream_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* blocks);
+void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, std::vector<u8>& proof);
+void stream_free(sezkp_ctx* ctx, sezkp_stream* st);

@@ -326,6 +326,51 @@ def test_column_sharded_prove_identical_on_every_rank(oracle, world):
     assert all(p == ref for p in proofs)
 
 
+def test_jsonl_stream_prove_matches_one_shot(ctx, tmp_path):
+    """f2: JSONL -> ProvingBackendStream -> same proof bytes as the one-shot prove; copies overlap the ingest."""
+    m = pkg()
+    ct = m.simulate(4096, 64, 3)
+    root = m.manifest_root(ct)
+    path = str(tmp_path / "blocks.jsonl")
+    m.io_jsonl.write_jsonl(path, ct)
+    one = ctx.prove_v1(ct, root)
+    got = ctx.prove_v1_stream(m.io_jsonl.stream_jsonl(path, blocks_per_piece=5), root)
+    assert got == one
+    tm = ctx.timings()
+    assert "stream_h2d_copy_ms" in tm and "stream_copy_hidden_frac" in tm
+
+
+def test_stream_prove_large_ring_wraps(ctx):
+    """more rows than the 3 x 2^20-row staging ring holds, ragged piece sizes, unknown length (device trace grows)"""
+    m = pkg()
+    ct = m.simulate(1 << 22, 512, 1)
+    root = m.manifest_root(ct)
+    one = ctx.prove_v1(ct, root)
+
+    def pieces():
+        k = 0
+        sizes = [1, 700, 3, 2048, 5000]
+        i = 0
+        while k < ct.n_blocks:
+            e = min(ct.n_blocks, k + sizes[i % len(sizes)])
+            r = slice(k * 512, e * 512)
+            yield m.CompactTrace(tau=1, block_len=ct.block_len[k:e], win_left=ct.win_left[k:e], win_right=ct.win_right[k:e],
+                                 head_in_off=ct.head_in_off[k:e], head_out_off=ct.head_out_off[k:e], input_mv=ct.input_mv[r],
+                                 mv=ct.mv[r], write_flag=ct.write_flag[r], write_sym=ct.write_sym[r])
+            k, i = e, i + 1
+
+    assert ctx.prove_v1_stream(pieces(), root) == one
+    assert ctx.prove_v1_stream(pieces(), root, expected_rows=1 << 22) == one
+
+
+def test_stream_errors(ctx):
+    m = pkg()
+    ct = m.simulate(1000, 100, 2)  # not a power of two -> EINVAL at finish, handle must be abortable
+    with pytest.raises(m.SezkpCudaError) as ei:
+        ctx.prove_v1_stream([ct], bytes(32))
+    assert ei.value.code == -1
+
+
 def test_invalid_inputs_return_einval(ctx):
     m = pkg()
     ct = m.simulate(1000, 512, 2)  # not a power of two (reference asserts, v1/lde.rs:51)
