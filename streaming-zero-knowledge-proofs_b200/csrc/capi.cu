@@ -104,6 +104,8 @@ void sezkp_cuda_destroy(sezkp_ctx* ctx) {
     for (auto& kv : ctx->pool.live) cudaFree(kv.first);
     ctx->pool.live.clear();
     ctx->pool.trim();
+    for (auto e : ctx->slab_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -122,6 +122,8 @@ struct sezkp_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;          // side stream for slab uploads (created on first use)
+    std::vector<cudaEvent_t> slab_events;
     std::string last_error;
     std::map<u64, NttTables*> ntt_tables;  // key: (log_n, inverse, coset params)
     DevPool pool;

@@ -90,10 +90,10 @@ template <bool FOLD>
 __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(u64* __restrict__ values, u64 n, u64 col_stride, int cl,
                                                                     const b3::LabelTemplate* __restrict__ templates,
                                                                     u32* __restrict__ upper, u64 n_ch,
-                                                                    const u64* __restrict__ fold_src, u64 beta) {
+                                                                    const u64* __restrict__ fold_src, u64 beta, u64 chunk0) {
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
     const int pitch = (1 << MAX_CL) + 2;
-    const u64 chunk = blockIdx.x;
+    const u64 chunk = chunk0 + blockIdx.x;
     const int col = blockIdx.y;
     const int leaves = 1 << cl;
     u64* v = values + (u64)col * col_stride + (chunk << cl);
@@ -197,10 +197,10 @@ __device__ __forceinline__ void st_release_u32(u32* p, u32 v) {
 
 __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, u64 col_stride, int cl,
                                                                           const b3::LabelTemplate* __restrict__ templates,
-                                                                          u32* __restrict__ upper, u64 n_ch, u32* memo) {
+                                                                          u32* __restrict__ upper, u64 n_ch, u32* memo, u64 chunk0) {
     extern __shared__ __align__(16) unsigned char dd_raw[];
     DedupSmem& sm = *reinterpret_cast<DedupSmem*>(dd_raw);
-    const u64 chunk = blockIdx.x;
+    const u64 chunk = chunk0 + blockIdx.x;
     const int col = blockIdx.y;
     const int leaves = 1 << cl;
     const u64* v = values + (u64)col * col_stride + (chunk << cl);
@@ -494,8 +494,10 @@ void Commit::release(sezkp_ctx* ctx) {
     templates = nullptr;
 }
 
-void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,
-                  const char* const* labels, const CommitOpts& opt) {
+// commit_begin / commit_chunks / commit_finish: the three stages of commit_build, exposed so that a caller can hash
+// ranges of chunks as their rows become available (pipelined H2D in the prover) and build the upper levels at the end.
+void commit_begin(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2, const char* const* labels,
+                  const CommitOpts& opt) {
     REQUIRE(n >= 1 && (n & (n - 1)) == 0, "column length %llu is not a power of two", (unsigned long long)n);
     REQUIRE(cols >= 1 && cols <= 65535, "column count %d out of range", cols);
     REQUIRE(chunk_log2 >= 0 && chunk_log2 <= MAX_CL, "chunk_log2 %d out of range (0..10)", chunk_log2);
@@ -517,14 +519,8 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
         CUDA_CHECK(cudaMemcpyAsync(cm.templates, h.data(), sizeof(b3::LabelTemplate) * cols, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // h goes out of scope
     }
-    const size_t upper_bytes = (size_t)cols * (2 * cm.n_ch - 1) * 32;
-    cm.upper = (u32*)ctx->pool.alloc(upper_bytes);
-    dim3 grid((unsigned)cm.n_ch, (unsigned)cols);
-    if (opt.fold_src) {
-        REQUIRE(cols == 1 && !labels, "internal: fused fold needs a single unlabeled column");
-        chunk_commit_kernel<true><<<grid, HASH_THREADS, 0, ctx->stream>>>((u64*)values_dev, n, cm.col_stride, cm.cl, nullptr, cm.upper, cm.n_ch,
-                                                                           opt.fold_src, opt.fold_beta);
-    } else if (opt.dedup && ctx->dedup_enabled) {
+    cm.upper = (u32*)ctx->pool.alloc((size_t)cols * (2 * cm.n_ch - 1) * 32);
+    if (opt.dedup && ctx->dedup_enabled && !opt.fold_src) {
         static bool configured = false;
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(chunk_commit_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem)));
@@ -532,19 +528,36 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
         }
         u32* memo = (u32*)ctx->scratch[8].ensure((size_t)MEMO_SLOTS * MEMO_WORDS * 4);
         CUDA_CHECK(cudaMemsetAsync(memo, 0, (size_t)MEMO_SLOTS * MEMO_WORDS * 4, ctx->stream));
-        chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(values_dev, n, cm.col_stride, cm.cl, cm.templates, cm.upper,
-                                                                                           cm.n_ch, memo);
+    }
+}
+
+void commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, const CommitOpts& opt) {
+    if (chunk1 <= chunk0) return;
+    REQUIRE(chunk1 <= cm.n_ch, "internal: chunk range out of bounds");
+    dim3 grid((unsigned)(chunk1 - chunk0), (unsigned)cm.cols);
+    u64* vals = (u64*)cm.values;
+    if (opt.fold_src) {
+        REQUIRE(cm.cols == 1 && !cm.templates, "internal: fused fold needs a single unlabeled column");
+        chunk_commit_kernel<true><<<grid, HASH_THREADS, 0, ctx->stream>>>(vals, cm.n, cm.col_stride, cm.cl, nullptr, cm.upper, cm.n_ch,
+                                                                           opt.fold_src, opt.fold_beta, chunk0);
+    } else if (opt.dedup && ctx->dedup_enabled) {
+        u32* memo = (u32*)ctx->scratch[8].p;
+        chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl, cm.templates,
+                                                                                           cm.upper, cm.n_ch, memo, chunk0);
     } else {
-        chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>((u64*)values_dev, n, cm.col_stride, cm.cl, cm.templates, cm.upper, cm.n_ch,
-                                                                            nullptr, 0);
+        chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>(vals, cm.n, cm.col_stride, cm.cl, cm.templates, cm.upper, cm.n_ch,
+                                                                            nullptr, 0, chunk0);
     }
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
+}
+
+void commit_finish(sezkp_ctx* ctx, Commit& cm, const CommitOpts& opt) {
     const int depth = ilog2(cm.n_ch);
     int l0 = 0;
     while (l0 < depth) {
         const int k = (depth - l0) < MAX_CL ? (depth - l0) : MAX_CL;
-        dim3 g((unsigned)(cm.n_ch >> (l0 + k)), (unsigned)cols);
+        dim3 g((unsigned)(cm.n_ch >> (l0 + k)), (unsigned)cm.cols);
         upper_reduce_kernel<<<g, HASH_THREADS, 0, ctx->stream>>>(cm.upper, cm.n_ch, l0, k);
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
@@ -552,11 +565,18 @@ void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
     }
     const u8* root0 = (const u8*)cm.upper + (2 * cm.n_ch - 2) * 32;
     const size_t col_pitch = (2 * cm.n_ch - 1) * 32;
-    if (opt.roots_dev) CUDA_CHECK(cudaMemcpy2DAsync(opt.roots_dev, 32, root0, col_pitch, 32, cols, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (opt.roots_dev) CUDA_CHECK(cudaMemcpy2DAsync(opt.roots_dev, 32, root0, col_pitch, 32, cm.cols, cudaMemcpyDeviceToDevice, ctx->stream));
     if (opt.roots_host) {
-        CUDA_CHECK(cudaMemcpy2DAsync(opt.roots_host, 32, root0, col_pitch, 32, cols, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpy2DAsync(opt.roots_host, 32, root0, col_pitch, 32, cm.cols, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
+}
+
+void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,
+                  const char* const* labels, const CommitOpts& opt) {
+    commit_begin(ctx, cm, values_dev, n, cols, chunk_log2, labels, opt);
+    commit_chunks(ctx, cm, 0, cm.n_ch, opt);
+    commit_finish(ctx, cm, opt);
 }
 
 OpenReq make_open_req(const Commit& cm, u32 col, u64 row, u32 out_off) {

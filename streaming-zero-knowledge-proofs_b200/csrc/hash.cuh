@@ -35,6 +35,10 @@ struct CommitOpts {
 // Build a commitment over device values (all launches on ctx->stream).
 void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,
                   const char* const* labels_or_null, const CommitOpts& opt);
+void commit_begin(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2, const char* const* labels_or_null,
+                  const CommitOpts& opt);
+void commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, const CommitOpts& opt);
+void commit_finish(sezkp_ctx* ctx, Commit& cm, const CommitOpts& opt);
 // Generic opening request: one CTA rebuilds the chunk containing `row` of one committed column.
 struct OpenReq {
     const u64* values;             // the column

@@ -19,10 +19,10 @@ namespace {
 /* column expansion                                                                            */
 /* ------------------------------------------------------------------------------------------ */
 // One thread per (block, tape): running head position (post-move, relative to 0 at block entry).
-__global__ void head_scan_kernel(DeviceTrace t, u64* __restrict__ cols) {
+__global__ void head_scan_kernel(DeviceTrace t, u64* __restrict__ cols, u64 blk0, u64 blk1) {
     const u64 id = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= t.n_blocks * t.tau) return;
-    const u64 k = id / t.tau;
+    if (id >= (blk1 - blk0) * t.tau) return;
+    const u64 k = blk0 + id / t.tau;
     const u32 r = (u32)(id % t.tau);
     const u64 start = t.block_start[k], len = t.block_len[k];
     u64* head = cols + (3 + 3ULL * t.tau + r) * t.n_rows;  // group order: mv, wflag, wsym, head, ...
@@ -33,9 +33,9 @@ __global__ void head_scan_kernel(DeviceTrace t, u64* __restrict__ cols) {
     }
 }
 // One thread per row: everything except head.
-__global__ void expand_rows_kernel(DeviceTrace t, u64* __restrict__ cols) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= t.n_rows) return;
+__global__ void expand_rows_kernel(DeviceTrace t, u64* __restrict__ cols, u64 row0, u64 row1) {
+    const u64 i = row0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row1) return;
     // block containing row i: largest k with block_start[k] <= i (blocks of length 0 are skipped by the search)
     u64 lo = 0, hi = t.n_blocks;
     while (hi - lo > 1) {
@@ -178,25 +178,30 @@ void validate_trace(const sezkp_trace_desc* d) {
     REQUIRE(sum == d->n_rows, "n_rows != sum(block_len)");
 }
 
-void DeviceTraceOwner::upload(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
+// One packed allocation, 16-byte aligned sections: per-block metadata first, then the row arrays.
+void DeviceTraceOwner::layout(const sezkp_trace_desc* d) {
     const u64 nb = d->n_blocks, n = d->n_rows, tau = d->tau;
-    std::vector<u64> starts(nb);
-    u64 acc = 0;
-    for (u64 k = 0; k < nb; k++) {
-        starts[k] = acc;
-        acc += d->block_len[k];
-    }
-    // one packed allocation, 16-byte aligned sections
     size_t off = 0;
     auto sect = [&](size_t bytes) {
         size_t o = off;
         off += (bytes + 15) & ~(size_t)15;
         return o;
     };
-    const size_t o_start = sect(nb * 8), o_len = sect(nb * 8), o_wl = sect(nb * tau * 8), o_wr = sect(nb * tau * 8),
-                 o_io = sect(nb * tau * 4), o_oo = sect(nb * tau * 4), o_imv = sect(n), o_mv = sect(n * tau),
-                 o_wf = sect(n * tau), o_ws = sect(n * tau * 2);
-    u8* base = (u8*)buf.ensure(off);
+    o_start = sect(nb * 8); o_len = sect(nb * 8); o_wl = sect(nb * tau * 8); o_wr = sect(nb * tau * 8);
+    o_io = sect(nb * tau * 4); o_oo = sect(nb * tau * 4); o_imv = sect(n); o_mv = sect(n * tau);
+    o_wf = sect(n * tau); o_ws = sect(n * tau * 2);
+    total = off;
+}
+void DeviceTraceOwner::upload_meta(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
+    const u64 nb = d->n_blocks, n = d->n_rows, tau = d->tau;
+    layout(d);
+    std::vector<u64> starts(nb);
+    u64 acc = 0;
+    for (u64 k = 0; k < nb; k++) {
+        starts[k] = acc;
+        acc += d->block_len[k];
+    }
+    u8* base = (u8*)buf.ensure(total);
     auto put = [&](size_t o, const void* src, size_t bytes) {
         CUDA_CHECK(cudaMemcpyAsync(base + o, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     };
@@ -206,10 +211,6 @@ void DeviceTraceOwner::upload(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
     put(o_wr, d->win_right, nb * tau * 8);
     put(o_io, d->head_in_off, nb * tau * 4);
     put(o_oo, d->head_out_off, nb * tau * 4);
-    put(o_imv, d->input_mv, n);
-    put(o_mv, d->mv, n * tau);
-    put(o_wf, d->write_flag, n * tau);
-    put(o_ws, d->write_sym, n * tau * 2);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // `starts` is a local
     t.tau = (u32)tau;
     t.n_blocks = nb;
@@ -224,15 +225,37 @@ void DeviceTraceOwner::upload(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
     t.mv = (const int8_t*)(base + o_mv);
     t.write_flag = (const u8*)(base + o_wf);
     t.write_sym = (const uint16_t*)(base + o_ws);
-    h2d_bytes = off;
+    h2d_bytes = total;
+}
+void DeviceTraceOwner::upload_rows_async(cudaStream_t stream, const sezkp_trace_desc* d, u64 r0, u64 r1) {
+    const u64 tau = d->tau, r = r1 - r0;
+    u8* base = (u8*)buf.p;
+    CUDA_CHECK(cudaMemcpyAsync(base + o_imv + r0, d->input_mv + r0, r, cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaMemcpyAsync(base + o_mv + r0 * tau, d->mv + r0 * tau, r * tau, cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaMemcpyAsync(base + o_wf + r0 * tau, d->write_flag + r0 * tau, r * tau, cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaMemcpyAsync(base + o_ws + r0 * tau * 2, d->write_sym + r0 * tau, r * tau * 2, cudaMemcpyHostToDevice, stream));
+}
+void DeviceTraceOwner::upload(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
+    upload_meta(ctx, d);
+    upload_rows_async(ctx->stream, d, 0, d->n_rows);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 
+// rows [row0,row1) of every non-head column and the head columns of blocks [blk0,blk1)
+void expand_columns_range(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols, u64 row0, u64 row1, u64 blk0, u64 blk1) {
+    if (blk1 > blk0) {
+        head_scan_kernel<<<blocks_for((blk1 - blk0) * t.tau, 128), 128, 0, ctx->stream>>>(t, cols, blk0, blk1);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (row1 > row0) {
+        expand_rows_kernel<<<blocks_for(row1 - row0, 256), 256, 0, ctx->stream>>>(t, cols, row0, row1);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+    }
+}
 void expand_columns_device(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols) {
-    head_scan_kernel<<<blocks_for(t.n_blocks * t.tau, 128), 128, 0, ctx->stream>>>(t, cols);
-    CUDA_CHECK(cudaGetLastError());
-    expand_rows_kernel<<<blocks_for(t.n_rows, 256), 256, 0, ctx->stream>>>(t, cols);
-    CUDA_CHECK(cudaGetLastError());
-    ctx->launches += 2;
+    expand_columns_range(ctx, t, cols, 0, t.n_rows, 0, t.n_blocks);
 }
 
 void compose_device(sezkp_ctx* ctx, const u64* cols, u64 n, u32 tau, const u64 alphas8[8], const u64* mask, size_t mask_deg,
@@ -408,29 +431,54 @@ struct TranscriptAbsorb : HostAbsorb {
 
 }  // namespace
 
+// Host-descriptor entry: the row arrays are copied in slabs of 2^20 rows on a side stream and every slab is expanded
+// and committed as soon as it has landed, so all but the first slab's H2D time hides behind the column hashing.
 void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out,
                      const ShardInfo* shard) {
     validate_trace(desc);
-    ctx->timings.clear();
-    const double t0 = now_ms();
+    const u64 n = desc->n_rows, nb = desc->n_blocks, tau = desc->tau;
+    constexpr u64 SLAB = 1ULL << 20;
+    SlabPlan plan;
     DeviceTraceOwner dt;
     dt.buf = ctx->scratch[2];
     ctx->scratch[2] = DevBuf();
     try {
-        dt.upload(ctx, desc);
+        dt.upload_meta(ctx, desc);
     } catch (...) {
         ctx->scratch[2] = dt.buf;
         throw;
     }
     ctx->scratch[2] = dt.buf;
-    const double t1 = now_ms();
-    prove_v1_resident(ctx, dt.t, manifest_root, proof_out, shard);
-    ctx->timings.insert(ctx->timings.begin(), {"h2d_trace", t1 - t0});
+    if (!ctx->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    // slab s covers rows [s*SLAB, min(n,(s+1)*SLAB)); blocks are assigned to the slab in which they END
+    u64 blk = 0, row_acc = 0;
+    for (u64 r0 = 0; r0 < n; r0 += SLAB) {
+        const u64 r1 = r0 + SLAB < n ? r0 + SLAB : n;
+        SlabPlan::Slab sl;
+        sl.row0 = r0;
+        sl.row1 = r1;
+        sl.blk0 = blk;
+        while (blk < nb && row_acc + desc->block_len[blk] <= r1) row_acc += desc->block_len[blk++];
+        sl.blk1 = blk;
+        sl.complete_rows = row_acc;  // every block that ends at or before this row is fully on the device
+        if (ctx->slab_events.size() <= plan.slabs.size()) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->slab_events.push_back(e);
+        }
+        sl.ready = ctx->slab_events[plan.slabs.size()];
+        dt.upload_rows_async(ctx->copy_stream, desc, r0, r1);
+        CUDA_CHECK(cudaEventRecord(sl.ready, ctx->copy_stream));
+        plan.slabs.push_back(sl);
+    }
+    (void)tau;
+    prove_v1_resident(ctx, dt.t, manifest_root, proof_out, shard, &plan);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
 }
 
 // The whole prover from a device-resident compact trace.
 void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out,
-                       const ShardInfo* shard) {
+                       const ShardInfo* shard, const SlabPlan* plan) {
     const int world = shard ? shard->world : 1, rank = shard ? shard->rank : 0;
     auto exchange = [&](const void* send, size_t bytes, void* recv) {  // all-gather through the host callback
         const int32_t rc = shard->allgather(shard->user, send, bytes, recv);
@@ -453,8 +501,10 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
 
     // A. compact trace -> committed columns
     u64* cols = (u64*)ctx->scratch[3].ensure((size_t)n_cols * n * 8);
-    expand_columns_device(ctx, trace, cols);
-    lap("expand_columns");
+    if (!plan) {
+        expand_columns_device(ctx, trace, cols);
+        lap("expand_columns");
+    }
 
     // B. transcript prelude (v1/prover.rs:67-70)
     host::Transcript tr("sezkp-stark/v1");
@@ -480,7 +530,21 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             copt.dedup = true;
             copt.roots_host = local_roots.data();
             copt.col_stride = (u64)world * n;
-            commit_build(ctx, cm, cols + (u64)rank * n, n, n_local, COL_CHUNK_LOG2, local_labels.data(), copt);
+            if (!plan) {
+                commit_build(ctx, cm, cols + (u64)rank * n, n, n_local, COL_CHUNK_LOG2, local_labels.data(), copt);
+            } else {  // slab pipeline: wait for the slab's copy, expand it, hash the chunks whose rows are all final
+                commit_begin(ctx, cm, cols + (u64)rank * n, n, n_local, COL_CHUNK_LOG2, local_labels.data(), copt);
+                u64 c_done = 0;
+                for (size_t si = 0; si < plan->slabs.size(); si++) {
+                    const SlabPlan::Slab& sl = plan->slabs[si];
+                    CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, sl.ready, 0));
+                    expand_columns_range(ctx, trace, cols, sl.row0, sl.row1, sl.blk0, sl.blk1);
+                    const u64 c_new = (si + 1 == plan->slabs.size()) ? cm.n_ch : (sl.complete_rows >> cm.cl);
+                    commit_chunks(ctx, cm, c_done, c_new, copt);
+                    if (c_new > c_done) c_done = c_new;
+                }
+                commit_finish(ctx, cm, copt);
+            }
             if (world == 1) col_roots = local_roots;
             else {  // C1 of SURVEY §2b: all-gather of 32-byte column roots
                 std::vector<u8> all((size_t)world * max_local * 32);

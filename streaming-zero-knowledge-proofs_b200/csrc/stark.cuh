@@ -23,7 +23,18 @@ struct DeviceTraceOwner {
     DevBuf buf;
     DeviceTrace t{};
     size_t h2d_bytes = 0;
-    void upload(sezkp_ctx* ctx, const sezkp_trace_desc* d);
+    size_t o_start = 0, o_len = 0, o_wl = 0, o_wr = 0, o_io = 0, o_oo = 0, o_imv = 0, o_mv = 0, o_wf = 0, o_ws = 0, total = 0;
+    void layout(const sezkp_trace_desc* d);
+    void upload_meta(sezkp_ctx* ctx, const sezkp_trace_desc* d);                                    // allocation + per-block metadata
+    void upload_rows_async(cudaStream_t stream, const sezkp_trace_desc* d, u64 row0, u64 row1);     // a slab of the row arrays
+    void upload(sezkp_ctx* ctx, const sezkp_trace_desc* d);                                         // everything, synchronous
+};
+struct SlabPlan {  // pipelined upload: per slab the rows, the blocks that end in it, and the event of its copy
+    struct Slab {
+        u64 row0, row1, blk0, blk1, complete_rows;
+        cudaEvent_t ready;
+    };
+    std::vector<Slab> slabs;
 };
 void validate_trace(const sezkp_trace_desc* d);
 void expand_columns_device(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols_dev);
@@ -53,7 +64,8 @@ struct ShardInfo {  // column sharding across the GPUs of one box (one process p
     void* user;
 };
 void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out,
-                       const ShardInfo* shard = nullptr);
+                       const ShardInfo* shard = nullptr, const SlabPlan* plan = nullptr);
+void expand_columns_range(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols_dev, u64 row0, u64 row1, u64 blk0, u64 blk1);
 void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out,
                      const ShardInfo* shard = nullptr);
 
