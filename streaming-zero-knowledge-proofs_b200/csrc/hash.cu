@@ -169,19 +169,24 @@ __device__ __forceinline__ void bitmap_prefix(DedupSmem& sm, int words) {
 __device__ __forceinline__ u32 bitmap_rank(const DedupSmem& sm, u32 key) {
     return sm.wprefix[key >> 5] + __popc(sm.bitmap[key >> 5] & ((1u << (key & 31)) - 1u));
 }
-// Set bit `key` for every valid lane with one shared-memory atomic per distinct bitmap word per warp
-// (all lanes of a low-entropy chunk hit the same word; unaggregated atomics would serialise).  Whole warp must call.
-__device__ __forceinline__ void bitmap_set_warp(u32* bitmap, u32 key, bool valid) {
-    unsigned todo = __ballot_sync(0xffffffffu, valid);
-    const u32 word = key >> 5, bit = 1u << (key & 31);
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const u32 w = __shfl_sync(0xffffffffu, word, leader);
-        const unsigned peers = __ballot_sync(0xffffffffu, valid && word == w);
-        const u32 bits = __reduce_or_sync(0xffffffffu, (valid && word == w) ? bit : 0u);
-        if ((int)(threadIdx.x & 31) == leader) atomicOr(&bitmap[w], bits);
-        todo &= ~peers;
+// Set bit `key` for every valid lane.  Returns true for exactly one lane per key that was not yet set ("owner"), which
+// later writes the key into the compacted list — no scan over the key space.  Small key spaces (one bitmap word) are
+// aggregated into one atomic per warp (all lanes of a low-entropy chunk hit the same word; unaggregated atomics
+// would serialise); larger spaces use one atomic per lane.  Whole warp must call.
+__device__ __forceinline__ bool bitmap_set_owner(u32* bitmap, u32 key, bool valid, bool single_word) {
+    const u32 bit = 1u << (key & 31);
+    if (single_word) {
+        const u32 bits = __reduce_or_sync(0xffffffffu, valid ? bit : 0u);
+        u32 old = 0;
+        if ((threadIdx.x & 31) == 0 && bits) old = atomicOr(&bitmap[0], bits);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        // first lane (lowest id) carrying a newly set bit owns it
+        const unsigned same = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
+        return valid && !(old & bit) && ((int)(threadIdx.x & 31) == __ffs(same) - 1);
     }
+    if (!valid) return false;
+    const u32 old = atomicOr(&bitmap[key >> 5], bit);
+    return !(old & bit);
 }
 
 constexpr int MEMO_SLOTS = 4096;  // power of two
@@ -244,9 +249,11 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
     }
     int D = 0;
     bool dedup = (mx - mn) < (u64)(1 << MAX_CL);
+    bool own[4] = {false, false, false, false};
     if (dedup) {  // ids of the distinct values
+        const bool one_word = (mx - mn) < 32;
 #pragma unroll
-        for (int k = 0; k < 4; k++) bitmap_set_warp(sm.bitmap, (u32)(key[k] - mn), tid + k * HASH_THREADS < leaves);
+        for (int k = 0; k < 4; k++) own[k] = bitmap_set_owner(sm.bitmap, (u32)(key[k] - mn), tid + k * HASH_THREADS < leaves, one_word);
         __syncthreads();
         bitmap_prefix(sm, ((int)(mx - mn) + 32) >> 5);
         __syncthreads();
@@ -262,14 +269,15 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
     }
 
     // ---- level 0: one leaf hash per distinct value (table in the low half of A) ----
-    const int range = (int)(mx - mn) + 1;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int i = tid + k * HASH_THREADS;
-        if (i < leaves) sm.idA[i] = (unsigned short)bitmap_rank(sm, (u32)(key[k] - mn));
+        if (i < leaves) {
+            const u32 kk = (u32)(key[k] - mn), rk = bitmap_rank(sm, kk);
+            sm.idA[i] = (unsigned short)rk;
+            if (own[k]) sm.list[rk] = (unsigned short)kk;
+        }
     }
-    for (int j = tid; j < range; j += HASH_THREADS)
-        if (sm.bitmap[j >> 5] & (1u << (j & 31))) sm.list[bitmap_rank(sm, (u32)j)] = (unsigned short)j;
     __syncthreads();
     HASH_LEAVES_INTO(sm.A, DD_PA, D, gl::sub(mn + (u64)sm.list[i], HALF), templates != nullptr, t)
     __syncthreads();
@@ -334,16 +342,22 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
             __syncthreads();
             const u32 k0 = (i0 < half) ? (u32)idcur[2 * i0] * D + idcur[2 * i0 + 1] : 0u;
             const u32 k1 = (i1 < half) ? (u32)idcur[2 * i1] * D + idcur[2 * i1 + 1] : 0u;
-            bitmap_set_warp(sm.bitmap, k0, i0 < half);
-            bitmap_set_warp(sm.bitmap, k1, i1 < half);
+            const bool own0 = bitmap_set_owner(sm.bitmap, k0, i0 < half, space <= 32);
+            const bool own1 = bitmap_set_owner(sm.bitmap, k1, i1 < half, space <= 32);
             __syncthreads();
             bitmap_prefix(sm, (space + 31) >> 5);
             __syncthreads();
             const int Dn = (int)sm.total;
-            if (i0 < half) idnext[i0] = (unsigned short)bitmap_rank(sm, k0);
-            if (i1 < half) idnext[i1] = (unsigned short)bitmap_rank(sm, k1);
-            for (int j = tid; j < space; j += HASH_THREADS)
-                if (sm.bitmap[j >> 5] & (1u << (j & 31))) sm.list[bitmap_rank(sm, (u32)j)] = (unsigned short)j;
+            if (i0 < half) {
+                const u32 rk = bitmap_rank(sm, k0);
+                idnext[i0] = (unsigned short)rk;
+                if (own0) sm.list[rk] = (unsigned short)k0;
+            }
+            if (i1 < half) {
+                const u32 rk = bitmap_rank(sm, k1);
+                idnext[i1] = (unsigned short)rk;
+                if (own1) sm.list[rk] = (unsigned short)k1;
+            }
             __syncthreads();
             for (int r = tid; r < Dn; r += HASH_THREADS) {
                 const int kk = sm.list[r], a = kk / D, b = kk - a * D;
