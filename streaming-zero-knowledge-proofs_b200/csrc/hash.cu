@@ -202,13 +202,11 @@ __device__ __forceinline__ void st_release_u32(u32* p, u32 v) {
 
 __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, u64 col_stride, int cl,
                                                                           const b3::LabelTemplate* __restrict__ templates,
-                                                                          u32* __restrict__ upper, u64 n_ch, u32* memo, u64 chunk0, u32 n_cols) {
+                                                                          u32* __restrict__ upper, u64 n_ch, u32* memo, u64 chunk0) {
     extern __shared__ __align__(16) unsigned char dd_raw[];
     DedupSmem& sm = *reinterpret_cast<DedupSmem*>(dd_raw);
-    // 1-D grid with the column index fastest: co-resident CTAs then belong to different columns, so the latency-bound
-    // chunks of low-entropy columns overlap with the throughput-bound chunks of the others
-    const int col = (int)(blockIdx.x % n_cols);
-    const u64 chunk = chunk0 + blockIdx.x / n_cols;
+    const u64 chunk = chunk0 + blockIdx.x;
+    const int col = blockIdx.y;
     const int leaves = 1 << cl;
     const u64* v = values + (u64)col * col_stride + (chunk << cl);
     const int tid = threadIdx.x;
@@ -558,10 +556,8 @@ void commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, const Com
                                                                            opt.fold_src, opt.fold_beta, chunk0);
     } else if (opt.dedup && ctx->dedup_enabled) {
         u32* memo = (u32*)ctx->scratch[8].p;
-        const u64 ctas = (chunk1 - chunk0) * (u64)cm.cols;
-        REQUIRE(ctas < (1ULL << 31), "internal: commit grid too large");
-        chunk_commit_dedup_kernel<<<(unsigned)ctas, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(
-            cm.values, cm.n, cm.col_stride, cm.cl, cm.templates, cm.upper, cm.n_ch, memo, chunk0, (u32)cm.cols);
+        chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl, cm.templates,
+                                                                                           cm.upper, cm.n_ch, memo, chunk0);
     } else {
         chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>(vals, cm.n, cm.col_stride, cm.cl, cm.templates, cm.upper, cm.n_ch,
                                                                             nullptr, 0, chunk0);
