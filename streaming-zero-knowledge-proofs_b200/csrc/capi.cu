@@ -137,7 +137,10 @@ int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx) {
 int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value) {
     API_BEGIN(ctx)
     REQUIRE(name != nullptr, "bad argument");
-    if (std::strcmp(name, "dedup") == 0) ctx->dedup_enabled = value != 0;
+    if (std::strcmp(name, "dedup") == 0) {
+        ctx->dedup_enabled = value != 0;
+        if (value == 1 || value == 2) ctx->dedup_variant = (int)value;
+    }
     else sezkp_fail(SEZKP_CUDA_EINVAL, "unknown option '%s'", name);
     API_END(ctx)
 }

@@ -129,6 +129,7 @@ struct sezkp_ctx {
     DevPool pool;
     DevBuf scratch[12];                      // reusable work buffers (per purpose, see users)
     std::vector<std::pair<std::string, double>> timings;  // phase -> ms (last prove)
+    int dedup_variant = 2;                  // 1: 256-thread kernel, 2: 128-thread kernel (more chunks in flight per SM)
     bool dedup_enabled = true;              // value-aware column commit (SEZKP_NO_DEDUP=1 or sezkp_cuda_set_option disables)
     u64 launches = 0;                       // kernels launched since last reset
 };

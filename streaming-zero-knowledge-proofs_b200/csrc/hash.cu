@@ -402,6 +402,307 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
     if (tid < 8) out_root[tid] = Tcur[tid * DD_PA];  // single node left: id 0
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* value-aware chunk commit, 128-thread variant: ~32 KB of shared memory per CTA so that 7 chunks   */
+/* (instead of 4) are in flight per SM — the low-entropy phases are latency-bound chains of         */
+/* dependent compressions, so concurrency across chunks is what buys throughput.                    */
+/* ------------------------------------------------------------------------------------------ */
+constexpr int DT = 128;
+constexpr int D2_PX = 512 + 2, D2_PY = 256 + 2;
+struct Dedup128Smem {
+    u32 X[8 * D2_PX];  // 512 digests
+    u32 Y[8 * D2_PY];  // 256 digests
+    u32 bitmap[DD_PAIR_CAP / 32];
+    u32 wprefix[DD_PAIR_CAP / 32];
+    unsigned short idA[1 << MAX_CL];
+    unsigned short idB[1 << (MAX_CL - 1)];
+    unsigned short list[DD_PAIR_CAP];
+    u64 red[2 * (DT / 32)];
+    u32 total;
+};
+__device__ __forceinline__ void bitmap_prefix128(Dedup128Smem& sm, int words) {
+    if (threadIdx.x < 32) {
+        const int per = (words + 31) >> 5;  // <= 2
+        u32 cnt[2], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int w = threadIdx.x * per + j;
+            cnt[j] = (j < per && w < words) ? __popc(sm.bitmap[w]) : 0;
+            sum += cnt[j];
+        }
+        u32 incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += y;
+        }
+        u32 run = incl - sum;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int w = threadIdx.x * per + j;
+            if (j < per && w < words) sm.wprefix[w] = run;
+            run += cnt[j];
+        }
+        if (threadIdx.x == 31) sm.total = incl;
+    }
+}
+__device__ __forceinline__ u32 bitmap_rank128(const Dedup128Smem& sm, u32 key) {
+    return sm.wprefix[key >> 5] + __popc(sm.bitmap[key >> 5] & ((1u << (key & 31)) - 1u));
+}
+__device__ __forceinline__ void load_pair(const u32* T, int pitch, int a, int b, u32 (&l)[8], u32 (&r)[8]) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        l[w] = T[w * pitch + a];
+        r[w] = T[w * pitch + b];
+    }
+}
+__device__ __forceinline__ void store_digest(u32* T, int pitch, int i, const u32 (&d)[8]) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) T[w * pitch + i] = d[w];
+}
+
+__global__ void __launch_bounds__(DT, 7) chunk_commit_dedup128_kernel(const u64* __restrict__ values, u64 n, u64 col_stride, int cl,
+                                                                      const b3::LabelTemplate* __restrict__ templates,
+                                                                      u32* __restrict__ upper, u64 n_ch, u32* memo, u64 chunk0) {
+    extern __shared__ __align__(16) unsigned char dd_raw[];
+    Dedup128Smem& sm = *reinterpret_cast<Dedup128Smem*>(dd_raw);
+    const u64 chunk = chunk0 + blockIdx.x;
+    const int col = blockIdx.y;
+    const int leaves = 1 << cl;
+    const u64* v = values + (u64)col * col_stride + (chunk << cl);
+    const int tid = threadIdx.x;
+    b3::LabelTemplate t;
+    if (templates) t = templates[col];
+    u32* out_root = upper + ((u64)col * (2 * n_ch - 1) + chunk) * 8;
+
+    constexpr u64 HALF = 1ULL << 31;
+    constexpr int LPT = (1 << MAX_CL) / DT;  // leaves per thread (8)
+    u64 mn = ~0ULL, mx = 0;
+#pragma unroll
+    for (int k = 0; k < LPT; k++) {
+        const int i = tid + k * DT;
+        if (i < leaves) {
+            const u64 kk = gl::add(v[i], HALF);
+            mn = kk < mn ? kk : mn;
+            mx = kk > mx ? kk : mx;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const u64 a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((tid & 31) == 0) {
+        sm.red[tid >> 5] = mn;
+        sm.red[DT / 32 + (tid >> 5)] = mx;
+    }
+    if (tid < DD_PAIR_CAP / 32) sm.bitmap[tid] = 0;
+    __syncthreads();
+    mn = sm.red[0];
+    mx = sm.red[DT / 32];
+#pragma unroll
+    for (int w = 1; w < DT / 32; w++) {
+        mn = sm.red[w] < mn ? sm.red[w] : mn;
+        mx = sm.red[DT / 32 + w] > mx ? sm.red[DT / 32 + w] : mx;
+    }
+    int D = 0;
+    bool dedup = (mx - mn) < (u64)(1 << MAX_CL);
+    u32 ownmask = 0;
+    if (dedup) {
+        const bool one_word = (mx - mn) < 32;
+#pragma unroll
+        for (int k = 0; k < LPT; k++) {
+            const int i = tid + k * DT;
+            const u32 kk = i < leaves ? (u32)(gl::add(v[i], HALF) - mn) : 0u;
+            if (bitmap_set_owner(sm.bitmap, kk, i < leaves, one_word)) ownmask |= 1u << k;
+        }
+        __syncthreads();
+        bitmap_prefix128(sm, ((int)(mx - mn) + 32) >> 5);
+        __syncthreads();
+        D = (int)sm.total;
+        dedup = D <= 256;
+    }
+    u32 *Tcur, *Tnext;
+    int Pcur, Pnext, nodes;
+    bool identity;
+    unsigned short* idcur = sm.idA;
+    unsigned short* idnext = sm.idB;
+    if (!dedup) {
+        // plain path in quarters of 256 leaves: leaf digests into Y, their 128 parents into X (level 1, <= 512 nodes)
+        const int per = leaves < 256 ? leaves : 256;
+        for (int base = 0; base < leaves; base += per) {
+            if (templates) {
+                B3_DISPATCH_LABELED(t, {
+                    for (int i = tid; i < per; i += DT) {
+                        u32 d[8];
+                        b3::leaf_labeled_w<B3W>(t, v[base + i], d);
+                        store_digest(sm.Y, D2_PY, i, d);
+                    }
+                })
+            } else {
+                for (int i = tid; i < per; i += DT) {
+                    u32 d[8];
+                    b3::leaf(v[base + i], d);
+                    store_digest(sm.Y, D2_PY, i, d);
+                }
+            }
+            __syncthreads();
+            if (leaves == 1) break;
+            for (int i = tid; i < (per >> 1); i += DT) {
+                u32 l[8], r[8], d[8];
+                load_pair(sm.Y, D2_PY, 2 * i, 2 * i + 1, l, r);
+                b3::parent(l, r, d);
+                store_digest(sm.X, D2_PX, (base >> 1) + i, d);
+            }
+            __syncthreads();
+        }
+        if (leaves == 1) {  // a single leaf is the root itself
+            if (tid < 8) out_root[tid] = sm.Y[tid * D2_PY];
+            return;
+        }
+        Tcur = sm.X; Pcur = D2_PX; Tnext = sm.Y; Pnext = D2_PY;
+        nodes = leaves >> 1;
+        identity = true;
+    } else {
+#pragma unroll
+        for (int k = 0; k < LPT; k++) {
+            const int i = tid + k * DT;
+            if (i < leaves) {
+                const u32 kk = (u32)(gl::add(v[i], HALF) - mn), rk = bitmap_rank128(sm, kk);
+                sm.idA[i] = (unsigned short)rk;
+                if (ownmask & (1u << k)) sm.list[rk] = (unsigned short)kk;
+            }
+        }
+        __syncthreads();
+        // one leaf hash per distinct value -> table in Y
+        if (templates) {
+            B3_DISPATCH_LABELED(t, {
+                for (int r = tid; r < D; r += DT) {
+                    u32 d[8];
+                    b3::leaf_labeled_w<B3W>(t, gl::sub(mn + (u64)sm.list[r], HALF), d);
+                    store_digest(sm.Y, D2_PY, r, d);
+                }
+            })
+        } else {
+            for (int r = tid; r < D; r += DT) {
+                u32 d[8];
+                b3::leaf(gl::sub(mn + (u64)sm.list[r], HALF), d);
+                store_digest(sm.Y, D2_PY, r, d);
+            }
+        }
+        __syncthreads();
+        Tcur = sm.Y; Pcur = D2_PY; Tnext = sm.X; Pnext = D2_PX;
+        nodes = leaves;
+        identity = false;
+    }
+    while (nodes > 1) {
+        const int half = nodes >> 1;
+        if (identity) {  // plain level: parents of entries 2i, 2i+1 into the other buffer
+            for (int i = tid; i < half; i += DT) {
+                u32 l[8], r[8], d[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    const uint2 pr = *reinterpret_cast<const uint2*>(&Tcur[w * Pcur + 2 * i]);
+                    l[w] = pr.x;
+                    r[w] = pr.y;
+                }
+                b3::parent(l, r, d);
+                store_digest(Tnext, Pnext, i, d);
+            }
+            __syncthreads();
+        } else if (D == 1) {
+            // all nodes equal: the rest of the tree is the chain x -> H(x,x), memoised across chunks
+            if (tid == 0) {
+                u32 d[8], e[8], x[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) x[w] = d[w] = Tcur[w * Pcur];
+                const u32 height = (u32)nodes;
+                u32* ent = memo + (size_t)((d[0] ^ (d[1] * 0x9E3779B1u) ^ height) & (MEMO_SLOTS - 1)) * MEMO_WORDS;
+                bool hit = false;
+                if (ld_acquire_u32(ent) == 2u && ent[1] == height) {
+                    hit = true;
+#pragma unroll
+                    for (int w = 0; w < 8; w++) hit = hit && (ent[2 + w] == d[w]);
+                    if (hit) {
+#pragma unroll
+                        for (int w = 0; w < 8; w++) out_root[w] = ent[10 + w];
+                    }
+                }
+                if (!hit) {
+                    for (int m2 = nodes; m2 > 1; m2 >>= 1) {
+                        b3::parent(d, d, e);
+#pragma unroll
+                        for (int w = 0; w < 8; w++) d[w] = e[w];
+                    }
+#pragma unroll
+                    for (int w = 0; w < 8; w++) out_root[w] = d[w];
+                    if (atomicCAS(ent, 0u, 1u) == 0u) {
+                        ent[1] = height;
+#pragma unroll
+                        for (int w = 0; w < 8; w++) {
+                            ent[2 + w] = x[w];
+                            ent[10 + w] = d[w];
+                        }
+                        __threadfence();
+                        st_release_u32(ent, 2u);
+                    }
+                }
+            }
+            return;
+        } else if (D * D <= DD_PAIR_CAP) {  // dedup level: one compression per distinct (left id, right id)
+            const int space = D * D;
+            for (int w = tid; w < ((space + 31) >> 5); w += DT) sm.bitmap[w] = 0;
+            __syncthreads();
+            u32 keyv[4];
+            u32 own = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = tid + k * DT;
+                keyv[k] = (i < half) ? (u32)idcur[2 * i] * D + idcur[2 * i + 1] : 0u;
+                if (bitmap_set_owner(sm.bitmap, keyv[k], i < half, space <= 32)) own |= 1u << k;
+            }
+            __syncthreads();
+            bitmap_prefix128(sm, (space + 31) >> 5);
+            __syncthreads();
+            const int Dn = (int)sm.total;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = tid + k * DT;
+                if (i < half) {
+                    const u32 rk = bitmap_rank128(sm, keyv[k]);
+                    idnext[i] = (unsigned short)rk;
+                    if (own & (1u << k)) sm.list[rk] = (unsigned short)keyv[k];
+                }
+            }
+            __syncthreads();
+            for (int r = tid; r < Dn; r += DT) {
+                const int kk = sm.list[r], a = kk / D, b = kk - a * D;
+                u32 l[8], rr[8], d[8];
+                load_pair(Tcur, Pcur, a, b, l, rr);
+                b3::parent(l, rr, d);
+                store_digest(Tnext, Pnext, r, d);
+            }
+            __syncthreads();
+            D = Dn;
+            unsigned short* ip = idcur; idcur = idnext; idnext = ip;
+        } else {  // too many distinct digests: next level through the ids, plain afterwards
+            for (int i = tid; i < half; i += DT) {
+                u32 l[8], rr[8], d[8];
+                load_pair(Tcur, Pcur, idcur[2 * i], idcur[2 * i + 1], l, rr);
+                b3::parent(l, rr, d);
+                store_digest(Tnext, Pnext, i, d);
+            }
+            __syncthreads();
+            identity = true;
+        }
+        nodes = half;
+        u32* tp = Tcur; Tcur = Tnext; Tnext = tp;
+        const int pp = Pcur; Pcur = Pnext; Pnext = pp;
+    }
+    if (tid < 8) out_root[tid] = Tcur[tid * Pcur];
+}
+
 // digests at level l0 of `upper` -> reduce groups of 2^k -> levels l0+1..l0+k stored.  grid (count>>k, cols)
 __global__ void __launch_bounds__(HASH_THREADS) upper_reduce_kernel(u32* __restrict__ upper, u64 n_ch, int l0, int k) {
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
@@ -538,6 +839,7 @@ void commit_begin(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
         static bool configured = false;
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(chunk_commit_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem)));
+            CUDA_CHECK(cudaFuncSetAttribute(chunk_commit_dedup128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dedup128Smem)));
             configured = true;
         }
         u32* memo = (u32*)ctx->scratch[8].ensure((size_t)MEMO_SLOTS * MEMO_WORDS * 4);
@@ -556,8 +858,12 @@ void commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, const Com
                                                                            opt.fold_src, opt.fold_beta, chunk0);
     } else if (opt.dedup && ctx->dedup_enabled) {
         u32* memo = (u32*)ctx->scratch[8].p;
-        chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl, cm.templates,
-                                                                                           cm.upper, cm.n_ch, memo, chunk0);
+        if (ctx->dedup_variant == 2)
+            chunk_commit_dedup128_kernel<<<grid, DT, sizeof(Dedup128Smem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl, cm.templates,
+                                                                                          cm.upper, cm.n_ch, memo, chunk0);
+        else
+            chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl,
+                                                                                               cm.templates, cm.upper, cm.n_ch, memo, chunk0);
     } else {
         chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>(vals, cm.n, cm.col_stride, cm.cl, cm.templates, cm.upper, cm.n_ch,
                                                                             nullptr, 0, chunk0);
