@@ -336,7 +336,7 @@ def main():
         ctx.set_option("dedup", 0)  # for transparency: the same commitment with one compression per node
         ctx.column_commit(cols_dev, labels, dev=True, n=ct.n_rows)
         kms_plain = timed(torch, lambda: ctx.column_commit(cols_dev, labels, dev=True, n=ct.n_rows), max(3, args.steps))
-        ctx.set_option("dedup", 1)
+        ctx.set_option("dedup", 2)
         del cols_dev, cols_host
         alg_bytes = 8 * ct.n_rows * n_cols
         achieved = alg_bytes / kms / 1e6

@@ -597,8 +597,8 @@ __global__ void __launch_bounds__(DT, 7) chunk_commit_dedup128_kernel(const u64*
         identity = false;
     }
     while (nodes > 1) {
-        const int half = nodes >> 1;
         if (identity) {  // plain level: parents of entries 2i, 2i+1 into the other buffer
+            const int half = nodes >> 1;
             for (int i = tid; i < half; i += DT) {
                 u32 l[8], r[8], d[8];
 #pragma unroll
@@ -611,34 +611,50 @@ __global__ void __launch_bounds__(DT, 7) chunk_commit_dedup128_kernel(const u64*
                 store_digest(Tnext, Pnext, i, d);
             }
             __syncthreads();
-        } else if (D == 1) {
-            // all nodes equal: the rest of the tree is the chain x -> H(x,x), memoised across chunks
-            if (tid == 0) {
+            nodes = half;
+            u32* tp = Tcur; Tcur = Tnext; Tnext = tp;
+            const int pp = Pcur; Pcur = Pnext; Pnext = pp;
+            continue;
+        }
+        // ---- uniform runs: while every node pairs with an identical sibling, level l+1 has the same ids and
+        // digest'[id] = H(digest[id], digest[id]); k such levels are k-step chains per distinct id (memoised across
+        // chunks by (x, k)) — block-constant columns and all-equal subtrees collapse here without per-level machinery
+        int k = 0;
+        while (nodes > 1) {
+            const int half = nodes >> 1;
+            int ok = 1;
+            for (int i = tid; i < half; i += DT) ok &= (idcur[2 * i] == idcur[2 * i + 1]);
+            if (!__syncthreads_and(ok)) break;
+            for (int i = tid; i < half; i += DT) idnext[i] = idcur[2 * i];
+            __syncthreads();
+            unsigned short* ip = idcur; idcur = idnext; idnext = ip;
+            nodes = half;
+            k++;
+        }
+        if (k > 0) {
+            for (int r = tid; r < D; r += DT) {
                 u32 d[8], e[8], x[8];
 #pragma unroll
-                for (int w = 0; w < 8; w++) x[w] = d[w] = Tcur[w * Pcur];
-                const u32 height = (u32)nodes;
-                u32* ent = memo + (size_t)((d[0] ^ (d[1] * 0x9E3779B1u) ^ height) & (MEMO_SLOTS - 1)) * MEMO_WORDS;
+                for (int w = 0; w < 8; w++) x[w] = d[w] = Tcur[w * Pcur + r];
+                u32* ent = memo + (size_t)((d[0] ^ (d[1] * 0x9E3779B1u) ^ (u32)k) & (MEMO_SLOTS - 1)) * MEMO_WORDS;
                 bool hit = false;
-                if (ld_acquire_u32(ent) == 2u && ent[1] == height) {
+                if (ld_acquire_u32(ent) == 2u && ent[1] == (u32)k) {
                     hit = true;
 #pragma unroll
                     for (int w = 0; w < 8; w++) hit = hit && (ent[2 + w] == d[w]);
                     if (hit) {
 #pragma unroll
-                        for (int w = 0; w < 8; w++) out_root[w] = ent[10 + w];
+                        for (int w = 0; w < 8; w++) d[w] = ent[10 + w];
                     }
                 }
                 if (!hit) {
-                    for (int m2 = nodes; m2 > 1; m2 >>= 1) {
+                    for (int j = 0; j < k; j++) {
                         b3::parent(d, d, e);
 #pragma unroll
                         for (int w = 0; w < 8; w++) d[w] = e[w];
                     }
-#pragma unroll
-                    for (int w = 0; w < 8; w++) out_root[w] = d[w];
-                    if (atomicCAS(ent, 0u, 1u) == 0u) {
-                        ent[1] = height;
+                    if (atomicCAS(ent, 0u, 1u) == 0u) {  // claim an empty slot; busy / occupied slots are left alone
+                        ent[1] = (u32)k;
 #pragma unroll
                         for (int w = 0; w < 8; w++) {
                             ent[2 + w] = x[w];
@@ -648,31 +664,51 @@ __global__ void __launch_bounds__(DT, 7) chunk_commit_dedup128_kernel(const u64*
                         st_release_u32(ent, 2u);
                     }
                 }
+                store_digest(Tcur, Pcur, r, d);  // in place: entry r is read and written by this thread only
             }
-            return;
-        } else if (D * D <= DD_PAIR_CAP) {  // dedup level: one compression per distinct (left id, right id)
+            __syncthreads();
+            if (nodes == 1) break;
+        }
+        const int half = nodes >> 1;
+        if (D * D <= DD_PAIR_CAP) {  // dedup level: one compression per distinct (left id, right id)
             const int space = D * D;
+            const bool light = space <= 32;  // one bitmap word: ranks by popcount, no block-wide prefix
             for (int w = tid; w < ((space + 31) >> 5); w += DT) sm.bitmap[w] = 0;
             __syncthreads();
             u32 keyv[4];
             u32 own = 0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = tid + k * DT;
-                keyv[k] = (i < half) ? (u32)idcur[2 * i] * D + idcur[2 * i + 1] : 0u;
-                if (bitmap_set_owner(sm.bitmap, keyv[k], i < half, space <= 32)) own |= 1u << k;
+            for (int kq = 0; kq < 4; kq++) {
+                const int i = tid + kq * DT;
+                keyv[kq] = (i < half) ? (u32)idcur[2 * i] * D + idcur[2 * i + 1] : 0u;
+                if (bitmap_set_owner(sm.bitmap, keyv[kq], i < half, light)) own |= 1u << kq;
             }
             __syncthreads();
-            bitmap_prefix128(sm, (space + 31) >> 5);
-            __syncthreads();
-            const int Dn = (int)sm.total;
+            int Dn;
+            if (light) {
+                const u32 word = sm.bitmap[0];
+                Dn = __popc(word);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int i = tid + k * DT;
-                if (i < half) {
-                    const u32 rk = bitmap_rank128(sm, keyv[k]);
-                    idnext[i] = (unsigned short)rk;
-                    if (own & (1u << k)) sm.list[rk] = (unsigned short)keyv[k];
+                for (int kq = 0; kq < 4; kq++) {
+                    const int i = tid + kq * DT;
+                    if (i < half) {
+                        const u32 rk = __popc(word & ((1u << keyv[kq]) - 1u));
+                        idnext[i] = (unsigned short)rk;
+                        if (own & (1u << kq)) sm.list[rk] = (unsigned short)keyv[kq];
+                    }
+                }
+            } else {
+                bitmap_prefix128(sm, (space + 31) >> 5);
+                __syncthreads();
+                Dn = (int)sm.total;
+#pragma unroll
+                for (int kq = 0; kq < 4; kq++) {
+                    const int i = tid + kq * DT;
+                    if (i < half) {
+                        const u32 rk = bitmap_rank128(sm, keyv[kq]);
+                        idnext[i] = (unsigned short)rk;
+                        if (own & (1u << kq)) sm.list[rk] = (unsigned short)keyv[kq];
+                    }
                 }
             }
             __syncthreads();

@@ -163,7 +163,8 @@ def test_column_commit_and_openings_vs_oracle(ctx, oracle, n, c):
     tree.free()
 
 
-@pytest.mark.parametrize("kind", ["const", "flags", "moves", "sym16", "walk", "counter", "wide_small", "mixed_sign", "random"])
+@pytest.mark.parametrize("kind", ["const", "flags", "moves", "sym16", "walk", "counter", "wide_small", "mixed_sign", "random",
+                                  "blocks512", "blocks96", "abab", "sparse_ones", "two_halves"])
 @pytest.mark.parametrize("n", [4, 256, 1024, 8192])
 def test_value_aware_commit_matches_plain_and_oracle(ctx, oracle, kind, n):
     """The dedup kernel (identical leaves / sibling pairs hashed once) must give the same roots and openings as one
@@ -179,6 +180,11 @@ def test_value_aware_commit_matches_plain_and_oracle(ctx, oracle, kind, n):
         "counter": i % 1024,                       # 1024 distinct values in range 1024
         "wide_small": (i * 37) % 1000,             # many distinct, still inside the key range
         "mixed_sign": np.where(i % 2 == 0, -(i % 50), i % 60),
+        "blocks512": 10 + (i // 512) % 7,          # block-constant, aligned runs (uniform-run chains + memo)
+        "blocks96": 3 + (i // 96) % 5,             # block-constant, unaligned runs
+        "abab": i % 2,                             # every pair identical one level up
+        "sparse_ones": (i % 512 == 0).astype(np.int64),
+        "two_halves": (i >= n // 2).astype(np.int64) * 9,
         "random": None,
     }[kind]
     if col is None:
@@ -188,12 +194,14 @@ def test_value_aware_commit_matches_plain_and_oracle(ctx, oracle, kind, n):
     cols = np.stack([vals, vals[::-1].copy()])
     labels = ["head_3", "wsym_11"]
     exp = oracle.column_commit(cols, labels)
-    ctx.set_option("dedup", 1)
-    got = ctx.column_commit(cols, labels)
+    ctx.set_option("dedup", 1)  # 256-thread variant
+    got1 = ctx.column_commit(cols, labels)
+    ctx.set_option("dedup", 2)  # 128-thread variant (default)
+    got2 = ctx.column_commit(cols, labels)
     ctx.set_option("dedup", 0)
     plain = ctx.column_commit(cols, labels)
-    ctx.set_option("dedup", 1)
-    assert np.array_equal(got, exp) and np.array_equal(plain, exp)
+    ctx.set_option("dedup", 2)
+    assert np.array_equal(got1, exp) and np.array_equal(got2, exp) and np.array_equal(plain, exp)
 
 
 @pytest.mark.parametrize("k,lb,c", [(1, 3, 2), (6, 3, 3), (10, 2, 2), (12, 3, 5), (14, 3, 2)])
@@ -282,6 +290,30 @@ def test_prove_v1_kats_and_accept(ctx, oracle):
     p2 = ctx.prove_v1(m.blocks_to_compact(fx["blocks"]), bytes.fromhex(fx["manifest"]["root"]))
     assert len(p2) == 270967
     assert oracle.blake3(p2).hex() == "7852805e6d6c64027aafe0c2672927715bcd92aaa08f83383de1fc6a183ba6ca"
+
+
+def _digest_cases():
+    import json, os
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prove_digests.json")
+    return sorted(json.load(open(p)).items()) if os.path.exists(p) else []
+
+
+@pytest.mark.parametrize("name,exp", _digest_cases())
+def test_prove_v1_large_sizes_match_oracle_digests(ctx, oracle, name, exp):
+    """BASELINE configs[2] (T=2^22) and smaller: proof bytes equal the CPU oracle's (length + BLAKE3 committed by
+    tests/golden/make_prove_digests.py, which ran the oracle once — minutes of CPU — in the build container)."""
+    m = pkg()
+    ct = m.simulate(1 << exp["log_T"], 512, 8, seed=42)
+    root = m.manifest_root(ct)
+    assert root.hex() == exp["manifest_root"]
+    proof = ctx.prove_v1(ct, root)
+    assert len(proof) == exp["proof_len"]
+    assert oracle.blake3(proof).hex() == exp["proof_blake3"]
+    ctx.set_option("dedup", 0)
+    try:
+        assert ctx.prove_v1(ct, root) == proof  # same bytes with one compression per node
+    finally:
+        ctx.set_option("dedup", 2)
 
 
 def test_prove_v1_reject_cases_match_reference_tests(ctx, oracle):
