@@ -189,7 +189,13 @@ __device__ __forceinline__ bool bitmap_set_owner(u32* bitmap, u32 key, bool vali
     return !(old & bit);
 }
 
-constexpr int MEMO_SLOTS = 4096;  // power of two
+__device__ unsigned long long g_memo_stats[4];  // debug counters: hits, misses, claimed, chains (SEZKP_MEMO_STATS builds only)
+#ifdef SEZKP_MEMO_STATS
+#define MEMO_STAT(i) atomicAdd(&g_memo_stats[i], 1ULL)
+#else
+#define MEMO_STAT(i)
+#endif
+constexpr int MEMO_SLOTS = 16384;  // power of two
 constexpr int MEMO_WORDS = 18;    // state, height, x[8], root[8]
 __device__ __forceinline__ u32 ld_acquire_u32(const u32* p) {
     u32 v;
@@ -302,13 +308,13 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const 
                 const u32 height = (u32)nodes;
                 u32* ent = memo + (size_t)((d[0] ^ (d[1] * 0x9E3779B1u) ^ height) & (MEMO_SLOTS - 1)) * MEMO_WORDS;
                 bool hit = false;
-                if (ld_acquire_u32(ent) == 2u && ent[1] == height) {
+                if (ld_acquire_u32(ent) == 2u && __ldcg(ent + 1) == height) {
                     hit = true;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) hit = hit && (ent[2 + w] == d[w]);
+                    for (int w = 0; w < 8; w++) hit = hit && (__ldcg(ent + 2 + w) == d[w]);
                     if (hit) {
 #pragma unroll
-                        for (int w = 0; w < 8; w++) out_root[w] = ent[10 + w];
+                        for (int w = 0; w < 8; w++) out_root[w] = __ldcg(ent + 10 + w);
                     }
                 }
                 if (!hit) {
@@ -637,23 +643,38 @@ __global__ void __launch_bounds__(DT, 7) chunk_commit_dedup128_kernel(const u64*
 #pragma unroll
                 for (int w = 0; w < 8; w++) x[w] = d[w] = Tcur[w * Pcur + r];
                 u32* ent = memo + (size_t)((d[0] ^ (d[1] * 0x9E3779B1u) ^ (u32)k) & (MEMO_SLOTS - 1)) * MEMO_WORDS;
+                // slot states: 0 empty, 1 being computed by a resident CTA, 2 published.  The first arrival claims the
+                // slot and computes; concurrent arrivals (a whole wave of chunks of the same column starts together)
+                // wait for the publication instead of redoing the chain — the owner never waits on anyone, so this
+                // cannot deadlock.  A published or awaited slot that turns out to hold another key is simply a miss.
+                u32 st = ld_acquire_u32(ent);
+                bool owner = false;
+                if (st == 0u) {
+                    owner = atomicCAS(ent, 0u, 1u) == 0u;
+                    st = owner ? 0u : 1u;
+                }
+                if (st == 1u) {
+                    while ((st = ld_acquire_u32(ent)) != 2u) __nanosleep(200);
+                }
                 bool hit = false;
-                if (ld_acquire_u32(ent) == 2u && ent[1] == (u32)k) {
+                if (st == 2u && __ldcg(ent + 1) == (u32)k) {  // fields via L2: L1 is not coherent
                     hit = true;
 #pragma unroll
-                    for (int w = 0; w < 8; w++) hit = hit && (ent[2 + w] == d[w]);
+                    for (int w = 0; w < 8; w++) hit = hit && (__ldcg(ent + 2 + w) == d[w]);
                     if (hit) {
 #pragma unroll
-                        for (int w = 0; w < 8; w++) d[w] = ent[10 + w];
+                        for (int w = 0; w < 8; w++) d[w] = __ldcg(ent + 10 + w);
                     }
                 }
+                MEMO_STAT(hit ? 0 : 1);
                 if (!hit) {
                     for (int j = 0; j < k; j++) {
                         b3::parent(d, d, e);
 #pragma unroll
                         for (int w = 0; w < 8; w++) d[w] = e[w];
                     }
-                    if (atomicCAS(ent, 0u, 1u) == 0u) {  // claim an empty slot; busy / occupied slots are left alone
+                    if (owner) {
+                        MEMO_STAT(2);
                         ent[1] = (u32)k;
 #pragma unroll
                         for (int w = 0; w < 8; w++) {
@@ -834,6 +855,14 @@ b3::LabelTemplate make_label_template(const char* label) {
     t.off = (u32)(12 + L);
     t.block_len = (u32)(20 + L);
     return t;
+}
+
+extern "C" void sezkp_debug_memo_stats(unsigned long long out[4], int reset) {
+    cudaMemcpyFromSymbol(out, g_memo_stats, sizeof(unsigned long long) * 4);
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_memo_stats, z, sizeof z);
+    }
 }
 
 void Commit::release(sezkp_ctx* ctx) {
