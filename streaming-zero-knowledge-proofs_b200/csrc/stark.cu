@@ -113,7 +113,7 @@ __global__ void compose_kernel(const u64* __restrict__ cols, u64 n, u32 tau, Com
 /* ------------------------------------------------------------------------------------------ */
 /* DEEP quotient: y[i] *= (shift*w^i - z)^-1, Montgomery batch inversion per thread              */
 /* ------------------------------------------------------------------------------------------ */
-constexpr int DEEP_PER_THREAD = 8;
+constexpr int DEEP_PER_THREAD = 16;
 __global__ void __launch_bounds__(256) deep_kernel(u64* __restrict__ y, u64 N, u64 shift, u64 w, u64 w_step, u64 z) {
     // thread handles i = base + lane + 32*k, k < DEEP_PER_THREAD (coalesced)
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
