@@ -646,21 +646,29 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             col_val[req_slot[i]] = req_val[i];
             std::memcpy(&col_cr[(size_t)req_slot[i] * 32], &req_cr[i * 32], 32);
         }
-        if (world > 1) {  // gather the opening records (value, chunk root, path) of every rank and keep each owner's
-            const size_t rec = 8 + 32 + (size_t)cdepth * 32, bytes = k_open * rec;
+        if (world > 1) {  // gather the opening records (value, chunk root, path): every rank sends only the ones it owns
+            const size_t rec = 8 + 32 + (size_t)cdepth * 32;
+            std::vector<std::vector<u32>> owned(world);
+            for (size_t o = 0; o < k_open; o++) owned[o_col[o] % world].push_back((u32)o);
+            size_t max_own = 0;
+            for (auto& v : owned) max_own = v.size() > max_own ? v.size() : max_own;
+            const size_t bytes = max_own * rec;
             std::vector<u8> mine(bytes, 0), all((size_t)world * bytes);
-            for (size_t o = 0; o < k_open; o++) {
-                std::memcpy(&mine[o * rec], &col_val[o], 8);
-                std::memcpy(&mine[o * rec + 8], &col_cr[o * 32], 32);
-                std::memcpy(&mine[o * rec + 40], &all_paths[o * (size_t)cdepth * 32], (size_t)cdepth * 32);
+            for (size_t j = 0; j < owned[rank].size(); j++) {
+                const size_t o = owned[rank][j];
+                std::memcpy(&mine[j * rec], &col_val[o], 8);
+                std::memcpy(&mine[j * rec + 8], &col_cr[o * 32], 32);
+                std::memcpy(&mine[j * rec + 40], &all_paths[o * (size_t)cdepth * 32], (size_t)cdepth * 32);
             }
             exchange(mine.data(), bytes, all.data());
-            for (size_t o = 0; o < k_open; o++) {
-                const u8* src = &all[(size_t)(o_col[o] % world) * bytes + o * rec];
-                std::memcpy(&col_val[o], src, 8);
-                std::memcpy(&col_cr[o * 32], src + 8, 32);
-                std::memcpy(&all_paths[o * (size_t)cdepth * 32], src + 40, (size_t)cdepth * 32);
-            }
+            for (int r = 0; r < world; r++)
+                for (size_t j = 0; j < owned[r].size(); j++) {
+                    const size_t o = owned[r][j];
+                    const u8* src = &all[(size_t)r * bytes + j * rec];
+                    std::memcpy(&col_val[o], src, 8);
+                    std::memcpy(&col_cr[o * 32], src + 8, 32);
+                    std::memcpy(&all_paths[o * (size_t)cdepth * 32], src + 40, (size_t)cdepth * 32);
+                }
         }
         const u64* o_val = col_val.data();
         const u8* o_cr = col_cr.data();
