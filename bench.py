@@ -341,8 +341,13 @@ def main():
         alg_bytes = 8 * ct.n_rows * n_cols
         achieved = alg_bytes / kms / 1e6
         compressions = n_cols * (2 * ct.n_rows - 1)
-        roofline = {"bound": "hbm", "kernel": "chunk_commit_dedup_kernel (+upper_reduce_kernel)", "achieved": achieved, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+        traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tpath) and wl["log_T"] == 22:
+            traffic = json.load(open(tpath))["dram_bytes_read_plus_write_per_launch"]
+        roofline = {"bound": "hbm", "kernel": "chunk_commit_dedup128_kernel (+upper_reduce_kernel)", "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu)",
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": kms,
                     "share_of_step": kms / ms,
                     "note": "BLAKE3 hashing is integer-ALU bound (8 B in, 2 compressions out per leaf); the value-aware kernel "
