@@ -117,6 +117,12 @@ class Context:
     def set_option(self, name: str, value: int):
         self._ck(self.lib.sezkp_cuda_set_option(self.h, name.encode(), C.c_int64(value)))
 
+    def tab_stats(self) -> tuple:
+        """(columns served from subtree tables, chunks redone by the generic kernel) of the last value-aware commit"""
+        out = (C.c_ulonglong * 2)()
+        self.lib.sezkp_debug_tab_stats(self.h, out)
+        return int(out[0]), int(out[1])
+
     def launch_count(self, reset=False) -> int:
         return int(self.lib.sezkp_cuda_launch_count(self.h, C.c_int(int(reset))))
 

@@ -131,6 +131,9 @@ struct sezkp_ctx {
     std::vector<std::pair<std::string, double>> timings;  // phase -> ms (last prove)
     int dedup_variant = 2;                  // 1: 256-thread kernel, 2: 128-thread kernel (more chunks in flight per SM)
     bool dedup_enabled = true;              // value-aware column commit (SEZKP_NO_DEDUP=1 or sezkp_cuda_set_option disables)
+    bool tabled_enabled = true;             // subtree tables for structured columns (option "tabled"; needs dedup)
+    u64 tab_redone_chunks = 0;              // chunks the tabled pass handed back to the generic kernel (last commit)
+    int tab_columns = 0;                    // columns served from subtree tables (last commit)
     u64 launches = 0;                       // kernels launched since last reset
 };
 

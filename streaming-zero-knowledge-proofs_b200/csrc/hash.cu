@@ -4,6 +4,7 @@
 // StreamingLayerBuilder (v1/fri_stream.rs:55-122).  For a power-of-two number of leaves the chunked
 // tree (2^10-leaf chunk trees under an outer tree of chunk roots) is the plain binary tree, so one
 // kernel reduces a whole chunk in shared memory and only chunk roots and the levels above are stored.
+#include <algorithm>
 #include <cstring>
 
 #include "hash.cuh"
@@ -469,11 +470,19 @@ __device__ __forceinline__ void store_digest(u32* T, int pitch, int i, const u32
 
 __global__ void __launch_bounds__(DT, 7) chunk_commit_dedup128_kernel(const u64* __restrict__ values, u64 n, u64 col_stride, int cl,
                                                                       const b3::LabelTemplate* __restrict__ templates,
-                                                                      u32* __restrict__ upper, u64 n_ch, u32* memo, u64 chunk0) {
+                                                                      u32* __restrict__ upper, u64 n_ch, u32* memo, u64 chunk0,
+                                                                      const int* __restrict__ col_list, const u32* __restrict__ work) {
     extern __shared__ __align__(16) unsigned char dd_raw[];
     Dedup128Smem& sm = *reinterpret_cast<Dedup128Smem*>(dd_raw);
-    const u64 chunk = chunk0 + blockIdx.x;
-    const int col = blockIdx.y;
+    // three addressing modes: dense grid (chunk, column); grid over a column list; or a work list of (column, chunk)
+    // pairs — work[0] = count, pairs from work[2] — used to redo single chunks that a tabled kernel could not serve
+    u64 chunk = chunk0 + blockIdx.x;
+    int col = col_list ? col_list[blockIdx.y] : (int)blockIdx.y;
+    if (work) {
+        if (blockIdx.x >= work[0]) return;
+        col = (int)work[2 + 2 * blockIdx.x];
+        chunk = work[3 + 2 * blockIdx.x];
+    }
     const int leaves = 1 << cl;
     const u64* v = values + (u64)col * col_stride + (chunk << cl);
     const int tid = threadIdx.x;
@@ -760,6 +769,333 @@ __global__ void __launch_bounds__(DT, 7) chunk_commit_dedup128_kernel(const u64*
     if (tid < 8) out_root[tid] = Tcur[tid * Pcur];
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* structured columns: subtree tables                                                            */
+/* ------------------------------------------------------------------------------------------ */
+// BLAKE3 is a function, so the digest of an aligned subtree of g = 2^k leaves depends only on its g values.  Trace
+// columns are highly structured, and for three structures the set of subtrees that can occur is small enough to
+// hash ONCE per column into a table (<= 65536 entries, L2-resident) before the chunks are reduced:
+//   ALPHA  every value lies in a range of A consecutive residues (flags, moves in {-1,0,1}, 4-bit symbols):
+//          A^g subtrees; g = 16 (A = 2), 8 (A <= 4), 4 (A <= 16) or 2 (A <= 256)
+//   WALK   consecutive rows differ by -1, 0 or +1 inside aligned groups of 4 (a head position): 27*A subtrees, g = 4
+//   CONST  aligned runs of g = 2^k equal values (block constants: window length, head offsets): A subtrees, k <= 10
+// A chunk kernel then reads the values (8 B/row, the only HBM traffic), forms each group's table index, gathers the
+// 1024/g level-k digests and hashes only the levels above: 1 - 1/g of the compressions of a tree are never executed.
+// The classification comes from a sample of the column and is only a performance hint: every value is checked
+// against the table's assumptions while it is read, and any chunk holding a value that breaks them is redone by
+// the generic value-aware kernel through a work list, so roots never depend on the classification being right.
+enum { TAB_NONE = 0, TAB_ALPHA = 1, TAB_WALK = 2, TAB_CONST = 3 };
+struct ColTab {
+    u64 min_key;       // key = value + 2^31 (mod p); the table covers keys min_key .. min_key + A - 1
+    u32 A;
+    u32 cls;           // TAB_*
+    u32 logg;          // log2 of the leaves under one table entry
+    u32 pad;
+    u32* lv[4];        // ALPHA: tables of levels 1..4 (lv[logg-1] is the one gathered from); others: lv[0]
+};
+struct ColStats {
+    u64 min_key, max_key;
+    u32 kconst;        // all sampled aligned runs of 2^kconst rows are constant (10 = whole chunks)
+    u32 walk_ok;       // sampled rows move by at most one inside aligned groups of 4
+};
+constexpr u64 KEY_HALF = 1ULL << 31;
+constexpr int VIO_CAP = 16384;  // (column, chunk) pairs a tabled pass may hand to the generic kernel
+
+// Sampled column statistics: up to 64 whole chunks spread evenly over the rows that are already final.
+// grid (columns), 256 threads, 4 consecutive rows per thread and chunk.
+__global__ void __launch_bounds__(256) column_stats_kernel(const u64* __restrict__ values, u64 col_stride, u64 avail_chunks,
+                                                           ColStats* __restrict__ out) {
+    const u64* v = values + (u64)blockIdx.x * col_stride;
+    const u64 segs = avail_chunks < 64 ? avail_chunks : 64;
+    u64 mn = ~0ULL, mx = 0;
+    u32 kc = MAX_CL, walk = 1;
+    const int i0 = 4 * threadIdx.x;
+    for (u64 sgi = 0; sgi < segs; sgi++) {
+        const u64* c = v + (((avail_chunks * sgi) / segs) << MAX_CL);
+        u64 prev = i0 ? gl::add(c[i0 - 1], KEY_HALF) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = i0 + j;
+            const u64 a = gl::add(c[i], KEY_HALF);
+            mn = a < mn ? a : mn;
+            mx = a > mx ? a : mx;
+            if (i > 0 && a != prev) {
+                const u32 tz = (u32)__ffs(i) - 1;
+                kc = tz < kc ? tz : kc;
+                if (j > 0) {
+                    const u64 d = gl::sub(a, prev);
+                    if (d != 1 && d != gl::P - 1) walk = 0;
+                }
+            }
+            prev = a;
+        }
+    }
+    __shared__ u64 smn[256], smx[256];
+    __shared__ u32 skc[256], swk[256];
+    const int t = threadIdx.x;
+    smn[t] = mn; smx[t] = mx; skc[t] = kc; swk[t] = walk;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) {
+            smn[t] = smn[t + o] < smn[t] ? smn[t + o] : smn[t];
+            smx[t] = smx[t + o] > smx[t] ? smx[t + o] : smx[t];
+            skc[t] = skc[t + o] < skc[t] ? skc[t + o] : skc[t];
+            swk[t] &= swk[t + o];
+        }
+        __syncthreads();
+    }
+    if (t == 0) out[blockIdx.x] = ColStats{smn[0], smx[0], skc[0], swk[0]};
+}
+
+__device__ __forceinline__ void tab_leaf(const b3::LabelTemplate* tpl, u64 v, u32 (&d)[8]) {
+    if (tpl) {
+        const b3::LabelTemplate t = *tpl;
+        B3_DISPATCH_LABELED(t, { b3::leaf_labeled_w<B3W>(t, v, d); })
+    } else b3::leaf(v, d);
+}
+__device__ __forceinline__ void st_digest_g(u32* dst, const u32 (&d)[8]) {
+    uint4* o = reinterpret_cast<uint4*>(dst);
+    o[0] = make_uint4(d[0], d[1], d[2], d[3]);
+    o[1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+__device__ __forceinline__ void ld_digest_g(const u32* src, u32 (&d)[8]) {
+    const uint4* e = reinterpret_cast<const uint4*>(src);
+    const uint4 e0 = __ldg(e), e1 = __ldg(e + 1);
+    d[0] = e0.x; d[1] = e0.y; d[2] = e0.z; d[3] = e0.w;
+    d[4] = e1.x; d[5] = e1.y; d[6] = e1.z; d[7] = e1.w;
+}
+
+// First table of every tabled column (grid.y indexes `list`): ALPHA lv[0][a0 + A*a1] = H(leaf a0, leaf a1);
+// WALK lv[0][a0 + A*(d1 + 3*d2 + 9*d3)] = the 4-leaf subtree of a0, a0+d1-1, ...; CONST lv[0][a] = 2^logg equal leaves.
+__global__ void __launch_bounds__(128) tab_build_first_kernel(const ColTab* __restrict__ tabs, const int* __restrict__ list,
+                                                              const b3::LabelTemplate* __restrict__ templates) {
+    const int col = list[blockIdx.y];
+    const ColTab tb = tabs[col];
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const b3::LabelTemplate* tpl = templates ? templates + col : nullptr;
+    auto val = [&](u32 a) { return gl::sub(gl::add(tb.min_key, (u64)a), KEY_HALF); };  // key offset -> field element
+    u32 d[8];
+    if (tb.cls == TAB_ALPHA) {
+        if (i >= tb.A * tb.A) return;
+        u32 l[8], r[8];
+        tab_leaf(tpl, val(i % tb.A), l);
+        tab_leaf(tpl, val(i / tb.A), r);
+        b3::parent(l, r, d);
+    } else if (tb.cls == TAB_WALK) {
+        if (i >= 27 * tb.A) return;
+        const u32 a0 = i % tb.A, code = i / tb.A;
+        // offsets relative to a0 lie in [-3, 3]; keys outside the table range are still field elements
+        const u64 k0 = gl::add(tb.min_key, (u64)a0);
+        const u64 k1 = gl::sub(gl::add(k0, (u64)(code % 3)), 1), k2 = gl::sub(gl::add(k1, (u64)((code / 3) % 3)), 1),
+                  k3 = gl::sub(gl::add(k2, (u64)(code / 9)), 1);
+        u32 l[8], r[8], p0[8], p1[8];
+        tab_leaf(tpl, gl::sub(k0, KEY_HALF), l);
+        tab_leaf(tpl, gl::sub(k1, KEY_HALF), r);
+        b3::parent(l, r, p0);
+        tab_leaf(tpl, gl::sub(k2, KEY_HALF), l);
+        tab_leaf(tpl, gl::sub(k3, KEY_HALF), r);
+        b3::parent(l, r, p1);
+        b3::parent(p0, p1, d);
+    } else {
+        if (i >= tb.A) return;
+        u32 e[8];
+        tab_leaf(tpl, val(i), d);
+        for (u32 j = 0; j < tb.logg; j++) {
+            b3::parent(d, d, e);
+#pragma unroll
+            for (int w = 0; w < 8; w++) d[w] = e[w];
+        }
+    }
+    st_digest_g(tb.lv[0] + (size_t)i * 8, d);
+}
+// ALPHA level s+1 from level s: lv[s][i] = H(lv[s-1][i % cnt], lv[s-1][i / cnt]), cnt = A^(2^s) entries below.
+__global__ void __launch_bounds__(128) tab_build_up_kernel(const ColTab* __restrict__ tabs, const int* __restrict__ list, int s) {
+    const ColTab tb = tabs[list[blockIdx.y]];
+    if (tb.cls != TAB_ALPHA || (int)tb.logg <= s) return;
+    u32 cnt = tb.A;
+    for (int j = 0; j < s; j++) cnt *= cnt;
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (u64)cnt * cnt) return;
+    u32 l[8], r[8], d[8];
+    ld_digest_g(tb.lv[s - 1] + (size_t)(i % cnt) * 8, l);
+    ld_digest_g(tb.lv[s - 1] + (size_t)(i / cnt) * 8, r);
+    b3::parent(l, r, d);
+    st_digest_g(tb.lv[s] + (size_t)i * 8, d);
+}
+
+// Chunk roots of tabled columns.  One CTA gathers the table entries of 2^(LOGG-1) <= 8 chunks (at most 512 nodes)
+// and reduces them to chunk roots.  Each warp walks over contiguous 256-row steps (8 consecutive rows per lane, two
+// full sectors), so a group of up to 256 rows is keyed with warp shuffles and longer runs are carried across steps.
+// grid (ceil(chunks / tab_chunks_per_cta(LOGG)), columns of this LOGG), 128 threads.
+constexpr int tab_chunks_per_cta(int logg) { return logg <= 4 ? (1 << (logg - 1)) : 8; }
+template <int LOGG>
+__global__ void __launch_bounds__(DT, 8) chunk_commit_tabled_kernel(const u64* __restrict__ values, u64 col_stride,
+                                                                    const ColTab* __restrict__ tabs, const int* __restrict__ col_list,
+                                                                    u32* __restrict__ upper, u64 n_ch, u64 chunk0, u64 chunk1,
+                                                                    u32* __restrict__ vio) {
+    __shared__ __align__(16) u32 X[8 * D2_PX];
+    __shared__ __align__(16) u32 Y[8 * D2_PY];
+    constexpr int CH = tab_chunks_per_cta(LOGG);                 // chunks per CTA
+    constexpr int STEPS_PER_WARP = CH;                           // CH*4 steps of 256 rows over 4 warps
+    constexpr int NODES = (CH << MAX_CL) >> LOGG;                // table entries gathered per CTA (<= 512)
+    constexpr int NPS = LOGG <= 8 ? (256 >> LOGG) : 0;           // nodes per step (0: a node spans several steps)
+    const int col = col_list[blockIdx.y];
+    const ColTab tb = tabs[col];
+    const u32* table = tb.lv[tb.cls == TAB_ALPHA ? LOGG - 1 : 0];
+    const u64 cta_chunk0 = chunk0 + (u64)blockIdx.x * CH;
+    const u64* v = values + (u64)col * col_stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 A = tb.A;
+
+    u32 run_key = 0;   // LOGG > 8: key and state of the run being assembled
+    bool run_bad = false;
+    for (int st = 0; st < STEPS_PER_WARP; st++) {
+        const int step = warp * STEPS_PER_WARP + st;             // 256-row step inside the CTA's rows
+        const u64 row = (cta_chunk0 << MAX_CL) + ((u64)step << 8);
+        const u64 chunk = row >> MAX_CL;
+        if (chunk >= chunk1) break;                              // warp-uniform
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(v + row + 8 * lane);
+        const ulonglong2 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+        const u64 raw[8] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y, q3.x, q3.y};
+        u32 a[8];
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const u64 k = gl::sub(gl::add(raw[j], KEY_HALF), tb.min_key);
+            bad |= k >= (u64)A;
+            a[j] = (u32)k;
+        }
+        u32 idx[4] = {0, 0, 0, 0};   // table indices of this lane's nodes (LOGG = 1: 4, 2: 2, >= 3: at most one)
+        bool lead = true;            // this lane gathers idx[0]
+        if (tb.cls == TAB_ALPHA) {
+            if (LOGG == 1) {
+#pragma unroll
+                for (int m = 0; m < 4; m++) idx[m] = a[2 * m] + A * a[2 * m + 1];
+            } else if (LOGG == 2) {
+#pragma unroll
+                for (int m = 0; m < 2; m++) idx[m] = a[4 * m] + A * (a[4 * m + 1] + A * (a[4 * m + 2] + A * a[4 * m + 3]));
+            } else {
+                u32 h = 0;
+#pragma unroll
+                for (int j = 7; j >= 0; j--) h = h * A + a[j];
+                if (LOGG == 4) {   // A = 2: two lanes per node
+                    const u32 o = __shfl_xor_sync(0xffffffffu, h, 1);
+                    bad |= (bool)__shfl_xor_sync(0xffffffffu, (int)bad, 1);
+                    h += o << 8;
+                    lead = (lane & 1) == 0;
+                }
+                idx[0] = h;
+            }
+        } else if (tb.cls == TAB_WALK) {  // LOGG == 2
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                const u32 d1 = a[4 * m + 1] - a[4 * m] + 1, d2 = a[4 * m + 2] - a[4 * m + 1] + 1, d3 = a[4 * m + 3] - a[4 * m + 2] + 1;
+                bad |= (d1 > 2) | (d2 > 2) | (d3 > 2);
+                idx[m] = a[4 * m] + A * (d1 + 3 * d2 + 9 * d3);
+            }
+        } else {  // TAB_CONST: runs of 2^LOGG equal values
+            if (LOGG == 1) {
+#pragma unroll
+                for (int m = 0; m < 4; m++) {
+                    bad |= a[2 * m] != a[2 * m + 1];
+                    idx[m] = a[2 * m];
+                }
+            } else if (LOGG == 2) {
+#pragma unroll
+                for (int m = 0; m < 2; m++) {
+                    bad |= (a[4 * m] != a[4 * m + 1]) | (a[4 * m] != a[4 * m + 2]) | (a[4 * m] != a[4 * m + 3]);
+                    idx[m] = a[4 * m];
+                }
+            } else {
+#pragma unroll
+                for (int j = 1; j < 8; j++) bad |= a[j] != a[0];
+                constexpr int SEG = LOGG >= 8 ? 32 : (1 << (LOGG >= 3 ? LOGG - 3 : 0));   // lanes per run inside a step
+                const int leader = lane & ~(SEG - 1);
+                bad |= a[0] != __shfl_sync(0xffffffffu, a[0], leader);
+                const u32 bm = __ballot_sync(0xffffffffu, bad);
+                const u32 segmask = (SEG == 32 ? 0xffffffffu : ((1u << SEG) - 1u)) << leader;
+                bad = (bm & segmask) != 0;
+                lead = lane == leader;
+                idx[0] = a[0];
+                if (LOGG > 8) {   // the run spans 2^(LOGG-8) steps of this warp
+                    constexpr int SPN = 1 << (LOGG > 8 ? LOGG - 8 : 0);
+                    if ((st & (SPN - 1)) == 0) {
+                        run_key = a[0];
+                        run_bad = false;
+                    }
+                    run_bad |= bad | (a[0] != run_key);
+                    bad = run_bad;
+                    lead = lead && ((st & (SPN - 1)) == SPN - 1);
+                }
+            }
+        }
+        if (__any_sync(0xffffffffu, bad)) {
+            // hand the chunk to the generic kernel (one entry per warp and step is enough; duplicates are harmless)
+            if (lane == 0) {
+                const u32 slot = atomicAdd(&vio[0], 1u);
+                if (slot < VIO_CAP) {
+                    vio[2 + 2 * slot] = (u32)col;
+                    vio[3 + 2 * slot] = (u32)chunk;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 4; m++) idx[m] = 0;
+        }
+        // gather
+        if (LOGG == 1) {
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                u32 d[8];
+                ld_digest_g(table + (size_t)idx[m] * 8, d);
+                store_digest(X, D2_PX, step * 128 + lane * 4 + m, d);
+            }
+        } else if (LOGG == 2) {
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                u32 d[8];
+                ld_digest_g(table + (size_t)idx[m] * 8, d);
+                store_digest(X, D2_PX, step * 64 + lane * 2 + m, d);
+            }
+        } else if (lead) {
+            u32 d[8];
+            ld_digest_g(table + (size_t)idx[0] * 8, d);
+            int node;
+            if (LOGG <= 8) node = step * NPS + (lane >> (LOGG - 3 > 0 ? LOGG - 3 : 0));
+            else node = step >> (LOGG - 8);
+            store_digest(X, D2_PX, node, d);
+        }
+    }
+    __syncthreads();
+    // NODES nodes of level LOGG -> chunk roots (level 10): 10 - LOGG plain levels, ping-pong X -> Y -> X ...
+    u32* Tcur = X;
+    u32* Tnext = Y;
+    int Pcur = D2_PX, Pnext = D2_PY;
+    int nodes = NODES;
+#pragma unroll 1
+    for (int lvl = LOGG; lvl < MAX_CL; lvl++) {
+        const int half = nodes >> 1;
+        for (int i = threadIdx.x; i < half; i += DT) {
+            u32 l[8], r[8], d[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint2 pr = *reinterpret_cast<const uint2*>(&Tcur[w * Pcur + 2 * i]);
+                l[w] = pr.x;
+                r[w] = pr.y;
+            }
+            b3::parent(l, r, d);
+            store_digest(Tnext, Pnext, i, d);
+        }
+        __syncthreads();
+        nodes = half;
+        u32* tp = Tcur; Tcur = Tnext; Tnext = tp;
+        const int pp = Pcur; Pcur = Pnext; Pnext = pp;
+    }
+    // nodes == CH chunk roots
+    u32* out = upper + ((u64)col * (2 * n_ch - 1) + cta_chunk0) * 8;
+    const u64 valid = chunk1 > cta_chunk0 ? (chunk1 - cta_chunk0 < (u64)CH ? chunk1 - cta_chunk0 : (u64)CH) : 0;
+    for (int i = threadIdx.x; i < (int)valid * 8; i += DT) out[i] = Tcur[(i & 7) * Pcur + (i >> 3)];
+}
+
 // digests at level l0 of `upper` -> reduce groups of 2^k -> levels l0+1..l0+k stored.  grid (count>>k, cols)
 __global__ void __launch_bounds__(HASH_THREADS) upper_reduce_kernel(u32* __restrict__ upper, u64 n_ch, int l0, int k) {
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
@@ -865,14 +1201,212 @@ extern "C" void sezkp_debug_memo_stats(unsigned long long out[4], int reset) {
     }
 }
 
+// debug: columns served from subtree tables / chunks handed back to the generic kernel in the last value-aware commit
+extern "C" void sezkp_debug_tab_stats(sezkp_ctx* ctx, unsigned long long out[2]) {
+    out[0] = (unsigned long long)ctx->tab_columns;
+    out[1] = ctx->tab_redone_chunks;
+}
+
 void Commit::release(sezkp_ctx* ctx) {
     if (owns_values && values) ctx->pool.free((void*)values);
     ctx->pool.free(upper);
     ctx->pool.free(templates);
+    ctx->pool.free(tab_dev);
+    tab_dev = nullptr;
+    tab_classified = false;
     values = nullptr;
     upper = nullptr;
     templates = nullptr;
 }
+
+// ---- host side of the subtree tables --------------------------------------------------------------------------
+namespace {
+struct TabLayout {
+    size_t off_tabs, off_stats, off_lists, off_vio, bytes;
+    explicit TabLayout(int cols) {
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        off_tabs = 0;
+        off_stats = al(off_tabs + sizeof(ColTab) * cols);
+        off_lists = al(off_stats + sizeof(ColStats) * cols);
+        off_vio = al(off_lists + sizeof(int) * cols);
+        bytes = al(off_vio + sizeof(u32) * (2 + 2 * VIO_CAP));
+    }
+};
+template <int LOGG>
+void launch_tabled(sezkp_ctx* ctx, const Commit& cm, const ColTab* tabs, const int* list, int count, u64 chunk0, u64 chunk1, u32* vio) {
+    constexpr u64 CH = tab_chunks_per_cta(LOGG);
+    dim3 grid((unsigned)((chunk1 - chunk0 + CH - 1) / CH), (unsigned)count);
+    chunk_commit_tabled_kernel<LOGG><<<grid, DT, 0, ctx->stream>>>(cm.values, cm.col_stride, tabs, list, cm.upper, cm.n_ch, chunk0, chunk1, vio);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+
+// Sample the columns, pick a table class per column, build the tables.  Rows of chunks [0, avail_chunks) are final.
+void tab_classify(sezkp_ctx* ctx, Commit& cm, u64 avail_chunks) {
+    const int cols = cm.cols;
+    const TabLayout lay(cols);
+    u8* base = (u8*)ctx->pool.alloc(lay.bytes);
+    cm.tab_dev = base;
+    ColTab* tabs_dev = (ColTab*)(base + lay.off_tabs);
+    ColStats* stats_dev = (ColStats*)(base + lay.off_stats);
+    int* lists_dev = (int*)(base + lay.off_lists);
+    u32* vio = (u32*)(base + lay.off_vio);
+    column_stats_kernel<<<cols, 256, 0, ctx->stream>>>(cm.values, cm.col_stride, avail_chunks, stats_dev);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    std::vector<ColStats> st(cols);
+    CUDA_CHECK(cudaMemcpyAsync(st.data(), stats_dev, sizeof(ColStats) * cols, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(vio, 0, 8, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+
+    std::vector<ColTab> tabs(cols);
+    std::vector<size_t> entries(cols, 0);
+    cm.tab_logg.assign(cols, 0);
+    size_t total_entries = 0;
+    for (int c = 0; c < cols; c++) {
+        ColTab& tb = tabs[c];
+        std::memset(&tb, 0, sizeof tb);
+        const ColStats& s = st[c];
+        if (s.max_key < s.min_key || s.max_key - s.min_key >= 16384) continue;
+        const u32 A0 = (u32)(s.max_key - s.min_key) + 1;
+        const int la = A0 <= 2 ? 4 : A0 <= 4 ? 3 : A0 <= 16 ? 2 : A0 <= 256 ? 1 : 0;
+        const int lw = (s.walk_ok && A0 <= 680) ? 2 : 0;
+        const int lc = (int)s.kconst;
+        int logg = la, cls = TAB_ALPHA;
+        if (lw > logg) logg = lw, cls = TAB_WALK;
+        if (lc > logg) logg = lc, cls = TAB_CONST;
+        if (logg == 0) continue;
+        // ranges come from a sample: pad them where the table stays small (values outside still only cost a redo)
+        u32 A = A0;
+        if (cls == TAB_ALPHA) {
+            if (logg == 4) A = 2;
+            else if (logg == 1) A = std::min<u32>(256, 2 * A0 + 8);
+        } else if (cls == TAB_WALK) A = std::min<u32>(2048, 3 * A0 + 64);
+        else A = std::min<u32>(65536, 3 * A0 + 64);
+        u64 lo = (A - A0) / 2;
+        if (lo > s.min_key) lo = s.min_key;
+        tb.min_key = s.min_key - lo;
+        tb.A = A;
+        tb.cls = (u32)cls;
+        tb.logg = (u32)logg;
+        size_t e = 0;
+        if (cls == TAB_ALPHA) {
+            size_t cnt = A;
+            for (int l = 0; l < logg; l++) {
+                cnt *= cnt;
+                e += cnt;
+            }
+        } else e = cls == TAB_WALK ? 27 * (size_t)A : (size_t)A;
+        entries[c] = e;
+        total_entries += e;
+        cm.tab_logg[c] = logg;
+    }
+    u32* tables = (u32*)ctx->scratch[11].ensure(total_entries * 32 + 256);
+    size_t off = 0, max_first = 0, max_up[4] = {0, 0, 0, 0};
+    std::vector<int> order;  // tabled columns sorted by logg, then the generic ones
+    for (int l = 1; l <= MAX_CL; l++)
+        for (int c = 0; c < cols; c++)
+            if (cm.tab_logg[c] == l) order.push_back(c);
+    const int n_tab = (int)order.size();
+    for (int c = 0; c < cols; c++)
+        if (cm.tab_logg[c] == 0) order.push_back(c);
+    for (int c = 0; c < cols; c++) {
+        ColTab& tb = tabs[c];
+        if (!tb.cls) continue;
+        if (tb.cls == TAB_ALPHA) {
+            size_t cnt = tb.A;
+            for (u32 l = 0; l < tb.logg; l++) {
+                cnt *= cnt;
+                tb.lv[l] = tables + off * 8;
+                off += cnt;
+                if (l == 0) max_first = std::max(max_first, cnt);
+                else max_up[l] = std::max(max_up[l], cnt);
+            }
+        } else {
+            tb.lv[0] = tables + off * 8;
+            off += entries[c];
+            max_first = std::max(max_first, entries[c]);
+        }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(tabs_dev, tabs.data(), sizeof(ColTab) * cols, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(lists_dev, order.data(), sizeof(int) * cols, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    if (n_tab) {
+        tab_build_first_kernel<<<dim3((unsigned)((max_first + 127) / 128), (unsigned)n_tab), 128, 0, ctx->stream>>>(tabs_dev, lists_dev, cm.templates);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+        for (int l = 1; l < 4; l++) {
+            if (!max_up[l]) continue;
+            tab_build_up_kernel<<<dim3((unsigned)((max_up[l] + 127) / 128), (unsigned)n_tab), 128, 0, ctx->stream>>>(tabs_dev, lists_dev, l);
+            CUDA_CHECK(cudaGetLastError());
+            ctx->launches++;
+        }
+    }
+    cm.tab_classified = true;
+    ctx->tab_columns = n_tab;
+}
+
+void tab_commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, u32* memo) {
+    if (!cm.tab_classified) tab_classify(ctx, cm, chunk1);
+    const TabLayout lay(cm.cols);
+    u8* base = (u8*)cm.tab_dev;
+    const ColTab* tabs = (const ColTab*)(base + lay.off_tabs);
+    const int* lists = (const int*)(base + lay.off_lists);
+    u32* vio = (u32*)(base + lay.off_vio);
+    int pos = 0;
+    for (int l = 1; l <= MAX_CL; l++) {
+        int count = 0;
+        for (int c = 0; c < cm.cols; c++) count += cm.tab_logg[c] == l;
+        if (!count) continue;
+        switch (l) {
+            case 1: launch_tabled<1>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+            case 2: launch_tabled<2>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+            case 3: launch_tabled<3>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+            case 4: launch_tabled<4>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+            case 5: launch_tabled<5>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+            case 6: launch_tabled<6>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+            case 7: launch_tabled<7>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+            case 8: launch_tabled<8>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+            case 9: launch_tabled<9>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+            default: launch_tabled<10>(ctx, cm, tabs, lists + pos, count, chunk0, chunk1, vio); break;
+        }
+        pos += count;
+    }
+    if (pos < cm.cols) {
+        dim3 grid((unsigned)(chunk1 - chunk0), (unsigned)(cm.cols - pos));
+        chunk_commit_dedup128_kernel<<<grid, DT, sizeof(Dedup128Smem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl, cm.templates, cm.upper,
+                                                                                      cm.n_ch, memo, chunk0, lists + pos, nullptr);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+    }
+    cm.tab_chunks_done = chunk1;
+}
+
+// Chunks that broke their column's table assumptions are redone by the generic kernel (same outputs).
+void tab_commit_finish(sezkp_ctx* ctx, Commit& cm, u32* memo) {
+    const TabLayout lay(cm.cols);
+    u8* base = (u8*)cm.tab_dev;
+    const int* lists = (const int*)(base + lay.off_lists);
+    u32* vio = (u32*)(base + lay.off_vio);
+    u32 count = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&count, vio, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->tab_redone_chunks = count;
+    if (count == 0) return;
+    if (count <= VIO_CAP) {
+        chunk_commit_dedup128_kernel<<<count, DT, sizeof(Dedup128Smem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl, cm.templates, cm.upper,
+                                                                                       cm.n_ch, memo, 0, nullptr, vio);
+    } else {  // the sample misjudged the columns: redo every tabled column
+        int n_tab = 0;
+        for (int c = 0; c < cm.cols; c++) n_tab += cm.tab_logg[c] != 0;
+        dim3 grid((unsigned)cm.tab_chunks_done, (unsigned)n_tab);
+        chunk_commit_dedup128_kernel<<<grid, DT, sizeof(Dedup128Smem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl, cm.templates, cm.upper,
+                                                                                      cm.n_ch, memo, 0, lists, nullptr);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+}
+}  // namespace
 
 // commit_begin / commit_chunks / commit_finish: the three stages of commit_build, exposed so that a caller can hash
 // ranges of chunks as their rows become available (pipelined H2D in the prover) and build the upper levels at the end.
@@ -923,9 +1457,13 @@ void commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, const Com
                                                                            opt.fold_src, opt.fold_beta, chunk0);
     } else if (opt.dedup && ctx->dedup_enabled) {
         u32* memo = (u32*)ctx->scratch[8].p;
+        if (ctx->dedup_variant == 2 && ctx->tabled_enabled && cm.cl == MAX_CL) {
+            tab_commit_chunks(ctx, cm, chunk0, chunk1, memo);
+            return;
+        }
         if (ctx->dedup_variant == 2)
             chunk_commit_dedup128_kernel<<<grid, DT, sizeof(Dedup128Smem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl, cm.templates,
-                                                                                          cm.upper, cm.n_ch, memo, chunk0);
+                                                                                          cm.upper, cm.n_ch, memo, chunk0, nullptr, nullptr);
         else
             chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl,
                                                                                                cm.templates, cm.upper, cm.n_ch, memo, chunk0);
@@ -938,6 +1476,7 @@ void commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, const Com
 }
 
 void commit_finish(sezkp_ctx* ctx, Commit& cm, const CommitOpts& opt) {
+    if (cm.tab_classified) tab_commit_finish(ctx, cm, (u32*)ctx->scratch[8].p);
     const int depth = ilog2(cm.n_ch);
     int l0 = 0;
     while (l0 < depth) {

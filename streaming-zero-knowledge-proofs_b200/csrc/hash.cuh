@@ -19,6 +19,11 @@ struct Commit {
     u64 n_ch = 0;                  // chunks per column = n >> cl
     u32* upper = nullptr;          // device [cols][2*n_ch-1][8]: level l (count n_ch>>l) at offset 2*n_ch-(2*n_ch>>l)
     b3::LabelTemplate* templates = nullptr;  // device [cols] or null (unlabeled)
+    // subtree-table state of the value-aware commit (hash.cu, "structured columns"); null/empty when not used
+    void* tab_dev = nullptr;       // device: ColTab[cols], column lists, work list of chunks to redo
+    std::vector<int> tab_logg;     // per column: log2 of the leaves under one table entry, 0 = generic kernel
+    bool tab_classified = false;
+    u64 tab_chunks_done = 0;       // chunks hashed so far (the work list refers to them)
     void release(sezkp_ctx* ctx);
 };
 inline u64 upper_off(u64 n_ch, int l) { return 2 * n_ch - ((2 * n_ch) >> l); }

@@ -164,8 +164,9 @@ def test_column_commit_and_openings_vs_oracle(ctx, oracle, n, c):
 
 
 @pytest.mark.parametrize("kind", ["const", "flags", "moves", "sym16", "walk", "counter", "wide_small", "mixed_sign", "random",
-                                  "blocks512", "blocks96", "abab", "sparse_ones", "two_halves"])
-@pytest.mark.parametrize("n", [4, 256, 1024, 8192])
+                                  "blocks512", "blocks96", "abab", "sparse_ones", "two_halves", "blocks2048", "blocks64",
+                                  "flags_outlier", "walk_jump", "blocks_broken", "sym16_late_outliers", "neg_blocks"])
+@pytest.mark.parametrize("n", [4, 256, 1024, 8192, 1 << 17])
 def test_value_aware_commit_matches_plain_and_oracle(ctx, oracle, kind, n):
     """The dedup kernel (identical leaves / sibling pairs hashed once) must give the same roots and openings as one
     compression per node, for every value distribution that steers it through a different branch."""
@@ -185,6 +186,14 @@ def test_value_aware_commit_matches_plain_and_oracle(ctx, oracle, kind, n):
         "abab": i % 2,                             # every pair identical one level up
         "sparse_ones": (i % 512 == 0).astype(np.int64),
         "two_halves": (i >= n // 2).astype(np.int64) * 9,
+        # subtree-table classes (ALPHA / WALK / CONST) and inputs that break the sampled classification in some chunks
+        "blocks2048": 40 + (i // 2048) % 11,       # whole chunks constant
+        "blocks64": (i // 64) % 3 - 1,
+        "flags_outlier": np.where(i == (5 * n) // 7, 5, (rng.random(n) < 0.4).astype(np.int64)),
+        "walk_jump": np.cumsum(rng.integers(-1, 2, n)) + np.where(i >= (2 * n) // 3 + 1, 40, 0),
+        "blocks_broken": np.where(i == n // 3 + 1, 99, 10 + (i // 512) % 7),
+        "sym16_late_outliers": np.where((i > n - 700) & (i % 97 == 0), 1000 + i % 5, rng.integers(0, 16, n)),
+        "neg_blocks": -((i // 512) % 90) - 1,
         "random": None,
     }[kind]
     if col is None:
@@ -196,12 +205,16 @@ def test_value_aware_commit_matches_plain_and_oracle(ctx, oracle, kind, n):
     exp = oracle.column_commit(cols, labels)
     ctx.set_option("dedup", 1)  # 256-thread variant
     got1 = ctx.column_commit(cols, labels)
-    ctx.set_option("dedup", 2)  # 128-thread variant (default)
+    ctx.set_option("dedup", 2)  # 128-thread variant (default) + subtree tables for structured columns
     got2 = ctx.column_commit(cols, labels)
+    ctx.set_option("tabled", 0)
+    got3 = ctx.column_commit(cols, labels)
+    ctx.set_option("tabled", 1)
     ctx.set_option("dedup", 0)
     plain = ctx.column_commit(cols, labels)
     ctx.set_option("dedup", 2)
-    assert np.array_equal(got1, exp) and np.array_equal(got2, exp) and np.array_equal(plain, exp)
+    assert np.array_equal(got2, exp), "tabled"
+    assert np.array_equal(got1, exp) and np.array_equal(got3, exp) and np.array_equal(plain, exp)
 
 
 @pytest.mark.parametrize("k,lb,c", [(1, 3, 2), (6, 3, 3), (10, 2, 2), (12, 3, 5), (14, 3, 2)])

@@ -24,7 +24,14 @@ def timed(fn, k=3):
 for name, (a, b) in groups.items():
     sub = dev[a:b].contiguous()
     res = []
-    for dd in (1, 0):
-        ctx.set_option("dedup", 2 if dd else 0)
+    for dd, tb in ((2, 1), (2, 0), (0, 0)):
+        ctx.set_option("dedup", dd)
+        ctx.set_option("tabled", tb)
         res.append(timed(lambda: ctx.column_commit(sub, names[a:b], dev=True, n=n)))
-    print(f"{name:8s} cols={b-a} dedup {res[0]:.3f} ms  plain {res[1]:.3f} ms  ({res[0]/(b-a):.3f} / {res[1]/(b-a):.3f} per column)")
+        if tb: stats = ctx.tab_stats()
+    ctx.set_option("dedup", 2); ctx.set_option("tabled", 1)
+    print(f"{name:8s} cols={b-a} tabled {res[0]:.3f} ms (tab cols {stats[0]}, redone chunks {stats[1]})  dedup {res[1]:.3f} ms  plain {res[2]:.3f} ms  "
+          f"({res[0]/(b-a):.3f} / {res[1]/(b-a):.3f} / {res[2]/(b-a):.3f} per column)")
+for dd, tb in ((2, 1), (2, 0), (0, 0)):
+    ctx.set_option("dedup", dd); ctx.set_option("tabled", tb)
+    print(f"all 59 columns dedup={dd} tabled={tb}: {timed(lambda: ctx.column_commit(dev, names, dev=True, n=n)):.3f} ms", ctx.tab_stats())
