@@ -100,6 +100,9 @@ void sezkp_cuda_destroy(sezkp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ntt_free_tables(ctx);
+    for (auto& pb : ctx->pinned) pb.release();
+    for (auto& kv : ctx->power_tables) cudaFree(kv.second);
+    ctx->power_tables.clear();
     for (auto& b : ctx->scratch) b.release();
     for (auto& kv : ctx->pool.live) cudaFree(kv.first);
     ctx->pool.live.clear();
@@ -536,7 +539,7 @@ int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, cons
                              size_t cap, size_t* len) {
     API_BEGIN(ctx)
     REQUIRE(manifest_root && len, "bad argument");
-    std::vector<u8> proof;
+    std::vector<u8>& proof = ctx->proof_buf;
     prove_v1_device(ctx, trace, manifest_root, proof);
     deliver(proof, proof_buf, cap, len);
     API_END(ctx)
@@ -548,7 +551,7 @@ int32_t sezkp_stark_v1_prove_sharded(sezkp_ctx* ctx, const sezkp_trace_desc* tra
     REQUIRE(manifest_root && len && world >= 1 && rank >= 0 && rank < world, "bad argument");
     REQUIRE(world == 1 || allgather != nullptr, "allgather callback is NULL");
     ShardInfo sh{rank, world, allgather, user};
-    std::vector<u8> proof;
+    std::vector<u8>& proof = ctx->proof_buf;
     prove_v1_device(ctx, trace, manifest_root, proof, world > 1 ? &sh : nullptr);
     deliver(proof, proof_buf, cap, len);
     API_END(ctx)
@@ -580,7 +583,7 @@ int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* tra
                                       uint8_t* proof_buf, size_t cap, size_t* len) {
     API_BEGIN(ctx)
     REQUIRE(trace && manifest_root && len, "bad argument");
-    std::vector<u8> proof;
+    std::vector<u8>& proof = ctx->proof_buf;
     prove_v1_resident(ctx, trace->owner.t, manifest_root, proof);
     deliver(proof, proof_buf, cap, len);
     API_END(ctx)
@@ -602,7 +605,7 @@ int32_t sezkp_stark_v1_finish(sezkp_ctx* ctx, sezkp_stream* st, uint8_t* proof_b
     API_BEGIN(ctx)
     if (!st) sezkp_fail(SEZKP_CUDA_ESTATE, "stream handle is NULL");
     REQUIRE(proof_buf && len, "finish needs a proof buffer (use sezkp_stark_v1_proof_bound for its size)");
-    std::vector<u8> proof;
+    std::vector<u8>& proof = ctx->proof_buf;
     stream_finish(ctx, st, proof);
     deliver(proof, proof_buf, cap, len);
     stream_free(ctx, st);  // the handle is consumed once the proof has been delivered

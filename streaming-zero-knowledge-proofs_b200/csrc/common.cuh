@@ -66,6 +66,32 @@ struct DevBuf {
     T* as() const { return (T*)p; }
 };
 
+// Grow-only pinned host buffer (staging for small H2D/D2H transfers: pageable copies go through the driver's bounce
+// buffer at a fraction of the PCIe rate and block the host).
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* ensure(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+            cap = 0;
+            cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) {
+                p = nullptr;
+                sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            }
+            cap = bytes;
+        }
+        return p;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 struct NttTables;  // ntt.cu
 
 // Size-keyed caching device allocator: repeated proofs reuse their buffers instead of paying
@@ -126,8 +152,11 @@ struct sezkp_ctx {
     std::vector<cudaEvent_t> slab_events;
     std::string last_error;
     std::map<u64, NttTables*> ntt_tables;  // key: (log_n, inverse, coset params)
+    std::map<int, u64*> power_tables;      // log_n -> device table of the low powers of w_n (composition mask)
     DevPool pool;
     DevBuf scratch[12];                      // reusable work buffers (per purpose, see users)
+    PinnedBuf pinned[2];                     // host staging: [0] opening requests / results
+    std::vector<u8> proof_buf;               // serialised proof of the last prove (capacity kept across calls)
     std::vector<std::pair<std::string, double>> timings;  // phase -> ms (last prove)
     int dedup_variant = 2;                  // 1: 256-thread kernel, 2: 128-thread kernel (more chunks in flight per SM)
     bool dedup_enabled = true;              // value-aware column commit (SEZKP_NO_DEDUP=1 or sezkp_cuda_set_option disables)

@@ -1110,6 +1110,24 @@ __global__ void __launch_bounds__(HASH_THREADS) upper_reduce_kernel(u32* __restr
     reduce_levels_smem(s, pitch, cnt, base, grp, l0, n_ch, nullptr, 0);
 }
 
+// The same for several single-column commitments in one launch (the FRI layers: their upper levels are off the
+// critical path of the fold chain, so they are reduced together at the end instead of 2-3 latency-bound launches per
+// layer).  Job j owns CTAs [cta0[j], cta0[j+1]); a job that reaches its root also writes it to root_out.
+__global__ void __launch_bounds__(HASH_THREADS) upper_reduce_multi_kernel(const UpperJobs jobs) {
+    __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
+    const int pitch = (1 << MAX_CL) + 2;
+    int j = 0;
+    while (j + 1 < jobs.n && blockIdx.x >= jobs.cta0[j + 1]) j++;
+    const UpperJob jb = jobs.j[j];
+    const u64 grp = blockIdx.x - jobs.cta0[j];
+    const u32* src = jb.upper + ((2 * jb.n_ch - ((2 * jb.n_ch) >> jb.l0)) + (grp << jb.k)) * 8;
+    const int cnt = 1 << jb.k;
+    for (int i = threadIdx.x; i < cnt * 8; i += HASH_THREADS) s[(i & 7) * pitch + (i >> 3)] = src[i];
+    __syncthreads();
+    reduce_levels_smem(s, pitch, cnt, jb.upper, grp, jb.l0, jb.n_ch, nullptr, 0);
+    if (jb.root_out && (jb.n_ch >> (jb.l0 + jb.k)) == 1 && threadIdx.x < 8) jb.root_out[threadIdx.x] = s[threadIdx.x * pitch];
+}
+
 // One CTA per opening: rebuild the chunk, record the in-chunk sibling path and chunk root, gather the upper path.
 // Requests carry their own commitment pointers so that openings into many commitments (all FRI layers, all
 // columns) go out in ONE launch.
@@ -1496,6 +1514,38 @@ void commit_finish(sezkp_ctx* ctx, Commit& cm, const CommitOpts& opt) {
     }
 }
 
+// commit_finish for a batch of single-column commitments: all upper levels in at most three launches, roots to
+// roots_dev[32 * index] (device).
+void commit_finish_multi(sezkp_ctx* ctx, Commit* cms, int count, u8* roots_dev) {
+    for (int base = 0; base < count; base += UPPER_MAX_JOBS) {
+        const int m = std::min(UPPER_MAX_JOBS, count - base);
+        for (int l0 = 0;; l0 += MAX_CL) {
+            UpperJobs jobs;
+            jobs.n = 0;
+            u32 ctas = 0;
+            for (int i = 0; i < m; i++) {
+                const Commit& cm = cms[base + i];
+                REQUIRE(cm.cols == 1, "internal: batched finish needs single-column commitments");
+                const int depth = ilog2(cm.n_ch);
+                if (l0 > depth || (l0 == depth && l0 > 0)) continue;  // done in an earlier round (depth 0: copy the root once)
+                UpperJob& jb = jobs.j[jobs.n];
+                jb.upper = cm.upper;
+                jb.n_ch = cm.n_ch;
+                jb.l0 = l0;
+                jb.k = std::min(depth - l0, MAX_CL);
+                jb.root_out = roots_dev ? (u32*)(roots_dev + 32 * (size_t)(base + i)) : nullptr;
+                jobs.cta0[jobs.n] = ctas;
+                ctas += (u32)(cm.n_ch >> (l0 + jb.k));
+                jobs.n++;
+            }
+            if (jobs.n == 0) break;
+            upper_reduce_multi_kernel<<<ctas, HASH_THREADS, 0, ctx->stream>>>(jobs);
+            CUDA_CHECK(cudaGetLastError());
+            ctx->launches++;
+        }
+    }
+}
+
 void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,
                   const char* const* labels, const CommitOpts& opt) {
     commit_begin(ctx, cm, values_dev, n, cols, chunk_log2, labels, opt);
@@ -1529,14 +1579,18 @@ void open_batch(sezkp_ctx* ctx, const std::vector<OpenReq>& reqs, size_t path_di
     u64* d_val = (u64*)(d + b_req);
     u32* d_cr = (u32*)(d + b_req + b_val);
     u32* d_path = (u32*)(d + b_req + b_val + b_cr);
-    CUDA_CHECK(cudaMemcpyAsync(d_req, reqs.data(), b_req, cudaMemcpyHostToDevice, ctx->stream));
+    // requests and results are staged in pinned host memory (one H2D, one D2H at full PCIe rate)
+    u8* h = (u8*)ctx->pinned[0].ensure(b_req + b_val + b_cr + b_path + 64);
+    std::memcpy(h, reqs.data(), b_req);
+    CUDA_CHECK(cudaMemcpyAsync(d_req, h, b_req, cudaMemcpyHostToDevice, ctx->stream));
     open_kernel<<<(unsigned)k, HASH_THREADS, 0, ctx->stream>>>(d_req, d_val, d_cr, d_path);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
-    CUDA_CHECK(cudaMemcpyAsync(values, d_val, b_val, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaMemcpyAsync(chunk_roots, d_cr, b_cr, cudaMemcpyDeviceToHost, ctx->stream));
-    if (b_path) CUDA_CHECK(cudaMemcpyAsync(paths_host, d_path, b_path, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h + b_req, d + b_req, b_val + b_cr + b_path, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(values, h + b_req, b_val);
+    std::memcpy(chunk_roots, h + b_req + b_val, b_cr);
+    if (b_path) std::memcpy(paths_host, h + b_req + b_val + b_cr, b_path);
 }
 
 void commit_open(sezkp_ctx* ctx, const Commit& cm, const u32* col_idx, const u64* row_idx, size_t k, u64* values,

@@ -44,6 +44,21 @@ void commit_begin(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
                   const CommitOpts& opt);
 void commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, const CommitOpts& opt);
 void commit_finish(sezkp_ctx* ctx, Commit& cm, const CommitOpts& opt);
+// Upper levels of `count` single-column commitments (begin + chunks done) in at most three launches; root i goes to
+// roots_dev + 32*i (device memory, may be null).
+constexpr int UPPER_MAX_JOBS = 40;
+struct UpperJob {
+    u32* upper;
+    u64 n_ch;
+    int l0, k;
+    u32* root_out;
+};
+struct UpperJobs {
+    UpperJob j[UPPER_MAX_JOBS];
+    u32 cta0[UPPER_MAX_JOBS];
+    int n;
+};
+void commit_finish_multi(sezkp_ctx* ctx, Commit* cms, int count, u8* roots_dev);
 // Generic opening request: one CTA rebuilds the chunk containing `row` of one committed column.
 struct OpenReq {
     const u64* values;             // the column

@@ -71,17 +71,21 @@ struct ComposeParams {
     u64 a[8];        // alphas as drawn (mapping of v1/prover.rs:86-98 applied in the kernel)
     u64 mask[8];     // ascending mask coefficients
     int mask_deg;
-    u64 w_base;      // w_n
+    u64 w_hi[64];    // w_n^(j << lo_bits): with w_lo (device table) w_n^i = w_hi[i >> lo_bits] * w_lo[i & (2^lo_bits - 1)]
+    int lo_bits;
 };
-__global__ void compose_kernel(const u64* __restrict__ cols, u64 n, u32 tau, ComposeParams cp, u64* __restrict__ out) {
+// One thread per row.  The composition is linear in the alphas, so the per-tape constraint values are summed per
+// constraint kind first and the alphas (and the row-level selectors is_first / is_last / 1 - is_last) are applied
+// once per row: 6 multiplications per tape + 13 per row instead of 19 per tape + a 22-bit power per row.  All sums are
+// lazy representatives (gl::lazy); only values whose BITS matter (range terms) are canonical.
+__global__ void __launch_bounds__(128) compose_kernel(const u64* __restrict__ cols, u64 n, u32 tau, ComposeParams cp,
+                                                      const u64* __restrict__ w_lo, u64* __restrict__ out) {
+    namespace L = gl::lazy;
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u64 ip1 = (i + 1 == n) ? 0 : i + 1;
     const u64 is_first = cols[1 * n + i], is_last = cols[2 * n + i];
-    const u64 one_minus_last = gl::sub(1, is_last);
-    const u64 a_bool = cp.a[0], a_mv = cp.a[1], a_hu = cp.a[2], a_hr = cp.a[4], a_sr = cp.a[6], a_symr = cp.a[0],
-              a_bf = cp.a[2], a_bl = cp.a[2];
-    u64 acc = 0;
+    u64 s_bool = 0, s_mv = 0, s_hu = 0, s_hr = 0, s_sr = 0, s_bf = 0, s_bl = 0;
     for (u32 r = 0; r < tau; r++) {
         const u64 mv = cols[(3 + 0ULL * tau + r) * n + i], mv_next = cols[(3 + 0ULL * tau + r) * n + ip1];
         const u64 flg = cols[(3 + 1ULL * tau + r) * n + i];
@@ -90,53 +94,127 @@ __global__ void compose_kernel(const u64* __restrict__ cols, u64 n, u32 tau, Com
         const u64 wlen = cols[(3 + 4ULL * tau + r) * n + i];
         const u64 in_off = cols[(3 + 5ULL * tau + r) * n + i], out_off = cols[(3 + 6ULL * tau + r) * n + i];
         // C1, C2, C3 (v1/air.rs:64-72)
-        acc = gl::add(acc, gl::mul(gl::mul(a_bool, flg), gl::sub(flg, 1)));
-        acc = gl::add(acc, gl::mul(gl::mul(gl::mul(a_mv, mv), gl::sub(mv, 1)), gl::add(mv, 1)));
-        acc = gl::add(acc, gl::mul(gl::mul(a_hu, one_minus_last), gl::sub(gl::sub(head_next, head), mv_next)));
+        s_bool = L::add(s_bool, L::mul(flg, gl::sub(flg, 1)));
+        s_mv = L::add(s_mv, L::mul(L::mul(mv, gl::sub(mv, 1)), gl::add(mv, 1)));
+        s_hu = L::add(s_hu, L::sub(L::sub(head_next, head), mv_next));
         // Bit columns are the honest decompositions of the canonical residues (v1/columns.rs:324-342), so every
         // b*(b-1) term is zero and the reconstructed sums are the low bits of the residue (v1/air.rs:74-112).
-        acc = gl::add(acc, gl::mul(gl::mul(a_hr, flg), gl::sub(head, head & 0xFFFFULL)));
+        s_hr = L::add(s_hr, L::mul(flg, head - (head & 0xFFFFULL)));
         const u64 slack = gl::sub(gl::sub(wlen, 1), head);
-        acc = gl::add(acc, gl::mul(gl::mul(a_sr, flg), gl::sub(slack, slack & 0xFFFFULL)));
-        acc = gl::add(acc, gl::mul(gl::mul(a_symr, flg), gl::sub(sym, sym & 0xFULL)));
+        s_sr = L::add(s_sr, L::mul(flg, slack - (slack & 0xFFFFULL)));
+        s_bool = L::add(s_bool, L::mul(flg, sym - (sym & 0xFULL)));  // symbol range shares alpha[0] with the booleanity term
         // boundary (v1/air.rs:116-136)
-        acc = gl::add(acc, gl::mul(gl::mul(a_bf, is_first), gl::sub(gl::sub(head, mv), in_off)));
-        acc = gl::add(acc, gl::mul(gl::mul(a_bl, is_last), gl::sub(head, out_off)));
+        s_bf = L::add(s_bf, L::sub(L::sub(head, mv), in_off));
+        s_bl = L::add(s_bl, L::sub(head, out_off));
     }
+    // alphas: bool = sym range = a[0], mv = a[1], head update = both boundaries = a[2], head range = a[4], slack = a[6]
+    const u64 t2 = L::add(L::add(L::mul(gl::sub(1, is_last), s_hu), L::mul(is_first, s_bf)), L::mul(is_last, s_bl));
+    u64 acc = L::mul(cp.a[0], s_bool);
+    acc = L::add(acc, L::mul(cp.a[1], s_mv));
+    acc = L::add(acc, L::mul(cp.a[2], t2));
+    acc = L::add(acc, L::mul(cp.a[4], s_hr));
+    acc = L::add(acc, L::mul(cp.a[6], s_sr));
     // mask R(w^i), Horner over ascending coefficients (v1/masking.rs:86-103)
-    const u64 x = gl::pow(cp.w_base, i);
+    const u64 x = L::mul(cp.w_hi[i >> cp.lo_bits], w_lo[i & ((1ULL << cp.lo_bits) - 1)]);
     u64 m = 0;
-    for (int j = cp.mask_deg - 1; j >= 0; j--) m = gl::add(gl::mul(m, x), cp.mask[j]);
-    out[i] = gl::add(acc, m);
+    for (int j = cp.mask_deg - 1; j >= 0; j--) m = L::add(L::mul(m, x), cp.mask[j]);
+    out[i] = L::canon(L::add(acc, m));
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* DEEP quotient: y[i] *= (shift*w^i - z)^-1, Montgomery batch inversion per thread              */
+/* DEEP quotient: y[i] *= (shift*w^i - z)^-1, one field inversion per 4096 elements              */
 /* ------------------------------------------------------------------------------------------ */
+// Montgomery batch inversion at CTA scope: every thread multiplies up its 16 denominators, warp shuffles and one
+// shared-memory step give each thread the product of all OTHER threads' denominators, one thread inverts the CTA
+// total (Fermat, 127 multiplications — the reference pays that per element, v1/lde.rs:84), and the per-element
+// inverses are peeled off backwards.  6.3 multiplications per element; inverses are unique, so the canonical
+// results equal the reference's.
 constexpr int DEEP_PER_THREAD = 16;
-__global__ void __launch_bounds__(256) deep_kernel(u64* __restrict__ y, u64 N, u64 shift, u64 w, u64 w_step, u64 z) {
-    // thread handles i = base + lane + 32*k, k < DEEP_PER_THREAD (coalesced)
-    const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const u32 lane = threadIdx.x & 31;
-    const u64 i0 = warp * (32 * DEEP_PER_THREAD) + lane;
-    if (i0 >= N) return;
-    u64 x = gl::mul(shift, gl::pow(w, i0));
-    u64 den[DEEP_PER_THREAD], pre[DEEP_PER_THREAD];
-    u64 run = 1;
+constexpr int DEEP_THREADS = 256;
+struct DeepParams {
+    u64 shift, z;
+    u64 w_cta;        // w^(DEEP_THREADS * DEEP_PER_THREAD)
+    u64 w_k[DEEP_PER_THREAD];       // w^(32 * k)
+    u64 w_warp[DEEP_THREADS / 32];  // w^(32 * DEEP_PER_THREAD * j)
+    u64 w_lane[32];   // w^l
+};
+__global__ void __launch_bounds__(DEEP_THREADS, 2) deep_kernel(u64* __restrict__ y, u64 N, const DeepParams dp) {
+    namespace L = gl::lazy;
+    __shared__ u64 s_x0, s_inv, s_wtot[DEEP_THREADS / 32];
+    const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {  // shift * w^(first index of this CTA)
+        u64 acc = dp.shift, base = dp.w_cta;
+        for (u32 e = blockIdx.x; e; e >>= 1) {
+            if (e & 1) acc = L::mul(acc, base);
+            base = L::mul(base, base);
+        }
+        s_x0 = acc;
+    }
+    __syncthreads();
+    // thread handles i = i0 + 32*k, k < DEEP_PER_THREAD (coalesced).  Everything below is arranged as shallow trees
+    // of independent multiplications (groups of 4) rather than one running product: the kernel is latency-bound.
+    const u64 i0 = (u64)blockIdx.x * (DEEP_THREADS * DEEP_PER_THREAD) + warp * (32 * DEEP_PER_THREAD) + lane;
+    const u64 x0 = L::mul(L::mul(s_x0, dp.w_warp[warp]), dp.w_lane[lane]);
+    u64 den[DEEP_PER_THREAD], yv[DEEP_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < DEEP_PER_THREAD; k++) {
-        den[k] = gl::sub(x, z);
-        pre[k] = run;
-        run = gl::mul(run, den[k]);
-        x = gl::mul(x, w_step);
+        const bool ok = i0 + 32ULL * k < N;
+        den[k] = ok ? L::sub(k ? L::mul(x0, dp.w_k[k]) : x0, dp.z) : 1;
+        yv[k] = ok ? y[i0 + 32ULL * k] : 0;
     }
-    u64 inv = gl::inv(run);
+    u64 ab[4], cd[4], g[4];
 #pragma unroll
-    for (int k = DEEP_PER_THREAD - 1; k >= 0; k--) {
-        const u64 i = i0 + 32ULL * k;
-        const u64 dinv = gl::mul(inv, pre[k]);
-        inv = gl::mul(inv, den[k]);
-        if (i < N) y[i] = gl::mul(y[i], dinv);
+    for (int j = 0; j < 4; j++) {
+        ab[j] = L::mul(den[4 * j], den[4 * j + 1]);
+        cd[j] = L::mul(den[4 * j + 2], den[4 * j + 3]);
+        g[j] = L::mul(ab[j], cd[j]);
+    }
+    const u64 g01 = L::mul(g[0], g[1]), g23 = L::mul(g[2], g[3]);
+    const u64 run = L::mul(g01, g23);
+    // products of the other lanes of the warp: exclusive prefix * exclusive suffix
+    u64 pf = run, sf = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 u = __shfl_up_sync(0xffffffffu, pf, o), d = __shfl_down_sync(0xffffffffu, sf, o);
+        if ((int)lane >= o) pf = L::mul(pf, u);
+        if ((int)lane + o < 32) sf = L::mul(sf, d);
+    }
+    if (lane == 31) s_wtot[warp] = pf;  // warp total
+    u64 others = 1;
+    {
+        const u64 pe = __shfl_up_sync(0xffffffffu, pf, 1), se = __shfl_down_sync(0xffffffffu, sf, 1);
+        if (lane > 0) others = pe;
+        if (lane < 31) others = L::mul(others, se);
+    }
+    __syncthreads();
+    {
+        u64 w[DEEP_THREADS / 32];
+#pragma unroll
+        for (int j = 0; j < DEEP_THREADS / 32; j++) w[j] = (j != (int)warp) ? s_wtot[j] : 1;
+        others = L::mul(L::mul(others, L::mul(L::mul(w[0], w[1]), L::mul(w[2], w[3]))), L::mul(L::mul(w[4], w[5]), L::mul(w[6], w[7])));
+    }
+    if (tid == 0) {  // CTA total = others * run of thread 0; Fermat inverse, square and multiply chains interleaved
+        const u64 total = L::mul(others, run);
+        u64 acc = 1, base = total;
+        for (u64 e = gl::P - 2; e; e >>= 1) {
+            if (e & 1) acc = L::mul(acc, base);
+            base = L::mul(base, base);
+        }
+        s_inv = acc;
+    }
+    __syncthreads();
+    const u64 inv = L::mul(s_inv, others);  // 1 / run
+    const u64 ig[4] = {L::mul(inv, L::mul(g[1], g23)), L::mul(inv, L::mul(g[0], g23)), L::mul(inv, L::mul(g01, g[3])),
+                       L::mul(inv, L::mul(g01, g[2]))};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const u64 iab = L::mul(ig[j], cd[j]), icd = L::mul(ig[j], ab[j]);
+        const u64 di[4] = {L::mul(iab, den[4 * j + 1]), L::mul(iab, den[4 * j]), L::mul(icd, den[4 * j + 3]), L::mul(icd, den[4 * j + 2])};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const u64 i = i0 + 32ULL * (4 * j + t);
+            if (i < N) y[i] = L::canon(L::mul(yv[4 * j + t], di[t]));
+        }
     }
 }
 
@@ -258,6 +336,24 @@ void expand_columns_device(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols) {
     expand_columns_range(ctx, t, cols, 0, t.n_rows, 0, t.n_blocks);
 }
 
+// w_n^j for j < 2^lo_bits (n = 2^L), cached per L in the context (device, read-only after the first call).
+static const u64* power_table_device(sezkp_ctx* ctx, int L, int lo_bits) {
+    auto it = ctx->power_tables.find(L);
+    if (it != ctx->power_tables.end()) return it->second;
+    const u64 w = gl::root_2exp((unsigned)L);
+    std::vector<u64> h((size_t)1 << lo_bits);
+    u64 x = 1;
+    for (auto& e : h) {
+        e = x;
+        x = gl::mul(x, w);
+    }
+    u64* d = nullptr;
+    CUDA_CHECK(cudaMalloc(&d, h.size() * 8));
+    CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    ctx->power_tables[L] = d;
+    return d;
+}
+
 void compose_device(sezkp_ctx* ctx, const u64* cols, u64 n, u32 tau, const u64 alphas8[8], const u64* mask, size_t mask_deg,
                     u64* out) {
     REQUIRE(mask_deg <= 8, "mask degree %zu > 8 unsupported", mask_deg);
@@ -271,8 +367,18 @@ void compose_device(sezkp_ctx* ctx, const u64* cols, u64 n, u32 tau, const u64 a
         cp.mask[i] = mask[i];
     }
     cp.mask_deg = (int)mask_deg;
-    cp.w_base = gl::root_2exp((unsigned)ilog2(n));
-    compose_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(cols, n, tau, cp, out);
+    // w_n^i = w_hi[i >> lo_bits] * w_lo[i & mask]: 64 high powers in the launch parameters, the low table on the device
+    const int L = ilog2(n);
+    cp.lo_bits = L > 6 ? L - 6 : 0;
+    const u64 w = gl::root_2exp((unsigned)L);
+    const u64 w_lo_step = gl::pow(w, 1ULL << cp.lo_bits);
+    u64 x = 1;
+    for (u64 j = 0; j < (n >> cp.lo_bits); j++) {
+        cp.w_hi[j] = x;
+        x = gl::mul(x, w_lo_step);
+    }
+    const u64* w_lo = power_table_device(ctx, L, cp.lo_bits);
+    compose_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(cols, n, tau, cp, w_lo, out);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -293,9 +399,14 @@ void deep_lde_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, 
     u64* inter = (u64*)ctx->scratch[1].ensure(N * 8);
     coset_lde_device(ctx, base_vals, out, inter, L, logB, shift, 1);
     const u64 w = gl::root_2exp((unsigned)(L + logB));
-    const u64 w_step = gl::pow(w, 32);
-    const u64 threads = (N + DEEP_PER_THREAD - 1) / DEEP_PER_THREAD;
-    deep_kernel<<<blocks_for(threads, 256), 256, 0, ctx->stream>>>(out, N, shift, w, w_step, z);
+    DeepParams dp;
+    dp.shift = shift;
+    dp.z = z;
+    dp.w_cta = gl::pow(w, (u64)DEEP_THREADS * DEEP_PER_THREAD);
+    for (int k = 0; k < DEEP_PER_THREAD; k++) dp.w_k[k] = gl::pow(w, 32ULL * k);
+    for (int j = 0; j < DEEP_THREADS / 32; j++) dp.w_warp[j] = gl::pow(w, 32ULL * DEEP_PER_THREAD * j);
+    for (int l = 0; l < 32; l++) dp.w_lane[l] = gl::pow(w, (u64)l);
+    deep_kernel<<<blocks_for(N, DEEP_THREADS * DEEP_PER_THREAD), DEEP_THREADS, 0, ctx->stream>>>(out, N, dp);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -342,11 +453,14 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
         CommitOpts o;
         o.fold_src = fl.values + (off - 2 * len);
         o.fold_beta = betas[l - 1];
-        o.roots_dev = d_roots + 32 * l;
-        commit_build(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
+        // fold + leaf hash + chunk trees now; the levels above the chunk roots do not feed the next fold and are
+        // reduced for all layers together below
+        commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
+        commit_chunks(ctx, fl.commits[l], 0, fl.commits[l].n_ch, o);
         off += len;
         len >>= 1;
     }
+    commit_finish_multi(ctx, fl.commits.data() + 1, log_N, d_roots + 32);
     CUDA_CHECK(cudaMemcpyAsync(roots_host + 32, d_roots + 32, (size_t)log_N * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(final_value, fl.values + (2 * N - 2), 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -390,7 +504,8 @@ void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_
 namespace {
 
 struct Writer {  // bincode 1.3 default: fixint little-endian, u64 lengths, arrays raw
-    std::vector<u8> b;
+    std::vector<u8>& b;
+    explicit Writer(std::vector<u8>& out) : b(out) { b.clear(); }
     void u64le(u64 v) {
         u8 t[8];
         std::memcpy(t, &v, 8);
@@ -486,6 +601,7 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
     };
     ctx->timings.clear();
     double t0 = now_ms();
+    const double t_begin = t0;
     auto lap = [&](const char* name) {
         cudaStreamSynchronize(ctx->stream);
         double t1 = now_ms();
@@ -678,7 +794,7 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         lap("openings");
 
         // J. ProofV1 in declaration order (v1/proof.rs:80-98)
-        Writer w;
+        Writer w(proof_out);  // the caller's vector keeps its capacity across proofs: no reallocation, no page faults
         w.u64le(N);
         w.u64le(tau);
         w.u64le((u64)n_cols);
@@ -719,8 +835,8 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         }
         w.raw(&final_value, 8);
         w.raw(manifest_root, 32);
-        proof_out.swap(w.b);
         lap("serialize");
+        ctx->timings.push_back({"total", now_ms() - t_begin});
     } catch (...) {
         cm.release(ctx);
         fl.release(ctx);
