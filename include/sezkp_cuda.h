@@ -89,7 +89,9 @@ int32_t sezkp_leaf_hash(sezkp_ctx* ctx, const uint64_t* vals, size_t n, const ch
 int32_t sezkp_merkle_root(sezkp_ctx* ctx, const uint8_t* leaves, size_t n, uint8_t out_root[32]);
 /* OnDemandOpenings::build_roots over arbitrary columns (v1/openings.rs:306-398): cols [c][n] with one label per
  * column, labeled leaves -> 2^chunk_log2-row chunk trees -> outer tree over chunk roots.  n must be a power of two
- * (then the result equals one binary tree over n labeled leaves).  keep != NULL retains what openings need. */
+ * (then the result equals one binary tree over n labeled leaves).  keep != NULL retains what openings need.
+ * labels == NULL: unlabeled leaves BLAKE3(le8), i.e. the root StreamingLayerBuilder computes for an FRI layer
+ * (v1/fri_stream.rs:55-122). */
 int32_t sezkp_column_commit_batch(sezkp_ctx* ctx, const uint64_t* cols, const char* const* labels, int c, size_t n,
                                   int chunk_log2, uint8_t* roots /* [c][32] */, sezkp_tree** keep_or_null);
 int32_t sezkp_column_commit_batch_dev(sezkp_ctx* ctx, const uint64_t* cols_dev, const char* const* labels, int c, size_t n,

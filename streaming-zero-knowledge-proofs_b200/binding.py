@@ -195,15 +195,16 @@ class Context:
         self._ck(self.lib.sezkp_merkle_root(self.h, _p(l), C.c_size_t(l.shape[0]), out))
         return out.raw
 
-    def column_commit(self, cols, labels: Sequence[str], chunk_log2=10, keep=False, dev=False, n=None):
+    def column_commit(self, cols, labels: Optional[Sequence[str]], chunk_log2=10, keep=False, dev=False, n=None, c=None):
+        """labels=None commits unlabeled leaves (FRI-layer style); then `c` gives the column count for device input."""
         if dev:
-            c = len(labels)
+            c = len(labels) if labels is not None else c
             ptr = _vp(cols)
         else:
             a = np.ascontiguousarray(cols, np.uint64)
             c, n = a.shape
             ptr = _p(a)
-        arr = (C.c_char_p * c)(*[l.encode() for l in labels])
+        arr = (C.c_char_p * c)(*[l.encode() for l in labels]) if labels is not None else None
         roots = np.empty((c, 32), np.uint8)
         tree = C.c_void_p()
         fn = self.lib.sezkp_column_commit_batch_dev if dev else self.lib.sezkp_column_commit_batch
@@ -257,7 +258,9 @@ class Context:
         return out
 
     # ---- prover ----
-    def prove_v1(self, ct: CompactTrace, manifest_root: bytes, buf: Optional[np.ndarray] = None) -> bytes:
+    def prove_v1(self, ct: CompactTrace, manifest_root: bytes, buf: Optional[np.ndarray] = None, view: bool = False):
+        """Proof bytes.  `buf` (e.g. pinned) receives the proof; view=True returns the filled slice of `buf` instead of a
+        copy (what a native caller of the C ABI gets)."""
         if len(manifest_root) != 32:
             raise SezkpCudaError(-1, "manifest_root must be 32 bytes")
         d = ct.as_desc()
@@ -265,7 +268,7 @@ class Context:
         if buf is None:
             buf = np.empty(proof_size_bound(ct.n_rows, ct.tau), np.uint8)
         self._ck(self.lib.sezkp_stark_v1_prove(self.h, C.byref(d), manifest_root, _p(buf), C.c_size_t(buf.size), C.byref(n)))
-        return buf[: n.value].tobytes()
+        return buf[: n.value] if view else buf[: n.value].tobytes()
 
     def prove_v1_sharded(self, ct: CompactTrace, manifest_root: bytes, rank: int, world: int, allgather_cb,
                          buf: Optional[np.ndarray] = None) -> bytes:
@@ -284,12 +287,12 @@ class Context:
         self._ck(self.lib.sezkp_trace_upload(self.h, C.byref(d), C.byref(h)))
         return ResidentTrace(self, h, ct.n_rows, ct.tau)
 
-    def prove_v1_resident(self, rt: "ResidentTrace", manifest_root: bytes, buf: Optional[np.ndarray] = None) -> bytes:
+    def prove_v1_resident(self, rt: "ResidentTrace", manifest_root: bytes, buf: Optional[np.ndarray] = None, view: bool = False):
         n = C.c_size_t(0)
         if buf is None:
             buf = np.empty(proof_size_bound(rt.n_rows, rt.tau), np.uint8)
         self._ck(self.lib.sezkp_stark_v1_prove_resident(self.h, rt.h, manifest_root, _p(buf), C.c_size_t(buf.size), C.byref(n)))
-        return buf[: n.value].tobytes()
+        return buf[: n.value] if view else buf[: n.value].tobytes()
 
     def prove_v1_stream(self, blocks, manifest_root: bytes, tau: Optional[int] = None, expected_rows: int = 0) -> bytes:
         """begin_stream / ingest_block / finish_stream (reference sezkp-core/src/prover.rs:21-33).  `blocks` is any

@@ -101,6 +101,8 @@ void sezkp_cuda_destroy(sezkp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ntt_free_tables(ctx);
     for (auto& pb : ctx->pinned) pb.release();
+    for (auto& kv : ctx->deep_tables) cudaFree(kv.second);
+    ctx->deep_tables.clear();
     for (auto& kv : ctx->power_tables) cudaFree(kv.second);
     ctx->power_tables.clear();
     for (auto& b : ctx->scratch) b.release();
@@ -358,7 +360,7 @@ int32_t sezkp_merkle_root(sezkp_ctx* ctx, const uint8_t* leaves, size_t n, uint8
 static int32_t column_commit_impl(sezkp_ctx* ctx, const u64* cols_host, const u64* cols_dev, const char* const* labels, int c,
                                   size_t n, int chunk_log2, uint8_t* roots, sezkp_tree** keep) {
     API_BEGIN(ctx)
-    REQUIRE((cols_host || cols_dev) && labels && roots && c >= 1, "bad argument");
+    REQUIRE((cols_host || cols_dev) && roots && c >= 1, "bad argument");
     REQUIRE(n >= 1 && (n & (n - 1)) == 0, "column length must be a power of two");
     if (keep) *keep = nullptr;
     const size_t bytes = (size_t)c * n * 8;
@@ -528,18 +530,17 @@ int32_t sezkp_compose_base(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const 
 }
 
 /* --------------------------------------------------------------- prover ------ */
-static void deliver(const std::vector<u8>& proof, uint8_t* buf, size_t cap, size_t* len) {
-    *len = proof.size();
-    if (!buf) return;
-    if (cap < proof.size()) sezkp_fail(SEZKP_CUDA_ERANGE, "proof buffer too small: need %zu bytes, have %zu", proof.size(), cap);
-    std::memcpy(buf, proof.data(), proof.size());
+static void deliver(const ProofSink& proof, uint8_t* buf, size_t cap, size_t* len) {
+    *len = proof.len;
+    if (!buf) return;  // size query
+    if (cap < proof.len) sezkp_fail(SEZKP_CUDA_ERANGE, "proof buffer too small: need %zu bytes, have %zu", proof.len, cap);
 }
 
 int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, const uint8_t manifest_root[32], uint8_t* proof_buf,
                              size_t cap, size_t* len) {
     API_BEGIN(ctx)
     REQUIRE(manifest_root && len, "bad argument");
-    std::vector<u8>& proof = ctx->proof_buf;
+    ProofSink proof(proof_buf, cap);
     prove_v1_device(ctx, trace, manifest_root, proof);
     deliver(proof, proof_buf, cap, len);
     API_END(ctx)
@@ -551,7 +552,7 @@ int32_t sezkp_stark_v1_prove_sharded(sezkp_ctx* ctx, const sezkp_trace_desc* tra
     REQUIRE(manifest_root && len && world >= 1 && rank >= 0 && rank < world, "bad argument");
     REQUIRE(world == 1 || allgather != nullptr, "allgather callback is NULL");
     ShardInfo sh{rank, world, allgather, user};
-    std::vector<u8>& proof = ctx->proof_buf;
+    ProofSink proof(proof_buf, cap);
     prove_v1_device(ctx, trace, manifest_root, proof, world > 1 ? &sh : nullptr);
     deliver(proof, proof_buf, cap, len);
     API_END(ctx)
@@ -583,7 +584,7 @@ int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* tra
                                       uint8_t* proof_buf, size_t cap, size_t* len) {
     API_BEGIN(ctx)
     REQUIRE(trace && manifest_root && len, "bad argument");
-    std::vector<u8>& proof = ctx->proof_buf;
+    ProofSink proof(proof_buf, cap);
     prove_v1_resident(ctx, trace->owner.t, manifest_root, proof);
     deliver(proof, proof_buf, cap, len);
     API_END(ctx)
@@ -605,7 +606,7 @@ int32_t sezkp_stark_v1_finish(sezkp_ctx* ctx, sezkp_stream* st, uint8_t* proof_b
     API_BEGIN(ctx)
     if (!st) sezkp_fail(SEZKP_CUDA_ESTATE, "stream handle is NULL");
     REQUIRE(proof_buf && len, "finish needs a proof buffer (use sezkp_stark_v1_proof_bound for its size)");
-    std::vector<u8>& proof = ctx->proof_buf;
+    ProofSink proof(proof_buf, cap);
     stream_finish(ctx, st, proof);
     deliver(proof, proof_buf, cap, len);
     stream_free(ctx, st);  // the handle is consumed once the proof has been delivered

@@ -152,11 +152,11 @@ struct sezkp_ctx {
     std::vector<cudaEvent_t> slab_events;
     std::string last_error;
     std::map<u64, NttTables*> ntt_tables;  // key: (log_n, inverse, coset params)
+    std::map<u64, u64*> deep_tables;       // (log N, shift) -> device table of the first coset point of every DEEP CTA
     std::map<int, u64*> power_tables;      // log_n -> device table of the low powers of w_n (composition mask)
     DevPool pool;
     DevBuf scratch[12];                      // reusable work buffers (per purpose, see users)
     PinnedBuf pinned[2];                     // host staging: [0] opening requests / results
-    std::vector<u8> proof_buf;               // serialised proof of the last prove (capacity kept across calls)
     std::vector<std::pair<std::string, double>> timings;  // phase -> ms (last prove)
     int dedup_variant = 2;                  // 1: 256-thread kernel, 2: 128-thread kernel (more chunks in flight per SM)
     bool dedup_enabled = true;              // value-aware column commit (SEZKP_NO_DEDUP=1 or sezkp_cuda_set_option disables)

@@ -118,6 +118,29 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(u64* __restr
     if (threadIdx.x < 8) upper[((u64)col * (2 * n_ch - 1) + chunk) * 8 + threadIdx.x] = s[threadIdx.x * pitch];
 }
 
+// Unlabeled chunk commit of several single-column commitments in one launch (the small FRI layers, whose values are
+// folded beforehand: hashing a layer does not feed the next fold, so all of them can be hashed side by side).
+// Job j owns CTAs [cta0[j], cta0[j+1]); one CTA per chunk of 2^cl leaves.
+__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_multi_kernel(const CommitJobs jobs) {
+    __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
+    const int pitch = (1 << MAX_CL) + 2;
+    int j = 0;
+    while (j + 1 < jobs.n && blockIdx.x >= jobs.cta0[j + 1]) j++;
+    const CommitJob jb = jobs.j[j];
+    const u64 chunk = blockIdx.x - jobs.cta0[j];
+    const int leaves = 1 << jb.cl;
+    const u64* v = jb.values + (chunk << jb.cl);
+    for (int i = threadIdx.x; i < leaves; i += HASH_THREADS) {
+        u32 d[8];
+        b3::leaf(v[i], d);
+#pragma unroll
+        for (int w = 0; w < 8; w++) s[w * pitch + i] = d[w];
+    }
+    __syncthreads();
+    reduce_levels_smem(s, pitch, leaves, nullptr, 0, 0, 0, nullptr, 0);
+    if (threadIdx.x < 8) jb.upper[chunk * 8 + threadIdx.x] = s[threadIdx.x * pitch];
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* value-aware chunk commit: identical leaves / identical sibling pairs are hashed once         */
 /* ------------------------------------------------------------------------------------------ */
@@ -1514,6 +1537,28 @@ void commit_finish(sezkp_ctx* ctx, Commit& cm, const CommitOpts& opt) {
     }
 }
 
+// commit_chunks for a batch of single-column unlabeled commitments (begin done, values final): one launch.
+void commit_chunks_multi(sezkp_ctx* ctx, Commit* cms, int count) {
+    for (int base = 0; base < count; base += UPPER_MAX_JOBS) {
+        const int m = std::min(UPPER_MAX_JOBS, count - base);
+        CommitJobs jobs;
+        jobs.n = m;
+        u32 ctas = 0;
+        for (int i = 0; i < m; i++) {
+            const Commit& cm = cms[base + i];
+            REQUIRE(cm.cols == 1 && !cm.templates, "internal: batched chunk commit needs single unlabeled columns");
+            jobs.j[i].values = cm.values;
+            jobs.j[i].upper = cm.upper;
+            jobs.j[i].cl = cm.cl;
+            jobs.cta0[i] = ctas;
+            ctas += (u32)cm.n_ch;
+        }
+        chunk_commit_multi_kernel<<<ctas, HASH_THREADS, 0, ctx->stream>>>(jobs);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+    }
+}
+
 // commit_finish for a batch of single-column commitments: all upper levels in at most three launches, roots to
 // roots_dev[32 * index] (device).
 void commit_finish_multi(sezkp_ctx* ctx, Commit* cms, int count, u8* roots_dev) {
@@ -1569,28 +1614,35 @@ OpenReq make_open_req(const Commit& cm, u32 col, u64 row, u32 out_off) {
     return r;
 }
 
-// One launch for any mix of openings.  paths_host receives, per request, cl + depth_out digests at out_off (32 B units).
-void open_batch(sezkp_ctx* ctx, const std::vector<OpenReq>& reqs, size_t path_digests, u64* values, u8* chunk_roots, u8* paths_host) {
+// One launch for any mix of openings.  Results land in the context's pinned staging buffer: per request a value, a chunk
+// root and, at out_off (32 B units), cl + depth_out path digests.  The returned pointers stay valid until the next
+// open_batch_staged on this context.
+void open_batch_staged(sezkp_ctx* ctx, const std::vector<OpenReq>& reqs, size_t path_digests, u64** values, u8** chunk_roots, u8** paths) {
     const size_t k = reqs.size();
-    if (k == 0) return;
-    const size_t b_req = k * sizeof(OpenReq), b_val = k * 8, b_cr = k * 32, b_path = path_digests * 32;
+    const size_t b_req = (k * sizeof(OpenReq) + 63) & ~(size_t)63, b_val = (k * 8 + 63) & ~(size_t)63, b_cr = k * 32, b_path = path_digests * 32;
     u8* d = (u8*)ctx->scratch[7].ensure(b_req + b_val + b_cr + b_path + 64);
-    OpenReq* d_req = (OpenReq*)d;
-    u64* d_val = (u64*)(d + b_req);
-    u32* d_cr = (u32*)(d + b_req + b_val);
-    u32* d_path = (u32*)(d + b_req + b_val + b_cr);
-    // requests and results are staged in pinned host memory (one H2D, one D2H at full PCIe rate)
     u8* h = (u8*)ctx->pinned[0].ensure(b_req + b_val + b_cr + b_path + 64);
-    std::memcpy(h, reqs.data(), b_req);
-    CUDA_CHECK(cudaMemcpyAsync(d_req, h, b_req, cudaMemcpyHostToDevice, ctx->stream));
-    open_kernel<<<(unsigned)k, HASH_THREADS, 0, ctx->stream>>>(d_req, d_val, d_cr, d_path);
+    *values = (u64*)(h + b_req);
+    *chunk_roots = h + b_req + b_val;
+    *paths = h + b_req + b_val + b_cr;
+    if (k == 0) return;
+    std::memcpy(h, reqs.data(), k * sizeof(OpenReq));
+    CUDA_CHECK(cudaMemcpyAsync(d, h, b_req, cudaMemcpyHostToDevice, ctx->stream));
+    open_kernel<<<(unsigned)k, HASH_THREADS, 0, ctx->stream>>>((const OpenReq*)d, (u64*)(d + b_req), (u32*)(d + b_req + b_val),
+                                                               (u32*)(d + b_req + b_val + b_cr));
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
     CUDA_CHECK(cudaMemcpyAsync(h + b_req, d + b_req, b_val + b_cr + b_path, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    std::memcpy(values, h + b_req, b_val);
-    std::memcpy(chunk_roots, h + b_req + b_val, b_cr);
-    if (b_path) std::memcpy(paths_host, h + b_req + b_val + b_cr, b_path);
+}
+void open_batch(sezkp_ctx* ctx, const std::vector<OpenReq>& reqs, size_t path_digests, u64* values, u8* chunk_roots, u8* paths_host) {
+    if (reqs.empty()) return;
+    u64* v;
+    u8 *cr, *pa;
+    open_batch_staged(ctx, reqs, path_digests, &v, &cr, &pa);
+    std::memcpy(values, v, reqs.size() * 8);
+    std::memcpy(chunk_roots, cr, reqs.size() * 32);
+    if (path_digests) std::memcpy(paths_host, pa, path_digests * 32);
 }
 
 void commit_open(sezkp_ctx* ctx, const Commit& cm, const u32* col_idx, const u64* row_idx, size_t k, u64* values,

@@ -59,6 +59,18 @@ struct UpperJobs {
     int n;
 };
 void commit_finish_multi(sezkp_ctx* ctx, Commit* cms, int count, u8* roots_dev);
+// Leaf hashes + chunk trees of `count` single-column unlabeled commitments (begin done, values final) in one launch.
+struct CommitJob {
+    const u64* values;
+    u32* upper;
+    int cl;
+};
+struct CommitJobs {
+    CommitJob j[UPPER_MAX_JOBS];
+    u32 cta0[UPPER_MAX_JOBS];
+    int n;
+};
+void commit_chunks_multi(sezkp_ctx* ctx, Commit* cms, int count);
 // Generic opening request: one CTA rebuilds the chunk containing `row` of one committed column.
 struct OpenReq {
     const u64* values;             // the column
@@ -69,6 +81,8 @@ struct OpenReq {
     u32 out_off, pad;              // path position in the output (32 B units): cl in-chunk siblings then depth_out upper siblings
 };
 OpenReq make_open_req(const Commit& cm, u32 col, u64 row, u32 out_off);
+// Same launch, results left in the context's pinned staging buffer (valid until the next call).
+void open_batch_staged(sezkp_ctx* ctx, const std::vector<OpenReq>& reqs, size_t path_digests, u64** values, u8** chunk_roots, u8** paths);
 void open_batch(sezkp_ctx* ctx, const std::vector<OpenReq>& reqs, size_t path_digests, u64* values, u8* chunk_roots, u8* paths_host);
 // k openings; outputs are host arrays: values[k], chunk_roots[k][32], path_in[k][cl][32], path_to[k][log2(n_ch)][32].
 void commit_open(sezkp_ctx* ctx, const Commit& cm, const u32* col_idx, const u64* row_idx, size_t k, u64* values,

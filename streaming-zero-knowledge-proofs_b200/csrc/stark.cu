@@ -18,18 +18,29 @@ namespace {
 /* ------------------------------------------------------------------------------------------ */
 /* column expansion                                                                            */
 /* ------------------------------------------------------------------------------------------ */
-// One thread per (block, tape): running head position (post-move, relative to 0 at block entry).
-__global__ void head_scan_kernel(DeviceTrace t, u64* __restrict__ cols, u64 blk0, u64 blk1) {
-    const u64 id = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per (block, tape): running head position (post-move, relative to 0 at block entry).  Lanes take
+// consecutive rows, so the prefix sum is a warp scan plus a carry and the stores are coalesced.
+__global__ void __launch_bounds__(256) head_scan_kernel(DeviceTrace t, u64* __restrict__ cols, u64 blk0, u64 blk1) {
+    const u64 id = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
     if (id >= (blk1 - blk0) * t.tau) return;
     const u64 k = blk0 + id / t.tau;
     const u32 r = (u32)(id % t.tau);
     const u64 start = t.block_start[k], len = t.block_len[k];
-    u64* head = cols + (3 + 3ULL * t.tau + r) * t.n_rows;  // group order: mv, wflag, wsym, head, ...
-    int64_t cur = 0;
-    for (u64 j = 0; j < len; j++) {
-        cur += t.mv[(start + j) * t.tau + r];
-        head[start + j] = gl::from_i64(cur);
+    u64* head = cols + (3 + 3ULL * t.tau + r) * t.n_rows + start;  // group order: mv, wflag, wsym, head, ...
+    const signed char* mv = (const signed char*)t.mv + start * t.tau + r;
+    int64_t carry = 0;
+#pragma unroll 4
+    for (u64 j0 = 0; j0 < len; j0 += 32) {
+        const u64 j = j0 + lane;
+        int v = j < len ? (int)mv[j * t.tau] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o);
+            if ((int)lane >= o) v += u;
+        }
+        if (j < len) head[j] = gl::from_i64(carry + v);
+        carry += __shfl_sync(0xffffffffu, v, 31);
     }
 }
 // One thread per row: everything except head.
@@ -93,22 +104,32 @@ __global__ void __launch_bounds__(128) compose_kernel(const u64* __restrict__ co
         const u64 head = cols[(3 + 3ULL * tau + r) * n + i], head_next = cols[(3 + 3ULL * tau + r) * n + ip1];
         const u64 wlen = cols[(3 + 4ULL * tau + r) * n + i];
         const u64 in_off = cols[(3 + 5ULL * tau + r) * n + i], out_off = cols[(3 + 6ULL * tau + r) * n + i];
-        // C1, C2, C3 (v1/air.rs:64-72)
-        s_bool = L::add(s_bool, L::mul(flg, gl::sub(flg, 1)));
-        s_mv = L::add(s_mv, L::mul(L::mul(mv, gl::sub(mv, 1)), gl::add(mv, 1)));
+        // C1, C2, C3 (v1/air.rs:64-72).  Selector-like factors (flags, is_first, is_last) are 0 or 1 on every well-formed
+        // trace: then the product is a select; any other value takes the general multiplication (same result).
+        if (flg > 1) s_bool = L::add(s_bool, L::mul(flg, gl::sub(flg, 1)));
+        if (mv > 1 && mv != gl::P - 1) s_mv = L::add(s_mv, L::mul(L::mul(mv, gl::sub(mv, 1)), gl::add(mv, 1)));
         s_hu = L::add(s_hu, L::sub(L::sub(head_next, head), mv_next));
         // Bit columns are the honest decompositions of the canonical residues (v1/columns.rs:324-342), so every
         // b*(b-1) term is zero and the reconstructed sums are the low bits of the residue (v1/air.rs:74-112).
-        s_hr = L::add(s_hr, L::mul(flg, head - (head & 0xFFFFULL)));
         const u64 slack = gl::sub(gl::sub(wlen, 1), head);
-        s_sr = L::add(s_sr, L::mul(flg, slack - (slack & 0xFFFFULL)));
-        s_bool = L::add(s_bool, L::mul(flg, sym - (sym & 0xFULL)));  // symbol range shares alpha[0] with the booleanity term
+        // head range (alpha[4]); slack range (alpha[6]); symbol range shares alpha[0] with the booleanity term
+        const u64 hr = head - (head & 0xFFFFULL), sr = slack - (slack & 0xFFFFULL), yr = sym - (sym & 0xFULL);
+        if (flg == 1) {
+            s_hr = L::add(s_hr, hr);
+            s_sr = L::add(s_sr, sr);
+            s_bool = L::add(s_bool, yr);
+        } else if (flg != 0) {
+            s_hr = L::add(s_hr, L::mul(flg, hr));
+            s_sr = L::add(s_sr, L::mul(flg, sr));
+            s_bool = L::add(s_bool, L::mul(flg, yr));
+        }
         // boundary (v1/air.rs:116-136)
         s_bf = L::add(s_bf, L::sub(L::sub(head, mv), in_off));
         s_bl = L::add(s_bl, L::sub(head, out_off));
     }
     // alphas: bool = sym range = a[0], mv = a[1], head update = both boundaries = a[2], head range = a[4], slack = a[6]
-    const u64 t2 = L::add(L::add(L::mul(gl::sub(1, is_last), s_hu), L::mul(is_first, s_bf)), L::mul(is_last, s_bl));
+    auto sel = [](u64 f, u64 x) { return f == 0 ? 0 : (f == 1 ? x : gl::lazy::mul(f, x)); };
+    const u64 t2 = L::add(L::add(sel(gl::sub(1, is_last), s_hu), sel(is_first, s_bf)), sel(is_last, s_bl));
     u64 acc = L::mul(cp.a[0], s_bool);
     acc = L::add(acc, L::mul(cp.a[1], s_mv));
     acc = L::add(acc, L::mul(cp.a[2], t2));
@@ -130,7 +151,7 @@ __global__ void __launch_bounds__(128) compose_kernel(const u64* __restrict__ co
 // inverses are peeled off backwards.  6.3 multiplications per element; inverses are unique, so the canonical
 // results equal the reference's.
 constexpr int DEEP_PER_THREAD = 16;
-constexpr int DEEP_THREADS = 256;
+constexpr int DEEP_THREADS = 128;
 struct DeepParams {
     u64 shift, z;
     u64 w_cta;        // w^(DEEP_THREADS * DEEP_PER_THREAD)
@@ -138,23 +159,15 @@ struct DeepParams {
     u64 w_warp[DEEP_THREADS / 32];  // w^(32 * DEEP_PER_THREAD * j)
     u64 w_lane[32];   // w^l
 };
-__global__ void __launch_bounds__(DEEP_THREADS, 2) deep_kernel(u64* __restrict__ y, u64 N, const DeepParams dp) {
+__global__ void __launch_bounds__(DEEP_THREADS, 4) deep_kernel(u64* __restrict__ y, u64 N, const DeepParams dp, const u64* __restrict__ x0_table) {
     namespace L = gl::lazy;
-    __shared__ u64 s_x0, s_inv, s_wtot[DEEP_THREADS / 32];
+    __shared__ u64 s_inv, s_wtot[DEEP_THREADS / 32];
     const u32 tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {  // shift * w^(first index of this CTA)
-        u64 acc = dp.shift, base = dp.w_cta;
-        for (u32 e = blockIdx.x; e; e >>= 1) {
-            if (e & 1) acc = L::mul(acc, base);
-            base = L::mul(base, base);
-        }
-        s_x0 = acc;
-    }
-    __syncthreads();
+    const u64 cta_x0 = x0_table[blockIdx.x];  // shift * w^(first index of this CTA)
     // thread handles i = i0 + 32*k, k < DEEP_PER_THREAD (coalesced).  Everything below is arranged as shallow trees
     // of independent multiplications (groups of 4) rather than one running product: the kernel is latency-bound.
     const u64 i0 = (u64)blockIdx.x * (DEEP_THREADS * DEEP_PER_THREAD) + warp * (32 * DEEP_PER_THREAD) + lane;
-    const u64 x0 = L::mul(L::mul(s_x0, dp.w_warp[warp]), dp.w_lane[lane]);
+    const u64 x0 = L::mul(L::mul(cta_x0, dp.w_warp[warp]), dp.w_lane[lane]);
     u64 den[DEEP_PER_THREAD], yv[DEEP_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < DEEP_PER_THREAD; k++) {
@@ -187,12 +200,9 @@ __global__ void __launch_bounds__(DEEP_THREADS, 2) deep_kernel(u64* __restrict__
         if (lane < 31) others = L::mul(others, se);
     }
     __syncthreads();
-    {
-        u64 w[DEEP_THREADS / 32];
 #pragma unroll
-        for (int j = 0; j < DEEP_THREADS / 32; j++) w[j] = (j != (int)warp) ? s_wtot[j] : 1;
-        others = L::mul(L::mul(others, L::mul(L::mul(w[0], w[1]), L::mul(w[2], w[3]))), L::mul(L::mul(w[4], w[5]), L::mul(w[6], w[7])));
-    }
+    for (int j = 0; j < DEEP_THREADS / 32; j++)
+        if (j != (int)warp) others = L::mul(others, s_wtot[j]);
     if (tid == 0) {  // CTA total = others * run of thread 0; Fermat inverse, square and multiply chains interleaved
         const u64 total = L::mul(others, run);
         u64 acc = 1, base = total;
@@ -222,6 +232,22 @@ __global__ void fri_fold_kernel(const u64* __restrict__ in, u64 half, u64 beta, 
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= half) return;
     out[i] = gl::add(in[i], gl::mul(beta, in[i + half]));
+}
+// All folds from a layer of 2*len0 values down to the single final value in one CTA (the layers are contiguous in
+// `buf`: layer of 2*len0 at buf, its fold of len0 behind it, and so on).  betas[k] folds the k-th of these layers.
+constexpr int FRI_TAIL_MAX_LAYERS = 16;
+struct TailBetas { u64 b[FRI_TAIL_MAX_LAYERS]; };
+__global__ void __launch_bounds__(1024) fri_tail_fold_kernel(u64* __restrict__ buf, u64 len0, int layers, const TailBetas betas) {
+    u64* in = buf;
+    u64 len = len0;
+    for (int k = 0; k < layers; k++) {
+        u64* out = in + 2 * len;
+        const u64 beta = betas.b[k];
+        for (u64 i = threadIdx.x; i < len; i += blockDim.x) out[i] = gl::add(in[i], gl::mul(beta, in[i + len]));
+        __syncthreads();  // writes of this CTA are visible to its own threads after the barrier
+        in = out;
+        len >>= 1;
+    }
 }
 
 inline unsigned blocks_for(u64 n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
@@ -322,7 +348,7 @@ void DeviceTraceOwner::upload(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
 // rows [row0,row1) of every non-head column and the head columns of blocks [blk0,blk1)
 void expand_columns_range(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols, u64 row0, u64 row1, u64 blk0, u64 blk1) {
     if (blk1 > blk0) {
-        head_scan_kernel<<<blocks_for((blk1 - blk0) * t.tau, 128), 128, 0, ctx->stream>>>(t, cols, blk0, blk1);
+        head_scan_kernel<<<blocks_for((blk1 - blk0) * t.tau * 32, 256), 256, 0, ctx->stream>>>(t, cols, blk0, blk1);
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
     }
@@ -406,7 +432,21 @@ void deep_lde_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, 
     for (int k = 0; k < DEEP_PER_THREAD; k++) dp.w_k[k] = gl::pow(w, 32ULL * k);
     for (int j = 0; j < DEEP_THREADS / 32; j++) dp.w_warp[j] = gl::pow(w, 32ULL * DEEP_PER_THREAD * j);
     for (int l = 0; l < 32; l++) dp.w_lane[l] = gl::pow(w, (u64)l);
-    deep_kernel<<<blocks_for(N, DEEP_THREADS * DEEP_PER_THREAD), DEEP_THREADS, 0, ctx->stream>>>(out, N, dp);
+    // shift * w^(cta * elements per CTA), cached per (log N, shift)
+    const u64 n_cta = blocks_for(N, DEEP_THREADS * DEEP_PER_THREAD);
+    const u64 key = ((u64)(L + logB) << 56) ^ shift;
+    u64*& x0_table = ctx->deep_tables[key];
+    if (!x0_table) {
+        std::vector<u64> h(n_cta);
+        u64 x = shift;
+        for (auto& e : h) {
+            e = x;
+            x = gl::mul(x, dp.w_cta);
+        }
+        CUDA_CHECK(cudaMalloc(&x0_table, n_cta * 8));
+        CUDA_CHECK(cudaMemcpy(x0_table, h.data(), n_cta * 8, cudaMemcpyHostToDevice));
+    }
+    deep_kernel<<<(unsigned)n_cta, DEEP_THREADS, 0, ctx->stream>>>(out, N, dp, x0_table);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -447,19 +487,46 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
         }
     }
     REQUIRE(betas != nullptr, "internal: FRI betas missing");
+    // Layers of at least 2^FUSE_MIN_LOG values: one fused kernel each (fold of the previous layer + leaf hash + chunk
+    // trees).  Smaller layers are latency-bound one by one (a single wave of CTAs, ~25 us each), and hashing a layer
+    // does not feed the next fold: their values are folded first (one small launch per layer, then one CTA for the
+    // last 2^14), and all of them are hashed side by side in ONE launch.  The levels above the chunk roots of every
+    // layer are reduced together at the end.
+    constexpr int FUSE_MIN_LOG = 20, TAIL_ONE_CTA_LOG = 14;
     u64 off = N, len = N >> 1;
+    int first_small = log_N + 1;
     for (int l = 1; l <= log_N; l++) {
         REQUIRE(betas[l - 1] < gl::P, "beta %d is not canonical", l - 1);
         CommitOpts o;
-        o.fold_src = fl.values + (off - 2 * len);
-        o.fold_beta = betas[l - 1];
-        // fold + leaf hash + chunk trees now; the levels above the chunk roots do not feed the next fold and are
-        // reduced for all layers together below
-        commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
-        commit_chunks(ctx, fl.commits[l], 0, fl.commits[l].n_ch, o);
+        const int log_len = log_N - l;
+        if (log_len >= FUSE_MIN_LOG) {
+            o.fold_src = fl.values + (off - 2 * len);
+            o.fold_beta = betas[l - 1];
+            commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
+            commit_chunks(ctx, fl.commits[l], 0, fl.commits[l].n_ch, o);
+        } else {
+            if (first_small > log_N) first_small = l;
+            commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
+            if (log_len >= TAIL_ONE_CTA_LOG) {
+                fri_fold_kernel<<<blocks_for(len, 256), 256, 0, ctx->stream>>>(fl.values + (off - 2 * len), len, betas[l - 1], fl.values + off);
+                CUDA_CHECK(cudaGetLastError());
+                ctx->launches++;
+            } else if (log_len == TAIL_ONE_CTA_LOG - 1 || l == 1) {  // this and all remaining layers in one CTA
+                TailBetas tb{};
+                const int layers = log_len + 1;
+                for (int k = 0; k < layers; k++) {
+                    REQUIRE(betas[l - 1 + k] < gl::P, "beta %d is not canonical", l - 1 + k);
+                    tb.b[k] = betas[l - 1 + k];
+                }
+                fri_tail_fold_kernel<<<1, 1024, 0, ctx->stream>>>(fl.values + (off - 2 * len), len, layers, tb);
+                CUDA_CHECK(cudaGetLastError());
+                ctx->launches++;
+            }
+        }
         off += len;
         len >>= 1;
     }
+    if (first_small <= log_N) commit_chunks_multi(ctx, fl.commits.data() + first_small, log_N - first_small + 1);
     commit_finish_multi(ctx, fl.commits.data() + 1, log_N, d_roots + 32);
     CUDA_CHECK(cudaMemcpyAsync(roots_host + 32, d_roots + 32, (size_t)log_N * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(final_value, fl.values + (2 * N - 2), 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -504,14 +571,10 @@ void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_
 namespace {
 
 struct Writer {  // bincode 1.3 default: fixint little-endian, u64 lengths, arrays raw
-    std::vector<u8>& b;
-    explicit Writer(std::vector<u8>& out) : b(out) { b.clear(); }
-    void u64le(u64 v) {
-        u8 t[8];
-        std::memcpy(t, &v, 8);
-        b.insert(b.end(), t, t + 8);
-    }
-    void raw(const void* p, size_t n) { b.insert(b.end(), (const u8*)p, (const u8*)p + n); }
+    ProofSink& b;
+    explicit Writer(ProofSink& out) : b(out) { b.len = 0; }
+    void u64le(u64 v) { b.put(&v, 8); }
+    void raw(const void* p, size_t n) { b.put(p, n); }
     void digest_vec(const u8* p, size_t count) {
         u64le(count);
         raw(p, count * 32);
@@ -548,7 +611,7 @@ struct TranscriptAbsorb : HostAbsorb {
 
 // Host-descriptor entry: the row arrays are copied in slabs of 2^20 rows on a side stream and every slab is expanded
 // and committed as soon as it has landed, so all but the first slab's H2D time hides behind the column hashing.
-void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out,
+void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], ProofSink& proof_out,
                      const ShardInfo* shard) {
     validate_trace(desc);
     const u64 n = desc->n_rows, nb = desc->n_blocks, tau = desc->tau;
@@ -592,7 +655,7 @@ void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 mani
 }
 
 // The whole prover from a device-resident compact trace.
-void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out,
+void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], ProofSink& proof_out,
                        const ShardInfo* shard, const SlabPlan* plan) {
     const int world = shard ? shard->world : 1, rank = shard ? shard->rank : 0;
     auto exchange = [&](const void* send, size_t bytes, void* recv) {  // all-gather through the host callback
@@ -753,9 +816,9 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         const size_t fri_base = k_open * (size_t)cdepth, fri_digests = (size_t)NUM_QUERIES * log_N * 2 * log_N;
         std::vector<u64> f_pos((size_t)NUM_QUERIES * (log_N + 1));
         fri_open_requests(fl, fri_idx.data(), NUM_QUERIES, f_pos.data(), reqs, (u32)fri_base);
-        std::vector<u64> req_val(reqs.size());
-        std::vector<u8> req_cr(reqs.size() * 32), all_paths((fri_base + fri_digests) * 32 + 32, 0);
-        open_batch(ctx, reqs, fri_base + fri_digests, req_val.data(), req_cr.data(), all_paths.data());
+        u64* req_val;  // results stay in the context's pinned staging buffer until the proof is serialised
+        u8 *req_cr, *all_paths;
+        open_batch_staged(ctx, reqs, fri_base + fri_digests, &req_val, &req_cr, &all_paths);
         std::vector<u64> col_val(k_open, 0);
         std::vector<u8> col_cr(k_open * 32, 0);
         for (size_t i = 0; i < n_col_reqs; i++) {
@@ -788,13 +851,13 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         }
         const u64* o_val = col_val.data();
         const u8* o_cr = col_cr.data();
-        const u8* o_paths = all_paths.data();
-        const u64* f_val = req_val.data() + n_col_reqs;
-        const u8* f_paths = all_paths.data() + fri_base * 32;
+        const u8* o_paths = all_paths;
+        const u64* f_val = req_val + n_col_reqs;
+        const u8* f_paths = all_paths + fri_base * 32;
         lap("openings");
 
         // J. ProofV1 in declaration order (v1/proof.rs:80-98)
-        Writer w(proof_out);  // the caller's vector keeps its capacity across proofs: no reallocation, no page faults
+        Writer w(proof_out);  // straight into the caller's buffer
         w.u64le(N);
         w.u64le(tau);
         w.u64le((u64)n_cols);

@@ -1,5 +1,6 @@
 // Internal interface of stark.cu.
 #pragma once
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -43,6 +44,18 @@ void compose_device(sezkp_ctx* ctx, const u64* cols_dev, u64 n, u32 tau, const u
 bool z_on_coset(u64 z, u64 shift, int log_N);
 void deep_lde_device(sezkp_ctx* ctx, u64* base_vals_dev /* destroyed */, u64* out_dev, int L, int logB, u64 shift, u64 z);
 
+// Where the serialised proof goes: straight into the caller's buffer (no intermediate copy).  Bytes beyond the
+// capacity are counted but not written, so a NULL / short buffer still yields the required length.
+struct ProofSink {
+    u8* buf = nullptr;
+    size_t cap = 0, len = 0;
+    ProofSink(u8* b, size_t c) : buf(b), cap(b ? c : 0) {}
+    void put(const void* p, size_t n) {
+        if (len + n <= cap) std::memcpy(buf + len, p, n);
+        len += n;
+    }
+};
+
 struct HostAbsorb {  // transcript hooks of the FRI commit loop
     virtual void on_root(int layer, const u8* root) = 0;
     virtual std::vector<u64> draw_betas(int n) = 0;
@@ -63,15 +76,15 @@ struct ShardInfo {  // column sharding across the GPUs of one box (one process p
     sezkp_allgather_fn allgather;
     void* user;
 };
-void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], std::vector<u8>& proof_out,
+void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], ProofSink& proof_out,
                        const ShardInfo* shard = nullptr, const SlabPlan* plan = nullptr);
 void expand_columns_range(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols_dev, u64 row0, u64 row1, u64 blk0, u64 blk1);
-void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], std::vector<u8>& proof_out,
+void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], ProofSink& proof_out,
                      const ShardInfo* shard = nullptr);
 
 // stream.cu
 struct sezkp_stream;
 sezkp_stream* stream_begin(sezkp_ctx* ctx, u32 tau, const u8 manifest_root[32], u64 expected_rows);
 void stream_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* blocks);
-void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, std::vector<u8>& proof);
+void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof);
 void stream_free(sezkp_ctx* ctx, sezkp_stream* st);

@@ -172,7 +172,7 @@ void stream_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* b) 
     }
 }
 
-void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, std::vector<u8>& proof) {
+void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof) {
     flush_stage(ctx, st);
     const double ingest_ms = now_ms() - st->ingest_t0;
     const u64 n = st->rows, nb = st->block_len.size();

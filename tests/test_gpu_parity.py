@@ -163,6 +163,16 @@ def test_column_commit_and_openings_vs_oracle(ctx, oracle, n, c):
     tree.free()
 
 
+@pytest.mark.parametrize("n", [1, 8, 1024, 1 << 13])
+def test_unlabeled_column_commit_is_streaming_layer_root(ctx, oracle, n):
+    """labels == NULL: the root of StreamingLayerBuilder over the column (v1/fri_stream.rs:55-122)."""
+    rng = np.random.default_rng(n)
+    cols = np.stack([rand_field(rng, n), np.arange(n, dtype=np.uint64) % 3])
+    roots = ctx.column_commit(cols, None)
+    for c in range(2):
+        assert roots[c].tobytes() == oracle.streaming_layer_root(cols[c])
+
+
 @pytest.mark.parametrize("kind", ["const", "flags", "moves", "sym16", "walk", "counter", "wide_small", "mixed_sign", "random",
                                   "blocks512", "blocks96", "abab", "sparse_ones", "two_halves", "blocks2048", "blocks64",
                                   "flags_outlier", "walk_jump", "blocks_broken", "sym16_late_outliers", "neg_blocks"])

@@ -7,7 +7,13 @@ d = json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
 print(f"value {d['value']:.4g} {d['unit']}  ms/step {d['ms_per_step']:.2f}  e2e {d['e2e']['value']:.4g} ({d['e2e']['ms_per_step']:.2f} ms)  launches {d['gpu_launches']}")
 print("phases", {k: round(v, 2) for k, v in d["phases_ms"].items()})
 r = d["roofline"]
-print(f"roofline {r['kernel']}: {r['ms_per_launch']:.2f} ms, {r['achieved']:.1f} GB/s, frac {r['frac']:.4f}, plain {r['int_alu']['plain_ms_per_launch']:.2f} ms ({r['int_alu']['plain_frac_of_alu_pipe_bound']:.3f} of ALU-pipe bound)")
+ia = r["int_alu"]
+print(f"roofline {r['kernel']}: {r['ms_per_launch']:.2f} ms, {r['achieved']:.1f} GB/s, frac {r['frac']:.4f}, share {r['share_of_step']:.2f}, "
+      f"{ia.get('compressions_per_s', ia.get('plain_compressions_per_s', 0)):.3g} compr/s = {ia.get('frac_of_alu_pipe_bound', ia.get('plain_frac_of_alu_pipe_bound', 0)):.3f} of ALU-pipe bound")
+if "column_commit" in r:
+    c = r["column_commit"]
+    print(f"column commit: tables {c['ms_per_launch']:.2f} ms ({c['achieved']:.0f} GB/s, frac {c['frac']:.3f}, {c['tabled_columns']} cols tabled, "
+          f"{c['chunks_redone_by_generic_kernel']} chunks redone), dedup only {c['dedup_only_ms_per_launch']:.2f} ms, plain {c['plain_ms_per_launch']:.2f} ms")
 if d.get("micro"):
     print("micro", {k: (round(v["ms"], 3), round(v["GBps"], 1), round(v["frac_of_hbm_peak"], 4)) for k, v in d["micro"].items()})
 print("cpu", d["cpu_baseline"]["value"], d["cpu_baseline"].get("gpu_proof_identical"), "clocks", d["clocks"])
