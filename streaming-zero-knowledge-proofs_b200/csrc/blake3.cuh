@@ -27,52 +27,91 @@ __device__ __forceinline__ u32 rotr8(u32 x) { return __byte_perm(x, x, 0x0321); 
 __device__ __forceinline__ u32 rotr12(u32 x) { return __funnelshift_r(x, x, 12); }
 __device__ __forceinline__ u32 rotr7(u32 x) { return __funnelshift_r(x, x, 7); }
 
-// The XORs and rotations can only issue on the ALU pipe (LOP3 / SHF / PRMT); the additions are written as
-// multiply-adds by a run-time 1 so that they issue on the otherwise idle FMA pipe (IMAD) instead of
-// competing for the ALU pipe: 448 ALU + 336 FMA issue slots per compression instead of 560 + 112.
+// Pipe balance.  XOR and rotate can only issue on the ALU pipe (LOP3 / SHF / PRMT, 64 lanes/clk/SM), which is the
+// binding unit of every hashing kernel here; the FMA pipe (IMAD) is otherwise idle.  Two rewrites move work across:
+//  (1) the additions are multiply-adds by a run-time 1 (IMAD): 448 ALU + 336 FMA issue slots per compression instead
+//      of 560 + 112;
+//  (2) a rotation of the b word can be a widening multiply by a run-time power of two (IMAD.WIDE: the high half is
+//      x >> r, the low half x << (32-r)); the two halves are never OR-ed together — the following addition takes
+//      both (one more IMAD) and the following XOR is a three-input LOP3 anyway — so each such rotation trades one
+//      ALU slot for two FMA slots.  B3_SCHED selects which rotations do this: one hex digit per round, bit 0 / 1 =
+//      the 12- / 7-bit rotation of the column step, bit 2 / 3 = of the diagonal step.
 __device__ __constant__ u32 k_one = 1;
+__device__ __constant__ u32 k_pow20 = 1u << 20;  // rotr 12
+__device__ __constant__ u32 k_pow25 = 1u << 25;  // rotr 7
 #ifndef B3_ADD_ON_FMA
 #define B3_ADD_ON_FMA 1
+#endif
+#ifndef B3_SCHED
+#define B3_SCHED 0x0202000u
 #endif
 #if B3_ADD_ON_FMA
 #define B3_ADD(x, y) ((y) * one + (x))
 #else
 #define B3_ADD(x, y) ((x) + (y))
 #endif
-#define B3_G(a, b, c, d, mx, my)  \
-    a = B3_ADD(B3_ADD(a, b), mx); \
-    d = rotr16(d ^ a);            \
-    c = B3_ADD(c, d);             \
-    b = rotr12(b ^ c);            \
-    a = B3_ADD(B3_ADD(a, b), my); \
-    d = rotr8(d ^ a);             \
-    c = B3_ADD(c, d);             \
-    b = rotr7(b ^ c);
+struct Consts {
+    u32 one, p20, p25;
+};
+// b word = b | bl when SI (split in); on return split iff W7.
+template <bool SI, bool W12, bool W7>
+__device__ __forceinline__ void g_fn(u32& a, u32& b, u32& bl, u32& c, u32& d, u32 mx, u32 my, const Consts& k) {
+    const u32 one = k.one;
+    (void)one;
+    a = B3_ADD(B3_ADD(a, b), mx);
+    if (SI) a = B3_ADD(a, bl);
+    d = rotr16(d ^ a);
+    c = B3_ADD(c, d);
+    u32 t = SI ? (b ^ bl ^ c) : (b ^ c);
+    u32 h, l = 0;
+    if (W12) {
+        const u64 w = (u64)t * k.p20;
+        h = (u32)(w >> 32);
+        l = (u32)w;
+    } else h = rotr12(t);
+    a = B3_ADD(B3_ADD(a, h), my);
+    if (W12) a = B3_ADD(a, l);
+    d = rotr8(d ^ a);
+    c = B3_ADD(c, d);
+    t = W12 ? (h ^ l ^ c) : (h ^ c);
+    if (W7) {
+        const u64 w = (u64)t * k.p25;
+        b = (u32)(w >> 32);
+        bl = (u32)w;
+    } else b = rotr7(t);
+}
 
-// message word schedule: round r reads the message through BLAKE3's fixed permutation, applied r times
-#define B3_ROUND(m, i0, i1, i2, i3, i4, i5, i6, i7, i8, i9, i10, i11, i12, i13, i14, i15) \
-    B3_G(s0, s4, s8, s12, m[i0], m[i1])                                                   \
-    B3_G(s1, s5, s9, s13, m[i2], m[i3])                                                   \
-    B3_G(s2, s6, s10, s14, m[i4], m[i5])                                                  \
-    B3_G(s3, s7, s11, s15, m[i6], m[i7])                                                  \
-    B3_G(s0, s5, s10, s15, m[i8], m[i9])                                                  \
-    B3_G(s1, s6, s11, s12, m[i10], m[i11])                                                \
-    B3_G(s2, s7, s8, s13, m[i12], m[i13])                                                 \
-    B3_G(s3, s4, s9, s14, m[i14], m[i15])
+// One round; message words are read through BLAKE3's fixed permutation (indices are literals at every call site).
+// SI: the b words enter split (previous round's diagonal step used the widening rotation); M: this round's digit.
+#define B3_ROUND(SI, M, m, i0, i1, i2, i3, i4, i5, i6, i7, i8, i9, i10, i11, i12, i13, i14, i15)                  \
+    g_fn<SI, ((M) & 1) != 0, ((M) & 2) != 0>(s0, s4, l4, s8, s12, m[i0], m[i1], k);                                \
+    g_fn<SI, ((M) & 1) != 0, ((M) & 2) != 0>(s1, s5, l5, s9, s13, m[i2], m[i3], k);                                \
+    g_fn<SI, ((M) & 1) != 0, ((M) & 2) != 0>(s2, s6, l6, s10, s14, m[i4], m[i5], k);                               \
+    g_fn<SI, ((M) & 1) != 0, ((M) & 2) != 0>(s3, s7, l7, s11, s15, m[i6], m[i7], k);                               \
+    g_fn<((M) & 2) != 0, ((M) & 4) != 0, ((M) & 8) != 0>(s0, s5, l5, s10, s15, m[i8], m[i9], k);                   \
+    g_fn<((M) & 2) != 0, ((M) & 4) != 0, ((M) & 8) != 0>(s1, s6, l6, s11, s12, m[i10], m[i11], k);                 \
+    g_fn<((M) & 2) != 0, ((M) & 4) != 0, ((M) & 8) != 0>(s2, s7, l7, s8, s13, m[i12], m[i13], k);                  \
+    g_fn<((M) & 2) != 0, ((M) & 4) != 0, ((M) & 8) != 0>(s3, s4, l4, s9, s14, m[i14], m[i15], k);
 
 // One-block hash: out[8] = BLAKE3(message of block_len bytes held zero-padded in m[16]).
+template <u32 SCHED = B3_SCHED>
 __device__ __forceinline__ void hash_block(const u32 (&m)[16], u32 block_len, u32 (&out)[8]) {
     u32 s0 = B3_IV0, s1 = B3_IV1, s2 = B3_IV2, s3 = B3_IV3, s4 = B3_IV4, s5 = B3_IV5, s6 = B3_IV6, s7 = B3_IV7;
     u32 s8 = B3_IV0, s9 = B3_IV1, s10 = B3_IV2, s11 = B3_IV3, s12 = 0, s13 = 0, s14 = block_len, s15 = B3_FLAGS_ONE_BLOCK;
-    const u32 one = k_one;
-    (void)one;
-    B3_ROUND(m, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
-    B3_ROUND(m, 2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8)
-    B3_ROUND(m, 3, 4, 10, 12, 13, 2, 7, 14, 6, 5, 9, 0, 11, 15, 8, 1)
-    B3_ROUND(m, 10, 7, 12, 9, 14, 3, 13, 15, 4, 0, 11, 2, 5, 8, 1, 6)
-    B3_ROUND(m, 12, 13, 9, 11, 15, 10, 14, 8, 7, 2, 5, 3, 0, 1, 6, 4)
-    B3_ROUND(m, 9, 14, 11, 5, 8, 12, 15, 1, 13, 3, 0, 10, 2, 6, 4, 7)
-    B3_ROUND(m, 11, 15, 5, 0, 1, 9, 8, 6, 14, 10, 2, 12, 3, 4, 7, 13)
+    u32 l4 = 0, l5 = 0, l6 = 0, l7 = 0;
+    const Consts k = {k_one, k_pow20, k_pow25};
+    constexpr u32 M0 = SCHED & 15, M1 = (SCHED >> 4) & 15, M2 = (SCHED >> 8) & 15, M3 = (SCHED >> 12) & 15, M4 = (SCHED >> 16) & 15,
+                  M5 = (SCHED >> 20) & 15, M6 = (SCHED >> 24) & 15;
+    B3_ROUND(false, M0, m, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    B3_ROUND((M0 & 8) != 0, M1, m, 2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8)
+    B3_ROUND((M1 & 8) != 0, M2, m, 3, 4, 10, 12, 13, 2, 7, 14, 6, 5, 9, 0, 11, 15, 8, 1)
+    B3_ROUND((M2 & 8) != 0, M3, m, 10, 7, 12, 9, 14, 3, 13, 15, 4, 0, 11, 2, 5, 8, 1, 6)
+    B3_ROUND((M3 & 8) != 0, M4, m, 12, 13, 9, 11, 15, 10, 14, 8, 7, 2, 5, 3, 0, 1, 6, 4)
+    B3_ROUND((M4 & 8) != 0, M5, m, 9, 14, 11, 5, 8, 12, 15, 1, 13, 3, 0, 10, 2, 6, 4, 7)
+    B3_ROUND((M5 & 8) != 0, M6, m, 11, 15, 5, 0, 1, 9, 8, 6, 14, 10, 2, 12, 3, 4, 7, 13)
+    if ((M6 & 8) != 0) {  // b words still split: fold the halves into the output XOR
+        s4 ^= l4; s5 ^= l5; s6 ^= l6; s7 ^= l7;
+    }
     out[0] = s0 ^ s8;  out[1] = s1 ^ s9;  out[2] = s2 ^ s10; out[3] = s3 ^ s11;
     out[4] = s4 ^ s12; out[5] = s5 ^ s13; out[6] = s6 ^ s14; out[7] = s7 ^ s15;
 }

@@ -88,7 +88,7 @@ __device__ __forceinline__ void reduce_levels_smem(u32* s, int pitch, int count,
 // FOLD: the values are produced on the fly as the FRI fold of the previous layer,
 //   y'[i] = y[i] + beta*y[i+half]  (reference v1/prover.rs:204-238), written to `values` and hashed in one pass.
 template <bool FOLD>
-__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(u64* __restrict__ values, u64 n, u64 col_stride, int cl,
+__global__ void __launch_bounds__(HASH_THREADS, 5) chunk_commit_kernel(u64* __restrict__ values, u64 n, u64 col_stride, int cl,
                                                                     const b3::LabelTemplate* __restrict__ templates,
                                                                     u32* __restrict__ upper, u64 n_ch,
                                                                     const u64* __restrict__ fold_src, u64 beta, u64 chunk0) {
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(HASH_THREADS) chunk_commit_kernel(u64* __restr
 // Unlabeled chunk commit of several single-column commitments in one launch (the small FRI layers, whose values are
 // folded beforehand: hashing a layer does not feed the next fold, so all of them can be hashed side by side).
 // Job j owns CTAs [cta0[j], cta0[j+1]); one CTA per chunk of 2^cl leaves.
-__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_multi_kernel(const CommitJobs jobs) {
+__global__ void __launch_bounds__(HASH_THREADS, 5) chunk_commit_multi_kernel(const CommitJobs jobs) {
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
     const int pitch = (1 << MAX_CL) + 2;
     int j = 0;
@@ -230,7 +230,7 @@ __device__ __forceinline__ void st_release_u32(u32* p, u32 v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(HASH_THREADS) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, u64 col_stride, int cl,
+__global__ void __launch_bounds__(HASH_THREADS, 5) chunk_commit_dedup_kernel(const u64* __restrict__ values, u64 n, u64 col_stride, int cl,
                                                                           const b3::LabelTemplate* __restrict__ templates,
                                                                           u32* __restrict__ upper, u64 n_ch, u32* memo, u64 chunk0) {
     extern __shared__ __align__(16) unsigned char dd_raw[];
@@ -1120,7 +1120,7 @@ __global__ void __launch_bounds__(DT, 8) chunk_commit_tabled_kernel(const u64* _
 }
 
 // digests at level l0 of `upper` -> reduce groups of 2^k -> levels l0+1..l0+k stored.  grid (count>>k, cols)
-__global__ void __launch_bounds__(HASH_THREADS) upper_reduce_kernel(u32* __restrict__ upper, u64 n_ch, int l0, int k) {
+__global__ void __launch_bounds__(HASH_THREADS, 5) upper_reduce_kernel(u32* __restrict__ upper, u64 n_ch, int l0, int k) {
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
     const int pitch = (1 << MAX_CL) + 2;
     const u64 grp = blockIdx.x;
@@ -1136,7 +1136,7 @@ __global__ void __launch_bounds__(HASH_THREADS) upper_reduce_kernel(u32* __restr
 // The same for several single-column commitments in one launch (the FRI layers: their upper levels are off the
 // critical path of the fold chain, so they are reduced together at the end instead of 2-3 latency-bound launches per
 // layer).  Job j owns CTAs [cta0[j], cta0[j+1]); a job that reaches its root also writes it to root_out.
-__global__ void __launch_bounds__(HASH_THREADS) upper_reduce_multi_kernel(const UpperJobs jobs) {
+__global__ void __launch_bounds__(HASH_THREADS, 5) upper_reduce_multi_kernel(const UpperJobs jobs) {
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
     const int pitch = (1 << MAX_CL) + 2;
     int j = 0;
@@ -1154,7 +1154,7 @@ __global__ void __launch_bounds__(HASH_THREADS) upper_reduce_multi_kernel(const 
 // One CTA per opening: rebuild the chunk, record the in-chunk sibling path and chunk root, gather the upper path.
 // Requests carry their own commitment pointers so that openings into many commitments (all FRI layers, all
 // columns) go out in ONE launch.
-__global__ void __launch_bounds__(HASH_THREADS) open_kernel(const OpenReq* __restrict__ reqs, u64* __restrict__ out_values,
+__global__ void __launch_bounds__(HASH_THREADS, 5) open_kernel(const OpenReq* __restrict__ reqs, u64* __restrict__ out_values,
                                                             u32* __restrict__ out_chunk_roots, u32* __restrict__ out_paths) {
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
     const int pitch = (1 << MAX_CL) + 2;
