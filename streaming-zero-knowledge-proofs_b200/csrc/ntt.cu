@@ -23,7 +23,7 @@ constexpr int MAX_LOG_R = 6;
 struct PassDesc {
     const u64* in;
     u64* out;
-    int b, logR;
+    int b, logR, pitch, canon_in, inv;
     u32 col_tiles, U;
     u64 total_cols;
     // input addressing
@@ -37,7 +37,7 @@ struct PassDesc {
     u64 out_cs_lo, out_cs_hi, out_u_stride, out_v_stride;
     int load_rows_fast, store_rows_fast;
     // tables
-    const u64* W;  // w_{2^b}^e, e < 2^(b-1)
+    const u64* W;  // w_{2^b}^e, e < 2^b (inter-step twiddles of a two-step pass)
     const u64* tw_lo;
     const u64* tw_hi;
     int tw_lb, use_tw;
@@ -53,49 +53,70 @@ struct PassDesc {
     u32 ga_pitch, gb_pitch;
 };
 
-// One radix-2^K DIF step (stages s0..s0+K-1 of a 2^b-point transform) on every column of the tile.
-template <int K, bool LAST>
-__device__ __forceinline__ void dif_step(u64* tile, const u64* Ws, int b, int s0, int logR, int pitch) {
-    const int lo_bits = LAST ? 0 : b - s0 - K;
-    const int groups = (1 << (b - K)) << logR;
+// Tile layout: element (column c, row r) lives at c*pitch + pos(r), pos(r) = r + (r >> K2) — one word of skew per
+// group of B = 2^K2 rows, so that both register steps (stride B+1 in the first, contiguous runs in the second) and the
+// digit-swapped read of the store phase touch all sixteen 8-byte banks evenly; the host picks pitch mod 16 to spread
+// the columns a warp covers over the remaining banks (tile_pitch()).
+//
+// The 2^b-point transform of a column is the Cooley-Tukey split 2^b = A*B (A = 2^K1, B = 2^K2), rows r = B*r1 + r2,
+// outputs k = k1 + A*k2:   X[k1 + A*k2] = sum_{r2} w_B^{r2*k2} * ( w_{2^b}^{r2*k1} * sum_{r1} x[B*r1 + r2] * w_A^{r1*k1} )
+//   step 1: one thread = one (column, r2): A-point DFT over r1 in registers (power-of-two twiddles: shifts), then the
+//           inter-step twiddle Ws[r2*k1] — the only general multiplication of the step — back to position (k1, r2);
+//   step 2: one thread = one (column, k1): B-point DFT over r2 in registers, result at position (k1, k2).
+// Values in the tile are canonical (<= p) when a step starts and arbitrary 64-bit representatives after the last one;
+// the store phase canonicalises.
+template <int K1, int K2, bool INV>
+__device__ __forceinline__ void dft_step1(u64* tile, const u64* Ws, int logR, int pitch, u32 eps) {
+    constexpr int A = 1 << K1, B = 1 << K2;
+    constexpr int stride = K2 ? B + 1 : 1;
+    const int tasks = B << logR;
     const int R = 1 << logR;
-    for (int g = threadIdx.x; g < groups; g += NTT_THREADS) {
+    for (int g = threadIdx.x; g < tasks; g += NTT_THREADS) {
         const int c = g & (R - 1);
-        const int gi = g >> logR;
-        const int lo = gi & ((1 << lo_bits) - 1);
-        const int hi = gi >> lo_bits;
-        u64* col = tile + c * pitch + (hi << (b - s0)) + lo;
-        u64 x[1 << K];
+        const int r2 = g >> logR;
+        u64* col = tile + c * pitch + r2;
+        u64 x[A];
 #pragma unroll
-        for (int t = 0; t < (1 << K); t++) x[t] = col[t << lo_bits];
+        for (int t = 0; t < A; t++) x[t] = col[t * stride];
+        gl::lazy::dft_pow2<K1, INV>(x, eps);
 #pragma unroll
-        for (int u = 0; u < K; u++) {
-            const int half = 1 << (K - 1 - u);
-#pragma unroll
-            for (int t = 0; t < (1 << K); t++) {
-                if (t & half) continue;
-                const int e = (((t & (half - 1)) << lo_bits) + lo) << (s0 + u);
-                const u64 a = x[t], bb = x[t | half];
-                x[t] = gl::lazy::add(a, bb);
-                const u64 df = gl::lazy::sub(a, bb);
-                // in the last step of a pass (lo_bits == 0) the exponent is a compile-time constant: skip w^0
-                x[t | half] = (LAST && (t & (half - 1)) == 0) ? df : gl::lazy::mul(df, Ws[e]);
-            }
+        for (int k = 0; k < A; k++) {
+            const u64 y = x[gl::lazy::brev_bits(k, K1)];
+            if (K2 == 0) col[k * stride] = y;                                  // single-step pass: stays lazy
+            else if (k == 0) col[0] = gl::lazy::canon2(y);
+            else col[k * stride] = gl::lazy::mulc(y, Ws[r2 * k], eps);
         }
+    }
+}
+template <int K1, int K2, bool INV>
+__device__ __forceinline__ void dft_step2(u64* tile, int logR, int pitch, u32 eps) {
+    constexpr int A = 1 << K1, B = 1 << K2;
+    const int tasks = A << logR;
+    const int R = 1 << logR;
+    for (int g = threadIdx.x; g < tasks; g += NTT_THREADS) {
+        const int c = g & (R - 1);
+        const int k1 = g >> logR;
+        u64* col = tile + c * pitch + k1 * (B + 1);
+        u64 x[B];
 #pragma unroll
-        for (int t = 0; t < (1 << K); t++) col[t << lo_bits] = x[t];
+        for (int t = 0; t < B; t++) x[t] = col[t];
+        gl::lazy::dft_pow2<K2, INV>(x, eps);
+#pragma unroll
+        for (int k = 0; k < B; k++) col[k] = x[gl::lazy::brev_bits(k, K2)];
     }
 }
 
-template <int K1, int K2>
+template <int K1, int K2, bool INV>
 __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const PassDesc d) {
     extern __shared__ u64 smem[];
     constexpr int b = K1 + K2;
     constexpr int rows = 1 << b;
-    constexpr int pitch = rows | 1;  // odd pitch: conflict-free for lanes over columns and over rows
+    const int pitch = d.pitch;
     const int logR = d.logR, R = 1 << logR;
     u64* tile = smem;
     u64* Ws = smem + (size_t)R * pitch;
+    const u32 eps = gl::lazy::k_eps32;
+    auto pos = [](int r) { return K2 ? r + (r >> K2) : r; };
 
     const u32 tile_id = blockIdx.x;
     const u32 ct = tile_id % d.col_tiles;
@@ -106,7 +127,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const PassDesc
     const u64* in_base = d.in + u * d.in_u_stride + (v >> d.in_v_shift) * d.in_v_stride;
     u64* out_base = d.out + u * d.out_u_stride + v * d.out_v_stride;
 
-    for (int i = threadIdx.x; i < (rows >> 1); i += NTT_THREADS) Ws[i] = d.W[i];
+    if (K2 > 0)
+        for (int i = threadIdx.x; i < rows; i += NTT_THREADS) Ws[i] = d.W[i];
 
     // ---- load (optionally pre-scaled by the coset powers); per-thread invariants hoisted out of the loops ----
     const int tid = threadIdx.x;
@@ -114,7 +136,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const PassDesc
         const u64 C = C0 + c;
         u64* dst = tile + c * pitch;
         if (C >= d.total_cols) {
-            for (int row = row0; row < rows; row += rstep) dst[row] = 0;
+            for (int row = row0; row < rows; row += rstep) dst[pos(row)] = 0;
             return;
         }
         const u64* src = in_base + (C & ((1ULL << d.in_clog) - 1)) * d.in_cs_lo + (C >> d.in_clog) * d.in_cs_hi;
@@ -126,27 +148,52 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const PassDesc
 #pragma unroll 4
             for (int row = row0; row < rows; row += rstep) {
                 u64 g = ga[row];
-                if (d.use_gb) g = gl::lazy::mul(g, gbc);
-                dst[row] = gl::lazy::mul(src[(u64)row * rs], g);
+                if (d.use_gb) g = gl::lazy::mulc(g, gbc, eps);
+                dst[pos(row)] = gl::lazy::mulc(src[(u64)row * rs], g, eps);
             }
+        } else if (d.canon_in) {  // caller-supplied device data: accept any 64-bit representative
+#pragma unroll 8
+            for (int row = row0; row < rows; row += rstep) dst[pos(row)] = gl::lazy::canon2(src[(u64)row * rs]);
         } else {
 #pragma unroll 8
-            for (int row = row0; row < rows; row += rstep) dst[row] = src[(u64)row * rs];
+            for (int row = row0; row < rows; row += rstep) dst[pos(row)] = src[(u64)row * rs];
         }
     };
-    if (d.load_rows_fast) {
+    if (d.load_rows_fast && !d.use_pre) {
+        // rows are contiguous in memory (last pass): flat index over (column, row), row fastest, eight independent
+        // loads in flight per thread — with one load per loop trip this pass was bound by memory latency
+        const int total = R << b;
+        for (int i0 = tid; i0 < total; i0 += 8 * NTT_THREADS) {
+            u64 w[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int i = i0 + j * NTT_THREADS;
+                const int c = i >> b, row = i & (rows - 1);
+                const u64 C = C0 + c;
+                w[j] = 0;
+                if (i < total && C < d.total_cols)
+                    w[j] = in_base[(C & ((1ULL << d.in_clog) - 1)) * d.in_cs_lo + (C >> d.in_clog) * d.in_cs_hi + (u64)row * d.in_row_stride];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int i = i0 + j * NTT_THREADS;
+                if (i < total) tile[(i >> b) * pitch + pos(i & (rows - 1))] = d.canon_in ? gl::lazy::canon2(w[j]) : w[j];
+            }
+        }
+    } else if (d.load_rows_fast) {
         for (int c = 0; c < R; c++) load_column(c, tid, NTT_THREADS);
     } else {
         load_column(tid & (R - 1), tid >> logR, NTT_THREADS >> logR);
     }
     __syncthreads();
-    dif_step<K1, K2 == 0>(tile, Ws, b, 0, logR, pitch);
+    dft_step1<K1, K2, INV>(tile, Ws, logR, pitch, eps);
     __syncthreads();
     if (K2 > 0) {
-        dif_step<(K2 > 0 ? K2 : 1), true>(tile, Ws, b, K1, logR, pitch);
+        dft_step2<K1, (K2 > 0 ? K2 : 1), INV>(tile, logR, pitch, eps);
         __syncthreads();
     }
-    // ---- store: bit-reversed row -> output index k, inter-pass twiddle, optional scale, canonicalise ----
+    // ---- store: output index k = k1 + A*k2 sits at position (k1, k2); inter-pass twiddle, optional scale; everything
+    //      written to HBM is the canonical residue ----
     auto store_column = [&](int c, int k0, int kstep) {
         const u64 C = C0 + c;
         if (C >= d.total_cols) return;
@@ -157,18 +204,22 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const PassDesc
         const u64 Cs = C * d.tw_stride;
 #pragma unroll 4
         for (int k = k0; k < rows; k += kstep) {
-            u64 x = src[__brev((unsigned)k) >> (32 - b)];
+            u64 x = src[K2 ? (k & ((1 << K1) - 1)) * ((1 << K2) + 1) + (k >> K1) : k];
             if (d.use_tw) {
                 u64 w;
                 if (twf) w = twf[(u64)k * d.tw_pitch];
                 else {
                     const u64 E = (u64)k * Cs;
-                    w = gl::lazy::mul(d.tw_lo[E & ((1ULL << d.tw_lb) - 1)], d.tw_hi[E >> d.tw_lb]);
+                    w = gl::lazy::mulc(d.tw_lo[E & ((1ULL << d.tw_lb) - 1)], d.tw_hi[E >> d.tw_lb], eps);
                 }
-                x = gl::lazy::mul(x, w);
+                x = gl::lazy::mulc(x, w, eps);
+                if (d.use_scale) x = gl::lazy::mulc(x, d.scale, eps);
+            } else if (d.use_scale) {
+                x = gl::lazy::mulc(x, d.scale, eps);
+            } else {
+                x = gl::lazy::canon2(x);
             }
-            if (d.use_scale) x = gl::lazy::mul(x, d.scale);
-            dst[(u64)k * rs] = gl::lazy::canon(x);  // values in HBM are canonical
+            dst[(u64)k * rs] = x;
         }
     };
     if (d.store_rows_fast) {
@@ -191,22 +242,36 @@ __global__ void tw_fill_kernel(u64* __restrict__ out, u64 count, u64 pitch, u64 
 
 typedef void (*pass_fn)(const PassDesc);
 template <int K1, int K2>
-pass_fn get_fn() { return ntt_pass_kernel<K1, K2>; }
+pass_fn get_fn(bool inv) { return inv ? ntt_pass_kernel<K1, K2, true> : ntt_pass_kernel<K1, K2, false>; }
 
-pass_fn kernel_for_bits(int b) {
+// register-step split of a pass of b bits
+void split_bits(int b, int& K1, int& K2) {
+    static const int k1[11] = {0, 1, 2, 3, 4, 5, 3, 4, 4, 5, 5};
+    K1 = k1[b];
+    K2 = b - K1;
+}
+pass_fn kernel_for_bits(int b, bool inv) {
     switch (b) {
-        case 1: return get_fn<1, 0>();
-        case 2: return get_fn<2, 0>();
-        case 3: return get_fn<3, 0>();
-        case 4: return get_fn<4, 0>();
-        case 5: return get_fn<5, 0>();
-        case 6: return get_fn<3, 3>();
-        case 7: return get_fn<4, 3>();
-        case 8: return get_fn<4, 4>();
-        case 9: return get_fn<5, 4>();
-        case 10: return get_fn<5, 5>();
+        case 1: return get_fn<1, 0>(inv);
+        case 2: return get_fn<2, 0>(inv);
+        case 3: return get_fn<3, 0>(inv);
+        case 4: return get_fn<4, 0>(inv);
+        case 5: return get_fn<5, 0>(inv);
+        case 6: return get_fn<3, 3>(inv);
+        case 7: return get_fn<4, 3>(inv);
+        case 8: return get_fn<4, 4>(inv);
+        case 9: return get_fn<5, 4>(inv);
+        case 10: return get_fn<5, 5>(inv);
         default: sezkp_fail(SEZKP_CUDA_EINVAL, "unsupported pass width %d", b);
     }
+}
+// shared-memory pitch of a tile column (see the layout note above the kernel)
+int tile_pitch(int b, int logR) {
+    int K1, K2;
+    split_bits(b, K1, K2);
+    const int base = (1 << b) + (K2 ? (1 << K1) : 0);
+    const int want = logR >= 5 ? 1 : ((32 >> logR) & 15);
+    return base + ((want - base) & 15);
 }
 
 }  // namespace
@@ -266,7 +331,7 @@ static NttTables* get_tables(sezkp_ctx* ctx, int L, bool inverse) {
         if (t->W[b]) continue;
         u64 w = gl::root_2exp((unsigned)b);
         if (inverse) w = gl::inv(w);
-        std::vector<u64> h((size_t)1 << (b - 1));
+        std::vector<u64> h((size_t)1 << b);
         u64 x = 1;
         for (auto& e : h) {
             e = x;
@@ -362,8 +427,9 @@ static int pick_logR(int b, u64 avail_cols, int min_logR) {
 static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
     const u64 tiles = (u64)d.col_tiles * d.U * V;
     REQUIRE(tiles > 0 && tiles < (1ULL << 31), "NTT grid too large (%llu tiles)", (unsigned long long)tiles);
-    const size_t smem = (((size_t)1 << d.logR) * ((1u << d.b) | 1) + ((size_t)1 << (d.b - 1))) * 8;
-    pass_fn fn = kernel_for_bits(d.b);
+    d.pitch = tile_pitch(d.b, d.logR);
+    const size_t smem = (((size_t)d.pitch << d.logR) + (d.b > 5 ? ((size_t)1 << d.b) : 0)) * 8;
+    pass_fn fn = kernel_for_bits(d.b, d.inv != 0);
     static std::map<pass_fn, size_t> configured;  // max dynamic smem already granted per kernel
     if (smem > 48 * 1024 && configured[fn] < smem) {
         CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -395,6 +461,7 @@ static void attach_full_twiddles(sezkp_ctx* ctx, NttTables* t, PassDesc& d, int 
 static void base_desc(PassDesc& d, const NttTables* t, int b) {
     d = PassDesc{};
     d.b = b;
+    d.inv = t->inverse ? 1 : 0;
     d.W = t->W[b];
     d.tw_lo = t->tw_lo;
     d.tw_hi = t->tw_hi;
@@ -427,6 +494,7 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
         d.store_rows_fast = 1;
         d.use_scale = inverse;
         d.scale = t->scale;
+        d.canon_in = 1;
         launch_pass(ctx, d, 1);
         return;
     }
@@ -457,6 +525,7 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
             d.out_v_stride = N;
             d.use_tw = 1;
             d.tw_stride = N / Mp;
+            d.canon_in = (p == 0);
             attach_full_twiddles(ctx, t, d, p, Np, Sp, N / Mp);
         } else {  // case B: columns are values of k_1, rows are contiguous
             const u64 N1 = 1ULL << plan[0], S1 = N / N1;

@@ -14,6 +14,59 @@ __global__ void k(const gl::u64* a, const gl::u64* b, int n, gl::u64* o_add, gl:
     o_sub[i] = gl::lazy::canon(gl::lazy::sub(a[i], b[i]));
     o_mul[i] = gl::lazy::canon(gl::lazy::mul(a[i], b[i]));
 }
+
+// ---- second-generation primitives (mulc / add1 / sub1 / canon2 / mul_pow2 / dft_pow2) ----
+__global__ void k2(const gl::u64* a, const gl::u64* b, int n, unsigned* bad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const gl::u32 eps = gl::lazy::k_eps32;
+    const gl::u64 x = a[i], y = b[i];
+    const gl::u64 xc = x >= gl::P ? x - gl::P : x, yc = y >= gl::P ? y - gl::P : y;
+    if (gl::lazy::mulc(x, y, eps) != gl::mul(xc, yc)) atomicAdd(&bad[0], 1u);
+    if (gl::lazy::canon2(x) != xc) atomicAdd(&bad[1], 1u);
+    // one operand <= p (also try exactly p), the other arbitrary
+    const gl::u64 yp = (i & 7) == 0 ? gl::P : yc;
+    if (gl::lazy::canon2(gl::lazy::add1(x, yp)) != gl::add(xc, yc % gl::P * ((i & 7) != 0))) atomicAdd(&bad[2], 1u);
+    if (gl::lazy::canon2(gl::lazy::add1(yp, x)) != gl::add(xc, yc % gl::P * ((i & 7) != 0))) atomicAdd(&bad[2], 1u);
+    if (gl::lazy::canon2(gl::lazy::sub1(x, yp)) != gl::sub(xc, yc % gl::P * ((i & 7) != 0))) atomicAdd(&bad[3], 1u);
+    gl::u64 pw = 1;
+#pragma unroll
+    for (int e = 1; e < 96; e++) {
+        pw = gl::add(pw, pw);
+        if (gl::lazy::mul_pow2(x, e, eps) != gl::mul(xc, pw)) atomicAdd(&bad[4], 1u);
+    }
+    if (gl::lazy::red3(x, (gl::u32)y, (gl::u32)(y >> 32), eps) !=
+        gl::sub(gl::add(xc, gl::mul((gl::u32)y, gl::EPS)), (gl::u32)(y >> 32))) atomicAdd(&bad[5], 1u);
+}
+template <int K, bool INV>
+__global__ void k3(const gl::u64* a, int n, unsigned* bad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((i + 1) * (1 << K) > n) return;
+    const gl::u32 eps = gl::lazy::k_eps32;
+    gl::u64 v[1 << K], in[1 << K];
+#pragma unroll
+    for (int t = 0; t < (1 << K); t++) {
+        gl::u64 x = a[i * (1 << K) + t];
+        x = x >= gl::P ? x - gl::P : x;
+        if ((i & 3) == 0 && x == 0) x = gl::P;  // the transform accepts p itself as an input representative
+        in[t] = v[t] = x;
+    }
+    gl::lazy::dft_pow2<K, INV>(v, eps);
+    gl::u64 w = gl::root_2exp(K);
+    if (INV) w = gl::inv(w);
+    for (int k = 0; k < (1 << K); k++) {
+        gl::u64 acc = 0, wk = gl::pow(w, k), x = 1;
+        for (int t = 0; t < (1 << K); t++) {
+            acc = gl::add(acc, gl::mul(in[t] % gl::P, x));
+            x = gl::mul(x, wk);
+        }
+        gl::u64 got = 0;
+#pragma unroll
+        for (int t = 0; t < (1 << K); t++)
+            if (t == gl::lazy::brev_bits(k, K)) got = v[t];
+        if (gl::lazy::canon2(got) != acc) atomicAdd(&bad[6 + (INV ? 1 : 0)], 1u);
+    }
+}
 static gl::u64 rnd() {
     gl::u64 x = 0;
     for (int i = 0; i < 5; i++) x = (x << 15) ^ (gl::u64)rand();
@@ -55,5 +108,22 @@ int main() {
         if (o3[i] != e3 && bad[2]++ < 5) printf("mul  a=%016llx b=%016llx got=%016llx exp=%016llx\n", (ull)a[i], (ull)b[i], (ull)o3[i], (ull)e3);
     }
     printf("n=%d bad add=%d sub=%d mul=%d\n", n, bad[0], bad[1], bad[2]);
+    unsigned* dbad;
+    cudaMalloc(&dbad, 8 * 4);
+    cudaMemset(dbad, 0, 8 * 4);
+    k2<<<(n + 255) / 256, 256>>>(da, db, n, dbad);
+    const int nd = 1 << 16;  // elements fed to the register DFTs (edge x edge pairs first, then random)
+    k3<5, false><<<nd / 32 / 64, 64>>>(da, nd, dbad);
+    k3<5, true><<<nd / 32 / 64, 64>>>(da, nd, dbad);
+    k3<4, false><<<nd / 16 / 64, 64>>>(db, nd, dbad);
+    k3<3, true><<<nd / 8 / 64, 64>>>(db, nd, dbad);
+    k3<2, false><<<nd / 4 / 64, 64>>>(da, nd, dbad);
+    k3<1, true><<<nd / 2 / 64, 64>>>(da, nd, dbad);
+    unsigned hb[8];
+    cudaMemcpy(hb, dbad, 32, cudaMemcpyDeviceToHost);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("cuda error (gen 2): %s\n", cudaGetErrorString(cudaGetLastError())); return 2; }
+    printf("gen2 bad mulc=%u canon2=%u add1=%u sub1=%u mul_pow2=%u red3=%u dft=%u idft=%u\n", hb[0], hb[1], hb[2], hb[3], hb[4], hb[5], hb[6], hb[7]);
+    for (int i = 0; i < 8; i++)
+        if (hb[i]) return 1;
     return (bad[0] || bad[1] || bad[2]) ? 1 : 0;
 }
