@@ -15,7 +15,7 @@ import numpy as np
 from .trace import CompactTrace, TraceDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsezkp_cuda.so")
+LIB_PATH = os.environ.get("SEZKP_CUDA_LIB") or os.path.join(_HERE, "libsezkp_cuda.so")  # override: A/B builds of the same ABI
 P = 0xFFFFFFFF00000001
 
 EXPORTS = [

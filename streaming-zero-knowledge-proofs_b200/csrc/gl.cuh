@@ -79,9 +79,6 @@ GL_HD u64 root_2exp(unsigned k) { return pow(7, (P - 1) >> k); }
 // 2^64 ≡ 2^32-1 corrections cost one masked add instead of compare + select sequences.
 // ---------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-#ifndef GL_ADD1_VARIANT
-#define GL_ADD1_VARIANT 0
-#endif
 namespace gl {
 namespace lazy {
 
@@ -262,17 +259,10 @@ __device__ __forceinline__ u64 add1(u64 a, u64 b) {
         "mov.b64 {b0,b1}, %2;\n\t"
         "add.cc.u32 a0, a0, b0;\n\t"
         "addc.cc.u32 a1, a1, b1;\n\t"
-#if GL_ADD1_VARIANT
-        "addc.u32 m, 0xffffffff, 0;\n\t"  // carry ? 0 : ~0
-        "not.b32 m, m;\n\t"
-        "add.cc.u32 a0, a0, m;\n\t"       // + carry*EPS
-        "addc.u32 a1, a1, 0;\n\t"
-#else
         "addc.u32 m, 0, 0;\n\t"
         "sub.cc.u32 a0, a0, m;\n\t"       // + carry*EPS = - carry + (carry << 32)
         "subc.u32 m, m, 0;\n\t"
         "add.u32 a1, a1, m;\n\t"
-#endif
         "mov.b64 %0, {a0,a1};\n\t"
         "}"
         : "=l"(r)

@@ -55,8 +55,8 @@ struct PassDesc {
 
 // Tile layout: element (column c, row r) lives at c*pitch + pos(r), pos(r) = r + (r >> K2) — one word of skew per
 // group of B = 2^K2 rows, so that both register steps (stride B+1 in the first, contiguous runs in the second) and the
-// digit-swapped read of the store phase touch all sixteen 8-byte banks evenly; the host picks pitch mod 16 to spread
-// the columns a warp covers over the remaining banks (tile_pitch()).
+// digit-swapped read of the store phase touch all sixteen 8-byte banks evenly; the host picks pitch = 16/R (mod 16) so
+// that the R columns and 16/R consecutive rows a half-warp covers fall into sixteen different banks (tile_pitch()).
 //
 // The 2^b-point transform of a column is the Cooley-Tukey split 2^b = A*B (A = 2^K1, B = 2^K2), rows r = B*r1 + r2,
 // outputs k = k1 + A*k2:   X[k1 + A*k2] = sum_{r2} w_B^{r2*k2} * ( w_{2^b}^{r2*k1} * sum_{r1} x[B*r1 + r2] * w_A^{r1*k1} )
@@ -270,7 +270,7 @@ int tile_pitch(int b, int logR) {
     int K1, K2;
     split_bits(b, K1, K2);
     const int base = (1 << b) + (K2 ? (1 << K1) : 0);
-    const int want = logR >= 5 ? 1 : ((32 >> logR) & 15);
+    const int want = logR >= 4 ? 1 : ((16 >> logR) & 15);  // a 64-bit access is served per half-warp: 16 lanes x 8 B
     return base + ((want - base) & 15);
 }
 
