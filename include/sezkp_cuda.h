@@ -169,6 +169,26 @@ int32_t sezkp_stark_v1_begin(sezkp_ctx* ctx, uint32_t tau, const uint8_t manifes
 int32_t sezkp_stark_v1_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* blocks);
 int32_t sezkp_stark_v1_finish(sezkp_ctx* ctx, sezkp_stream* st, uint8_t* proof_buf, size_t cap, size_t* len);
 void sezkp_stark_v1_abort(sezkp_ctx* ctx, sezkp_stream* st);
+/* Native JSONL front-end (reference: stream_block_summaries_jsonl, crates/sezkp-core/src/io_jsonl.rs:27-88; one
+ * serde-JSON BlockSummary per line, blank lines skipped).  The reference's stark arm rejects .jsonl input
+ * (sezkp-core/src/io.rs:78-88); these entry points are what its CLI would call to accept it.
+ *  - sezkp_jsonl_parse: text[0,len) (whole lines) -> a library-owned compact trace, parsed on n_threads host threads
+ *    (<= 0: all cores).  No ctx and no GPU needed.  *desc points into the handle; scalars (may be NULL) receives a
+ *    pointer to n_blocks records.  Errors: EINVAL with sezkp_jsonl_last_error() = "jsonl line N: ...".
+ *  - sezkp_stark_v1_ingest_jsonl: parse + ingest_block for every block of the text, in file order.
+ *  - sezkp_stark_v1_prove_jsonl_file: the whole StreamingProver loop over a file read in chunk_bytes pieces
+ *    (0: 64 MiB): parsing the next piece overlaps the H2D copies of the previous ones.  tau comes from the first
+ *    block.  sezkp_cuda_get_timings then also reports jsonl_read_ms, jsonl_parse_ms and jsonl_bytes. */
+typedef struct sezkp_jsonl_trace sezkp_jsonl_trace;
+int32_t sezkp_jsonl_parse(const char* text, size_t len, int n_threads, sezkp_jsonl_trace** out, sezkp_trace_desc* desc,
+                          const sezkp_block_scalars** scalars);
+void sezkp_jsonl_free(sezkp_jsonl_trace* t);
+const char* sezkp_jsonl_last_error(void);                     /* thread-local                                       */
+int32_t sezkp_stark_v1_ingest_jsonl(sezkp_ctx* ctx, sezkp_stream* st, const char* text, size_t len, int n_threads,
+                                    uint64_t* n_blocks, uint64_t* n_rows);
+int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const uint8_t manifest_root[32], int n_threads,
+                                        size_t chunk_bytes, uint64_t expected_rows, uint8_t* proof_buf, size_t cap,
+                                        size_t* len);
 /* upper bound of the serialized ProofV1 size for n_rows rows and tau tapes (for sizing proof_buf) */
 size_t sezkp_stark_v1_proof_bound(uint64_t n_rows, uint32_t tau);
 

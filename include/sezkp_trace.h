@@ -32,6 +32,17 @@ typedef struct sezkp_trace_desc {
     const uint16_t* write_sym;    /* [n_rows][tau]    steps[j].tapes[r].write.unwrap_or(0)       */
 } sezkp_trace_desc;
 
+/* The per-block scalars that only the manifest leaf hash reads (crates/sezkp-merkle/src/lib.rs:85-117); the native
+ * JSONL parser returns them next to the descriptor so a caller can rebuild `manifest_root` from a .jsonl file. */
+typedef struct sezkp_block_scalars {
+    uint64_t step_lo, step_hi;
+    int64_t  in_head_in, in_head_out;
+    uint32_t block_id;
+    uint16_t version, ctrl_in, ctrl_out;
+    uint16_t reserved;            /* 0 */
+    uint32_t reserved2;           /* 0; sizeof == 48 */
+} sezkp_block_scalars;
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ EXPORTS = [
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
     "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_stark_v1_proof_bound", "sezkp_trace_upload", "sezkp_trace_free",
     "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded",
+    "sezkp_jsonl_parse", "sezkp_jsonl_free", "sezkp_jsonl_last_error", "sezkp_stark_v1_ingest_jsonl", "sezkp_stark_v1_prove_jsonl_file",
 ]
 
 ERR_NAMES = {0: "OK", -1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENODEV", -5: "ERANGE", -6: "ESTATE"}
@@ -62,6 +63,12 @@ def load_library() -> C.CDLL:
         lib.sezkp_trace_free.argtypes = [C.c_void_p, C.c_void_p]
         lib.sezkp_stark_v1_proof_bound.restype = C.c_size_t
         lib.sezkp_stark_v1_proof_bound.argtypes = [C.c_uint64, C.c_uint32]
+        lib.sezkp_jsonl_last_error.restype = C.c_char_p
+        lib.sezkp_jsonl_free.argtypes = [C.c_void_p]
+        lib.sezkp_jsonl_parse.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.sezkp_stark_v1_ingest_jsonl.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
+        lib.sezkp_stark_v1_prove_jsonl_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_size_t, C.c_uint64,
+                                                        C.c_void_p, C.c_size_t, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -317,6 +324,72 @@ class Context:
         finally:
             if st is not None and st.value:
                 self.lib.sezkp_stark_v1_abort(self.h, st)
+
+
+    def prove_v1_jsonl_file(self, path: str, manifest_root: bytes, n_rows_bound: int, tau_bound: int = 8, threads: int = 0,
+                            chunk_bytes: int = 0, expected_rows: int = 0) -> bytes:
+        """StreamingProver loop over a .jsonl file with the native multi-threaded parser (sezkp_stark_v1_prove_jsonl_file).
+        n_rows_bound / tau_bound only size the proof buffer."""
+        buf = np.empty(proof_size_bound(n_rows_bound, tau_bound), np.uint8)
+        n = C.c_size_t(0)
+        self._ck(self.lib.sezkp_stark_v1_prove_jsonl_file(self.h, path.encode(), manifest_root, C.c_int(threads), C.c_size_t(chunk_bytes),
+                                                          C.c_uint64(expected_rows), _p(buf), C.c_size_t(buf.size), C.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def prove_v1_jsonl_text(self, pieces, manifest_root: bytes, tau: int, threads: int = 0, expected_rows: int = 0) -> bytes:
+        """begin_stream, then sezkp_stark_v1_ingest_jsonl for every piece of text (whole lines), then finish_stream."""
+        st = C.c_void_p()
+        self._ck(self.lib.sezkp_stark_v1_begin(self.h, C.c_uint32(tau), manifest_root, C.c_uint64(expected_rows), C.byref(st)))
+        try:
+            rows = 0
+            for text in pieces:
+                nb, nr = C.c_uint64(0), C.c_uint64(0)
+                self._ck(self.lib.sezkp_stark_v1_ingest_jsonl(self.h, st, text, C.c_size_t(len(text)), C.c_int(threads), C.byref(nb), C.byref(nr)))
+                rows += nr.value
+            buf = np.empty(proof_size_bound(rows, tau), np.uint8)
+            n = C.c_size_t(0)
+            self._ck(self.lib.sezkp_stark_v1_finish(self.h, st, _p(buf), C.c_size_t(buf.size), C.byref(n)))
+            st = None
+            return buf[: n.value].tobytes()
+        finally:
+            if st is not None and st.value:
+                self.lib.sezkp_stark_v1_abort(self.h, st)
+
+
+BLOCK_SCALARS_DTYPE = np.dtype({"names": ["step_lo", "step_hi", "in_head_in", "in_head_out", "block_id", "version", "ctrl_in", "ctrl_out"],
+                                "formats": ["<u8", "<u8", "<i8", "<i8", "<u4", "<u2", "<u2", "<u2"],
+                                "offsets": [0, 8, 16, 24, 32, 36, 38, 40], "itemsize": 48})  # sezkp_block_scalars
+
+
+def parse_jsonl(text: bytes, threads: int = 0) -> CompactTrace:
+    """Native JSONL parser (sezkp_jsonl_parse): bytes of whole lines -> CompactTrace (arrays copied out of the handle).
+    Needs the library but no GPU."""
+    lib = load_library()
+    h, d, sc = C.c_void_p(), TraceDesc(), C.c_void_p()
+    rc = lib.sezkp_jsonl_parse(text, C.c_size_t(len(text)), C.c_int(threads), C.byref(h), C.byref(d), C.byref(sc))
+    if rc != 0:
+        raise SezkpCudaError(rc, lib.sezkp_jsonl_last_error().decode())
+    try:
+        nb, n, tau = int(d.n_blocks), int(d.n_rows), int(d.tau)
+
+        def arr(ptr, dt, shape):
+            cnt = int(np.prod(shape))
+            if cnt == 0:
+                return np.zeros(shape, dt)
+            return np.frombuffer((C.c_char * (cnt * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt).reshape(shape).copy()
+
+        rec = arr(sc.value, BLOCK_SCALARS_DTYPE, (nb,))
+        return CompactTrace(
+            tau=tau, block_len=arr(d.block_len, np.uint64, (nb,)), win_left=arr(d.win_left, np.int64, (nb, tau)),
+            win_right=arr(d.win_right, np.int64, (nb, tau)), head_in_off=arr(d.head_in_off, np.uint32, (nb, tau)),
+            head_out_off=arr(d.head_out_off, np.uint32, (nb, tau)), input_mv=arr(d.input_mv, np.int8, (n,)),
+            mv=arr(d.mv, np.int8, (n, tau)), write_flag=arr(d.write_flag, np.uint8, (n, tau)),
+            write_sym=arr(d.write_sym, np.uint16, (n, tau)),
+            version=rec["version"].copy(), block_id=rec["block_id"].copy(), step_lo=rec["step_lo"].copy(),
+            step_hi=rec["step_hi"].copy(), ctrl_in=rec["ctrl_in"].copy(), ctrl_out=rec["ctrl_out"].copy(),
+            in_head_in=rec["in_head_in"].copy(), in_head_out=rec["in_head_out"].copy())
+    finally:
+        lib.sezkp_jsonl_free(h)
 
 
 def proof_size_bound(n_rows: int, tau: int) -> int:

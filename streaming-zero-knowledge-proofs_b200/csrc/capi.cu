@@ -1,5 +1,10 @@
 // extern "C" surface of libsezkp_cuda.so (include/sezkp_cuda.h).  Every entry point converts C++
 // exceptions into status codes + ctx->last_error; nothing aborts.
+#include <chrono>
+#include <cstdio>
+#include <thread>
+
+#include "jsonl.hpp"
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -616,6 +621,138 @@ void sezkp_stark_v1_abort(sezkp_ctx* ctx, sezkp_stream* st) {
     if (!ctx || !st) return;
     cudaSetDevice(ctx->device);
     stream_free(ctx, st);
+}
+
+/* ---- native JSONL front-end (jsonl.cpp) ---- */
+struct sezkp_jsonl_trace {
+    jsonl::Trace t;
+};
+static thread_local std::string g_jsonl_error;
+static int jsonl_threads(int n) {
+    if (n > 0) return n;
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? (int)hc : 1;
+}
+const char* sezkp_jsonl_last_error(void) { return g_jsonl_error.c_str(); }
+int32_t sezkp_jsonl_parse(const char* text, size_t len, int n_threads, sezkp_jsonl_trace** out, sezkp_trace_desc* desc,
+                          const sezkp_block_scalars** scalars) {
+    if (!out || !desc || (!text && len)) {
+        g_jsonl_error = "bad argument";
+        return SEZKP_CUDA_EINVAL;
+    }
+    *out = nullptr;
+    sezkp_jsonl_trace* h = new (std::nothrow) sezkp_jsonl_trace();
+    if (!h) return SEZKP_CUDA_ENOMEM;
+    try {
+        jsonl::parse(text, len, jsonl_threads(n_threads), 0, 1, h->t);
+    } catch (const std::bad_alloc&) {
+        delete h;
+        g_jsonl_error = "host allocation failed";
+        return SEZKP_CUDA_ENOMEM;
+    } catch (const std::exception& e) {
+        delete h;
+        g_jsonl_error = e.what();
+        return SEZKP_CUDA_EINVAL;
+    }
+    h->t.fill_desc(*desc);
+    if (scalars) *scalars = h->t.manifest.data();
+    *out = h;
+    return SEZKP_CUDA_OK;
+}
+void sezkp_jsonl_free(sezkp_jsonl_trace* t) { delete t; }
+
+static void jsonl_parse_or_fail(const char* text, size_t len, int n_threads, u32 tau, size_t first_line, jsonl::Trace& t) {
+    try {
+        jsonl::parse(text, len, jsonl_threads(n_threads), tau, first_line, t);
+    } catch (const std::bad_alloc&) {
+        throw;
+    } catch (const std::exception& e) {
+        sezkp_fail(SEZKP_CUDA_EINVAL, "%s", e.what());
+    }
+}
+int32_t sezkp_stark_v1_ingest_jsonl(sezkp_ctx* ctx, sezkp_stream* st, const char* text, size_t len, int n_threads,
+                                    uint64_t* n_blocks, uint64_t* n_rows) {
+    API_BEGIN(ctx)
+    if (!st) sezkp_fail(SEZKP_CUDA_ESTATE, "stream handle is NULL");
+    REQUIRE(text || !len, "text is NULL");
+    jsonl::Trace t;
+    jsonl_parse_or_fail(text, len, n_threads, stream_tau(st), 1, t);
+    if (n_blocks) *n_blocks = t.block_len.size();
+    if (n_rows) *n_rows = t.input_mv.size();
+    if (!t.block_len.empty()) {
+        sezkp_trace_desc d;
+        t.fill_desc(d);
+        stream_ingest(ctx, st, &d);
+    }
+    API_END(ctx)
+}
+int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const uint8_t manifest_root[32], int n_threads,
+                                        size_t chunk_bytes, uint64_t expected_rows, uint8_t* proof_buf, size_t cap,
+                                        size_t* len) {
+    API_BEGIN(ctx)
+    REQUIRE(path && manifest_root && proof_buf && len, "bad argument");
+    REQUIRE(expected_rows <= (1ULL << 29), "expected_rows too large");
+    if (chunk_bytes == 0) chunk_bytes = (size_t)64 << 20;
+    FILE* f = std::fopen(path, "rb");
+    if (!f) sezkp_fail(SEZKP_CUDA_EINVAL, "cannot open %s", path);
+    sezkp_stream* st = nullptr;
+    auto ms_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double read_ms = 0, parse_ms = 0;
+    size_t total_bytes = 0, line_no = 1;
+    try {
+        std::vector<char> buf;
+        size_t carry = 0;  // bytes of an incomplete last line kept at the front of buf
+        bool eof = false;
+        while (!eof) {
+            if (buf.size() < carry + chunk_bytes) buf.resize(carry + chunk_bytes);
+            double t0 = ms_now();
+            const size_t got = std::fread(buf.data() + carry, 1, chunk_bytes, f);
+            read_ms += ms_now() - t0;
+            if (got < chunk_bytes) {
+                if (std::ferror(f)) sezkp_fail(SEZKP_CUDA_EINVAL, "read error on %s", path);
+                eof = true;
+            }
+            total_bytes += got;
+            size_t avail = carry + got, use = avail;
+            if (!eof) {  // cut at the last complete line
+                while (use > 0 && buf[use - 1] != '\n') use--;
+                if (use == 0) {  // a single line longer than the chunk: grow and read on
+                    carry = avail;
+                    chunk_bytes *= 2;
+                    continue;
+                }
+            }
+            t0 = ms_now();
+            jsonl::Trace t;
+            jsonl_parse_or_fail(buf.data(), use, n_threads, st ? stream_tau(st) : 0, line_no, t);
+            parse_ms += ms_now() - t0;
+            for (size_t i = 0; i < use; i++) line_no += buf[i] == '\n';
+            if (!t.block_len.empty()) {
+                if (!st) st = stream_begin(ctx, t.tau, manifest_root, expected_rows);
+                sezkp_trace_desc d;
+                t.fill_desc(d);
+                stream_ingest(ctx, st, &d);
+            }
+            carry = avail - use;
+            if (carry) std::memmove(buf.data(), buf.data() + use, carry);
+        }
+        std::fclose(f);
+        f = nullptr;
+        if (!st) sezkp_fail(SEZKP_CUDA_EINVAL, "%s holds no blocks", path);
+        ProofSink proof(proof_buf, cap);
+        stream_finish(ctx, st, proof);
+        deliver(proof, proof_buf, cap, len);
+        stream_free(ctx, st);
+        st = nullptr;
+        ctx->timings.insert(ctx->timings.begin(), {"jsonl_bytes", (double)total_bytes});
+        ctx->timings.insert(ctx->timings.begin(), {"jsonl_parse_ms", parse_ms});
+        ctx->timings.insert(ctx->timings.begin(), {"jsonl_read_ms", read_ms});
+    } catch (...) {
+        if (f) std::fclose(f);
+        if (st) stream_free(ctx, st);
+        throw;
+    }
+    API_END(ctx)
 }
 /* upper bound of the ProofV1 size for a trace of n_rows rows and tau tapes */
 size_t sezkp_stark_v1_proof_bound(uint64_t n_rows, uint32_t tau) {

@@ -166,6 +166,15 @@ struct sezkp_ctx {
     u64 launches = 0;                       // kernels launched since last reset
 };
 
+// Table upload from pageable host memory, ordered before everything later launched on ctx->stream.
+// A plain cudaMemcpy is NOT enough: for pageable sources it returns once the data sits in the driver's staging buffer
+// and the DMA runs on the legacy stream, which the library's non-blocking stream does not wait for — the first
+// kernel after a table build could read a half-written table.
+inline void upload_table(sezkp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
 inline int ilog2(u64 n) {
     int k = 0;
     while ((1ULL << k) < n) k++;

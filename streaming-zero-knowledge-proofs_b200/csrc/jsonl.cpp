@@ -1,0 +1,480 @@
+// Native JSONL front-end of the streaming prover (host code, no CUDA).
+//
+// Reference: `stream_block_summaries_jsonl` (crates/sezkp-core/src/io_jsonl.rs:27-88) reads one serde-JSON
+// `BlockSummary` (crates/sezkp-core/src/types.rs:116-151) per line, skipping blank lines, and hands the blocks to
+// `ProvingBackendStream::ingest_block` one at a time (sezkp-core/src/prover.rs:104-150).  This file does the same
+// for the GPU prover, but parses straight into the flat arrays of `sezkp_trace_desc` (include/sezkp_trace.h) —
+// the only fields `prove_v1` reads — on several host threads: lines are independent records, so a chunk of text is
+// split at line boundaries, every thread parses a contiguous run of lines into its own arrays, and the runs are
+// concatenated in file order.  The grammar accepted is JSON (RFC 8259) restricted to what serde_json emits for
+// this type: objects with string keys in any order, integers, `null`, arrays; unknown keys are skipped generically
+// (strings with escapes, nested containers, floats), so advisory fields such as the tags cost nothing but a scan.
+#include "jsonl.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <thread>
+
+namespace jsonl {
+
+namespace {
+
+struct Cursor {
+    const char* p;
+    const char* end;
+    size_t line_no;
+    [[noreturn]] void fail(const char* what) const {
+        char buf[160];
+        snprintf(buf, sizeof buf, "jsonl line %zu: %s", line_no, what);
+        throw std::runtime_error(buf);
+    }
+    void ws() {
+        while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) p++;
+    }
+    bool peek(char c) {
+        ws();
+        return p < end && *p == c;
+    }
+    void expect(char c) {
+        ws();
+        if (p >= end || *p != c) {
+            char m[48];
+            snprintf(m, sizeof m, "expected '%c'", c);
+            fail(m);
+        }
+        p++;
+    }
+    bool accept(char c) {
+        ws();
+        if (p < end && *p == c) {
+            p++;
+            return true;
+        }
+        return false;
+    }
+    // integer in [lo, hi]; rejects fractions and exponents (serde_json rejects them for integer fields as well)
+    int64_t integer(int64_t lo, uint64_t hi) {
+        ws();
+        bool neg = false;
+        if (p < end && *p == '-') {
+            neg = true;
+            p++;
+        }
+        if (p >= end || *p < '0' || *p > '9') fail("expected an integer");
+        uint64_t v = 0;
+        const char* start = p;
+        while (p < end && *p >= '0' && *p <= '9') {
+            const uint64_t d = (uint64_t)(*p - '0');
+            if (v > (UINT64_MAX - d) / 10) fail("integer out of range");
+            v = v * 10 + d;
+            p++;
+        }
+        if (p - start > 1 && *start == '0') fail("leading zero in a number");
+        if (p < end && (*p == '.' || *p == 'e' || *p == 'E')) fail("expected an integer, found a float");
+        if (neg) {
+            if (v > (uint64_t)INT64_MAX + 1) fail("integer out of range");
+            const int64_t val = v == 0 ? 0 : -(int64_t)(v - 1) - 1;
+            if (val < lo) fail("integer out of range");
+            return val;
+        }
+        if (v > hi) fail("integer out of range");
+        return (int64_t)v;
+    }
+    // string token -> [s, e) of its raw contents (keys of this schema never contain escapes; an escaped key just
+    // fails to match and is skipped as unknown)
+    void string_raw(const char*& s, const char*& e) {
+        expect('"');
+        s = p;
+        while (p < end && *p != '"') {
+            if (*p == '\\') {
+                p++;
+                if (p >= end) fail("unterminated string");
+            }
+            p++;
+        }
+        if (p >= end) fail("unterminated string");
+        e = p;
+        p++;
+    }
+    bool null_lit() {
+        ws();
+        if (end - p >= 4 && std::memcmp(p, "null", 4) == 0) {
+            p += 4;
+            return true;
+        }
+        return false;
+    }
+    void skip_value(int depth = 0) {
+        if (depth > 64) fail("nesting too deep");
+        ws();
+        if (p >= end) fail("unexpected end of line");
+        const char c = *p;
+        if (c == '"') {
+            const char *s, *e;
+            string_raw(s, e);
+        } else if (c == '{') {
+            p++;
+            if (accept('}')) return;
+            do {
+                const char *s, *e;
+                string_raw(s, e);
+                expect(':');
+                skip_value(depth + 1);
+            } while (accept(','));
+            expect('}');
+        } else if (c == '[') {
+            p++;
+            if (accept(']')) return;
+            do skip_value(depth + 1);
+            while (accept(','));
+            expect(']');
+        } else if (c == 't' && end - p >= 4 && std::memcmp(p, "true", 4) == 0) {
+            p += 4;
+        } else if (c == 'f' && end - p >= 5 && std::memcmp(p, "false", 5) == 0) {
+            p += 5;
+        } else if (c == 'n' && end - p >= 4 && std::memcmp(p, "null", 4) == 0) {
+            p += 4;
+        } else if (c == '-' || (c >= '0' && c <= '9')) {
+            p++;
+            while (p < end && ((*p >= '0' && *p <= '9') || *p == '.' || *p == 'e' || *p == 'E' || *p == '+' || *p == '-')) p++;
+        } else {
+            fail("unexpected character");
+        }
+    }
+};
+
+inline bool key_is(const char* s, const char* e, const char* name) {
+    const size_t n = std::strlen(name);
+    return (size_t)(e - s) == n && std::memcmp(s, name, n) == 0;
+}
+
+// {"write": null | u16, "mv": i8}
+void parse_tape_op(Cursor& c, int8_t& mv, uint8_t& wf, uint16_t& ws) {
+    bool have_mv = false, have_w = false;
+    c.expect('{');
+    if (!c.accept('}')) {
+        do {
+            const char *s, *e;
+            c.string_raw(s, e);
+            c.expect(':');
+            if (key_is(s, e, "mv")) {
+                mv = (int8_t)c.integer(-128, 127);
+                have_mv = true;
+            } else if (key_is(s, e, "write")) {
+                if (c.null_lit()) {
+                    wf = 0;
+                    ws = 0;
+                } else {
+                    wf = 1;
+                    ws = (uint16_t)c.integer(0, 65535);
+                }
+                have_w = true;
+            } else {
+                c.skip_value();
+            }
+        } while (c.accept(','));
+        c.expect('}');
+    }
+    if (!have_mv || !have_w) c.fail("tape op needs \"write\" and \"mv\"");
+}
+
+// {"input_mv": i8, "tapes": [TapeOp; tau]}
+void parse_step(Cursor& c, Trace& t, uint32_t& tau) {
+    bool have_in = false, have_tapes = false;
+    int8_t in_mv = 0;
+    c.expect('{');
+    if (!c.accept('}')) {
+        do {
+            const char *s, *e;
+            c.string_raw(s, e);
+            c.expect(':');
+            if (key_is(s, e, "input_mv")) {
+                in_mv = (int8_t)c.integer(-128, 127);
+                have_in = true;
+            } else if (key_is(s, e, "tapes")) {
+                if (have_tapes) c.fail("duplicate \"tapes\"");
+                uint32_t r = 0;
+                c.expect('[');
+                if (!c.accept(']')) {
+                    do {
+                        int8_t mv = 0;
+                        uint8_t wf = 0;
+                        uint16_t ws = 0;
+                        parse_tape_op(c, mv, wf, ws);
+                        t.mv.push_back(mv);
+                        t.write_flag.push_back(wf);
+                        t.write_sym.push_back(ws);
+                        r++;
+                    } while (c.accept(','));
+                    c.expect(']');
+                }
+                if (tau == 0) tau = r;
+                if (r != tau || r == 0) c.fail("step has a different number of tapes than the first block's windows");
+                have_tapes = true;
+            } else {
+                c.skip_value();
+            }
+        } while (c.accept(','));
+        c.expect('}');
+    }
+    if (!have_in || !have_tapes) c.fail("step needs \"input_mv\" and \"tapes\"");
+    t.input_mv.push_back(in_mv);
+}
+
+template <class T, class F>
+uint32_t parse_array(Cursor& c, std::vector<T>& out, F&& elem) {
+    uint32_t n = 0;
+    c.expect('[');
+    if (c.accept(']')) return 0;
+    do {
+        out.push_back(elem());
+        n++;
+    } while (c.accept(','));
+    c.expect(']');
+    return n;
+}
+
+// one BlockSummary object; appends to t.  tau: 0 = not known yet (taken from this block's windows)
+void parse_block(Cursor& c, Trace& t, uint32_t& tau) {
+    enum { STEP_LO = 1, STEP_HI = 2, WINDOWS = 4, IN_OFF = 8, OUT_OFF = 16, LOG = 32 };
+    unsigned seen = 0;
+    uint64_t step_lo = 0, step_hi = 0, n_steps = 0;
+    uint32_t n_win = 0, n_in = 0, n_out = 0;
+    Manifest mf{};
+    const size_t rows_before = t.input_mv.size();
+    c.expect('{');
+    if (!c.accept('}')) {
+        do {
+            const char *s, *e;
+            c.string_raw(s, e);
+            c.expect(':');
+            if (key_is(s, e, "step_lo")) {
+                step_lo = (uint64_t)c.integer(0, UINT64_MAX >> 1);
+                seen |= STEP_LO;
+            } else if (key_is(s, e, "step_hi")) {
+                step_hi = (uint64_t)c.integer(0, UINT64_MAX >> 1);
+                seen |= STEP_HI;
+            } else if (key_is(s, e, "version")) {
+                mf.version = (uint16_t)c.integer(0, 65535);
+            } else if (key_is(s, e, "block_id")) {
+                mf.block_id = (uint32_t)c.integer(0, UINT32_MAX);
+            } else if (key_is(s, e, "ctrl_in")) {
+                mf.ctrl_in = (uint16_t)c.integer(0, 65535);
+            } else if (key_is(s, e, "ctrl_out")) {
+                mf.ctrl_out = (uint16_t)c.integer(0, 65535);
+            } else if (key_is(s, e, "in_head_in")) {
+                mf.in_head_in = c.integer(INT64_MIN, INT64_MAX);
+            } else if (key_is(s, e, "in_head_out")) {
+                mf.in_head_out = c.integer(INT64_MIN, INT64_MAX);
+            } else if (key_is(s, e, "windows")) {
+                if (seen & WINDOWS) c.fail("duplicate \"windows\"");
+                c.expect('[');
+                if (!c.accept(']')) {
+                    do {
+                        bool hl = false, hr = false;
+                        int64_t l = 0, r = 0;
+                        c.expect('{');
+                        if (!c.accept('}')) {
+                            do {
+                                const char *ks, *ke;
+                                c.string_raw(ks, ke);
+                                c.expect(':');
+                                if (key_is(ks, ke, "left")) {
+                                    l = c.integer(INT64_MIN, INT64_MAX);
+                                    hl = true;
+                                } else if (key_is(ks, ke, "right")) {
+                                    r = c.integer(INT64_MIN, INT64_MAX);
+                                    hr = true;
+                                } else {
+                                    c.skip_value();
+                                }
+                            } while (c.accept(','));
+                            c.expect('}');
+                        }
+                        if (!hl || !hr) c.fail("window needs \"left\" and \"right\"");
+                        t.win_left.push_back(l);
+                        t.win_right.push_back(r);
+                        n_win++;
+                    } while (c.accept(','));
+                    c.expect(']');
+                }
+                seen |= WINDOWS;
+            } else if (key_is(s, e, "head_in_offsets")) {
+                if (seen & IN_OFF) c.fail("duplicate \"head_in_offsets\"");
+                n_in = parse_array(c, t.head_in_off, [&] { return (uint32_t)c.integer(0, UINT32_MAX); });
+                seen |= IN_OFF;
+            } else if (key_is(s, e, "head_out_offsets")) {
+                if (seen & OUT_OFF) c.fail("duplicate \"head_out_offsets\"");
+                n_out = parse_array(c, t.head_out_off, [&] { return (uint32_t)c.integer(0, UINT32_MAX); });
+                seen |= OUT_OFF;
+            } else if (key_is(s, e, "movement_log")) {
+                if (seen & LOG) c.fail("duplicate \"movement_log\"");
+                bool have_steps = false;
+                // the steps may precede "windows" in the object: tau is then fixed by the first step and checked below
+                c.expect('{');
+                if (!c.accept('}')) {
+                    do {
+                        const char *ks, *ke;
+                        c.string_raw(ks, ke);
+                        c.expect(':');
+                        if (key_is(ks, ke, "steps")) {
+                            c.expect('[');
+                            if (!c.accept(']')) {
+                                do {
+                                    parse_step(c, t, tau);
+                                    n_steps++;
+                                } while (c.accept(','));
+                                c.expect(']');
+                            }
+                            have_steps = true;
+                        } else {
+                            c.skip_value();
+                        }
+                    } while (c.accept(','));
+                    c.expect('}');
+                }
+                if (!have_steps) c.fail("movement_log needs \"steps\"");
+                seen |= LOG;
+            } else {
+                c.skip_value();  // pre_tags, post_tags, anything a newer schema adds
+            }
+        } while (c.accept(','));
+        c.expect('}');
+    }
+    c.ws();
+    if (c.p != c.end) c.fail("trailing characters after the block object");
+    if (seen != (STEP_LO | STEP_HI | WINDOWS | IN_OFF | OUT_OFF | LOG)) c.fail("block is missing a required field");
+    if (tau == 0) tau = n_win;
+    if (n_win != tau || n_in != tau || n_out != tau || tau == 0) c.fail("windows / head offsets do not have tau entries");
+    if (step_hi < step_lo || step_hi - step_lo + 1 != n_steps) c.fail("movement_log length differs from step_hi - step_lo + 1");
+    if (t.input_mv.size() - rows_before != n_steps) c.fail("internal: step count mismatch");
+    mf.step_lo = step_lo;
+    mf.step_hi = step_hi;
+    t.manifest.push_back(mf);
+    t.block_len.push_back(n_steps);
+}
+
+void append(Trace& dst, const Trace& src) {
+    auto cat = [](auto& a, const auto& b) { a.insert(a.end(), b.begin(), b.end()); };
+    cat(dst.block_len, src.block_len);
+    cat(dst.win_left, src.win_left);
+    cat(dst.win_right, src.win_right);
+    cat(dst.head_in_off, src.head_in_off);
+    cat(dst.head_out_off, src.head_out_off);
+    cat(dst.input_mv, src.input_mv);
+    cat(dst.mv, src.mv);
+    cat(dst.write_flag, src.write_flag);
+    cat(dst.write_sym, src.write_sym);
+    cat(dst.manifest, src.manifest);
+}
+
+}  // namespace
+
+void Trace::fill_desc(sezkp_trace_desc& d) const {
+    d.tau = tau;
+    d.reserved = 0;
+    d.n_blocks = block_len.size();
+    d.n_rows = input_mv.size();
+    d.block_len = block_len.data();
+    d.win_left = win_left.data();
+    d.win_right = win_right.data();
+    d.head_in_off = head_in_off.data();
+    d.head_out_off = head_out_off.data();
+    d.input_mv = input_mv.data();
+    d.mv = mv.data();
+    d.write_flag = write_flag.data();
+    d.write_sym = write_sym.data();
+}
+
+// Parse every non-blank line of text[0, len) (the last line may lack its '\n').  tau_hint = 0: take tau from the
+// first block.  first_line_no is only used in error messages.
+void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_t first_line_no, Trace& out) {
+    struct Line {
+        const char *b, *e;
+        size_t no;
+    };
+    std::vector<Line> lines;
+    {
+        const char* p = text;
+        const char* end = text + len;
+        size_t no = first_line_no;
+        while (p < end) {
+            const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+            const char* e = nl ? nl : end;
+            const char *b2 = p, *e2 = e;
+            while (b2 < e2 && (*b2 == ' ' || *b2 == '\t' || *b2 == '\r')) b2++;
+            while (e2 > b2 && (e2[-1] == ' ' || e2[-1] == '\t' || e2[-1] == '\r')) e2--;
+            if (e2 > b2) lines.push_back({b2, e2, no});  // blank lines are skipped (io_jsonl.rs:52-55)
+            no++;
+            p = nl ? nl + 1 : end;
+        }
+    }
+    out = Trace();
+    out.tau = tau_hint;
+    if (lines.empty()) return;
+    // the first block fixes tau for everybody
+    uint32_t tau = tau_hint;
+    {
+        Cursor c{lines[0].b, lines[0].e, lines[0].no};
+        parse_block(c, out, tau);
+    }
+    out.tau = tau;
+    const size_t rest = lines.size() - 1;
+    int T = std::max(1, std::min<int>(n_threads, (int)std::min<size_t>(rest, 256)));
+    if (rest == 0) return;
+    std::vector<Trace> parts((size_t)T);
+    std::vector<std::string> errors((size_t)T);
+    auto work = [&](int ti) {
+        const size_t lo = 1 + rest * (size_t)ti / (size_t)T, hi = 1 + rest * (size_t)(ti + 1) / (size_t)T;
+        Trace& t = parts[(size_t)ti];
+        try {
+            // rough reservation from the text size: ~26 bytes of JSON per (row, tape) cell
+            size_t bytes = 0;
+            for (size_t i = lo; i < hi; i++) bytes += (size_t)(lines[i].e - lines[i].b);
+            const size_t cells = bytes / 20 + 16;
+            t.mv.reserve(cells);
+            t.write_flag.reserve(cells);
+            t.write_sym.reserve(cells);
+            t.input_mv.reserve(cells / tau + 16);
+            uint32_t my_tau = tau;
+            for (size_t i = lo; i < hi; i++) {
+                Cursor c{lines[i].b, lines[i].e, lines[i].no};
+                parse_block(c, t, my_tau);
+            }
+        } catch (const std::exception& ex) {
+            errors[(size_t)ti] = ex.what();
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int ti = 0; ti < T; ti++) th.emplace_back(work, ti);
+        for (auto& x : th) x.join();
+    }
+    for (auto& e : errors)
+        if (!e.empty()) throw std::runtime_error(e);  // the first failing run in file order
+    size_t rows = out.input_mv.size(), blocks = out.block_len.size();
+    for (auto& p : parts) {
+        rows += p.input_mv.size();
+        blocks += p.block_len.size();
+    }
+    out.block_len.reserve(blocks);
+    out.manifest.reserve(blocks);
+    out.win_left.reserve(blocks * tau);
+    out.win_right.reserve(blocks * tau);
+    out.head_in_off.reserve(blocks * tau);
+    out.head_out_off.reserve(blocks * tau);
+    out.input_mv.reserve(rows);
+    out.mv.reserve(rows * tau);
+    out.write_flag.reserve(rows * tau);
+    out.write_sym.reserve(rows * tau);
+    for (auto& p : parts) {
+        append(out, p);
+        p = Trace();
+    }
+}
+
+}  // namespace jsonl

@@ -1,0 +1,30 @@
+// Native JSONL front-end (jsonl.cpp): serde-JSON BlockSummary lines -> the flat arrays of sezkp_trace_desc.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/sezkp_trace.h"
+
+namespace jsonl {
+
+typedef sezkp_block_scalars Manifest;  // per-block scalars only the manifest leaf hash reads
+
+struct Trace {
+    uint32_t tau = 0;
+    std::vector<uint64_t> block_len;
+    std::vector<int64_t> win_left, win_right;
+    std::vector<uint32_t> head_in_off, head_out_off;
+    std::vector<int8_t> input_mv, mv;
+    std::vector<uint8_t> write_flag;
+    std::vector<uint16_t> write_sym;
+    std::vector<Manifest> manifest;
+    void fill_desc(sezkp_trace_desc& d) const;
+};
+
+// Parse every non-blank line of text[0, len) on up to n_threads host threads; throws std::runtime_error
+// ("jsonl line N: ...") on malformed input.  tau_hint = 0 takes tau from the first block.
+void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_t first_line_no, Trace& out);
+
+}  // namespace jsonl

@@ -311,11 +311,11 @@ static std::vector<int> make_plan(int L) {
     return p;
 }
 
-static u64* upload(const std::vector<u64>& h) {
+static u64* upload(sezkp_ctx* ctx, const std::vector<u64>& h) {
     u64* d = nullptr;
     cudaError_t e = cudaMalloc(&d, h.size() * 8);
     if (e != cudaSuccess) sezkp_fail(SEZKP_CUDA_ENOMEM, "cudaMalloc(table %zu B): %s", h.size() * 8, cudaGetErrorString(e));
-    CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    upload_table(ctx, d, h.data(), h.size() * 8);
     return d;
 }
 
@@ -337,7 +337,7 @@ static NttTables* get_tables(sezkp_ctx* ctx, int L, bool inverse) {
             e = x;
             x = gl::mul(x, w);
         }
-        t->W[b] = upload(h);
+        t->W[b] = upload(ctx, h);
     }
     u64 wN = gl::root_2exp((unsigned)L);
     if (inverse) wN = gl::inv(wN);
@@ -355,15 +355,15 @@ static NttTables* get_tables(sezkp_ctx* ctx, int L, bool inverse) {
             e = x;
             x = gl::mul(x, step);
         }
-        t->tw_lo = upload(lo);
-        t->tw_hi = upload(hi);
+        t->tw_lo = upload(ctx, lo);
+        t->tw_hi = upload(ctx, hi);
     }
     t->scale = inverse ? gl::inv(gl::from_u64(1ULL << L)) : 1;
     ctx->ntt_tables[key] = t;
     return t;
 }
 
-static NttTables::Coset& get_coset(NttTables* t, int logB, u64 shift) {
+static NttTables::Coset& get_coset(sezkp_ctx* ctx, NttTables* t, int logB, u64 shift) {
     auto key = std::make_pair(logB, shift);
     auto it = t->cosets.find(key);
     if (it != t->cosets.end()) return it->second;
@@ -388,8 +388,8 @@ static NttTables::Coset& get_coset(NttTables* t, int logB, u64 shift) {
         g = gl::mul(g, wBig);
     }
     NttTables::Coset c;
-    c.GA = upload(ga);
-    c.GB = upload(gb);
+    c.GA = upload(ctx, ga);
+    c.GB = upload(ctx, gb);
     c.ga_pitch = (u32)N1;
     c.gb_pitch = (u32)S1;
     return t->cosets[key] = c;
@@ -561,7 +561,7 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
     REQUIRE(shift != 0 && shift < gl::P, "coset shift must be a non-zero canonical field element");
     if (cols == 0) return;
     NttTables* t = get_tables(ctx, L, false);
-    NttTables::Coset& cs = get_coset(t, logB, shift);
+    NttTables::Coset& cs = get_coset(ctx, t, logB, shift);
     const std::vector<int>& plan = t->plan;
     const int m = (int)plan.size();
     const u64 n = 1ULL << L, B = 1ULL << logB;

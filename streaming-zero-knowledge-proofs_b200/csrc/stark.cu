@@ -375,7 +375,7 @@ static const u64* power_table_device(sezkp_ctx* ctx, int L, int lo_bits) {
     }
     u64* d = nullptr;
     CUDA_CHECK(cudaMalloc(&d, h.size() * 8));
-    CUDA_CHECK(cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    upload_table(ctx, d, h.data(), h.size() * 8);
     ctx->power_tables[L] = d;
     return d;
 }
@@ -444,7 +444,7 @@ void deep_lde_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, 
             x = gl::mul(x, dp.w_cta);
         }
         CUDA_CHECK(cudaMalloc(&x0_table, n_cta * 8));
-        CUDA_CHECK(cudaMemcpy(x0_table, h.data(), n_cta * 8, cudaMemcpyHostToDevice));
+        upload_table(ctx, x0_table, h.data(), n_cta * 8);
     }
     deep_kernel<<<(unsigned)n_cta, DEEP_THREADS, 0, ctx->stream>>>(out, N, dp, x0_table);
     CUDA_CHECK(cudaGetLastError());

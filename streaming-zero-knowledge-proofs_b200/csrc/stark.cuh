@@ -88,3 +88,4 @@ sezkp_stream* stream_begin(sezkp_ctx* ctx, u32 tau, const u8 manifest_root[32], 
 void stream_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* blocks);
 void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof);
 void stream_free(sezkp_ctx* ctx, sezkp_stream* st);
+u32 stream_tau(const sezkp_stream* st);

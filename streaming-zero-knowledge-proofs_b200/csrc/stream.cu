@@ -238,6 +238,8 @@ void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof) {
     ctx->timings.insert(ctx->timings.begin(), {"stream_ingest_ms", ingest_ms});
 }
 
+u32 stream_tau(const sezkp_stream* st) { return st->tau; }
+
 void stream_free(sezkp_ctx* ctx, sezkp_stream* st) {
     if (!st) return;
     st->free_all(ctx);

@@ -17,33 +17,38 @@ from .trace import CompactTrace, blocks_to_compact
 
 
 def write_jsonl(path: str, ct: CompactTrace) -> None:
-    """CompactTrace -> JSONL of BlockSummary objects (field names and order of crates/sezkp-core/src/types.rs:116-151)."""
+    """CompactTrace -> JSONL of BlockSummary objects (field names and order of crates/sezkp-core/src/types.rs:116-151,
+    compact separators like serde_json::to_string)."""
     tau = ct.tau
     row = 0
+    tags = json.dumps([[0] * 16 for _ in range(tau)], separators=(",", ":"))
+    ops = {}  # (flag, sym, mv) -> '{"write":..,"mv":..}'
+
+    def op(f, s, v):
+        k = (f, s, v)
+        t = ops.get(k)
+        if t is None:
+            t = ops[k] = '{"write":%s,"mv":%d}' % (str(s) if f else "null", v)
+        return t
+
+    opt = lambda name, k, dflt: int(getattr(ct, name)[k]) if getattr(ct, name) is not None else dflt
     with open(path, "w") as f:
         for k in range(ct.n_blocks):
             n = int(ct.block_len[k])
-            steps = []
-            for j in range(row, row + n):
-                tapes = [{"write": (int(ct.write_sym[j, r]) if ct.write_flag[j, r] else None), "mv": int(ct.mv[j, r])} for r in range(tau)]
-                steps.append({"input_mv": int(ct.input_mv[j]), "tapes": tapes})
-            blk = {
-                "version": int(ct.version[k]) if ct.version is not None else 1,
-                "block_id": int(ct.block_id[k]) if ct.block_id is not None else k + 1,
-                "step_lo": int(ct.step_lo[k]) if ct.step_lo is not None else row + 1,
-                "step_hi": int(ct.step_hi[k]) if ct.step_hi is not None else row + n,
-                "ctrl_in": int(ct.ctrl_in[k]) if ct.ctrl_in is not None else 0,
-                "ctrl_out": int(ct.ctrl_out[k]) if ct.ctrl_out is not None else 0,
-                "in_head_in": int(ct.in_head_in[k]) if ct.in_head_in is not None else 0,
-                "in_head_out": int(ct.in_head_out[k]) if ct.in_head_out is not None else 0,
+            fl, sy, mv, im = (ct.write_flag[row:row + n].tolist(), ct.write_sym[row:row + n].tolist(), ct.mv[row:row + n].tolist(),
+                              ct.input_mv[row:row + n].tolist())
+            steps = ",".join('{"input_mv":%d,"tapes":[%s]}' % (im[j], ",".join(op(fl[j][r], sy[j][r], mv[j][r]) for r in range(tau)))
+                             for j in range(n))
+            head = {
+                "version": opt("version", k, 1), "block_id": opt("block_id", k, k + 1), "step_lo": opt("step_lo", k, row + 1),
+                "step_hi": opt("step_hi", k, row + n), "ctrl_in": opt("ctrl_in", k, 0), "ctrl_out": opt("ctrl_out", k, 0),
+                "in_head_in": opt("in_head_in", k, 0), "in_head_out": opt("in_head_out", k, 0),
                 "windows": [{"left": int(ct.win_left[k, r]), "right": int(ct.win_right[k, r])} for r in range(tau)],
                 "head_in_offsets": [int(x) for x in ct.head_in_off[k]],
                 "head_out_offsets": [int(x) for x in ct.head_out_off[k]],
-                "movement_log": {"steps": steps},
-                "pre_tags": [[0] * 16 for _ in range(tau)],
-                "post_tags": [[0] * 16 for _ in range(tau)],
             }
-            f.write(json.dumps(blk, separators=(",", ":")) + "\n")
+            f.write(json.dumps(head, separators=(",", ":"))[:-1] + ',"movement_log":{"steps":[' + steps + ']},"pre_tags":' + tags +
+                    ',"post_tags":' + tags + "}\n")
             row += n
 
 

@@ -2,6 +2,8 @@
 (bit-exact), the reference's structural tests replayed through the GPU path, and size-independent
 properties at larger sizes."""
 import numpy as np
+import os
+
 import pytest
 
 from conftest import load_fixture, pkg
@@ -393,6 +395,62 @@ def test_jsonl_stream_prove_matches_one_shot(ctx, tmp_path):
     assert got == one
     tm = ctx.timings()
     assert "stream_h2d_copy_ms" in tm and "stream_copy_hidden_frac" in tm
+
+
+@pytest.mark.parametrize("T,b,tau,chunk,threads", [(4096, 64, 3, 0, 0), (1 << 15, 512, 8, 300_000, 4), (1 << 13, 37 * 0 + 256, 2, 70_000, 1)])
+def test_native_jsonl_file_prove_matches_one_shot(ctx, tmp_path, T, b, tau, chunk, threads):
+    """f2, native front-end: .jsonl file -> multi-threaded parser -> pinned staging ring -> same proof bytes as the
+    one-shot prove, for files cut into many chunks (chunk boundaries fall mid-line) and for a single chunk."""
+    m = pkg()
+    ct = m.simulate(T, b, tau, seed=11)
+    root = m.manifest_root(ct)
+    path = str(tmp_path / "blocks.jsonl")
+    m.io_jsonl.write_jsonl(path, ct)
+    one = ctx.prove_v1(ct, root)
+    got = ctx.prove_v1_jsonl_file(path, root, T, tau, threads=threads, chunk_bytes=chunk)
+    assert got == one
+    tm = ctx.timings()
+    assert tm["jsonl_bytes"] == os.path.getsize(path) and "jsonl_parse_ms" in tm and "stream_copy_hidden_frac" in tm
+    # text pieces through ingest_jsonl (whole lines per piece)
+    lines = open(path, "rb").read().split(b"\n")
+    pieces = [b"\n".join(lines[i:i + 7]) + b"\n" for i in range(0, len(lines), 7)]
+    assert ctx.prove_v1_jsonl_text(pieces, root, tau, threads=2) == one
+
+
+def test_native_jsonl_file_errors(ctx, tmp_path):
+    m = pkg()
+    with pytest.raises(m.SezkpCudaError) as ei:
+        ctx.prove_v1_jsonl_file(str(tmp_path / "missing.jsonl"), bytes(32), 64)
+    assert ei.value.code == -1
+    p = str(tmp_path / "bad.jsonl")
+    ct = m.simulate(64, 16, 1)
+    m.io_jsonl.write_jsonl(p, ct)
+    with open(p, "ab") as f:
+        f.write(b"{not json}\n")
+    with pytest.raises(m.SezkpCudaError) as ei:
+        ctx.prove_v1_jsonl_file(p, m.manifest_root(ct), 64, 1, chunk_bytes=1000)
+    assert ei.value.code == -1 and "line 5" in str(ei.value)
+    open(p, "wb").close()
+    with pytest.raises(m.SezkpCudaError):
+        ctx.prove_v1_jsonl_file(p, bytes(32), 64)
+
+
+def test_first_proof_of_a_fresh_context_is_correct(ctx):
+    """Tables (twiddles, coset powers, DEEP points) are built on first use from pageable host memory; the upload must be
+    ordered before the first kernel that reads them on the library's non-blocking stream (regression: a plain cudaMemcpy
+    is not — the first large proof of a context could read half-written tables)."""
+    m = pkg()
+    ct = m.simulate(1 << 22, 512, 1)
+    root = m.manifest_root(ct)
+    want = ctx.prove_v1(ct, root)
+    for _ in range(3):
+        fresh = m.Context()
+        try:
+            rt = fresh.upload_trace(ct)
+            assert fresh.prove_v1_resident(rt, root) == want
+            rt.free()
+        finally:
+            fresh.close()
 
 
 def test_stream_prove_large_ring_wraps(ctx):

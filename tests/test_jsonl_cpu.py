@@ -1,0 +1,102 @@
+"""Native JSONL front-end (csrc/jsonl.cpp) against the Python restatement of the reference's reader
+(`stream_block_summaries_jsonl`, crates/sezkp-core/src/io_jsonl.rs:27-88): same blocks, same order, blank lines
+skipped, malformed lines rejected with their line number.  Host logic only — no GPU, no compute calls."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import pkg
+
+FIELDS = ("block_len", "win_left", "win_right", "head_in_off", "head_out_off", "input_mv", "mv", "write_flag", "write_sym",
+          "version", "block_id", "step_lo", "step_hi", "ctrl_in", "ctrl_out", "in_head_in", "in_head_out")
+
+
+def same(a, b):
+    assert a.tau == b.tau
+    for f in FIELDS:
+        x, y = np.asarray(getattr(a, f)), np.asarray(getattr(b, f))
+        assert x.shape == y.shape and (x.astype(np.int64) == y.astype(np.int64)).all(), f
+
+
+def jsonl_bytes(m, ct, tmp_path, name="t.jsonl"):
+    p = str(tmp_path / name)
+    m.io_jsonl.write_jsonl(p, ct)
+    return open(p, "rb").read()
+
+
+@pytest.mark.parametrize("T,b,tau,threads", [(64, 16, 1, 1), (512, 64, 3, 2), (4096, 512, 8, 8), (1000, 37, 2, 5), (8192, 512, 8, 0)])
+def test_native_parser_matches_python_reader(tmp_path, T, b, tau, threads):
+    m = pkg()
+    ct = m.simulate(T, b, tau, seed=7 + T)
+    text = jsonl_bytes(m, ct, tmp_path)
+    got = m.binding.parse_jsonl(text, threads)
+    same(got, ct)
+    ref = m.blocks_to_compact([json.loads(l) for l in text.decode().splitlines() if l.strip()])
+    same(got, ref)
+    assert m.manifest_root(got) == m.manifest_root(ct)
+
+
+def test_blank_lines_whitespace_key_order_and_unknown_keys(tmp_path):
+    m = pkg()
+    ct = m.simulate(256, 32, 2, seed=3)
+    lines = jsonl_bytes(m, ct, tmp_path).decode().splitlines()
+    out = []
+    for i, l in enumerate(lines):
+        d = json.loads(l)
+        if i % 2:
+            d = dict(reversed(list(d.items())))  # serde accepts any key order
+            d["movement_log"] = {"note": "x\\\"}]", "steps": d["movement_log"]["steps"]}
+            d["future_field"] = {"a": [1.5e3, True, None, "s{"], "b": {}}
+        out.append(json.dumps(d, indent=(None if i % 3 else 1)).replace("\n", " ") if i % 3 == 0 else json.dumps(d))
+        if i % 4 == 0:
+            out.append("   \t ")
+            out.append("")
+    text = ("\r\n".join(out) + "\n\n").encode()
+    same(m.binding.parse_jsonl(text, 3), ct)
+    same(m.binding.parse_jsonl(text.rstrip(b"\n"), 1), ct)  # last line without a newline
+
+
+def test_empty_input():
+    m = pkg()
+    got = m.binding.parse_jsonl(b"", 2)
+    assert got.n_blocks == 0 and got.n_rows == 0
+    got = m.binding.parse_jsonl(b"\n  \n", 2)
+    assert got.n_blocks == 0
+
+
+@pytest.mark.parametrize("mutate,needle", [
+    (lambda d: d.pop("windows"), "missing"),
+    (lambda d: d.__setitem__("step_hi", d["step_hi"] + 1), "movement_log length"),
+    (lambda d: d["movement_log"]["steps"][1]["tapes"].pop(), "tapes"),
+    (lambda d: d["movement_log"]["steps"][0].__setitem__("input_mv", 1.0), "float"),
+    (lambda d: d["movement_log"]["steps"][0]["tapes"][0].__setitem__("mv", 300), "out of range"),
+    (lambda d: d["head_in_offsets"].append(0), "tau"),
+    (lambda d: d["movement_log"]["steps"][0]["tapes"][0].__setitem__("write", -1), "out of range"),
+])
+def test_malformed_lines_are_rejected_with_line_number(tmp_path, mutate, needle):
+    m = pkg()
+    ct = m.simulate(128, 32, 2, seed=5)
+    lines = jsonl_bytes(m, ct, tmp_path).decode().splitlines()
+    d = json.loads(lines[2])
+    mutate(d)
+    lines[2] = json.dumps(d)
+    with pytest.raises(m.SezkpCudaError) as ei:
+        m.binding.parse_jsonl(("\n".join(lines) + "\n").encode(), 2)
+    assert ei.value.code == -1 and "line 3" in str(ei.value) and needle in str(ei.value), str(ei.value)
+
+
+def test_truncated_and_trailing_garbage(tmp_path):
+    m = pkg()
+    ct = m.simulate(64, 32, 1, seed=9)
+    text = jsonl_bytes(m, ct, tmp_path)
+    first = text.split(b"\n")[0]
+    for bad in (first[:-1], first + b" x", first[: len(first) // 2], b"[1,2]", b"{\"step_lo\":1"):
+        with pytest.raises(m.SezkpCudaError) as ei:
+            m.binding.parse_jsonl(bad + b"\n", 1)
+        assert "line 1" in str(ei.value)
+
+
+def test_block_scalars_layout():
+    m = pkg()
+    assert m.binding.BLOCK_SCALARS_DTYPE.itemsize == 48

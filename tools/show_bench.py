@@ -23,3 +23,8 @@ if d.get("sharded_single_proof"):
 if d.get("lde_commit"):
     lc = d["lde_commit"]
     print("lde_commit", round(lc["ms_per_step"], 2), "ms", round(lc["GBps"], 1), "GB/s alg", round(lc["frac_of_hbm_peak_per_gpu"], 4), "of HBM peak/GPU", f"{lc['leaf_compressions_per_s']:.3g} compressions/s")
+if d.get("jsonl_stream"):
+    j = d["jsonl_stream"]
+    print("jsonl_stream", f"{j['rows_per_s']:.4g} rows/s", round(j["ms_per_step"], 1), "ms", round(j["file_MBps"]), "MB/s", j["parser_threads"], "threads",
+          "parse", round(j["jsonl_parse_ms"], 1), "ms hidden", round(j["stream_copy_hidden_frac"], 3), "prove", round(j["prove_ms_after_last_line"], 2),
+          "ms  python reader", f"{j['python_reader_rows_per_s']:.3g} rows/s", "identical", j["proof_identical_to_one_shot"])
