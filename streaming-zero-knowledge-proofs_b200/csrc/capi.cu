@@ -1,6 +1,7 @@
 // extern "C" surface of libsezkp_cuda.so (include/sezkp_cuda.h).  Every entry point converts C++
 // exceptions into status codes + ctx->last_error; nothing aborts.
 #include <chrono>
+#include <memory>
 #include <cstdio>
 #include <thread>
 
@@ -106,6 +107,7 @@ void sezkp_cuda_destroy(sezkp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     ntt_free_tables(ctx);
     for (auto& pb : ctx->pinned) pb.release();
+    for (auto& pb : ctx->stream_stage) pb.release();
     for (auto& kv : ctx->deep_tables) cudaFree(kv.second);
     ctx->deep_tables.clear();
     for (auto& kv : ctx->power_tables) cudaFree(kv.second);
@@ -692,49 +694,76 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
     API_BEGIN(ctx)
     REQUIRE(path && manifest_root && proof_buf && len, "bad argument");
     REQUIRE(expected_rows <= (1ULL << 29), "expected_rows too large");
-    if (chunk_bytes == 0) chunk_bytes = (size_t)64 << 20;
+    if (chunk_bytes == 0) chunk_bytes = (size_t)16 << 20;
     FILE* f = std::fopen(path, "rb");
     if (!f) sezkp_fail(SEZKP_CUDA_EINVAL, "cannot open %s", path);
     sezkp_stream* st = nullptr;
     auto ms_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double read_ms = 0, parse_ms = 0;
     size_t total_bytes = 0, line_no = 1;
+    // Two text buffers: while the parser threads work on one, a reader thread fills the other (fread of the next piece).
+    // A piece is cut at its last newline; the tail is carried to the front of the next piece.
+    struct Piece {
+        std::unique_ptr<char[]> mem;
+        size_t cap = 0, len = 0;
+        bool eof = false, failed = false;
+        void need(size_t n, size_t keep) {  // grow without zero-filling; the first `keep` bytes are preserved
+            if (n <= cap) return;
+            std::unique_ptr<char[]> m(new char[n]);
+            if (keep) std::memcpy(m.get(), mem.get(), keep);
+            mem = std::move(m);
+            cap = n;
+        }
+    } piece[2];
+    auto fill = [&](Piece& p, size_t carry) {  // p.mem[0, carry) already holds the carried tail
+        p.need(carry + chunk_bytes, carry);
+        const double t0 = ms_now();
+        const size_t got = std::fread(p.mem.get() + carry, 1, chunk_bytes, f);
+        read_ms += ms_now() - t0;
+        p.failed = got < chunk_bytes && std::ferror(f);
+        p.eof = got < chunk_bytes;
+        p.len = carry + got;
+        total_bytes += got;
+    };
+    std::thread reader;
     try {
-        std::vector<char> buf;
-        size_t carry = 0;  // bytes of an incomplete last line kept at the front of buf
-        bool eof = false;
-        while (!eof) {
-            if (buf.size() < carry + chunk_bytes) buf.resize(carry + chunk_bytes);
-            double t0 = ms_now();
-            const size_t got = std::fread(buf.data() + carry, 1, chunk_bytes, f);
-            read_ms += ms_now() - t0;
-            if (got < chunk_bytes) {
-                if (std::ferror(f)) sezkp_fail(SEZKP_CUDA_EINVAL, "read error on %s", path);
-                eof = true;
-            }
-            total_bytes += got;
-            size_t avail = carry + got, use = avail;
-            if (!eof) {  // cut at the last complete line
-                while (use > 0 && buf[use - 1] != '\n') use--;
-                if (use == 0) {  // a single line longer than the chunk: grow and read on
-                    carry = avail;
+        int cur = 0;
+        fill(piece[cur], 0);
+        for (;;) {
+            Piece& p = piece[cur];
+            if (p.failed) sezkp_fail(SEZKP_CUDA_EINVAL, "read error on %s", path);
+            size_t use = p.len;
+            if (!p.eof) {
+                while (use > 0 && p.mem[use - 1] != '\n') use--;
+                if (use == 0) {  // a single line longer than the piece: read on into the same buffer
                     chunk_bytes *= 2;
+                    const size_t have = p.len;
+                    fill(p, have);
                     continue;
                 }
             }
-            t0 = ms_now();
+            Piece& nx = piece[cur ^ 1];
+            const size_t carry = p.len - use;
+            const bool more = !p.eof;
+            if (more) {  // start reading the next piece while this one is parsed
+                nx.need(carry + chunk_bytes, 0);
+                if (carry) std::memcpy(nx.mem.get(), p.mem.get() + use, carry);
+                reader = std::thread([&fill, &nx, carry] { fill(nx, carry); });
+            }
+            const double t0 = ms_now();
             jsonl::Trace t;
-            jsonl_parse_or_fail(buf.data(), use, n_threads, st ? stream_tau(st) : 0, line_no, t);
+            jsonl_parse_or_fail(p.mem.get(), use, n_threads, st ? stream_tau(st) : 0, line_no, t);
             parse_ms += ms_now() - t0;
-            for (size_t i = 0; i < use; i++) line_no += buf[i] == '\n';
+            line_no += t.n_lines;
             if (!t.block_len.empty()) {
                 if (!st) st = stream_begin(ctx, t.tau, manifest_root, expected_rows);
                 sezkp_trace_desc d;
                 t.fill_desc(d);
                 stream_ingest(ctx, st, &d);
             }
-            carry = avail - use;
-            if (carry) std::memmove(buf.data(), buf.data() + use, carry);
+            if (!more) break;
+            reader.join();
+            cur ^= 1;
         }
         std::fclose(f);
         f = nullptr;
@@ -748,6 +777,7 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
         ctx->timings.insert(ctx->timings.begin(), {"jsonl_parse_ms", parse_ms});
         ctx->timings.insert(ctx->timings.begin(), {"jsonl_read_ms", read_ms});
     } catch (...) {
+        if (reader.joinable()) reader.join();
         if (f) std::fclose(f);
         if (st) stream_free(ctx, st);
         throw;

@@ -157,6 +157,8 @@ struct sezkp_ctx {
     DevPool pool;
     DevBuf scratch[12];                      // reusable work buffers (per purpose, see users)
     PinnedBuf pinned[2];                     // host staging: [0] opening requests / results
+    PinnedBuf stream_stage[3];               // staging ring of the streaming ingest, kept across streams (cudaHostAlloc of ~100 MB costs ~50 ms)
+    bool stream_stage_busy = false;          // one stream at a time borrows the ring; a second concurrent stream allocates its own
     std::vector<std::pair<std::string, double>> timings;  // phase -> ms (last prove)
     int dedup_variant = 2;                  // 1: 256-thread kernel, 2: 128-thread kernel (more chunks in flight per SM)
     bool dedup_enabled = true;              // value-aware column commit (SEZKP_NO_DEDUP=1 or sezkp_cuda_set_option disables)

@@ -413,6 +413,19 @@ void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_
     }
     out = Trace();
     out.tau = tau_hint;
+    {
+        size_t nl = 0;
+        for (const char* q = text; q < text + len;) {
+            const char* x = (const char*)std::memchr(q, '\n', (size_t)(text + len - q));
+            if (!x) {
+                nl++;  // last line without a terminator
+                break;
+            }
+            nl++;
+            q = x + 1;
+        }
+        out.n_lines = nl;
+    }
     if (lines.empty()) return;
     // the first block fixes tau for everybody
     uint32_t tau = tau_hint;
@@ -471,10 +484,12 @@ void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_
     out.mv.reserve(rows * tau);
     out.write_flag.reserve(rows * tau);
     out.write_sym.reserve(rows * tau);
+    const size_t keep_lines = out.n_lines;
     for (auto& p : parts) {
         append(out, p);
         p = Trace();
     }
+    out.n_lines = keep_lines;
 }
 
 }  // namespace jsonl

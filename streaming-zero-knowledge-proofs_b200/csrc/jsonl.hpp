@@ -20,6 +20,7 @@ struct Trace {
     std::vector<uint8_t> write_flag;
     std::vector<uint16_t> write_sym;
     std::vector<Manifest> manifest;
+    size_t n_lines = 0;  // newline-terminated (or final unterminated) lines seen, blank ones included
     void fill_desc(sezkp_trace_desc& d) const;
 };
 

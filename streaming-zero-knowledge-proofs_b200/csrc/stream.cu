@@ -41,6 +41,7 @@ struct sezkp_stream {
         bool in_flight = false;
     } stage[N_STAGE];
     int cur = 0;
+    bool borrowed_ring = false;  // stage[].host belong to ctx->stream_stage
     cudaStream_t copy_stream = nullptr;
     double copy_ms = 0, ingest_t0 = 0, stall_ms = 0;
     size_t h2d_bytes = 0;
@@ -49,7 +50,7 @@ struct sezkp_stream {
     void free_all(sezkp_ctx* ctx) {
         if (copy_stream) cudaStreamSynchronize(copy_stream);
         for (auto& s : stage) {
-            if (s.host) cudaFreeHost(s.host);
+            if (s.host && !borrowed_ring) cudaFreeHost(s.host);
             if (s.done) cudaEventDestroy(s.done);
             if (s.start) cudaEventDestroy(s.start);
         }
@@ -57,6 +58,7 @@ struct sezkp_stream {
         ctx->pool.free(d_mv);
         ctx->pool.free(d_wflag);
         ctx->pool.free(d_wsym);
+        if (borrowed_ring) ctx->stream_stage_busy = false;
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
 };
@@ -125,8 +127,12 @@ sezkp_stream* stream_begin(sezkp_ctx* ctx, u32 tau, const u8 manifest_root[32], 
     std::memcpy(st->manifest_root, manifest_root, 32);
     try {
         CUDA_CHECK(cudaStreamCreateWithFlags(&st->copy_stream, cudaStreamNonBlocking));
-        for (auto& s : st->stage) {
-            CUDA_CHECK(cudaHostAlloc((void**)&s.host, STAGE_ROWS * st->row_bytes(), cudaHostAllocDefault));
+        st->borrowed_ring = !ctx->stream_stage_busy;
+        if (st->borrowed_ring) ctx->stream_stage_busy = true;
+        for (int i = 0; i < N_STAGE; i++) {
+            auto& s = st->stage[i];
+            if (st->borrowed_ring) s.host = (u8*)ctx->stream_stage[i].ensure(STAGE_ROWS * st->row_bytes());
+            else CUDA_CHECK(cudaHostAlloc((void**)&s.host, STAGE_ROWS * st->row_bytes(), cudaHostAllocDefault));
             CUDA_CHECK(cudaEventCreate(&s.done));
             CUDA_CHECK(cudaEventCreate(&s.start));
         }
