@@ -464,8 +464,15 @@ void FriLayers::release(sezkp_ctx* ctx) {
 // layer0 (device, N = 2^log_N values) is copied into the retained layer buffer; every further layer is folded and
 // hashed by one fused kernel.  Only root 0 is needed on the host before the betas exist (v1/prover.rs:187-198); the
 // other roots are collected on the device and copied back once, then absorbed in order (v1/prover.rs:219, 235).
+//
+// With `shard` (one process per GPU) the leaf + chunk-tree hashing of every layer of at least
+// 2^SHARD_MIN_LOG values — 98 % of the compressions — is split by chunk range: rank r hashes chunks
+// [n_ch*r/world, n_ch*(r+1)/world), the 32-byte chunk (subtree) roots are all-gathered, and the few levels above them
+// are reduced by every rank.  Folding is replicated (it is HBM-cheap and keeps every layer's values on every GPU, so
+// FRI openings need no exchange).  Two exchanges per proof: layer 0's subtree roots (its root gates the betas) and the
+// subtree roots of all other sharded layers together.  Outputs are byte-identical to the unsharded path.
 void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log_N, const u64* betas, u8* roots_host,
-                       u64* final_value, HostAbsorb* absorb) {
+                       u64* final_value, HostAbsorb* absorb, const ShardInfo* shard) {
     REQUIRE(log_N >= 1 && log_N <= 32, "log_N %d out of range", log_N);
     const u64 N = 1ULL << log_N;
     fl.log_N = log_N;
@@ -474,10 +481,54 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     CUDA_CHECK(cudaMemcpyAsync(fl.values, layer0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     fl.commits.resize(log_N + 1);
     std::vector<u64> beta_store;
+    constexpr int FUSE_MIN_LOG = 20, TAIL_ONE_CTA_LOG = 14, SHARD_MIN_LOG = 20;
+    const int world = shard ? shard->world : 1, rank = shard ? shard->rank : 0;
+    auto own_lo = [&](u64 n_ch) { return n_ch * (u64)rank / (u64)world; };
+    auto own_hi = [&](u64 n_ch) { return n_ch * (u64)(rank + 1) / (u64)world; };
+    auto max_own = [&](u64 n_ch) { return (n_ch + world - 1) / world + 1; };
+    // all-gather the chunk roots of `cnt` sharded layers (each rank hashed its own range) and complete level 0 of
+    // their `upper` arrays on every rank
+    auto gather_chunk_roots = [&](Commit* const* cms, int cnt) {
+        size_t per_rank = 0;
+        for (int i = 0; i < cnt; i++) per_rank += (size_t)max_own(cms[i]->n_ch) * 32;
+        std::vector<u8> mine(per_rank, 0), all(per_rank * (size_t)world);
+        size_t off = 0;
+        for (int i = 0; i < cnt; i++) {
+            const u64 lo = own_lo(cms[i]->n_ch), hi = own_hi(cms[i]->n_ch);
+            if (hi > lo)
+                CUDA_CHECK(cudaMemcpyAsync(mine.data() + off, cms[i]->upper + lo * 8, (hi - lo) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+            off += (size_t)max_own(cms[i]->n_ch) * 32;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        const int32_t rc = shard->allgather(shard->user, mine.data(), per_rank, all.data());
+        if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "allgather callback failed with status %d", rc);
+        off = 0;
+        for (int i = 0; i < cnt; i++) {
+            const u64 n_ch = cms[i]->n_ch;
+            for (int r = 0; r < world; r++) {
+                if (r == rank) continue;
+                const u64 lo = n_ch * (u64)r / (u64)world, hi = n_ch * (u64)(r + 1) / (u64)world;
+                if (hi > lo)
+                    CUDA_CHECK(cudaMemcpyAsync(cms[i]->upper + lo * 8, all.data() + (size_t)r * per_rank + off, (hi - lo) * 32,
+                                               cudaMemcpyHostToDevice, ctx->stream));
+            }
+            off += (size_t)max_own(n_ch) * 32;
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // `all` is a local
+    };
     {
         CommitOpts o;
         o.roots_host = roots_host;
-        commit_build(ctx, fl.commits[0], fl.values, N, 1, 10, nullptr, o);
+        if (world > 1 && log_N >= SHARD_MIN_LOG) {
+            Commit& c0 = fl.commits[0];
+            commit_begin(ctx, c0, fl.values, N, 1, 10, nullptr, o);
+            commit_chunks(ctx, c0, own_lo(c0.n_ch), own_hi(c0.n_ch), o);
+            Commit* one[1] = {&c0};
+            gather_chunk_roots(one, 1);
+            commit_finish(ctx, c0, o);
+        } else {
+            commit_build(ctx, fl.commits[0], fl.values, N, 1, 10, nullptr, o);
+        }
         if (absorb) {
             absorb->on_root(0, roots_host);
             if (!betas) {
@@ -492,18 +543,28 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     // does not feed the next fold: their values are folded first (one small launch per layer, then one CTA for the
     // last 2^14), and all of them are hashed side by side in ONE launch.  The levels above the chunk roots of every
     // layer are reduced together at the end.
-    constexpr int FUSE_MIN_LOG = 20, TAIL_ONE_CTA_LOG = 14;
     u64 off = N, len = N >> 1;
     int first_small = log_N + 1;
+    std::vector<Commit*> sharded;
     for (int l = 1; l <= log_N; l++) {
         REQUIRE(betas[l - 1] < gl::P, "beta %d is not canonical", l - 1);
         CommitOpts o;
         const int log_len = log_N - l;
         if (log_len >= FUSE_MIN_LOG) {
-            o.fold_src = fl.values + (off - 2 * len);
-            o.fold_beta = betas[l - 1];
-            commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
-            commit_chunks(ctx, fl.commits[l], 0, fl.commits[l].n_ch, o);
+            if (world > 1 && log_len >= SHARD_MIN_LOG) {  // fold everywhere, hash the own chunk range
+                fri_fold_kernel<<<blocks_for(len, 256), 256, 0, ctx->stream>>>(fl.values + (off - 2 * len), len, betas[l - 1], fl.values + off);
+                CUDA_CHECK(cudaGetLastError());
+                ctx->launches++;
+                Commit& c = fl.commits[l];
+                commit_begin(ctx, c, fl.values + off, len, 1, 10, nullptr, o);
+                commit_chunks(ctx, c, own_lo(c.n_ch), own_hi(c.n_ch), o);
+                sharded.push_back(&c);
+            } else {
+                o.fold_src = fl.values + (off - 2 * len);
+                o.fold_beta = betas[l - 1];
+                commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
+                commit_chunks(ctx, fl.commits[l], 0, fl.commits[l].n_ch, o);
+            }
         } else {
             if (first_small > log_N) first_small = l;
             commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
@@ -527,6 +588,7 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
         len >>= 1;
     }
     if (first_small <= log_N) commit_chunks_multi(ctx, fl.commits.data() + first_small, log_N - first_small + 1);
+    if (!sharded.empty()) gather_chunk_roots(sharded.data(), (int)sharded.size());
     commit_finish_multi(ctx, fl.commits.data() + 1, log_N, d_roots + 32);
     CUDA_CHECK(cudaMemcpyAsync(roots_host + 32, d_roots + 32, (size_t)log_N * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(final_value, fl.values + (2 * N - 2), 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -765,7 +827,7 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         std::vector<u8> fri_roots((size_t)(log_N + 1) * 32);
         u64 final_value = 0;
         TranscriptAbsorb ab(tr);
-        fri_commit_device(ctx, fl, lde, log_N, nullptr, fri_roots.data(), &final_value, &ab);
+        fri_commit_device(ctx, fl, lde, log_N, nullptr, fri_roots.data(), &final_value, &ab, shard);
         lap("fri_commit");
 
         // H. AIR row queries and column openings (v1/prover.rs:248-292)

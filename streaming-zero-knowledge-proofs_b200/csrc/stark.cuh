@@ -67,8 +67,10 @@ struct FriLayers {
     std::vector<Commit> commits;  // one per layer
     void release(sezkp_ctx* ctx);
 };
+struct ShardInfo;
+// shard != null: the hashing of the large layers is split by chunk range over the ranks (see stark.cu)
 void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0_dev, int log_N, const u64* betas_or_null, u8* roots_host,
-                       u64* final_value, HostAbsorb* absorb_or_null);
+                       u64* final_value, HostAbsorb* absorb_or_null, const ShardInfo* shard = nullptr);
 void fri_open_requests(const FriLayers& fl, const u64* idx0, size_t k, u64* positions, std::vector<OpenReq>& reqs, u32 base_off);
 void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_t k, u64* positions, u64* values, u8* paths);
 struct ShardInfo {  // column sharding across the GPUs of one box (one process per GPU)

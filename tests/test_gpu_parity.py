@@ -383,6 +383,24 @@ def test_column_sharded_prove_identical_on_every_rank(oracle, world):
     assert all(p == ref for p in proofs)
 
 
+@pytest.mark.parametrize("world,log_t", [(2, 18), (3, 18), (8, 19)])
+def test_sharded_prove_with_chunk_sharded_fri_hashing(ctx, world, log_t):
+    """C2 of SURVEY 8e: above 2^20 values the FRI layers' leaf / chunk-tree hashing is split by chunk range over the ranks
+    and the subtree roots are all-gathered (world 3: ragged ranges).  Every rank returns the single-GPU proof bytes."""
+    m = pkg()
+    ct = m.simulate(1 << log_t, 512, 2, seed=5)
+    root = m.manifest_root(ct)
+    ref = ctx.prove_v1(ct, root)
+    tg = m.parallel.ThreadGroup(world)
+    ctxs = [m.Context() for _ in range(world)]
+    try:
+        proofs = tg.run(lambda r: ctxs[r].prove_v1_sharded(ct, root, r, world, tg.callback(r)))
+    finally:
+        for c in ctxs:
+            c.close()
+    assert all(p == ref for p in proofs)
+
+
 def test_jsonl_stream_prove_matches_one_shot(ctx, tmp_path):
     """f2: JSONL -> ProvingBackendStream -> same proof bytes as the one-shot prove; copies overlap the ingest."""
     m = pkg()
