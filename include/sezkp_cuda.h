@@ -144,8 +144,9 @@ int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, cons
                              uint8_t* proof_buf, size_t cap, size_t* len);
 /* Column-sharded prover for the GPUs of one box, one process (and one ctx) per GPU: rank r commits and
  * opens only the columns c with c % world == r; everything that depends on all columns (composition, LDE, FRI) is
- * replicated.  The only exchange steps are two all-gathers of small host buffers — the 32-byte column roots and the
- * opening records — done through `allgather`, which the host binding implements over NCCL (or any collective):
+ * replicated, except the leaf / chunk-tree hashing of the large FRI layers, which is split by chunk range.  The exchange
+ * steps are all-gathers of small host buffers — the 32-byte column roots, the FRI subtree roots (twice) and the opening
+ * records — done through `allgather`, which the host binding implements over NCCL (or any collective):
  * it must fill recv_all[world][bytes] with every rank's `send`, rank-major, and return 0.  Every rank returns the
  * identical proof, byte-equal to sezkp_stark_v1_prove. */
 typedef int32_t (*sezkp_allgather_fn)(void* user, const void* send, size_t bytes, void* recv_all);
@@ -158,6 +159,11 @@ int32_t sezkp_trace_upload(sezkp_ctx* ctx, const sezkp_trace_desc* trace, sezkp_
 void sezkp_trace_free(sezkp_ctx* ctx, sezkp_trace_dev* trace);
 int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* trace, const uint8_t manifest_root[32],
                                       uint8_t* proof_buf, size_t cap, size_t* len);
+/* The sharded prover over a trace every rank already holds in HBM (each rank uploaded the same trace): what the N-GPU
+ * single-proof latency is without the N-fold replicated H2D copy of sezkp_stark_v1_prove_sharded. */
+int32_t sezkp_stark_v1_prove_resident_sharded(sezkp_ctx* ctx, const sezkp_trace_dev* trace, const uint8_t manifest_root[32],
+                                              int rank, int world, sezkp_allgather_fn allgather, void* user,
+                                              uint8_t* proof_buf, size_t cap, size_t* len);
 /* ProvingBackendStream (sezkp-core/src/prover.rs:21-33): begin_stream / ingest_block / finish_stream, driven like
  * StreamingProver::prove_stream_iter (prover.rs:104-150) over a block iterator (core/io.rs:111-139).  Each ingest pushes
  * one or more blocks (a descriptor whose arrays cover just those blocks); rows are packed into pinned staging buffers

@@ -27,7 +27,7 @@ EXPORTS = [
     "sezkp_lde_commit_batch", "sezkp_lde_commit_batch_dev", "sezkp_column_open", "sezkp_tree_free", "sezkp_fri_commit", "sezkp_fri_commit_dev", "sezkp_fri_open", "sezkp_fri_free",
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
     "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_stark_v1_proof_bound", "sezkp_trace_upload", "sezkp_trace_free",
-    "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded",
+    "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded", "sezkp_stark_v1_prove_resident_sharded",
     "sezkp_jsonl_parse", "sezkp_jsonl_free", "sezkp_jsonl_last_error", "sezkp_stark_v1_ingest_jsonl", "sezkp_stark_v1_prove_jsonl_file",
 ]
 
@@ -286,6 +286,16 @@ class Context:
             buf = np.empty(proof_size_bound(ct.n_rows, ct.tau), np.uint8)
         self._ck(self.lib.sezkp_stark_v1_prove_sharded(self.h, C.byref(d), manifest_root, C.c_int(rank), C.c_int(world), allgather_cb,
                                                         None, _p(buf), C.c_size_t(buf.size), C.byref(n)))
+        return buf[: n.value].tobytes()
+
+    def prove_v1_resident_sharded(self, rt: "ResidentTrace", manifest_root: bytes, rank: int, world: int, allgather_cb,
+                                  buf: Optional[np.ndarray] = None) -> bytes:
+        """Sharded prove over a trace that is already resident on this rank's GPU (no per-rank H2D of the whole trace)."""
+        n = C.c_size_t(0)
+        if buf is None:
+            buf = np.empty(proof_size_bound(rt.n_rows, rt.tau), np.uint8)
+        self._ck(self.lib.sezkp_stark_v1_prove_resident_sharded(self.h, rt.h, manifest_root, C.c_int(rank), C.c_int(world), allgather_cb,
+                                                                 None, _p(buf), C.c_size_t(buf.size), C.byref(n)))
         return buf[: n.value].tobytes()
 
     def upload_trace(self, ct: CompactTrace) -> "ResidentTrace":

@@ -597,6 +597,19 @@ int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* tra
     API_END(ctx)
 }
 
+int32_t sezkp_stark_v1_prove_resident_sharded(sezkp_ctx* ctx, const sezkp_trace_dev* trace, const uint8_t manifest_root[32], int rank,
+                                              int world, sezkp_allgather_fn allgather, void* user, uint8_t* proof_buf, size_t cap,
+                                              size_t* len) {
+    API_BEGIN(ctx)
+    REQUIRE(trace && manifest_root && len && world >= 1 && rank >= 0 && rank < world, "bad argument");
+    REQUIRE(world == 1 || allgather != nullptr, "allgather callback is NULL");
+    ShardInfo sh{rank, world, allgather, user};
+    ProofSink proof(proof_buf, cap);
+    prove_v1_resident(ctx, trace->owner.t, manifest_root, proof, world > 1 ? &sh : nullptr);
+    deliver(proof, proof_buf, cap, len);
+    API_END(ctx)
+}
+
 int32_t sezkp_stark_v1_begin(sezkp_ctx* ctx, uint32_t tau, const uint8_t manifest_root[32], uint64_t expected_rows, sezkp_stream** out) {
     API_BEGIN(ctx)
     REQUIRE(out && manifest_root && tau >= 1 && tau <= 4096 && expected_rows <= (1ULL << 29), "bad argument");

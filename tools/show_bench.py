@@ -20,6 +20,9 @@ print("cpu", d["cpu_baseline"]["value"], d["cpu_baseline"].get("gpu_proof_identi
 if d.get("sharded_single_proof"):
     sh = d["sharded_single_proof"]
     print("sharded", round(sh["ms_per_proof"], 2), "ms/proof", f"{sh['rows_per_s']:.4g} rows/s", "identical", sh["identical_on_all_ranks"], {k: round(v, 2) for k, v in sh["phases_ms_rank0"].items()})
+    if sh.get("resident"):
+        r = sh["resident"]
+        print("sharded resident", round(r["ms_per_proof"], 2), "ms/proof", r["identical_to_e2e_proof"], {k: round(v, 2) for k, v in r["phases_ms_rank0"].items()})
 if d.get("lde_commit"):
     lc = d["lde_commit"]
     print("lde_commit", round(lc["ms_per_step"], 2), "ms", round(lc["GBps"], 1), "GB/s alg", round(lc["frac_of_hbm_peak_per_gpu"], 4), "of HBM peak/GPU", f"{lc['leaf_compressions_per_s']:.3g} compressions/s")
