@@ -1,5 +1,8 @@
 // extern "C" surface of libsezkp_cuda.so (include/sezkp_cuda.h).  Every entry point converts C++
 // exceptions into status codes + ctx->last_error; nothing aborts.
+#include <sys/mman.h>
+#include <sys/stat.h>
+
 #include <chrono>
 #include <memory>
 #include <cstdio>
@@ -676,13 +679,35 @@ int32_t sezkp_jsonl_parse(const char* text, size_t len, int n_threads, sezkp_jso
 }
 void sezkp_jsonl_free(sezkp_jsonl_trace* t) { delete t; }
 
-static void jsonl_parse_or_fail(const char* text, size_t len, int n_threads, u32 tau, size_t first_line, jsonl::Trace& t) {
+// parse on the host threads and ingest the workers' outputs one after the other (file order), without concatenating them
+static void jsonl_parse_and_ingest(sezkp_ctx* ctx, sezkp_stream*& st, const uint8_t* manifest_root, uint64_t expected_rows,
+                                   const char* text, size_t len, int n_threads, size_t first_line, size_t* lines, uint64_t* blocks,
+                                   uint64_t* rows, double* parse_ms) {
+    std::vector<jsonl::Trace> parts;
+    u32 tau = st ? stream_tau(st) : 0;
+    const auto t0 = std::chrono::steady_clock::now();
     try {
-        jsonl::parse(text, len, jsonl_threads(n_threads), tau, first_line, t);
+        const size_t nl = jsonl::parse_parts(text, len, jsonl_threads(n_threads), tau, first_line, parts, tau);
+        if (lines) *lines = nl;
     } catch (const std::bad_alloc&) {
         throw;
     } catch (const std::exception& e) {
         sezkp_fail(SEZKP_CUDA_EINVAL, "%s", e.what());
+    }
+    if (parse_ms) *parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (auto& t : parts) {
+        if (t.block_len.empty()) continue;
+        if (!st) {
+            REQUIRE(manifest_root != nullptr, "internal: stream not started");
+            st = stream_begin(ctx, tau, manifest_root, expected_rows);
+        }
+        sezkp_trace_desc d;
+        t.tau = tau;
+        t.fill_desc(d);
+        stream_ingest(ctx, st, &d);
+        if (blocks) *blocks += t.block_len.size();
+        if (rows) *rows += t.input_mv.size();
+        t = jsonl::Trace();
     }
 }
 int32_t sezkp_stark_v1_ingest_jsonl(sezkp_ctx* ctx, sezkp_stream* st, const char* text, size_t len, int n_threads,
@@ -690,15 +715,10 @@ int32_t sezkp_stark_v1_ingest_jsonl(sezkp_ctx* ctx, sezkp_stream* st, const char
     API_BEGIN(ctx)
     if (!st) sezkp_fail(SEZKP_CUDA_ESTATE, "stream handle is NULL");
     REQUIRE(text || !len, "text is NULL");
-    jsonl::Trace t;
-    jsonl_parse_or_fail(text, len, n_threads, stream_tau(st), 1, t);
-    if (n_blocks) *n_blocks = t.block_len.size();
-    if (n_rows) *n_rows = t.input_mv.size();
-    if (!t.block_len.empty()) {
-        sezkp_trace_desc d;
-        t.fill_desc(d);
-        stream_ingest(ctx, st, &d);
-    }
+    uint64_t nb = 0, nr = 0;
+    jsonl_parse_and_ingest(ctx, st, nullptr, 0, text, len, n_threads, 1, nullptr, &nb, &nr, nullptr);
+    if (n_blocks) *n_blocks = nb;
+    if (n_rows) *n_rows = nr;
     API_END(ctx)
 }
 int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const uint8_t manifest_root[32], int n_threads,
@@ -739,7 +759,40 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
         total_bytes += got;
     };
     std::thread reader;
+    void* map = MAP_FAILED;
+    size_t map_len = 0;
     try {
+        // Regular files are mapped: the parser threads read the page cache directly (no copy, page faults spread over
+        // the workers).  Pipes / special files fall back to the double-buffered fread loop below.
+        struct stat sb;
+        if (fstat(fileno(f), &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+            const double t0 = ms_now();
+            map_len = (size_t)sb.st_size;
+            map = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+            if (map != MAP_FAILED) madvise(map, map_len, MADV_SEQUENTIAL | MADV_WILLNEED);
+            read_ms += ms_now() - t0;
+        }
+        if (map != MAP_FAILED) {
+            const char* text = (const char*)map;
+            size_t pos = 0;
+            while (pos < map_len) {
+                size_t use = std::min(chunk_bytes, map_len - pos);
+                if (pos + use < map_len) {  // cut at the last newline of the piece (or extend to the next one)
+                    size_t e = use;
+                    while (e > 0 && text[pos + e - 1] != '\n') e--;
+                    if (e == 0) {
+                        const char* nl = (const char*)std::memchr(text + pos + use, '\n', map_len - pos - use);
+                        e = nl ? (size_t)(nl - (text + pos)) + 1 : map_len - pos;
+                    }
+                    use = e;
+                }
+                size_t nl = 0;
+                jsonl_parse_and_ingest(ctx, st, manifest_root, expected_rows, text + pos, use, n_threads, line_no, &nl, nullptr, nullptr, &parse_ms);
+                line_no += nl;
+                pos += use;
+            }
+            total_bytes = map_len;
+        } else {
         int cur = 0;
         fill(piece[cur], 0);
         for (;;) {
@@ -763,21 +816,16 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
                 if (carry) std::memcpy(nx.mem.get(), p.mem.get() + use, carry);
                 reader = std::thread([&fill, &nx, carry] { fill(nx, carry); });
             }
-            const double t0 = ms_now();
-            jsonl::Trace t;
-            jsonl_parse_or_fail(p.mem.get(), use, n_threads, st ? stream_tau(st) : 0, line_no, t);
-            parse_ms += ms_now() - t0;
-            line_no += t.n_lines;
-            if (!t.block_len.empty()) {
-                if (!st) st = stream_begin(ctx, t.tau, manifest_root, expected_rows);
-                sezkp_trace_desc d;
-                t.fill_desc(d);
-                stream_ingest(ctx, st, &d);
-            }
+            size_t nl = 0;
+            jsonl_parse_and_ingest(ctx, st, manifest_root, expected_rows, p.mem.get(), use, n_threads, line_no, &nl, nullptr, nullptr, &parse_ms);
+            line_no += nl;
             if (!more) break;
             reader.join();
             cur ^= 1;
         }
+        }
+        if (map != MAP_FAILED) munmap(map, map_len);
+        map = MAP_FAILED;
         std::fclose(f);
         f = nullptr;
         if (!st) sezkp_fail(SEZKP_CUDA_EINVAL, "%s holds no blocks", path);
@@ -791,6 +839,7 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
         ctx->timings.insert(ctx->timings.begin(), {"jsonl_read_ms", read_ms});
     } catch (...) {
         if (reader.joinable()) reader.join();
+        if (map != MAP_FAILED) munmap(map, map_len);
         if (f) std::fclose(f);
         if (st) stream_free(ctx, st);
         throw;

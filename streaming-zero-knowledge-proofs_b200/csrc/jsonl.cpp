@@ -21,15 +21,16 @@ namespace jsonl {
 
 namespace {
 
+// a malformed line: where it starts (the line number is only computed when the error is reported) and why
+struct LineError {
+    const char* line;
+    std::string what;
+};
 struct Cursor {
     const char* p;
     const char* end;
-    size_t line_no;
-    [[noreturn]] void fail(const char* what) const {
-        char buf[160];
-        snprintf(buf, sizeof buf, "jsonl line %zu: %s", line_no, what);
-        throw std::runtime_error(buf);
-    }
+    const char* line;  // first byte of the line being parsed
+    [[noreturn]] void fail(const char* what) const { throw LineError{line, what}; }
     void ws() {
         while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) p++;
     }
@@ -151,7 +152,58 @@ inline bool key_is(const char* s, const char* e, const char* name) {
 }
 
 // {"write": null | u16, "mv": i8}
+// Fast path for the exact bytes serde_json emits (`{"write":null,"mv":-1}`, no whitespace, struct field order); any
+// deviation falls through to the general parser below, which also produces the error messages.
+inline bool fast_small_int(const char*& q, const char* end, int64_t lo, int64_t hi, int64_t& out) {
+    const char* p = q;
+    bool neg = false;
+    if (p < end && *p == '-') {
+        neg = true;
+        p++;
+    }
+    if (p >= end || *p < '0' || *p > '9') return false;
+    if (*p == '0' && p + 1 < end && p[1] >= '0' && p[1] <= '9') return false;  // leading zero: let the general path reject it
+    int64_t v = 0;
+    int digits = 0;
+    while (p < end && *p >= '0' && *p <= '9' && digits < 6) {
+        v = v * 10 + (*p - '0');
+        p++;
+        digits++;
+    }
+    if (p < end && ((*p >= '0' && *p <= '9') || *p == '.' || *p == 'e' || *p == 'E')) return false;
+    if (neg) v = -v;
+    if (v < lo || v > hi) return false;
+    out = v;
+    q = p;
+    return true;
+}
+inline bool fast_tape_op(Cursor& c, int8_t& mv, uint8_t& wf, uint16_t& ws) {
+    const char* q = c.p;
+    const char* const end = c.end;
+    if (end - q < 20 || std::memcmp(q, "{\"write\":", 9) != 0) return false;
+    q += 9;
+    int64_t v;
+    if (*q == 'n') {
+        if (std::memcmp(q, "null", 4) != 0) return false;
+        q += 4;
+        wf = 0;
+        ws = 0;
+    } else {
+        if (!fast_small_int(q, end, 0, 65535, v)) return false;
+        wf = 1;
+        ws = (uint16_t)v;
+    }
+    if (end - q < 8 || std::memcmp(q, ",\"mv\":", 6) != 0) return false;
+    q += 6;
+    if (!fast_small_int(q, end, -128, 127, v)) return false;
+    if (q >= end || *q != '}') return false;
+    mv = (int8_t)v;
+    c.p = q + 1;
+    return true;
+}
+
 void parse_tape_op(Cursor& c, int8_t& mv, uint8_t& wf, uint16_t& ws) {
+    if (fast_tape_op(c, mv, wf, ws)) return;
     bool have_mv = false, have_w = false;
     c.expect('{');
     if (!c.accept('}')) {
@@ -388,76 +440,62 @@ void Trace::fill_desc(sezkp_trace_desc& d) const {
     d.write_sym = write_sym.data();
 }
 
-// Parse every non-blank line of text[0, len) (the last line may lack its '\n').  tau_hint = 0: take tau from the
-// first block.  first_line_no is only used in error messages.
-void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_t first_line_no, Trace& out) {
-    struct Line {
-        const char *b, *e;
-        size_t no;
+// Parse every non-blank line of text[0, len) (the last line may lack its '\n') into `parts`, one Trace per worker
+// in file order.  No pass over the text is serial: worker i owns the lines whose first byte lies in
+// [len*i/T, len*(i+1)/T), finds its first line start itself, and counts the newlines of its range on the way.
+// tau_hint = 0: every worker takes tau from its first block and the parts are checked against each other.
+// first_line_no is only used in error messages.  Returns the number of lines seen (blank ones included).
+size_t parse_parts(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_t first_line_no, std::vector<Trace>& parts,
+                   uint32_t& tau_out) {
+    const char* const end = text + len;
+    int T = std::max(1, std::min(n_threads, 256));
+    if (len < ((size_t)T << 16)) T = (int)std::max<size_t>(1, len >> 16);  // at least 64 KiB of text per worker
+    parts.assign((size_t)T, Trace());
+    struct Result {
+        const char* err_line = nullptr;
+        std::string err;
+        size_t newlines = 0;
+        bool oom = false;
     };
-    std::vector<Line> lines;
-    {
-        const char* p = text;
-        const char* end = text + len;
-        size_t no = first_line_no;
-        while (p < end) {
-            const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
-            const char* e = nl ? nl : end;
-            const char *b2 = p, *e2 = e;
-            while (b2 < e2 && (*b2 == ' ' || *b2 == '\t' || *b2 == '\r')) b2++;
-            while (e2 > b2 && (e2[-1] == ' ' || e2[-1] == '\t' || e2[-1] == '\r')) e2--;
-            if (e2 > b2) lines.push_back({b2, e2, no});  // blank lines are skipped (io_jsonl.rs:52-55)
-            no++;
-            p = nl ? nl + 1 : end;
-        }
-    }
-    out = Trace();
-    out.tau = tau_hint;
-    {
-        size_t nl = 0;
-        for (const char* q = text; q < text + len;) {
-            const char* x = (const char*)std::memchr(q, '\n', (size_t)(text + len - q));
-            if (!x) {
-                nl++;  // last line without a terminator
-                break;
-            }
-            nl++;
-            q = x + 1;
-        }
-        out.n_lines = nl;
-    }
-    if (lines.empty()) return;
-    // the first block fixes tau for everybody
-    uint32_t tau = tau_hint;
-    {
-        Cursor c{lines[0].b, lines[0].e, lines[0].no};
-        parse_block(c, out, tau);
-    }
-    out.tau = tau;
-    const size_t rest = lines.size() - 1;
-    int T = std::max(1, std::min<int>(n_threads, (int)std::min<size_t>(rest, 256)));
-    if (rest == 0) return;
-    std::vector<Trace> parts((size_t)T);
-    std::vector<std::string> errors((size_t)T);
+    std::vector<Result> res((size_t)T);
     auto work = [&](int ti) {
-        const size_t lo = 1 + rest * (size_t)ti / (size_t)T, hi = 1 + rest * (size_t)(ti + 1) / (size_t)T;
+        const char* lo = text + len * (size_t)ti / (size_t)T;
+        const char* const hi = text + len * (size_t)(ti + 1) / (size_t)T;
         Trace& t = parts[(size_t)ti];
+        Result& r = res[(size_t)ti];
+        t.tau = tau_hint;
+        // a line belongs to the worker in whose range its first byte lies
+        if (ti > 0 && lo[-1] != '\n') {
+            const char* nl = (const char*)std::memchr(lo, '\n', (size_t)(end - lo));
+            lo = nl ? nl + 1 : end;
+        }
         try {
-            // rough reservation from the text size: ~26 bytes of JSON per (row, tape) cell
-            size_t bytes = 0;
-            for (size_t i = lo; i < hi; i++) bytes += (size_t)(lines[i].e - lines[i].b);
-            const size_t cells = bytes / 20 + 16;
+            const size_t cells = (size_t)(hi > lo ? hi - lo : 0) / 20 + 16;  // ~26 bytes of JSON per (row, tape) cell
             t.mv.reserve(cells);
             t.write_flag.reserve(cells);
             t.write_sym.reserve(cells);
-            t.input_mv.reserve(cells / tau + 16);
-            uint32_t my_tau = tau;
-            for (size_t i = lo; i < hi; i++) {
-                Cursor c{lines[i].b, lines[i].e, lines[i].no};
-                parse_block(c, t, my_tau);
+            t.input_mv.reserve(cells / 2 + 16);
+            uint32_t tau = tau_hint;
+            const char* p = lo;
+            while (p < hi) {
+                const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+                const char* e = nl ? nl : end;
+                const char *b2 = p, *e2 = e;
+                while (b2 < e2 && (*b2 == ' ' || *b2 == '\t' || *b2 == '\r')) b2++;
+                while (e2 > b2 && (e2[-1] == ' ' || e2[-1] == '\t' || e2[-1] == '\r')) e2--;
+                if (e2 > b2) {  // blank lines are skipped (io_jsonl.rs:52-55)
+                    Cursor c{b2, e2, p};
+                    parse_block(c, t, tau);
+                }
+                r.newlines++;
+                p = nl ? nl + 1 : end;
             }
-        } catch (const std::exception& ex) {
-            errors[(size_t)ti] = ex.what();
+            t.tau = tau;
+        } catch (const LineError& le) {
+            r.err_line = le.line;
+            r.err = le.what;
+        } catch (const std::bad_alloc&) {
+            r.oom = true;
         }
     };
     if (T == 1) {
@@ -467,29 +505,71 @@ void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_
         for (int ti = 0; ti < T; ti++) th.emplace_back(work, ti);
         for (auto& x : th) x.join();
     }
-    for (auto& e : errors)
-        if (!e.empty()) throw std::runtime_error(e);  // the first failing run in file order
-    size_t rows = out.input_mv.size(), blocks = out.block_len.size();
-    for (auto& p : parts) {
-        rows += p.input_mv.size();
-        blocks += p.block_len.size();
+    auto report = [&](const char* line, const std::string& what) {
+        size_t no = first_line_no;
+        for (const char* q = text; q < line;) {
+            const char* x = (const char*)std::memchr(q, '\n', (size_t)(line - q));
+            if (!x) break;
+            no++;
+            q = x + 1;
+        }
+        char buf[200];
+        snprintf(buf, sizeof buf, "jsonl line %zu: %s", no, what.c_str());
+        throw std::runtime_error(buf);
+    };
+    size_t lines = 0;
+    uint32_t tau = tau_hint;
+    for (int ti = 0; ti < T; ti++) {  // the first failure in file order wins
+        if (res[(size_t)ti].oom) throw std::bad_alloc();
+        if (res[(size_t)ti].err_line) report(res[(size_t)ti].err_line, res[(size_t)ti].err);
+        lines += res[(size_t)ti].newlines;
+        const Trace& t = parts[(size_t)ti];
+        if (!t.block_len.empty()) {
+            if (tau == 0) tau = t.tau;
+            if (t.tau != tau) {  // blame the first line of the part that disagrees
+                const char* lo = text + len * (size_t)ti / (size_t)T;
+                if (ti > 0 && lo[-1] != '\n') {
+                    const char* nl = (const char*)std::memchr(lo, '\n', (size_t)(end - lo));
+                    lo = nl ? nl + 1 : end;
+                }
+                report(lo, "block has a different number of tapes (tau) than the blocks before it");
+            }
+        }
     }
-    out.block_len.reserve(blocks);
-    out.manifest.reserve(blocks);
-    out.win_left.reserve(blocks * tau);
-    out.win_right.reserve(blocks * tau);
-    out.head_in_off.reserve(blocks * tau);
-    out.head_out_off.reserve(blocks * tau);
-    out.input_mv.reserve(rows);
-    out.mv.reserve(rows * tau);
-    out.write_flag.reserve(rows * tau);
-    out.write_sym.reserve(rows * tau);
-    const size_t keep_lines = out.n_lines;
-    for (auto& p : parts) {
-        append(out, p);
-        p = Trace();
+    tau_out = tau;
+    return lines;
+}
+
+void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_t first_line_no, Trace& out) {
+    std::vector<Trace> parts;
+    uint32_t tau = tau_hint;
+    const size_t lines = parse_parts(text, len, n_threads, tau_hint, first_line_no, parts, tau);
+    if (parts.size() == 1) {
+        out = std::move(parts[0]);
+    } else {
+        out = Trace();
+        size_t rows = 0, blocks = 0;
+        for (auto& p : parts) {
+            rows += p.input_mv.size();
+            blocks += p.block_len.size();
+        }
+        out.block_len.reserve(blocks);
+        out.manifest.reserve(blocks);
+        out.win_left.reserve(blocks * tau);
+        out.win_right.reserve(blocks * tau);
+        out.head_in_off.reserve(blocks * tau);
+        out.head_out_off.reserve(blocks * tau);
+        out.input_mv.reserve(rows);
+        out.mv.reserve(rows * tau);
+        out.write_flag.reserve(rows * tau);
+        out.write_sym.reserve(rows * tau);
+        for (auto& p : parts) {
+            append(out, p);
+            p = Trace();
+        }
     }
-    out.n_lines = keep_lines;
+    out.tau = tau;
+    out.n_lines = lines;
 }
 
 }  // namespace jsonl

@@ -27,5 +27,9 @@ struct Trace {
 // Parse every non-blank line of text[0, len) on up to n_threads host threads; throws std::runtime_error
 // ("jsonl line N: ...") on malformed input.  tau_hint = 0 takes tau from the first block.
 void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_t first_line_no, Trace& out);
+// Same, but the workers' outputs are returned separately in file order (no concatenation pass); returns the number
+// of lines seen, tau_out = the common tau (tau_hint when no block was found).
+size_t parse_parts(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_t first_line_no, std::vector<Trace>& parts,
+                   uint32_t& tau_out);
 
 }  // namespace jsonl

@@ -439,6 +439,33 @@ def test_native_jsonl_file_prove_matches_one_shot(ctx, tmp_path, T, b, tau, chun
     assert ctx.prove_v1_jsonl_text(pieces, root, tau, threads=2) == one
 
 
+def test_native_jsonl_prove_from_a_pipe(ctx, tmp_path):
+    """A FIFO cannot be mapped: the double-buffered fread loop (reader thread, carried partial lines) must give the same
+    proof as the mmap path and the one-shot prove."""
+    import threading
+    m = pkg()
+    ct = m.simulate(1 << 13, 128, 3, seed=4)
+    root = m.manifest_root(ct)
+    path = str(tmp_path / "blocks.jsonl")
+    m.io_jsonl.write_jsonl(path, ct)
+    data = open(path, "rb").read()
+    fifo = str(tmp_path / "pipe.jsonl")
+    os.mkfifo(fifo)
+
+    def feed():
+        with open(fifo, "wb") as f:
+            for i in range(0, len(data), 50_000):
+                f.write(data[i:i + 50_000])
+
+    t = threading.Thread(target=feed)
+    t.start()
+    try:
+        got = ctx.prove_v1_jsonl_file(fifo, root, ct.n_rows, ct.tau, threads=3, chunk_bytes=40_000)
+    finally:
+        t.join()
+    assert got == ctx.prove_v1(ct, root) == ctx.prove_v1_jsonl_file(path, root, ct.n_rows, ct.tau)
+
+
 def test_native_jsonl_file_errors(ctx, tmp_path):
     m = pkg()
     with pytest.raises(m.SezkpCudaError) as ei:

@@ -100,3 +100,25 @@ def test_truncated_and_trailing_garbage(tmp_path):
 def test_block_scalars_layout():
     m = pkg()
     assert m.binding.BLOCK_SCALARS_DTYPE.itemsize == 48
+
+
+def test_errors_in_a_multi_worker_parse_report_the_first_bad_line(tmp_path):
+    """text large enough for several workers (>= 64 KiB each): the earliest malformed line in file order is reported,
+    with its line number counted across blank lines; a tau change between workers' ranges is caught as well."""
+    m = pkg()
+    ct = m.simulate(8192, 512, 8, seed=21)
+    lines = jsonl_bytes(m, ct, tmp_path).decode().splitlines()
+    assert len(lines) == 16 and sum(map(len, lines)) > (1 << 20)
+    bad = list(lines)
+    bad.insert(3, "")                      # blank line: counted, not parsed
+    bad[11] = bad[11].replace('"mv":', '"mv":1.5e0,"x":', 1)
+    bad[14] = bad[14][:-1]                 # truncated too, but later in the file
+    with pytest.raises(m.SezkpCudaError) as ei:
+        m.binding.parse_jsonl(("\n".join(bad) + "\n").encode(), 6)
+    assert "line 12:" in str(ei.value) and "float" in str(ei.value), str(ei.value)
+    other = m.simulate(512, 512, 3, seed=1)
+    odd = jsonl_bytes(m, other, tmp_path, "o.jsonl").decode().splitlines()[0]
+    mixed = lines[:13] + [odd] + lines[13:]
+    with pytest.raises(m.SezkpCudaError) as ei:
+        m.binding.parse_jsonl(("\n".join(mixed) + "\n").encode(), 8)
+    assert "tau" in str(ei.value) or "tapes" in str(ei.value), str(ei.value)
