@@ -140,7 +140,11 @@ def run_reference(args, rank):
 
 def pin_trace(torch, ct):
     """Move the compact trace's arrays into pinned host memory (so the e2e H2D runs at full PCIe rate)."""
-    for name in ("block_len", "win_left", "win_right", "head_in_off", "head_out_off", "input_mv", "mv", "write_flag", "write_sym"):
+    ct.pack_ops()  # SEZKP_TRACE_PACKED_OPS: 1 + tau bytes per row over PCIe instead of 1 + 4 tau (symbols < 32)
+    names = ["block_len", "win_left", "win_right", "head_in_off", "head_out_off", "input_mv", "mv", "write_flag", "write_sym"]
+    if ct.ops is not None:
+        names.append("ops")
+    for name in names:
         a = np.ascontiguousarray(getattr(ct, name))
         t = torch.empty(max(a.nbytes, 1), dtype=torch.uint8, pin_memory=True)
         v = t.numpy()[: a.nbytes].view(a.dtype).reshape(a.shape)

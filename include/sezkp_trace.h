@@ -6,7 +6,10 @@
  * (crates/sezkp-stark/src/v1/columns.rs:252-365, v1/openings.rs:182-273): per block the row count
  * and, per tape, window bounds and entry/exit offsets; per row the input move and, per tape, the
  * head move and optional write.  ≈ 1 + 4·tau bytes per row instead of the reference's in-memory
- * BlockSummary tree.  All arrays are caller-owned host memory.
+ * BlockSummary tree — or 1 + tau bytes per row with SEZKP_TRACE_PACKED_OPS, where the three per-tape arrays are one
+ * byte per (row, tape): bits 0-1 = mv + 1, bit 2 = write.is_some(), bits 3-7 = the written symbol (alphabets of up to
+ * 32 symbols; the host-to-device copy is the exposed part of an end-to-end prove, so a binding whose symbols fit should
+ * flatten into this form).  All arrays are caller-owned host memory.
  */
 #ifndef SEZKP_TRACE_H
 #define SEZKP_TRACE_H
@@ -18,7 +21,7 @@ extern "C" {
 
 typedef struct sezkp_trace_desc {
     uint32_t tau;                 /* tapes per step (blocks[0].windows.len())                    */
-    uint32_t reserved;            /* must be 0                                                   */
+    uint32_t flags;               /* 0 or SEZKP_TRACE_PACKED_OPS                                 */
     uint64_t n_blocks;            /* number of BlockSummary records                              */
     uint64_t n_rows;              /* Σ_k (step_hi − step_lo + 1); must be a power of two         */
     const uint64_t* block_len;    /* [n_blocks]       step_hi − step_lo + 1 (= movement_log len) */
@@ -27,10 +30,11 @@ typedef struct sezkp_trace_desc {
     const uint32_t* head_in_off;  /* [n_blocks][tau]  head_in_offsets[r]                         */
     const uint32_t* head_out_off; /* [n_blocks][tau]  head_out_offsets[r]                        */
     const int8_t*   input_mv;     /* [n_rows]         steps[j].input_mv                          */
-    const int8_t*   mv;           /* [n_rows][tau]    steps[j].tapes[r].mv                       */
-    const uint8_t*  write_flag;   /* [n_rows][tau]    steps[j].tapes[r].write.is_some()          */
-    const uint16_t* write_sym;    /* [n_rows][tau]    steps[j].tapes[r].write.unwrap_or(0)       */
+    const int8_t*   mv;           /* [n_rows][tau]    steps[j].tapes[r].mv; PACKED_OPS: the packed op bytes */
+    const uint8_t*  write_flag;   /* [n_rows][tau]    steps[j].tapes[r].write.is_some()  (ignored when packed) */
+    const uint16_t* write_sym;    /* [n_rows][tau]    steps[j].tapes[r].write.unwrap_or(0) (ignored when packed) */
 } sezkp_trace_desc;
+#define SEZKP_TRACE_PACKED_OPS 1u  /* flags bit 0: `mv` holds (mv + 1) | write.is_some() << 2 | symbol << 3 per (row, tape) */
 
 /* The per-block scalars that only the manifest leaf hash reads (crates/sezkp-merkle/src/lib.rs:85-117); the native
  * JSONL parser returns them next to the descriptor so a caller can rebuild `manifest_root` from a .jsonl file. */

@@ -6,7 +6,7 @@ use std::ffi::{c_char, c_void, CStr};
 
 #[repr(C)]
 pub struct TraceDesc {            // include/sezkp_trace.h
-    tau: u32, reserved: u32, n_blocks: u64, n_rows: u64,
+    tau: u32, flags: u32, n_blocks: u64, n_rows: u64,
     block_len: *const u64, win_left: *const i64, win_right: *const i64,
     head_in_off: *const u32, head_out_off: *const u32,
     input_mv: *const i8, mv: *const i8, write_flag: *const u8, write_sym: *const u16,
@@ -49,7 +49,7 @@ pub struct StarkV1Cuda;
 impl ProvingBackend for StarkV1Cuda {
     fn prove(blocks: &[BlockSummary], manifest_root: [u8; 32]) -> Result<ProofArtifact> {
         let f = flatten(blocks)?;
-        let d = TraceDesc { tau: f.tau, reserved: 0, n_blocks: f.block_len.len() as u64, n_rows: f.imv.len() as u64,
+        let d = TraceDesc { tau: f.tau, flags: 0, n_blocks: f.block_len.len() as u64, n_rows: f.imv.len() as u64,
             block_len: f.block_len.as_ptr(), win_left: f.wl.as_ptr(), win_right: f.wr.as_ptr(),
             head_in_off: f.io.as_ptr(), head_out_off: f.oo.as_ptr(), input_mv: f.imv.as_ptr(), mv: f.mv.as_ptr(),
             write_flag: f.wf.as_ptr(), write_sym: f.ws.as_ptr() };

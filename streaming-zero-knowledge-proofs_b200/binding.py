@@ -323,7 +323,7 @@ class Context:
             rows = 0
             import itertools
             for b in itertools.chain([first], it):
-                d = b.as_desc()
+                d = b.as_desc(packed=False)  # the staging ring holds the plain arrays
                 self._ck(self.lib.sezkp_stark_v1_ingest(self.h, st, C.byref(d)))
                 rows += b.n_rows
             buf = np.empty(proof_size_bound(rows, tau), np.uint8)

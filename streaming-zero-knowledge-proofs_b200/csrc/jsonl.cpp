@@ -426,7 +426,7 @@ void append(Trace& dst, const Trace& src) {
 
 void Trace::fill_desc(sezkp_trace_desc& d) const {
     d.tau = tau;
-    d.reserved = 0;
+    d.flags = 0;
     d.n_blocks = block_len.size();
     d.n_rows = input_mv.size();
     d.block_len = block_len.data();

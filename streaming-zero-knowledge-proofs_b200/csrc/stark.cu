@@ -28,12 +28,13 @@ __global__ void __launch_bounds__(256) head_scan_kernel(DeviceTrace t, u64* __re
     const u32 r = (u32)(id % t.tau);
     const u64 start = t.block_start[k], len = t.block_len[k];
     u64* head = cols + (3 + 3ULL * t.tau + r) * t.n_rows + start;  // group order: mv, wflag, wsym, head, ...
-    const signed char* mv = (const signed char*)t.mv + start * t.tau + r;
+    const signed char* mv = (const signed char*)(t.ops ? (const int8_t*)t.ops : t.mv) + start * t.tau + r;
+    const bool packed = t.ops != nullptr;
     int64_t carry = 0;
 #pragma unroll 4
     for (u64 j0 = 0; j0 < len; j0 += 32) {
         const u64 j = j0 + lane;
-        int v = j < len ? (int)mv[j * t.tau] : 0;
+        int v = j < len ? (packed ? (int)(((u8)mv[j * t.tau]) & 3) - 1 : (int)mv[j * t.tau]) : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int u = __shfl_up_sync(0xffffffffu, v, o);
@@ -63,10 +64,21 @@ __global__ void expand_rows_kernel(DeviceTrace t, u64* __restrict__ cols, u64 ro
     cols[2 * n + i] = (i + 1 == start + len) ? 1 : 0;
     for (u32 r = 0; r < tau; r++) {
         const u64 p = i * tau + r;
-        const int wf = t.write_flag[p] ? 1 : 0;
-        cols[(3 + 0ULL * tau + r) * n + i] = gl::from_i64((int64_t)t.mv[p]);
+        int wf, mvv;
+        u64 sym;
+        if (t.ops) {
+            const u32 o = t.ops[p];
+            mvv = (int)(o & 3) - 1;
+            wf = (o >> 2) & 1;
+            sym = o >> 3;
+        } else {
+            wf = t.write_flag[p] ? 1 : 0;
+            mvv = (int)t.mv[p];
+            sym = (u64)t.write_sym[p];
+        }
+        cols[(3 + 0ULL * tau + r) * n + i] = gl::from_i64((int64_t)mvv);
         cols[(3 + 1ULL * tau + r) * n + i] = (u64)wf;
-        cols[(3 + 2ULL * tau + r) * n + i] = wf ? gl::from_u64((u64)t.write_sym[p]) : 0;
+        cols[(3 + 2ULL * tau + r) * n + i] = wf ? sym : 0;
         const int64_t diff = t.win_right[k * tau + r] - t.win_left[k * tau + r];
         const u64 ad = diff < 0 ? (u64)0 - (u64)diff : (u64)diff;
         cols[(3 + 4ULL * tau + r) * n + i] = gl::from_u64(ad + 1);
@@ -264,7 +276,7 @@ double now_ms() {
 /* ------------------------------------------------------------------------------------------ */
 void validate_trace(const sezkp_trace_desc* d) {
     REQUIRE(d != nullptr, "trace descriptor is NULL");
-    REQUIRE(d->reserved == 0, "trace descriptor: reserved must be 0");
+    REQUIRE((d->flags & ~SEZKP_TRACE_PACKED_OPS) == 0, "trace descriptor: unknown flags 0x%x", d->flags);
     REQUIRE(d->tau >= 1 && d->tau <= 4096, "tau %u out of range", d->tau);
     REQUIRE(d->n_blocks >= 1, "empty trace");
     REQUIRE(d->n_rows >= 2 && (d->n_rows & (d->n_rows - 1)) == 0,
@@ -272,7 +284,7 @@ void validate_trace(const sezkp_trace_desc* d) {
             (unsigned long long)d->n_rows);
     REQUIRE(d->n_rows <= (1ULL << 29), "n_rows too large (LDE domain limited to 2^32)");
     REQUIRE(d->block_len && d->win_left && d->win_right && d->head_in_off && d->head_out_off && d->input_mv && d->mv &&
-                d->write_flag && d->write_sym,
+                ((d->flags & SEZKP_TRACE_PACKED_OPS) || (d->write_flag && d->write_sym)),
             "trace descriptor has NULL arrays");
     u64 sum = 0;
     for (u64 k = 0; k < d->n_blocks; k++) {
@@ -292,8 +304,9 @@ void DeviceTraceOwner::layout(const sezkp_trace_desc* d) {
         return o;
     };
     o_start = sect(nb * 8); o_len = sect(nb * 8); o_wl = sect(nb * tau * 8); o_wr = sect(nb * tau * 8);
+    packed = (d->flags & SEZKP_TRACE_PACKED_OPS) != 0;
     o_io = sect(nb * tau * 4); o_oo = sect(nb * tau * 4); o_imv = sect(n); o_mv = sect(n * tau);
-    o_wf = sect(n * tau); o_ws = sect(n * tau * 2);
+    o_wf = sect(packed ? 0 : n * tau); o_ws = sect(packed ? 0 : n * tau * 2);
     total = off;
 }
 void DeviceTraceOwner::upload_meta(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
@@ -326,9 +339,10 @@ void DeviceTraceOwner::upload_meta(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
     t.head_in_off = (const u32*)(base + o_io);
     t.head_out_off = (const u32*)(base + o_oo);
     t.input_mv = (const int8_t*)(base + o_imv);
-    t.mv = (const int8_t*)(base + o_mv);
-    t.write_flag = (const u8*)(base + o_wf);
-    t.write_sym = (const uint16_t*)(base + o_ws);
+    t.mv = packed ? nullptr : (const int8_t*)(base + o_mv);
+    t.write_flag = packed ? nullptr : (const u8*)(base + o_wf);
+    t.write_sym = packed ? nullptr : (const uint16_t*)(base + o_ws);
+    t.ops = packed ? (const u8*)(base + o_mv) : nullptr;
     h2d_bytes = total;
 }
 void DeviceTraceOwner::upload_rows_async(cudaStream_t stream, const sezkp_trace_desc* d, u64 r0, u64 r1) {
@@ -336,6 +350,7 @@ void DeviceTraceOwner::upload_rows_async(cudaStream_t stream, const sezkp_trace_
     u8* base = (u8*)buf.p;
     CUDA_CHECK(cudaMemcpyAsync(base + o_imv + r0, d->input_mv + r0, r, cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaMemcpyAsync(base + o_mv + r0 * tau, d->mv + r0 * tau, r * tau, cudaMemcpyHostToDevice, stream));
+    if (packed) return;
     CUDA_CHECK(cudaMemcpyAsync(base + o_wf + r0 * tau, d->write_flag + r0 * tau, r * tau, cudaMemcpyHostToDevice, stream));
     CUDA_CHECK(cudaMemcpyAsync(base + o_ws + r0 * tau * 2, d->write_sym + r0 * tau, r * tau * 2, cudaMemcpyHostToDevice, stream));
 }
@@ -691,9 +706,20 @@ void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 mani
     ctx->scratch[2] = dt.buf;
     if (!ctx->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     // slab s covers rows [s*SLAB, min(n,(s+1)*SLAB)); blocks are assigned to the slab in which they END
-    u64 blk = 0, row_acc = 0;
-    for (u64 r0 = 0; r0 < n; r0 += SLAB) {
-        const u64 r1 = r0 + SLAB < n ? r0 + SLAB : n;
+    // Slab boundaries.  Plain descriptors (1 + 4 tau bytes per row) are copy-bound — PCIe needs ~0.6 ms per 2^20 rows,
+    // expand + hashing ~0.5 ms — so equal slabs keep the exposed tail (the last slab's compute) short.  Packed
+    // descriptors (1 + tau bytes per row, ~0.17 ms per 2^20 rows) are compute-bound: what stays exposed is the FIRST
+    // slab's copy plus a per-slab launch overhead, so the slabs grow (n/8, n/4, the rest) — each copy hides behind the
+    // previous slab's compute.
+    std::vector<u64> cuts;
+    if ((desc->flags & SEZKP_TRACE_PACKED_OPS) && n >= 2 * SLAB) {
+        cuts = {n / 8, n / 8 + n / 4, n};
+    } else {
+        for (u64 r = SLAB; r < n; r += SLAB) cuts.push_back(r);
+        cuts.push_back(n);
+    }
+    u64 blk = 0, row_acc = 0, r0 = 0;
+    for (const u64 r1 : cuts) {
         SlabPlan::Slab sl;
         sl.row0 = r0;
         sl.row1 = r1;
@@ -710,6 +736,7 @@ void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 mani
         dt.upload_rows_async(ctx->copy_stream, desc, r0, r1);
         CUDA_CHECK(cudaEventRecord(sl.ready, ctx->copy_stream));
         plan.slabs.push_back(sl);
+        r0 = r1;
     }
     (void)tau;
     prove_v1_resident(ctx, dt.t, manifest_root, proof_out, shard, &plan);

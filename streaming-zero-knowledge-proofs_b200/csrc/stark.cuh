@@ -19,11 +19,13 @@ struct DeviceTrace {  // device image of sezkp_trace_desc (+ block_start prefix 
     const int8_t* mv;
     const u8* write_flag;
     const uint16_t* write_sym;
+    const u8* ops;  // non-null: packed per-tape ops (SEZKP_TRACE_PACKED_OPS), mv / write_flag / write_sym are null
 };
 struct DeviceTraceOwner {
     DevBuf buf;
     DeviceTrace t{};
     size_t h2d_bytes = 0;
+    bool packed = false;
     size_t o_start = 0, o_len = 0, o_wl = 0, o_wr = 0, o_io = 0, o_oo = 0, o_imv = 0, o_mv = 0, o_wf = 0, o_ws = 0, total = 0;
     void layout(const sezkp_trace_desc* d);
     void upload_meta(sezkp_ctx* ctx, const sezkp_trace_desc* d);                                    // allocation + per-block metadata

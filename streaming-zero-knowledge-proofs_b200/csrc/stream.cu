@@ -148,6 +148,7 @@ sezkp_stream* stream_begin(sezkp_ctx* ctx, u32 tau, const u8 manifest_root[32], 
 
 void stream_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* b) {
     REQUIRE(b && b->n_blocks >= 1 && b->tau == st->tau, "ingest: bad block descriptor (tau mismatch or empty)");
+    REQUIRE(b->flags == 0, "ingest: packed descriptors are not accepted by the streaming ingest");
     REQUIRE(b->block_len && b->win_left && b->win_right && b->head_in_off && b->head_out_off && b->input_mv && b->mv && b->write_flag &&
                 b->write_sym,
             "ingest: descriptor has NULL arrays");
@@ -223,6 +224,7 @@ void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof) {
             s.in_flight = false;
         }
     DeviceTrace t{};
+    t.ops = nullptr;
     t.tau = st->tau;
     t.n_blocks = nb;
     t.n_rows = n;

@@ -25,7 +25,7 @@ class TraceDesc(C.Structure):
 
     _fields_ = [
         ("tau", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("flags", C.c_uint32),
         ("n_blocks", C.c_uint64),
         ("n_rows", C.c_uint64),
         ("block_len", C.c_void_p),
@@ -61,6 +61,7 @@ class CompactTrace:
     ctrl_out: Optional[np.ndarray] = None    # u16
     in_head_in: Optional[np.ndarray] = None  # i64
     in_head_out: Optional[np.ndarray] = None # i64
+    ops: Optional[np.ndarray] = None         # u8 [n_rows, tau]: packed per-tape ops (pack_ops), sent instead of mv/flag/sym
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -72,8 +73,19 @@ class CompactTrace:
         return int(self.input_mv.shape[0])
 
     def nbytes(self) -> int:
-        return sum(a.nbytes for a in (self.block_len, self.win_left, self.win_right, self.head_in_off,
-                                      self.head_out_off, self.input_mv, self.mv, self.write_flag, self.write_sym))
+        rows = (self.input_mv, self.ops) if self.ops is not None else (self.input_mv, self.mv, self.write_flag, self.write_sym)
+        return sum(a.nbytes for a in (self.block_len, self.win_left, self.win_right, self.head_in_off, self.head_out_off) + rows)
+
+    def pack_ops(self) -> bool:
+        """Build the SEZKP_TRACE_PACKED_OPS form of the per-tape arrays (include/sezkp_trace.h): one byte per (row, tape)
+        = (mv + 1) | written << 2 | symbol << 3.  Possible when every move is in {-1, 0, 1} and every symbol < 32;
+        returns False (and leaves the trace unpacked) otherwise.  as_desc() sends the packed form once it exists."""
+        mv, fl, sy = np.asarray(self.mv), np.asarray(self.write_flag), np.asarray(self.write_sym)
+        if mv.size and (int(mv.min()) < -1 or int(mv.max()) > 1 or int(sy.max()) > 31 or int(fl.max()) > 1):
+            self.ops = None
+            return False
+        self.ops = np.ascontiguousarray((mv.astype(np.int16) + 1).astype(np.uint8) | (fl.astype(np.uint8) << 2) | (sy.astype(np.uint8) << 3))
+        return True
 
     def _c(self):
         """Contiguous, correctly typed views (kept alive on self)."""
@@ -87,16 +99,24 @@ class CompactTrace:
             out[name] = a
         return out
 
-    def as_desc(self) -> TraceDesc:
+    def as_desc(self, packed: bool = True) -> TraceDesc:
         a = self._c()
         d = TraceDesc()
         d.tau = self.tau
-        d.reserved = 0
+        d.flags = 0
         d.n_blocks = self.n_blocks
         d.n_rows = self.n_rows
         for name, arr in a.items():
             setattr(d, name, arr.ctypes.data if arr.size else None)
         self._desc_arrays = list(a.values())
+        if packed and self.ops is not None:  # packed per-tape ops replace the three arrays
+            ops = np.ascontiguousarray(self.ops, dtype=np.uint8)
+            self.ops = ops
+            d.flags = 1
+            d.mv = ops.ctypes.data if ops.size else None
+            d.write_flag = None
+            d.write_sym = None
+            self._desc_arrays.append(ops)
         return d
 
 

@@ -168,13 +168,13 @@ class Oracle:
         return out
 
     def trace_columns(self, ct) -> np.ndarray:
-        d = ct.as_desc()
+        d = ct.as_desc(packed=False)  # the oracle reads the plain arrays
         out = np.empty((3 + 7 * ct.tau, ct.n_rows), np.uint64)
         self._ck(self.lib.oracle_trace_columns(C.byref(d), out.ctypes.data_as(C.c_void_p)))
         return out
 
     def compose_base(self, ct, alphas8, mask_coeffs) -> np.ndarray:
-        d = ct.as_desc()
+        d = ct.as_desc(packed=False)  # the oracle reads the plain arrays
         a = np.ascontiguousarray(alphas8, np.uint64)
         m = np.ascontiguousarray(mask_coeffs, np.uint64)
         out = np.empty(ct.n_rows, np.uint64)
@@ -195,7 +195,7 @@ class Oracle:
 
     # ---- prover / verifier ----
     def prove_v1(self, ct, manifest_root: bytes, faithful_cost=False, taps=False):
-        d = ct.as_desc()
+        d = ct.as_desc(packed=False)  # the oracle reads the plain arrays
         n = C.c_size_t(0)
         t = Taps()
         cap = 64 << 20
@@ -207,7 +207,7 @@ class Oracle:
 
     def verify_v1(self, proof: bytes, ct):
         """returns (accepted: bool, reason: str)"""
-        d = ct.as_desc()
+        d = ct.as_desc(packed=False)  # the oracle reads the plain arrays
         rc = self.lib.oracle_verify_v1(proof, C.c_size_t(len(proof)), C.byref(d))
         if rc == 0:
             return True, ""

@@ -48,7 +48,15 @@ def test_trace_desc_layout_matches_header():
     assert C.sizeof(m.TraceDesc) == 4 + 4 + 8 + 8 + 9 * 8
     ct = m.demo_block(16)
     d = ct.as_desc()
-    assert d.tau == 1 and d.n_blocks == 1 and d.n_rows == 16
+    assert d.tau == 1 and d.n_blocks == 1 and d.n_rows == 16 and d.flags == 0
+    # packed per-tape ops (SEZKP_TRACE_PACKED_OPS): one byte per (row, tape) = (mv + 1) | written << 2 | symbol << 3
+    assert ct.pack_ops()
+    dp = ct.as_desc()
+    assert dp.flags == 1 and dp.write_flag is None and dp.write_sym is None
+    i = np.arange(16)
+    want = ((i % 2 == 0).astype(np.uint8) + 1) | ((i % 3 == 0).astype(np.uint8) << 2) | (np.where(i % 3 == 0, 5, 0).astype(np.uint8) << 3)
+    assert np.array_equal(ct.ops[:, 0], want)
+    assert ct.as_desc(packed=False).flags == 0
 
 
 def test_simulate_generator_and_partition():

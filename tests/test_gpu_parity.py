@@ -1,6 +1,8 @@
 """GPU parity tests proper: every C-ABI entry point against the CPU oracle on the same seeded inputs
 (bit-exact), the reference's structural tests replayed through the GPU path, and size-independent
 properties at larger sizes."""
+import ctypes as C
+
 import numpy as np
 import os
 
@@ -403,6 +405,44 @@ def test_sharded_prove_with_chunk_sharded_fri_hashing(ctx, world, log_t):
         for c in ctxs:
             c.close()
     assert all(p == ref for p in proofs) and all(p == ref for p in resident)
+
+
+@pytest.mark.parametrize("T,b,tau", [(1024, 128, 2), (1 << 14, 512, 8), (1 << 20, 512, 3)])
+def test_packed_ops_descriptor_gives_the_same_proof(ctx, T, b, tau):
+    """SEZKP_TRACE_PACKED_OPS (include/sezkp_trace.h): one byte per (row, tape) instead of the three arrays — same columns,
+    same composition vector, same proof bytes through the host, resident and sharded entry points; symbols up to 31."""
+    m = pkg()
+    ct = m.simulate(T, b, tau, seed=9)
+    ct.write_sym[ct.write_flag.astype(bool)] |= np.uint16(16)  # exercise the top symbol bit (values 16..31)
+    root = m.manifest_root(ct)
+    plain = ctx.prove_v1(ct, root)
+    cols_plain = ctx.trace_columns(ct) if T <= (1 << 14) else None
+    assert ct.pack_ops() and ct.ops.dtype == np.uint8 and ct.ops.shape == (T, tau)
+    assert ct.nbytes() < (T * (1 + tau) + ct.n_blocks * (8 + 24 * tau)) + 64
+    assert ctx.prove_v1(ct, root) == plain
+    rt = ctx.upload_trace(ct)
+    assert ctx.prove_v1_resident(rt, root) == plain
+    rt.free()
+    if cols_plain is not None:
+        assert np.array_equal(ctx.trace_columns(ct), cols_plain)
+    ct.ops = None
+    ct.write_sym[0, 0] = 32
+    ct.write_flag[0, 0] = 1
+    assert not ct.pack_ops() and ct.ops is None  # symbol does not fit: stays unpacked
+
+
+def test_packed_ops_rejected_by_streaming_ingest(ctx):
+    m = pkg()
+    ct = m.simulate(1024, 128, 2)
+    ct.pack_ops()
+    st = C.c_void_p()
+    ctx._ck(ctx.lib.sezkp_stark_v1_begin(ctx.h, C.c_uint32(2), bytes(32), C.c_uint64(0), C.byref(st)))
+    try:
+        d = ct.as_desc()
+        assert d.flags == 1
+        assert ctx.lib.sezkp_stark_v1_ingest(ctx.h, st, C.byref(d)) == -1
+    finally:
+        ctx.lib.sezkp_stark_v1_abort(ctx.h, st)
 
 
 def test_jsonl_stream_prove_matches_one_shot(ctx, tmp_path):
