@@ -154,8 +154,9 @@ __device__ __forceinline__ u64 reduce_words(u32 w0, u32 w1, u32 w2, u32 w3) {
         : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
     return r;
 }
-// a * b for arbitrary representatives: four 32x32->64 multiply-adds (FMA pipe) + special-form reduction.
-__device__ __forceinline__ u64 mul(u64 a, u64 b) {
+// a * b for arbitrary representatives (first-generation form: explicit partial products + reduce_words, 28 SASS
+// instructions).  Kept for tools/arith_test.cu; `mul` below is what the kernels call.
+__device__ __forceinline__ u64 mul_v1(u64 a, u64 b) {
     const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
     const u64 p00 = (u64)a0 * b0;
     const u64 p01 = (u64)a0 * b1 + (p00 >> 32);          // <= (2^32-1)^2 + 2^32 - 1 < 2^64
@@ -163,7 +164,12 @@ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
     const u64 p11 = (u64)a1 * b1 + (p01 >> 32) + (p10 >> 32);  // <= 2^64 - 1
     return reduce_words((u32)p00, (u32)p10, (u32)p11, (u32)(p11 >> 32));
 }
-
+__device__ __forceinline__ u64 mulc(u64 a, u64 b, u32 eps);
+static __device__ __constant__ u32 k_eps32 = 0xffffffffu;  // multiplier from the constant bank: keeps ptxas from
+                                                           // strength-reducing w*EPS into an ALU-pipe shift/sub pair
+// a * b for arbitrary representatives -> canonical residue (a valid representative for add/sub above): the
+// second-generation product below, 19 SASS instructions.
+__device__ __forceinline__ u64 mul(u64 a, u64 b) { return mulc(a, b, k_eps32); }
 
 // ---------------------------------------------------------------------------------------------
 // Second-generation primitives for the NTT (csrc/ntt.cu).  The first set above keeps every value an
@@ -175,9 +181,6 @@ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
 // operand, so `a` may stay lazy through all stages.  ptxas turns the mul.lo/mul.hi pair into four
 // IMAD.WIDE with carry predicates (7 instructions for the 128-bit product).
 // ---------------------------------------------------------------------------------------------
-static __device__ __constant__ u32 k_eps32 = 0xffffffffu;  // multiplier from the constant bank: keeps ptxas from
-                                                    // strength-reducing w*EPS into an ALU-pipe shift/sub pair
-
 // A + w*EPS - B (mod p): canonical result (< p) for ANY 64-bit A and 32-bit w, B.
 //   U = A - B (borrow k);  V = U + (w + 1 - k)*EPS (carry C) = T + EPS with T = A - B + w*EPS + k*p in [0, 2p)
 //   C ? V - 2^64 (= T - p) : V - EPS (= T)

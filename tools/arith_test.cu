@@ -12,7 +12,7 @@ __global__ void k(const gl::u64* a, const gl::u64* b, int n, gl::u64* o_add, gl:
     if (i >= n) return;
     o_add[i] = gl::lazy::canon(gl::lazy::add(a[i], b[i]));
     o_sub[i] = gl::lazy::canon(gl::lazy::sub(a[i], b[i]));
-    o_mul[i] = gl::lazy::canon(gl::lazy::mul(a[i], b[i]));
+    o_mul[i] = gl::lazy::canon(gl::lazy::mul_v1(a[i], b[i]));
 }
 
 // ---- second-generation primitives (mulc / add1 / sub1 / canon2 / mul_pow2 / dft_pow2) ----
