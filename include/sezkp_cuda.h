@@ -47,6 +47,12 @@ void sezkp_cuda_destroy(sezkp_ctx* ctx);
 const char* sezkp_cuda_last_error(const sezkp_ctx* ctx);     /* ctx may be NULL: error of the last failed create   */
 /* use_own != 0: (re)create a private non-blocking stream; else adopt the caller's cudaStream_t (NULL = legacy default
  * stream), e.g. torch.cuda.current_stream().cuda_stream, so that the caller's events bracket the library's work */
+/* Stream contract of every *_dev entry point: the library launches on the context's stream only and never waits for
+ * other streams.  Device buffers handed in must be complete with respect to that stream (write them on it, or
+ * synchronise first — the private stream is non-blocking, so not even the legacy default stream orders with it), and
+ * results are complete once sezkp_cuda_synchronize returns (entry points that return host data synchronise themselves).
+ * The *_dev NTT/LDE entry points accept any 64-bit representative of a field element; host-buffer entry points
+ * reject non-canonical values with EINVAL. */
 int32_t sezkp_cuda_set_stream(sezkp_ctx* ctx, void* cuda_stream, int use_own);
 int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx);
 /* tuning switches; "dedup" (default 1): value-aware column commit that hashes identical leaves / identical sibling

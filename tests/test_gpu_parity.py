@@ -69,6 +69,30 @@ def test_ntt_batched_columns(ctx, oracle, k, cols):
     assert np.array_equal(ctx.ntt(a, inverse=True), oracle.ntt(a, inverse=True))
 
 
+@pytest.mark.parametrize("k,cols", [(4, 3), (10, 2), (13, 2), (21, 1)])
+def test_ntt_device_entry_accepts_any_representative(ctx, oracle, k, cols):
+    """The device-pointer entry points cannot validate their input on the host: the first pass canonicalises on load, so
+    values in [p, 2^64) behave as their residues (edge operands p, p+1, 2^64-1 included), forward and inverse, and the
+    adversarial all-(p-1) / all-(2^64-1) vectors exercise every carry path of the single-correction butterflies."""
+    import torch
+    rng = np.random.default_rng(77 + k)
+    n = 1 << k
+    raw = rng.integers(0, 1 << 63, size=(cols, n), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(cols, n), dtype=np.uint64)
+    raw[0, :8] = np.array([P, P + 1, 2**64 - 1, P - 1, 0, 1, 2**64 - 2**32, 2**32 - 1], dtype=np.uint64)[: min(8, n)]
+    raw[-1, n // 2:] = np.uint64(2**64 - 1)
+    red = raw % np.uint64(P)
+    for inverse in (False, True):
+        d = torch.from_numpy(raw.view(np.int64).copy()).cuda()
+        torch.cuda.synchronize()  # torch copied on ITS stream; the library launches on its own non-blocking stream
+        ctx.ntt_dev(d, k, cols, inverse)
+        ctx.synchronize()
+        got = d.cpu().numpy().view(np.uint64)
+        want = oracle.ntt(red, inverse=inverse) if k <= 16 else ctx.ntt(red, inverse=inverse)
+        assert np.array_equal(got, want)
+    full = np.full((1, n), P - 1, np.uint64)
+    assert np.array_equal(ctx.ntt(ctx.ntt(full), inverse=True), full)
+
+
 def test_ntt_rejects_non_canonical(ctx):
     bad = np.full(8, P, np.uint64)
     with pytest.raises(pkg().SezkpCudaError) as ei:
