@@ -165,6 +165,14 @@ int32_t sezkp_trace_upload(sezkp_ctx* ctx, const sezkp_trace_desc* trace, sezkp_
 void sezkp_trace_free(sezkp_ctx* ctx, sezkp_trace_dev* trace);
 int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* trace, const uint8_t manifest_root[32],
                                       uint8_t* proof_buf, size_t cap, size_t* len);
+/* Optional device-side collective for the sharded prover (NCCL over NVLink in the host binding): all-gather `bytes`
+ * bytes from every rank's `send_dev` into `recv_all_dev` ([world][bytes], rank-major), both DEVICE pointers, ordered on
+ * `cuda_stream` (the context's stream: enqueue the collective there, or make that stream wait for it) — return 0.
+ * When registered, sezkp_stark_v1_prove_sharded uploads only rows [n*r/world, n*(r+1)/world) of the trace from the
+ * host and all-gathers the compact trace between the GPUs (instead of world replicated PCIe uploads), and the FRI subtree
+ * roots are exchanged without a host round trip.  Needs n_rows % world == 0; otherwise the host-callback path is used. */
+typedef int32_t (*sezkp_allgather_dev_fn)(void* user, const void* send_dev, size_t bytes, void* recv_all_dev, void* cuda_stream);
+int32_t sezkp_cuda_set_allgather_dev(sezkp_ctx* ctx, sezkp_allgather_dev_fn fn, void* user);
 /* The sharded prover over a trace every rank already holds in HBM (each rank uploaded the same trace): what the N-GPU
  * single-proof latency is without the N-fold replicated H2D copy of sezkp_stark_v1_prove_sharded. */
 int32_t sezkp_stark_v1_prove_resident_sharded(sezkp_ctx* ctx, const sezkp_trace_dev* trace, const uint8_t manifest_root[32],

@@ -28,7 +28,7 @@ EXPORTS = [
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
     "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_stark_v1_proof_bound", "sezkp_trace_upload", "sezkp_trace_free",
     "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded", "sezkp_stark_v1_prove_resident_sharded",
-    "sezkp_jsonl_parse", "sezkp_jsonl_free", "sezkp_jsonl_last_error", "sezkp_stark_v1_ingest_jsonl", "sezkp_stark_v1_prove_jsonl_file",
+    "sezkp_cuda_set_allgather_dev", "sezkp_jsonl_parse", "sezkp_jsonl_free", "sezkp_jsonl_last_error", "sezkp_stark_v1_ingest_jsonl", "sezkp_stark_v1_prove_jsonl_file",
 ]
 
 ERR_NAMES = {0: "OK", -1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENODEV", -5: "ERANGE", -6: "ESTATE"}
@@ -287,6 +287,11 @@ class Context:
         self._ck(self.lib.sezkp_stark_v1_prove_sharded(self.h, C.byref(d), manifest_root, C.c_int(rank), C.c_int(world), allgather_cb,
                                                         None, _p(buf), C.c_size_t(buf.size), C.byref(n)))
         return buf[: n.value].tobytes()
+
+    def set_allgather_dev(self, cb) -> None:
+        """Register (or clear with None) the device-side collective of the sharded prover (parallel.ALLGATHER_DEV_FN)."""
+        self._allgather_dev_cb = cb  # keep the ctypes thunk alive
+        self._ck(self.lib.sezkp_cuda_set_allgather_dev(self.h, cb if cb is not None else C.cast(None, C.c_void_p), None))
 
     def prove_v1_resident_sharded(self, rt: "ResidentTrace", manifest_root: bytes, rank: int, world: int, allgather_cb,
                                   buf: Optional[np.ndarray] = None) -> bytes:

@@ -568,6 +568,13 @@ int32_t sezkp_stark_v1_prove_sharded(sezkp_ctx* ctx, const sezkp_trace_desc* tra
     API_END(ctx)
 }
 
+int32_t sezkp_cuda_set_allgather_dev(sezkp_ctx* ctx, sezkp_allgather_dev_fn fn, void* user) {
+    if (!ctx) return SEZKP_CUDA_EINVAL;
+    ctx->allgather_dev = fn;
+    ctx->allgather_dev_user = user;
+    return SEZKP_CUDA_OK;
+}
+
 int32_t sezkp_trace_upload(sezkp_ctx* ctx, const sezkp_trace_desc* trace, sezkp_trace_dev** out) {
     API_BEGIN(ctx)
     REQUIRE(out != nullptr, "bad argument");

@@ -166,6 +166,8 @@ struct sezkp_ctx {
     u64 tab_redone_chunks = 0;              // chunks the tabled pass handed back to the generic kernel (last commit)
     int tab_columns = 0;                    // columns served from subtree tables (last commit)
     u64 launches = 0;                       // kernels launched since last reset
+    sezkp_allgather_dev_fn allgather_dev = nullptr;  // optional device-side collective of the sharded prover
+    void* allgather_dev_user = nullptr;
 };
 
 // Table upload from pageable host memory, ordered before everything later launched on ctx->stream.

@@ -504,6 +504,19 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     // all-gather the chunk roots of `cnt` sharded layers (each rank hashed its own range) and complete level 0 of
     // their `upper` arrays on every rank
     auto gather_chunk_roots = [&](Commit* const* cms, int cnt) {
+        bool even = ctx->allgather_dev != nullptr;
+        for (int i = 0; i < cnt; i++) even = even && cms[i]->n_ch % (u64)world == 0;
+        if (even) {  // device-side: own range -> staging -> all-gather straight into level 0 of `upper` (rank-major = chunk order)
+            for (int i = 0; i < cnt; i++) {
+                const u64 lo = own_lo(cms[i]->n_ch), hi = own_hi(cms[i]->n_ch);
+                const size_t bytes = (size_t)(hi - lo) * 32;
+                u8* stage = (u8*)ctx->scratch[6].ensure(bytes);
+                CUDA_CHECK(cudaMemcpyAsync(stage, cms[i]->upper + lo * 8, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+                const int32_t rc = ctx->allgather_dev(ctx->allgather_dev_user, stage, bytes, cms[i]->upper, (void*)ctx->stream);
+                if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "device allgather callback failed with status %d", rc);
+            }
+            return;
+        }
         size_t per_rank = 0;
         for (int i = 0; i < cnt; i++) per_rank += (size_t)max_own(cms[i]->n_ch) * 32;
         std::vector<u8> mine(per_rank, 0), all(per_rank * (size_t)world);
@@ -693,6 +706,37 @@ void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 mani
     validate_trace(desc);
     const u64 n = desc->n_rows, nb = desc->n_blocks, tau = desc->tau;
     constexpr u64 SLAB = 1ULL << 20;
+    if (shard && shard->world > 1 && ctx->allgather_dev && n % (u64)shard->world == 0 && n / (u64)shard->world >= 1024) {
+        // Sharded upload: this rank copies only its slice of the row arrays over PCIe; the compact trace is then
+        // all-gathered between the GPUs (NVLink) — world replicated uploads of the whole trace share the host's PCIe /
+        // memory bandwidth and were the slowest phase of an 8-GPU proof.
+        DeviceTraceOwner dt;
+        dt.buf = ctx->scratch[2];
+        ctx->scratch[2] = DevBuf();
+        try {
+            dt.upload_meta(ctx, desc);
+        } catch (...) {
+            ctx->scratch[2] = dt.buf;
+            throw;
+        }
+        ctx->scratch[2] = dt.buf;
+        const u64 world = (u64)shard->world, rank = (u64)shard->rank, per = n / world;
+        const u64 r0 = rank * per, r1 = r0 + per;
+        u8* base = (u8*)dt.buf.p;
+        u8* stage = (u8*)ctx->scratch[6].ensure(per * tau * 2 + 256);
+        struct Arr { size_t off; size_t width; const void* host; };
+        const Arr arrs[4] = {{dt.o_imv, 1, desc->input_mv}, {dt.o_mv, (size_t)tau, desc->mv},
+                             {dt.o_wf, (size_t)tau, desc->write_flag}, {dt.o_ws, (size_t)tau * 2, desc->write_sym}};
+        for (int a = 0; a < (dt.packed ? 2 : 4); a++) {
+            const size_t bytes = (size_t)per * arrs[a].width;
+            CUDA_CHECK(cudaMemcpyAsync(stage, (const u8*)arrs[a].host + (size_t)r0 * arrs[a].width, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            const int32_t rc = ctx->allgather_dev(ctx->allgather_dev_user, stage, bytes, base + arrs[a].off, (void*)ctx->stream);
+            if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "device allgather callback failed with status %d", rc);
+        }
+        (void)r1;
+        prove_v1_resident(ctx, dt.t, manifest_root, proof_out, shard, nullptr);
+        return;
+    }
     SlabPlan plan;
     DeviceTraceOwner dt;
     dt.buf = ctx->scratch[2];

@@ -19,6 +19,39 @@ from typing import Callable, List, Sequence
 import numpy as np
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+ALLGATHER_DEV_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p)  # + cuda_stream
+
+
+class _DevBytes:
+    """`nbytes` bytes of device memory at `ptr` as a __cuda_array_interface__ object (zero-copy torch.as_tensor)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def dist_allgather_dev_callback(device):
+    """Device-side all-gather (sezkp_allgather_dev_fn) over torch.distributed / NCCL: the library's device pointers are
+    wrapped zero-copy and `all_gather_into_tensor` is enqueued on the library's own stream, so nothing synchronises
+    with the host and later kernels of that stream see the gathered data."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+
+    def _cb(user, send, nbytes, recv, stream):
+        try:
+            n = int(nbytes)
+            st = torch.cuda.ExternalStream(int(stream or 0), device=device)
+            with torch.cuda.stream(st):
+                src = torch.as_tensor(_DevBytes(send, n), device=device)
+                dst = torch.as_tensor(_DevBytes(recv, n * world), device=device)
+                dist.all_gather_into_tensor(dst, src)
+            return 0
+        except Exception as e:  # never raise through the C frame
+            print("sezkp device allgather callback failed:", repr(e))
+            return -1
+
+    return ALLGATHER_DEV_FN(_cb)
 
 
 # ---------------------------------------------------------------------------------------------- sharding contract
@@ -124,6 +157,34 @@ class ThreadGroup:
                 return -1
 
         return ALLGATHER_FN(_cb)
+
+    def dev_callback(self, rank: int):
+        """Device-side all-gather among the threads (one GPU): every rank publishes its send pointer, all wait, every
+        rank copies the `world` pieces into its own receive buffer on the library's stream and synchronises it."""
+        import torch
+
+        if not hasattr(self, "dev_slots"):
+            self.dev_slots = [0] * self.world
+
+        def _cb(user, send, nbytes, recv, stream):
+            try:
+                n = int(nbytes)
+                st = torch.cuda.ExternalStream(int(stream or 0))
+                st.synchronize()  # the send buffer is final before the others read it
+                self.dev_slots[rank] = int(send)
+                self.barrier.wait(timeout=120)
+                with torch.cuda.stream(st):
+                    dst = torch.as_tensor(_DevBytes(recv, n * self.world), device="cuda")
+                    for r in range(self.world):
+                        dst[r * n:(r + 1) * n].copy_(torch.as_tensor(_DevBytes(self.dev_slots[r], n), device="cuda"))
+                st.synchronize()
+                self.barrier.wait(timeout=120)  # nobody reuses its send buffer before everyone has copied
+                return 0
+            except Exception as e:
+                print("sezkp thread device allgather failed:", repr(e))
+                return -1
+
+        return ALLGATHER_DEV_FN(_cb)
 
     def run(self, fn: Callable[[int], object]) -> list:
         """run fn(rank) on `world` threads, return the results in rank order (exceptions re-raised)"""

@@ -469,6 +469,30 @@ def test_packed_ops_rejected_by_streaming_ingest(ctx):
         ctx.lib.sezkp_stark_v1_abort(ctx.h, st)
 
 
+@pytest.mark.parametrize("world,log_t,packed", [(2, 18, False), (2, 18, True), (3, 18, True), (8, 19, True)])
+def test_sharded_prove_with_device_side_allgather(ctx, world, log_t, packed):
+    """sezkp_cuda_set_allgather_dev: every rank uploads only its slice of the rows and the compact trace is all-gathered
+    between the GPUs; the FRI subtree roots are exchanged on the device.  Same proof bytes as one GPU (world 3: sizes do
+    not divide, the host-callback path takes over)."""
+    m = pkg()
+    ct = m.simulate(1 << log_t, 512, 2, seed=6)
+    root = m.manifest_root(ct)
+    ref = ctx.prove_v1(ct, root)
+    if packed:
+        assert ct.pack_ops()
+    tg = m.parallel.ThreadGroup(world)
+    ctxs = [m.Context() for _ in range(world)]
+    try:
+        for r, c in enumerate(ctxs):
+            c.set_allgather_dev(tg.dev_callback(r))
+        proofs = tg.run(lambda r: ctxs[r].prove_v1_sharded(ct, root, r, world, tg.callback(r)))
+        again = tg.run(lambda r: ctxs[r].prove_v1_sharded(ct, root, r, world, tg.callback(r)))
+    finally:
+        for c in ctxs:
+            c.close()
+    assert all(p == ref for p in proofs) and all(p == ref for p in again)
+
+
 def test_jsonl_stream_prove_matches_one_shot(ctx, tmp_path):
     """f2: JSONL -> ProvingBackendStream -> same proof bytes as the one-shot prove; copies overlap the ingest."""
     m = pkg()
