@@ -389,6 +389,12 @@ static int32_t column_commit_impl(sezkp_ctx* ctx, const u64* cols_host, const u6
         CommitOpts o;
         o.dedup = true;
         o.roots_host = roots;
+        // root-only commit through the plain kernel (value-aware kernels off): the configuration the prover uses for
+        // its large FRI layers — a CTA hashes 2^10 leaves and leaves 32 sub-roots to upper_reduce (stark.cu)
+        if (!keep && !ctx->dedup_enabled && chunk_log2 == 10 && n >= ((size_t)1 << 20)) {
+            o.cta_log2 = 10;
+            chunk_log2 = 5;
+        }
         commit_build(ctx, t->cm, src, n, c, chunk_log2, labels, o);
     } catch (...) {
         t->cm.release(ctx);

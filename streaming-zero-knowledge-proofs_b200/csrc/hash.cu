@@ -40,9 +40,9 @@ __device__ __forceinline__ void put_digest(u32* s, int pitch, int i, const u32 (
 // produced level into the retained upper-tree array (`levels_base`, level l0+1.. of a column with n_ch_total
 // chunk roots, this group being number `grp` at level l0) and/or records the sibling path of leaf `path_idx`.
 __device__ __forceinline__ void reduce_levels_smem(u32* s, int pitch, int count, u32* levels_base, u64 grp, int l0,
-                                                   u64 n_ch_total, u32* path_out, int path_idx) {
+                                                   u64 n_ch_total, u32* path_out, int path_idx, int stop = 1) {
     int lvl = 0;
-    while (count > 1) {
+    while (count > stop) {
         if (path_out != nullptr && threadIdx.x < 8) {
             const int sib = (path_idx >> lvl) ^ 1;
             path_out[lvl * 8 + threadIdx.x] = s[threadIdx.x * pitch + sib];
@@ -88,15 +88,16 @@ __device__ __forceinline__ void reduce_levels_smem(u32* s, int pitch, int count,
 // FOLD: the values are produced on the fly as the FRI fold of the previous layer,
 //   y'[i] = y[i] + beta*y[i+half]  (reference v1/prover.rs:204-238), written to `values` and hashed in one pass.
 template <bool FOLD>
-__global__ void __launch_bounds__(HASH_THREADS, 5) chunk_commit_kernel(u64* __restrict__ values, u64 n, u64 col_stride, int cl,
+__global__ void __launch_bounds__(HASH_THREADS, 5) chunk_commit_kernel(u64* __restrict__ values, u64 n, u64 col_stride, int cl, int sub,
                                                                     const b3::LabelTemplate* __restrict__ templates,
                                                                     u32* __restrict__ upper, u64 n_ch,
                                                                     const u64* __restrict__ fold_src, u64 beta, u64 chunk0) {
+    // one CTA reduces 2^(cl+sub) leaves = 2^sub chunks of 2^cl leaves and writes their 2^sub roots (sub = 0: one chunk)
     __shared__ __align__(16) u32 s[8 * ((1 << MAX_CL) + 2)];
     const int pitch = (1 << MAX_CL) + 2;
-    const u64 chunk = chunk0 + blockIdx.x;
+    const u64 chunk = chunk0 + ((u64)blockIdx.x << sub);
     const int col = blockIdx.y;
-    const int leaves = 1 << cl;
+    const int leaves = 1 << (cl + sub);
     u64* v = values + (u64)col * col_stride + (chunk << cl);
     b3::LabelTemplate t;
     if (templates) t = templates[col];
@@ -114,8 +115,10 @@ __global__ void __launch_bounds__(HASH_THREADS, 5) chunk_commit_kernel(u64* __re
         HASH_LEAVES_INTO(s, pitch, leaves, v[i], templates != nullptr, t)
     }
     __syncthreads();
-    reduce_levels_smem(s, pitch, leaves, nullptr, 0, 0, 0, nullptr, 0);
-    if (threadIdx.x < 8) upper[((u64)col * (2 * n_ch - 1) + chunk) * 8 + threadIdx.x] = s[threadIdx.x * pitch];
+    const int roots = 1 << sub;
+    reduce_levels_smem(s, pitch, leaves, nullptr, 0, 0, 0, nullptr, 0, roots);
+    u32* dst = upper + ((u64)col * (2 * n_ch - 1) + chunk) * 8;
+    for (int i = threadIdx.x; i < 8 * roots; i += HASH_THREADS) dst[i] = s[(i & 7) * pitch + (i >> 3)];
 }
 
 // Unlabeled chunk commit of several single-column commitments in one launch (the small FRI layers, whose values are
@@ -1462,6 +1465,8 @@ void commit_begin(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
     cm.col_stride = opt.col_stride ? opt.col_stride : n;
     cm.cols = cols;
     cm.cl = ln < chunk_log2 ? ln : chunk_log2;
+    cm.cta_cl = cm.cl;
+    if (opt.cta_log2 > cm.cl) cm.cta_cl = std::min(std::min(opt.cta_log2, MAX_CL), ln);
     cm.n_ch = n >> cm.cl;
     REQUIRE(cm.n_ch < (1ULL << 31), "too many chunks per column");
     if (labels) {
@@ -1490,13 +1495,17 @@ void commit_begin(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
 void commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, const CommitOpts& opt) {
     if (chunk1 <= chunk0) return;
     REQUIRE(chunk1 <= cm.n_ch, "internal: chunk range out of bounds");
+    const int sub = cm.cta_cl - cm.cl;  // chunks per CTA of the plain kernel = 2^sub
+    REQUIRE(((chunk0 | chunk1) & ((1ULL << sub) - 1)) == 0, "internal: chunk range not aligned to the CTA granularity");
     dim3 grid((unsigned)(chunk1 - chunk0), (unsigned)cm.cols);
     u64* vals = (u64*)cm.values;
     if (opt.fold_src) {
         REQUIRE(cm.cols == 1 && !cm.templates, "internal: fused fold needs a single unlabeled column");
-        chunk_commit_kernel<true><<<grid, HASH_THREADS, 0, ctx->stream>>>(vals, cm.n, cm.col_stride, cm.cl, nullptr, cm.upper, cm.n_ch,
+        grid.x >>= sub;
+        chunk_commit_kernel<true><<<grid, HASH_THREADS, 0, ctx->stream>>>(vals, cm.n, cm.col_stride, cm.cl, sub, nullptr, cm.upper, cm.n_ch,
                                                                            opt.fold_src, opt.fold_beta, chunk0);
     } else if (opt.dedup && ctx->dedup_enabled) {
+        REQUIRE(sub == 0, "internal: the value-aware kernels reduce exactly one chunk per CTA");
         u32* memo = (u32*)ctx->scratch[8].p;
         if (ctx->dedup_variant == 2 && ctx->tabled_enabled && cm.cl == MAX_CL) {
             tab_commit_chunks(ctx, cm, chunk0, chunk1, memo);
@@ -1509,7 +1518,8 @@ void commit_chunks(sezkp_ctx* ctx, Commit& cm, u64 chunk0, u64 chunk1, const Com
             chunk_commit_dedup_kernel<<<grid, HASH_THREADS, sizeof(DedupSmem), ctx->stream>>>(cm.values, cm.n, cm.col_stride, cm.cl,
                                                                                                cm.templates, cm.upper, cm.n_ch, memo, chunk0);
     } else {
-        chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>(vals, cm.n, cm.col_stride, cm.cl, cm.templates, cm.upper, cm.n_ch,
+        grid.x >>= sub;
+        chunk_commit_kernel<false><<<grid, HASH_THREADS, 0, ctx->stream>>>(vals, cm.n, cm.col_stride, cm.cl, sub, cm.templates, cm.upper, cm.n_ch,
                                                                             nullptr, 0, chunk0);
     }
     CUDA_CHECK(cudaGetLastError());
@@ -1546,7 +1556,7 @@ void commit_chunks_multi(sezkp_ctx* ctx, Commit* cms, int count) {
         u32 ctas = 0;
         for (int i = 0; i < m; i++) {
             const Commit& cm = cms[base + i];
-            REQUIRE(cm.cols == 1 && !cm.templates, "internal: batched chunk commit needs single unlabeled columns");
+            REQUIRE(cm.cols == 1 && !cm.templates && cm.cta_cl == cm.cl, "internal: batched chunk commit needs single unlabeled columns");
             jobs.j[i].values = cm.values;
             jobs.j[i].upper = cm.upper;
             jobs.j[i].cl = cm.cl;

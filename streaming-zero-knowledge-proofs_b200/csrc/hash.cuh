@@ -16,6 +16,7 @@ struct Commit {
     u64 col_stride = 0;            // elements between consecutive committed columns (n when dense)
     int cols = 0;
     int cl = 0;                    // log2 leaves per chunk = min(chunk_log2, log2 n)
+    int cta_cl = 0;                // log2 leaves one CTA of the plain chunk kernel reduces (>= cl): it then writes 2^(cta_cl-cl) chunk roots
     u64 n_ch = 0;                  // chunks per column = n >> cl
     u32* upper = nullptr;          // device [cols][2*n_ch-1][8]: level l (count n_ch>>l) at offset 2*n_ch-(2*n_ch>>l)
     b3::LabelTemplate* templates = nullptr;  // device [cols] or null (unlabeled)
@@ -36,6 +37,9 @@ struct CommitOpts {
     u8* roots_host = nullptr;       // [cols][32]; copying to the host synchronises the stream
     u8* roots_dev = nullptr;        // [cols][32] device copy (no synchronisation)
     u64 col_stride = 0;             // 0 = dense (n); column sharding commits every world-th column of a dense array
+    int cta_log2 = 0;               // > chunk_log2: one CTA still reduces 2^cta_log2 leaves but stops at the 2^chunk_log2-leaf
+                                    // sub-roots (plain / fused-fold kernel only): the thin top of every CTA tree moves to
+                                    // upper_reduce, where a CTA is full again
 };
 // Build a commitment over device values (all launches on ctx->stream).
 void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,

@@ -497,15 +497,22 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     fl.commits.resize(log_N + 1);
     std::vector<u64> beta_store;
     constexpr int FUSE_MIN_LOG = 20, TAIL_ONE_CTA_LOG = 14, SHARD_MIN_LOG = 20;
+    // Large layers retain 32-leaf sub-roots instead of 1024-leaf chunk roots: a CTA still hashes 1024 leaves, but stops
+    // when 32 nodes are left — below that a 256-thread CTA runs 5 levels with one partly filled warp — and the top of
+    // all trees is reduced by upper_reduce with full CTAs.  Openings rebuild 32 leaves instead of 1024.
+    constexpr int BIG_CL = 5, BIG_CTA_LOG = 10;
     const int world = shard ? shard->world : 1, rank = shard ? shard->rank : 0;
-    auto own_lo = [&](u64 n_ch) { return n_ch * (u64)rank / (u64)world; };
-    auto own_hi = [&](u64 n_ch) { return n_ch * (u64)(rank + 1) / (u64)world; };
-    auto max_own = [&](u64 n_ch) { return (n_ch + world - 1) / world + 1; };
+    // own chunk range of a sharded layer, in units of the CTA granularity (2^(BIG_CTA_LOG - BIG_CL) chunks)
+    constexpr u64 CG = 1ULL << (BIG_CTA_LOG - BIG_CL);
+    auto range_lo = [&](u64 n_ch, int r) { return ((n_ch / CG) * (u64)r / (u64)world) * CG; };
+    auto own_lo = [&](u64 n_ch) { return range_lo(n_ch, rank); };
+    auto own_hi = [&](u64 n_ch) { return range_lo(n_ch, rank + 1); };
+    auto max_own = [&](u64 n_ch) { return ((n_ch / CG + world - 1) / world + 1) * CG; };
     // all-gather the chunk roots of `cnt` sharded layers (each rank hashed its own range) and complete level 0 of
     // their `upper` arrays on every rank
     auto gather_chunk_roots = [&](Commit* const* cms, int cnt) {
         bool even = ctx->allgather_dev != nullptr;
-        for (int i = 0; i < cnt; i++) even = even && cms[i]->n_ch % (u64)world == 0;
+        for (int i = 0; i < cnt; i++) even = even && (cms[i]->n_ch / CG) % (u64)world == 0;
         if (even) {  // device-side: own range -> staging -> all-gather straight into level 0 of `upper` (rank-major = chunk order)
             for (int i = 0; i < cnt; i++) {
                 const u64 lo = own_lo(cms[i]->n_ch), hi = own_hi(cms[i]->n_ch);
@@ -535,7 +542,7 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
             const u64 n_ch = cms[i]->n_ch;
             for (int r = 0; r < world; r++) {
                 if (r == rank) continue;
-                const u64 lo = n_ch * (u64)r / (u64)world, hi = n_ch * (u64)(r + 1) / (u64)world;
+                const u64 lo = range_lo(n_ch, r), hi = range_lo(n_ch, r + 1);
                 if (hi > lo)
                     CUDA_CHECK(cudaMemcpyAsync(cms[i]->upper + lo * 8, all.data() + (size_t)r * per_rank + off, (hi - lo) * 32,
                                                cudaMemcpyHostToDevice, ctx->stream));
@@ -547,15 +554,17 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     {
         CommitOpts o;
         o.roots_host = roots_host;
+        const bool big0 = log_N >= FUSE_MIN_LOG;
+        if (big0) o.cta_log2 = BIG_CTA_LOG;
         if (world > 1 && log_N >= SHARD_MIN_LOG) {
             Commit& c0 = fl.commits[0];
-            commit_begin(ctx, c0, fl.values, N, 1, 10, nullptr, o);
+            commit_begin(ctx, c0, fl.values, N, 1, BIG_CL, nullptr, o);
             commit_chunks(ctx, c0, own_lo(c0.n_ch), own_hi(c0.n_ch), o);
             Commit* one[1] = {&c0};
             gather_chunk_roots(one, 1);
             commit_finish(ctx, c0, o);
         } else {
-            commit_build(ctx, fl.commits[0], fl.values, N, 1, 10, nullptr, o);
+            commit_build(ctx, fl.commits[0], fl.values, N, 1, big0 ? BIG_CL : 10, nullptr, o);
         }
         if (absorb) {
             absorb->on_root(0, roots_host);
@@ -584,13 +593,15 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
                 CUDA_CHECK(cudaGetLastError());
                 ctx->launches++;
                 Commit& c = fl.commits[l];
-                commit_begin(ctx, c, fl.values + off, len, 1, 10, nullptr, o);
+                o.cta_log2 = BIG_CTA_LOG;
+                commit_begin(ctx, c, fl.values + off, len, 1, BIG_CL, nullptr, o);
                 commit_chunks(ctx, c, own_lo(c.n_ch), own_hi(c.n_ch), o);
                 sharded.push_back(&c);
             } else {
                 o.fold_src = fl.values + (off - 2 * len);
                 o.fold_beta = betas[l - 1];
-                commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
+                o.cta_log2 = BIG_CTA_LOG;
+                commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, BIG_CL, nullptr, o);
                 commit_chunks(ctx, fl.commits[l], 0, fl.commits[l].n_ch, o);
             }
         } else {
