@@ -285,8 +285,13 @@ static void lde_commit_device(sezkp_ctx* ctx, const u64* evals_dev, const char* 
         CommitOpts o;
         o.dedup = false;  // extended values are high-entropy
         o.roots_dev = d_roots + c0 * 32;
+        int cl = chunk_log2;
+        if (chunk_log2 == 10 && N >= ((size_t)1 << 20)) {  // roots only: 32-leaf sub-roots out of each 1024-leaf CTA (see stark.cu)
+            o.cta_log2 = 10;
+            cl = 5;
+        }
         try {
-            commit_build(ctx, cm, ext, N, (int)g, chunk_log2, labels + c0, o);
+            commit_build(ctx, cm, ext, N, (int)g, cl, labels + c0, o);
         } catch (...) {
             cm.release(ctx);
             throw;
