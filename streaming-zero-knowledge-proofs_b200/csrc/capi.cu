@@ -157,6 +157,8 @@ int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value) {
         if (value == 1 || value == 2) ctx->dedup_variant = (int)value;
     } else if (std::strcmp(name, "tabled") == 0) {
         ctx->tabled_enabled = value != 0;
+    } else if (std::strcmp(name, "deep_fused") == 0) {
+        ctx->deep_fused = value != 0;
     }
     else sezkp_fail(SEZKP_CUDA_EINVAL, "unknown option '%s'", name);
     API_END(ctx)

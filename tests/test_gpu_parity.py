@@ -493,6 +493,24 @@ def test_sharded_prove_with_device_side_allgather(ctx, world, log_t, packed):
     assert all(p == ref for p in proofs) and all(p == ref for p in again)
 
 
+def test_deep_lde_three_launch_path_equals_fused_kernel(ctx, oracle):
+    """Domains of >= 2^21 points run DEEP as forward / batched inversion / apply; option "deep_fused" forces the one-launch
+    kernel with a per-CTA inversion.  Same bytes, also against the oracle at a size it finishes quickly."""
+    rng = np.random.default_rng(5)
+    for k, lb in ((18, 3), (19, 2), (12, 3)):
+        base = rand_field(rng, 1 << k)
+        z = int(rng.integers(1, 1 << 62))
+        a = ctx.deep_lde(base, lb, 3, z)
+        ctx.set_option("deep_fused", 1)
+        try:
+            b = ctx.deep_lde(base, lb, 3, z)
+        finally:
+            ctx.set_option("deep_fused", 0)
+        assert np.array_equal(a, b)
+        if k <= 12:
+            assert np.array_equal(a, oracle.deep_lde(base, lb, 3, z))
+
+
 def test_jsonl_stream_prove_matches_one_shot(ctx, tmp_path):
     """f2: JSONL -> ProvingBackendStream -> same proof bytes as the one-shot prove; copies overlap the ingest."""
     m = pkg()
