@@ -603,9 +603,10 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     REQUIRE(log_N >= 1 && log_N <= 32, "log_N %d out of range", log_N);
     const u64 N = 1ULL << log_N;
     fl.log_N = log_N;
-    fl.values = (u64*)ctx->pool.alloc(2 * N * 8);
+    // the caller may have produced layer 0 in place: fl.values pre-allocated (2N elements) and layer0 == fl.values
+    if (!fl.values) fl.values = (u64*)ctx->pool.alloc(2 * N * 8);
     u8* d_roots = (u8*)ctx->scratch[10].ensure((size_t)(log_N + 1) * 32 + 64);
-    CUDA_CHECK(cudaMemcpyAsync(fl.values, layer0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (layer0 != fl.values) CUDA_CHECK(cudaMemcpyAsync(fl.values, layer0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     fl.commits.resize(log_N + 1);
     std::vector<u64> beta_store;
     constexpr int FUSE_MIN_LOG = 20, TAIL_ONE_CTA_LOG = 14, SHARD_MIN_LOG = 20;
@@ -1013,7 +1014,8 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         u64* base_vals = (u64*)ctx->scratch[4].ensure(n * 8);
         compose_device(ctx, cols, n, tau, alphas, mask, 4, base_vals);
         lap("compose");
-        u64* lde = (u64*)ctx->scratch[5].ensure(N * 8);
+        fl.values = (u64*)ctx->pool.alloc(2 * N * 8);  // the DEEP-LDE lands where FRI layer 0 lives: no 8N-byte copy
+        u64* lde = fl.values;
         deep_lde_device(ctx, base_vals, lde, L, logB, shift, z);
         lap("deep_lde");
 
