@@ -1375,7 +1375,16 @@ void tab_classify(sezkp_ctx* ctx, Commit& cm, u64 avail_chunks) {
     CUDA_CHECK(cudaMemcpyAsync(tabs_dev, tabs.data(), sizeof(ColTab) * cols, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(lists_dev, order.data(), sizeof(int) * cols, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
-    if (n_tab) {
+    // The tables are pure functions of (class, key range, label): a context that proves trace after trace of the same
+    // machine finds them already built (the key holds the table parameters with their addresses and the label templates).
+    std::vector<u8> key(sizeof(ColTab) * cols + sizeof(b3::LabelTemplate) * cm.templates_host.size() + sizeof(int) * cols);
+    std::memcpy(key.data(), tabs.data(), sizeof(ColTab) * cols);
+    std::memcpy(key.data() + sizeof(ColTab) * cols, order.data(), sizeof(int) * cols);
+    if (!cm.templates_host.empty())
+        std::memcpy(key.data() + (sizeof(ColTab) + sizeof(int)) * cols, cm.templates_host.data(), sizeof(b3::LabelTemplate) * cm.templates_host.size());
+    const bool cached = n_tab && key == ctx->tab_cache_key;
+    if (n_tab && !cached) {
+        ctx->tab_cache_key.clear();  // invalid while the kernels below rewrite the tables
         tab_build_first_kernel<<<dim3((unsigned)((max_first + 127) / 128), (unsigned)n_tab), 128, 0, ctx->stream>>>(tabs_dev, lists_dev, cm.templates);
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
@@ -1385,6 +1394,7 @@ void tab_classify(sezkp_ctx* ctx, Commit& cm, u64 avail_chunks) {
             CUDA_CHECK(cudaGetLastError());
             ctx->launches++;
         }
+        ctx->tab_cache_key = std::move(key);
     }
     cm.tab_classified = true;
     ctx->tab_columns = n_tab;
@@ -1478,6 +1488,7 @@ void commit_begin(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
         cm.templates = (b3::LabelTemplate*)ctx->pool.alloc(sizeof(b3::LabelTemplate) * cols);
         CUDA_CHECK(cudaMemcpyAsync(cm.templates, h.data(), sizeof(b3::LabelTemplate) * cols, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // h goes out of scope
+        cm.templates_host = h;
     }
     cm.upper = (u32*)ctx->pool.alloc((size_t)cols * (2 * cm.n_ch - 1) * 32);
     if (opt.dedup && ctx->dedup_enabled && !opt.fold_src) {

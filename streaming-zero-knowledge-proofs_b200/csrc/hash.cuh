@@ -20,6 +20,7 @@ struct Commit {
     u64 n_ch = 0;                  // chunks per column = n >> cl
     u32* upper = nullptr;          // device [cols][2*n_ch-1][8]: level l (count n_ch>>l) at offset 2*n_ch-(2*n_ch>>l)
     b3::LabelTemplate* templates = nullptr;  // device [cols] or null (unlabeled)
+    std::vector<b3::LabelTemplate> templates_host;  // the same on the host (key of the subtree-table cache)
     // subtree-table state of the value-aware commit (hash.cu, "structured columns"); null/empty when not used
     void* tab_dev = nullptr;       // device: ColTab[cols], column lists, work list of chunks to redo
     std::vector<int> tab_logg;     // per column: log2 of the leaves under one table entry, 0 = generic kernel
