@@ -305,6 +305,9 @@ def main():
     stream = torch.cuda.Stream()  # the library launches on torch's current stream so torch events bracket its work
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    # every timed proof builds its subtree tables: the cross-proof table cache (a serving optimisation: tables depend only on
+    # labels and value ranges) would otherwise hit on every repetition of the same synthetic trace
+    ctx.set_option("tab_cache", 0)
     hbm_peak, peak_src = peaks()
 
     wl = workload()

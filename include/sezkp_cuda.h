@@ -57,7 +57,8 @@ int32_t sezkp_cuda_set_stream(sezkp_ctx* ctx, void* cuda_stream, int use_own);
 int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx);
 /* tuning switches; "dedup" (default 1): value-aware column commit that hashes identical leaves / identical sibling
  * pairs of a chunk once (outputs are identical either way; 0 forces one compression per node); "tabled" (default 1):
- * subtree tables for structured columns; "deep_fused" (default 0): one-launch DEEP kernel also for large domains */
+ * subtree tables for structured columns; "deep_fused" (default 0): one-launch DEEP kernel also for large domains; "tab_cache" (default 1): keep the
+ * subtree tables across proofs while their parameters and labels are unchanged */
 int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value);
 /* number of kernels launched by this ctx since creation / since the last reset */
 uint64_t sezkp_cuda_launch_count(sezkp_ctx* ctx, int reset);

@@ -159,6 +159,9 @@ int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value) {
         ctx->tabled_enabled = value != 0;
     } else if (std::strcmp(name, "deep_fused") == 0) {
         ctx->deep_fused = value != 0;
+    } else if (std::strcmp(name, "tab_cache") == 0) {
+        ctx->tab_cache_enabled = value != 0;
+        ctx->tab_cache_key.clear();
     }
     else sezkp_fail(SEZKP_CUDA_EINVAL, "unknown option '%s'", name);
     API_END(ctx)

@@ -165,6 +165,7 @@ struct sezkp_ctx {
     bool tabled_enabled = true;             // subtree tables for structured columns (option "tabled"; needs dedup)
     u64 tab_redone_chunks = 0;              // chunks the tabled pass handed back to the generic kernel (last commit)
     int tab_columns = 0;                    // columns served from subtree tables (last commit)
+    bool tab_cache_enabled = true;           // option "tab_cache"
     std::vector<u8> tab_cache_key;           // subtree tables in scratch[11] were built for exactly these (ColTab[], label templates)
     bool deep_fused = false;                // option "deep_fused": one-launch DEEP kernel (per-CTA inversion) also for large domains
     u64 launches = 0;                       // kernels launched since last reset

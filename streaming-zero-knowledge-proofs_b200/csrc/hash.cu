@@ -1382,7 +1382,7 @@ void tab_classify(sezkp_ctx* ctx, Commit& cm, u64 avail_chunks) {
     std::memcpy(key.data() + sizeof(ColTab) * cols, order.data(), sizeof(int) * cols);
     if (!cm.templates_host.empty())
         std::memcpy(key.data() + (sizeof(ColTab) + sizeof(int)) * cols, cm.templates_host.data(), sizeof(b3::LabelTemplate) * cm.templates_host.size());
-    const bool cached = n_tab && key == ctx->tab_cache_key;
+    const bool cached = n_tab && ctx->tab_cache_enabled && key == ctx->tab_cache_key;
     if (n_tab && !cached) {
         ctx->tab_cache_key.clear();  // invalid while the kernels below rewrite the tables
         tab_build_first_kernel<<<dim3((unsigned)((max_first + 127) / 128), (unsigned)n_tab), 128, 0, ctx->stream>>>(tabs_dev, lists_dev, cm.templates);
