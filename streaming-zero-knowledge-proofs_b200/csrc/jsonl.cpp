@@ -233,7 +233,72 @@ void parse_tape_op(Cursor& c, int8_t& mv, uint8_t& wf, uint16_t& ws) {
 }
 
 // {"input_mv": i8, "tapes": [TapeOp; tau]}
+// Fast path for `{"input_mv":-1,"tapes":[{...},...]}` exactly as serde_json writes it; on any deviation the vectors are
+// rolled back and the general parser below takes the step again.
+inline bool fast_step(Cursor& c, Trace& t, uint32_t& tau) {
+    const char* q = c.p;
+    const char* const end = c.end;
+    if (end - q < 24 || std::memcmp(q, "{\"input_mv\":", 12) != 0) return false;
+    q += 12;
+    int64_t v;
+    if (!fast_small_int(q, end, -128, 127, v)) return false;
+    if (end - q < 11 || std::memcmp(q, ",\"tapes\":[", 10) != 0) return false;
+    q += 10;
+    const size_t n0 = t.mv.size();
+    uint32_t r = 0;
+    Cursor cc{q, end, c.line};
+    bool ok;
+    if (tau != 0) {  // known width: grow the three arrays once per step and write through raw pointers
+        t.mv.resize(n0 + tau);
+        t.write_flag.resize(n0 + tau);
+        t.write_sym.resize(n0 + tau);
+        int8_t* pm = t.mv.data() + n0;
+        uint8_t* pf = t.write_flag.data() + n0;
+        uint16_t* ps = t.write_sym.data() + n0;
+        ok = true;
+        for (; r < tau; r++) {
+            if (r && !(cc.p < end && *cc.p++ == ',')) {
+                ok = false;
+                break;
+            }
+            if (!fast_tape_op(cc, pm[r], pf[r], ps[r])) {
+                ok = false;
+                break;
+            }
+        }
+        ok = ok && end - cc.p >= 2 && cc.p[0] == ']' && cc.p[1] == '}';
+    } else {
+        for (;;) {
+            int8_t mv = 0;
+            uint8_t wf = 0;
+            uint16_t ws = 0;
+            if (!fast_tape_op(cc, mv, wf, ws)) break;
+            t.mv.push_back(mv);
+            t.write_flag.push_back(wf);
+            t.write_sym.push_back(ws);
+            r++;
+            if (cc.p < end && *cc.p == ',') {
+                cc.p++;
+                continue;
+            }
+            break;
+        }
+        ok = r > 0 && end - cc.p >= 2 && cc.p[0] == ']' && cc.p[1] == '}';
+    }
+    if (!ok) {
+        t.mv.resize(n0);
+        t.write_flag.resize(n0);
+        t.write_sym.resize(n0);
+        return false;
+    }
+    if (tau == 0) tau = r;
+    t.input_mv.push_back((int8_t)v);
+    c.p = cc.p + 2;
+    return true;
+}
+
 void parse_step(Cursor& c, Trace& t, uint32_t& tau) {
+    if (fast_step(c, t, tau)) return;
     bool have_in = false, have_tapes = false;
     int8_t in_mv = 0;
     c.expect('{');
