@@ -1,8 +1,7 @@
 """sezkp-b200: B200-native STARK v1 commitment path for SEZKP (host-side mirror of the reference API).
 
 The package directory name carries a hyphen (it mirrors the upstream repository name), so import it with
-``importlib.import_module("streaming-zero-knowledge-proofs_b200")`` or through the ``sezkp_b200`` shim at the
-repository root.
+``importlib.import_module("streaming-zero-knowledge-proofs_b200")`` (tests/conftest.py and bench.py do exactly that).
 """
 from .trace import CompactTrace, TraceDesc, blocks_to_compact, demo_block, manifest_root, simulate  # noqa: F401
 

@@ -152,7 +152,7 @@ struct sezkp_ctx {
     std::vector<cudaEvent_t> slab_events;
     std::string last_error;
     std::map<u64, NttTables*> ntt_tables;  // key: (log_n, inverse, coset params)
-    std::map<u64, u64*> deep_tables;       // (log N, shift) -> device table of the first coset point of every DEEP CTA
+    std::map<std::pair<int, u64>, u64*> deep_tables;  // (log N, shift) -> device table of the first coset point of every DEEP CTA (capped)
     std::map<int, u64*> power_tables;      // log_n -> device table of the low powers of w_n (composition mask)
     DevPool pool;
     DevBuf scratch[12];                      // reusable work buffers (per purpose, see users)

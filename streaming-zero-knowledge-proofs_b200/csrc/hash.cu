@@ -689,7 +689,9 @@ __global__ void __launch_bounds__(DT, 7) chunk_commit_dedup128_kernel(const u64*
                     st = owner ? 0u : 1u;
                 }
                 if (st == 1u) {
-                    while ((st = ld_acquire_u32(ent)) != 2u) __nanosleep(200);
+                    // bounded: the slot may hold another key, or sit in state 1 for ever after a faulted launch — after a
+                    // few polls (a chain of k <= 10 compressions takes ~2 us) it is treated as a miss and computed locally
+                    for (int spin = 0; spin < 64 && (st = ld_acquire_u32(ent)) != 2u; spin++) __nanosleep(200);
                 }
                 bool hit = false;
                 if (st == 2u && __ldcg(ent + 1) == (u32)k) {  // fields via L2: L1 is not coherent

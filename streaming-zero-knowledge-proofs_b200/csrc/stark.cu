@@ -551,7 +551,12 @@ void deep_lde_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, 
     for (int l = 0; l < 32; l++) dp.w_lane[l] = gl::pow(w, (u64)l);
     // shift * w^(cta * elements per CTA), cached per (log N, shift)
     const u64 n_cta = blocks_for(N, DEEP_THREADS * DEEP_PER_THREAD);
-    const u64 key = ((u64)(L + logB) << 56) ^ shift;
+    const auto key = std::make_pair(L + logB, shift);  // n_cta is a function of log N, so the entry's length is implied
+    if (!ctx->deep_tables.count(key) && ctx->deep_tables.size() >= 16) {  // callers that vary `shift`: bounded cache
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (auto& kv : ctx->deep_tables) cudaFree(kv.second);
+        ctx->deep_tables.clear();
+    }
     u64*& x0_table = ctx->deep_tables[key];
     if (!x0_table) {
         std::vector<u64> h(n_cta);
@@ -907,7 +912,13 @@ void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 mani
         r0 = r1;
     }
     (void)tau;
-    prove_v1_resident(ctx, dt.t, manifest_root, proof_out, shard, &plan);
+    try {
+        prove_v1_resident(ctx, dt.t, manifest_root, proof_out, shard, &plan);
+    } catch (...) {
+        // the slab copies read the CALLER's host arrays: never return (even with an error) while DMA may still be in flight
+        cudaStreamSynchronize(ctx->copy_stream);
+        throw;
+    }
     CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
 }
 
@@ -915,6 +926,7 @@ void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 mani
 void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], ProofSink& proof_out,
                        const ShardInfo* shard, const SlabPlan* plan) {
     const int world = shard ? shard->world : 1, rank = shard ? shard->rank : 0;
+    REQUIRE(world <= 3 + 7 * (int)trace.tau, "more ranks (%d) than committed columns (%d)", world, 3 + 7 * (int)trace.tau);
     auto exchange = [&](const void* send, size_t bytes, void* recv) {  // all-gather through the host callback
         const int32_t rc = shard->allgather(shard->user, send, bytes, recv);
         if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "allgather callback failed with status %d", rc);

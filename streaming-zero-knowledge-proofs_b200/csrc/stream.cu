@@ -153,13 +153,14 @@ void stream_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* b) 
                 b->write_sym,
             "ingest: descriptor has NULL arrays");
     const size_t tau = st->tau;
+    // validate the whole descriptor before touching the stream: a rejected ingest must leave the handle as it was
     u64 total = 0;
     for (u64 k = 0; k < b->n_blocks; k++) {
         REQUIRE(b->block_len[k] >= 1, "ingest: empty block");
         total += b->block_len[k];
-        st->block_len.push_back(b->block_len[k]);
     }
     REQUIRE(total == b->n_rows, "ingest: n_rows != sum(block_len)");
+    st->block_len.insert(st->block_len.end(), b->block_len, b->block_len + b->n_blocks);
     st->win_left.insert(st->win_left.end(), b->win_left, b->win_left + b->n_blocks * tau);
     st->win_right.insert(st->win_right.end(), b->win_right, b->win_right + b->n_blocks * tau);
     st->in_off.insert(st->in_off.end(), b->head_in_off, b->head_in_off + b->n_blocks * tau);
