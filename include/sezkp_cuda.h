@@ -9,7 +9,8 @@
  *     returns memory the caller must free except opaque handles with a matching *_free;
  *   - field elements are canonical Goldilocks residues (< p = 2^64-2^32+1) as little-endian uint64_t,
  *     digests are 32 raw bytes; pointers named *_dev are device pointers on the ctx's GPU, all others host;
- *   - a ctx is bound to one GPU (one process per GPU) and is not thread-safe;
+ *   - a ctx is bound to one GPU (sezkp_cuda_create) or to several GPUs of one box driven from this one process
+ *     (sezkp_cuda_create_multi); it is not thread-safe: one call at a time per ctx;
  *   - there is no CPU fallback: without a usable CUDA device sezkp_cuda_create fails with ENODEV.
  */
 #ifndef SEZKP_CUDA_H
@@ -23,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SEZKP_CUDA_ABI_VERSION 1u
+#define SEZKP_CUDA_ABI_VERSION 1u  /* additions only since round 1: still 1 */
 
 #define SEZKP_CUDA_OK 0
 #define SEZKP_CUDA_EINVAL (-1)  /* bad argument (non power-of-two size, label too long, NULL, ...) */
@@ -39,10 +40,23 @@ typedef struct sezkp_tree sezkp_tree; /* retained column commitments (chunk root
 typedef struct sezkp_fri sezkp_fri;   /* retained FRI layers (values + upper tree levels)                  */
 typedef struct sezkp_stream sezkp_stream;
 typedef struct sezkp_trace_dev sezkp_trace_dev; /* compact trace resident in HBM */
+typedef struct sezkp_columns sezkp_columns;     /* base-domain columns resident in HBM, column c on GPU c % n_gpus */
 
 /* ---------------------------------------------------------------- context ---- */
 uint32_t sezkp_cuda_abi_version(void);                       /* cf. sezkp_abi_version(), sezkp-ffi/src/lib.rs:55-68 */
 int32_t sezkp_cuda_create(int device_id, sezkp_ctx** out);   /* device_id < 0: current device                     */
+/* One context over n_dev GPUs of this box, driven from this single process — what the reference's stateless, single-
+ * process backend call (sezkp-core/src/backend.rs:41-61; CLI arms sezkp-cli/src/main.rs:503-513) needs to use a whole
+ * 8-GPU box (SURVEY §8b "threading").  The library keeps one worker thread + one internal context per GPU and implements
+ * every exchange itself over NVLink peer access (column roots, FRI subtree roots, opening records, compact trace, partial
+ * combination sums): no NCCL, no callbacks.  With such a ctx
+ *   sezkp_stark_v1_prove / _prove_resident / the streaming + JSONL entry points   shard ONE proof over the GPUs
+ *       (columns c % n_dev, FRI leaf hashing by chunk range; proof bytes identical to the single-GPU proof),
+ *   sezkp_lde_commit_batch, sezkp_columns_*, sezkp_lde_commit_fri                   shard columns c % n_dev,
+ * and every other entry point runs on device_ids[0] as with a plain ctx.  sezkp_cuda_destroy releases all of it.
+ * A device id may be listed more than once (its ranks then share that GPU): useful for testing on a single GPU. */
+int32_t sezkp_cuda_create_multi(const int* device_ids, int n_dev, sezkp_ctx** out);
+int32_t sezkp_cuda_group_size(const sezkp_ctx* ctx);         /* GPUs behind this ctx (1 for sezkp_cuda_create)       */
 void sezkp_cuda_destroy(sezkp_ctx* ctx);
 const char* sezkp_cuda_last_error(const sezkp_ctx* ctx);     /* ctx may be NULL: error of the last failed create   */
 /* use_own != 0: (re)create a private non-blocking stream; else adopt the caller's cudaStream_t (NULL = legacy default
@@ -111,6 +125,21 @@ int32_t sezkp_lde_commit_batch(sezkp_ctx* ctx, const uint64_t* evals, const char
                                uint64_t shift, int chunk_log2, uint8_t* roots /* [c][32] */);
 int32_t sezkp_lde_commit_batch_dev(sezkp_ctx* ctx, const uint64_t* evals_dev, const char* const* labels, int c, int log_n,
                                    int log_blow, uint64_t shift, int chunk_log2, uint8_t* roots /* host [c][32] */);
+/* BASELINE.json configs[3] / SURVEY §8d config 4 as one call: per column LDE + labeled commitment as above, then the
+ * transcript of prove_v1 restricted to what the shape has — new("sezkp-stark/v1"), absorb n, n_cols and every col_root,
+ * challenge "alphas" (8 bytes per column, from_u64 each; sezkp-crypto/src/lib.rs:74-124, v1/params.rs:76-126) — the
+ * base-domain combination C(i) = sum_c alpha_c * col_c[i], the OOD point nudged off the coset (v1/prover.rs:118-135),
+ * deep_coset_lde_stream (v1/lde.rs:42-97) and the FRI fold-and-commit loop (v1/prover.rs:184-243; no masks, no queries).
+ * The columns are a resident set (uploaded from host arrays, or synthesised on the device with SURVEY §8d's generator
+ * value(c,i) = splitmix64_step(seed ^ c<<40 ^ i) mod p, seed 0x5EED in the benchmark); on a multi-GPU ctx column c lives on
+ * GPU c % n_dev and the exchanges are: all-gather of column roots (C1), one kernel per GPU that sums the partial
+ * combinations straight out of the peers' HBM (C3), all-gather of FRI subtree roots (C2).
+ * Outputs (host): col_roots [c][32], fri_roots [log_n+log_blow+1][32], the final FRI value. */
+int32_t sezkp_columns_upload(sezkp_ctx* ctx, const uint64_t* evals /* [c][1<<log_n] */, int c, int log_n, sezkp_columns** out);
+int32_t sezkp_columns_synth(sezkp_ctx* ctx, uint64_t seed, int c, int log_n, sezkp_columns** out);
+void sezkp_columns_free(sezkp_ctx* ctx, sezkp_columns* cols);
+int32_t sezkp_lde_commit_fri(sezkp_ctx* ctx, const sezkp_columns* cols, const char* const* labels, int log_blow, uint64_t shift,
+                             int chunk_log2, uint8_t* col_roots, uint8_t* fri_roots, uint64_t* final_value);
 /* OnDemandOpenings::open (v1/openings.rs:403-497) for k (column, row) pairs.  Per opening the outputs are
  * value (8 B LE), chunk_root (32 B), path_in_chunk (min(chunk_log2, log2 n) siblings), path_to_chunk (the rest);
  * sibling arrays are [k][depth][32] with depth_in / depth_out returned. */

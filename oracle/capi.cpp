@@ -6,6 +6,7 @@
 #include <string>
 
 #include "stark.hpp"
+#include "wide.hpp"
 
 using namespace oracle;
 
@@ -230,6 +231,54 @@ int oracle_fri_commit(const uint64_t* layer0, int log_N, const uint64_t* betas, 
             std::memcpy(roots + 32 * l, d.data(), 32);
         }
         *final_value = layers.back()[0];
+    })
+}
+
+
+/* ---- config 4 (SURVEY §8d "W"): wide LDE + labeled column commit + FRI (oracle/wide.hpp) ---- */
+/* value(c, i) of the 0x5EED splitmix generator: out[1 << log_n] */
+int oracle_wide_column(uint64_t c, int log_n, uint64_t* out) {
+    ORACLE_TRY({
+        size_t n = (size_t)1 << log_n;
+        for (size_t i = 0; i < n; i++) out[i] = wide_value(c, i);
+    })
+}
+/* iNTT -> coset LDE -> labeled leaves -> root of one column of base-domain evaluations */
+int oracle_lde_commit_root(const uint64_t* evals, int log_n, int log_blow, uint64_t shift, const char* label, uint8_t* root) {
+    ORACLE_TRY({
+        Digest d = lde_commit_root(evals, (unsigned)log_n, (unsigned)log_blow, shift, label);
+        std::memcpy(root, d.data(), 32);
+    })
+}
+/* the same for column c of the generator, label "c_{c}" */
+int oracle_wide_column_root(uint64_t c, int log_n, int log_blow, uint64_t shift, uint8_t* root) {
+    ORACLE_TRY({
+        size_t n = (size_t)1 << log_n;
+        std::vector<u64> v(n);
+        for (size_t i = 0; i < n; i++) v[i] = wide_value(c, i);
+        Digest d = lde_commit_root(v.data(), (unsigned)log_n, (unsigned)log_blow, shift, "c_" + std::to_string(c));
+        std::memcpy(root, d.data(), 32);
+    })
+}
+/* transcript -> alphas -> combination -> z -> DEEP LDE -> FRI roots.  evals [n_cols][n] or NULL (generator columns).
+ * Outputs: alphas[n_cols], z, betas[log_n+log_blow], fri_roots[(log_n+log_blow+1)][32], final value. */
+int oracle_wide_tail(const uint64_t* evals, size_t n_cols, int log_n, int log_blow, uint64_t shift, const uint8_t* col_roots,
+                     uint64_t* alphas, uint64_t* z, uint64_t* betas, uint8_t* fri_roots, uint64_t* final_value) {
+    ORACLE_TRY({
+        size_t n = (size_t)1 << log_n;
+        auto roots = digests_from(col_roots, n_cols);
+        auto col = [&](size_t c) {
+            std::vector<u64> v(n);
+            if (evals) std::memcpy(v.data(), evals + c * n, 8 * n);
+            else for (size_t i = 0; i < n; i++) v[i] = wide_value(c, i);
+            return v;
+        };
+        WideOut w = wide_tail(col, n_cols, (unsigned)log_n, (unsigned)log_blow, shift, roots);
+        if (alphas) std::memcpy(alphas, w.alphas.data(), 8 * n_cols);
+        if (z) *z = w.z;
+        if (betas) std::memcpy(betas, w.betas.data(), 8 * w.betas.size());
+        for (size_t l = 0; l < w.fri_roots.size(); l++) std::memcpy(fri_roots + 32 * l, w.fri_roots[l].data(), 32);
+        *final_value = w.final_value;
     })
 }
 

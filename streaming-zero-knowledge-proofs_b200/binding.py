@@ -28,10 +28,11 @@ EXPORTS = [
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
     "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_stark_v1_proof_bound", "sezkp_trace_upload", "sezkp_trace_free",
     "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded", "sezkp_stark_v1_prove_resident_sharded",
-    "sezkp_cuda_set_allgather_dev", "sezkp_jsonl_parse", "sezkp_jsonl_free", "sezkp_jsonl_last_error", "sezkp_stark_v1_ingest_jsonl", "sezkp_stark_v1_prove_jsonl_file",
+    "sezkp_cuda_set_allgather_dev", "sezkp_cuda_create_multi", "sezkp_cuda_group_size", "sezkp_columns_upload", "sezkp_columns_synth",
+    "sezkp_columns_free", "sezkp_lde_commit_fri", "sezkp_jsonl_parse", "sezkp_jsonl_free", "sezkp_jsonl_last_error", "sezkp_stark_v1_ingest_jsonl", "sezkp_stark_v1_prove_jsonl_file",
 ]
 
-ERR_NAMES = {0: "OK", -1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENODEV", -5: "ERANGE", -6: "ESTATE"}
+ERR_NAMES = {0: "OK", -1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENODEV", -5: "ERANGE", -6: "ESTATE", -7: "ECOMM"}
 
 
 class SezkpCudaError(RuntimeError):
@@ -61,6 +62,8 @@ def load_library() -> C.CDLL:
         lib.sezkp_fri_free.argtypes = [C.c_void_p, C.c_void_p]
         lib.sezkp_stark_v1_abort.argtypes = [C.c_void_p, C.c_void_p]
         lib.sezkp_trace_free.argtypes = [C.c_void_p, C.c_void_p]
+        lib.sezkp_columns_free.argtypes = [C.c_void_p, C.c_void_p]
+        lib.sezkp_cuda_group_size.argtypes = [C.c_void_p]
         lib.sezkp_stark_v1_proof_bound.restype = C.c_size_t
         lib.sezkp_stark_v1_proof_bound.argtypes = [C.c_uint64, C.c_uint32]
         lib.sezkp_jsonl_last_error.restype = C.c_char_p
@@ -87,13 +90,23 @@ def _vp(x) -> C.c_void_p:
 class Context:
     """One GPU, one context (one process per GPU).  Mirrors ``sezkp_ctx``."""
 
-    def __init__(self, device: int = -1):
+    def __init__(self, device: int = -1, devices: Optional[Sequence[int]] = None):
+        """device: one GPU (sezkp_cuda_create).  devices=[...]: ONE context over several GPUs of this box, driven from this
+        single process (sezkp_cuda_create_multi): prove / lde_commit / lde_commit_fri then shard over all of them."""
         self.lib = load_library()
         h = C.c_void_p()
-        rc = self.lib.sezkp_cuda_create(C.c_int(device), C.byref(h))
+        if devices is not None:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.sezkp_cuda_create_multi(ids, C.c_int(len(devices)), C.byref(h))
+        else:
+            rc = self.lib.sezkp_cuda_create(C.c_int(device), C.byref(h))
         if rc != 0:
             raise SezkpCudaError(rc, self.lib.sezkp_cuda_last_error(None).decode())
         self.h = h
+
+    @property
+    def n_gpus(self) -> int:
+        return int(self.lib.sezkp_cuda_group_size(self.h))
 
     def close(self):
         if getattr(self, "h", None):
@@ -233,6 +246,33 @@ class Context:
         fn = self.lib.sezkp_lde_commit_batch_dev if dev else self.lib.sezkp_lde_commit_batch
         self._ck(fn(self.h, ptr, arr, C.c_int(c), C.c_int(log_n), C.c_int(log_blow), C.c_uint64(shift), C.c_int(chunk_log2), _p(roots)))
         return roots
+
+    # ---- config 4: resident column sets, LDE + commit + FRI ----
+    def columns_upload(self, evals) -> "ColumnSet":
+        a = np.ascontiguousarray(evals, np.uint64)
+        c, n = a.shape
+        h = C.c_void_p()
+        self._ck(self.lib.sezkp_columns_upload(self.h, _p(a), C.c_int(c), C.c_int(n.bit_length() - 1), C.byref(h)))
+        return ColumnSet(self, h, c, n.bit_length() - 1)
+
+    def columns_synth(self, c: int, log_n: int, seed: int = 0x5EED) -> "ColumnSet":
+        """SURVEY 8d config-4 generator on the device: value(c, i) = splitmix64 step of seed ^ c<<40 ^ i, mod p."""
+        h = C.c_void_p()
+        self._ck(self.lib.sezkp_columns_synth(self.h, C.c_uint64(seed), C.c_int(c), C.c_int(log_n), C.byref(h)))
+        return ColumnSet(self, h, c, log_n)
+
+    def lde_commit_fri(self, cols: "ColumnSet", labels: Optional[Sequence[str]] = None, log_blow: int = 3, shift: int = 3, chunk_log2=10):
+        """-> (col_roots [c][32], fri_roots [log_N+1][32], final value)"""
+        labels = list(labels) if labels is not None else [f"c_{k}" for k in range(cols.c)]
+        assert len(labels) == cols.c
+        arr = (C.c_char_p * cols.c)(*[l.encode() for l in labels])
+        lN = cols.log_n + log_blow
+        cr = np.empty((cols.c, 32), np.uint8)
+        fr = np.empty((lN + 1, 32), np.uint8)
+        fin = C.c_uint64(0)
+        self._ck(self.lib.sezkp_lde_commit_fri(self.h, cols.h, arr, C.c_int(log_blow), C.c_uint64(shift), C.c_int(chunk_log2), _p(cr), _p(fr),
+                                               C.byref(fin)))
+        return cr, fr, fin.value
 
     def fri_commit(self, layer0, betas, keep=False, dev=False, log_N=None):
         b = np.ascontiguousarray(betas, np.uint64)
@@ -422,6 +462,24 @@ class ResidentTrace:
     def free(self):
         if self.h:
             self.ctx.lib.sezkp_trace_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ColumnSet:
+    """base-domain columns resident in HBM (column c on GPU c % n_gpus of the context)"""
+
+    def __init__(self, ctx: Context, h, c, log_n):
+        self.ctx, self.h, self.c, self.log_n = ctx, h, c, log_n
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.sezkp_columns_free(self.ctx.h, self.h)
             self.h = None
 
     def __del__(self):

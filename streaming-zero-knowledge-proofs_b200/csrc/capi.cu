@@ -14,9 +14,11 @@
 #include <string>
 
 #include "gl.cuh"
+#include "group.cuh"
 #include "hash.cuh"
 #include "ntt.cuh"
 #include "stark.cuh"
+#include "wide.cuh"
 
 static std::string g_create_error;
 
@@ -27,8 +29,19 @@ struct sezkp_fri {
     FriLayers fl;
 };
 struct sezkp_trace_dev {
-    DeviceTraceOwner owner;
+    DeviceTraceOwner owner;                // the ctx's own GPU (rank 0 of a group)
+    std::vector<DeviceTraceOwner> peers;   // context group: the same trace on ranks 1..world-1
 };
+struct sezkp_columns {
+    std::vector<WideColumns> part;  // one per rank (a single entry without a group)
+    int c = 0, log_n = 0;
+};
+static int group_world(const sezkp_ctx* ctx) { return ctx->group ? ctx->group->world : 1; }
+// run fn(rank, ctx_of_rank) on every GPU of the ctx's group (or inline on a plain single-GPU ctx)
+static void on_all_gpus(sezkp_ctx* ctx, const std::function<void(int, sezkp_ctx*)>& fn) {
+    if (ctx->group) group_run(ctx->group, fn);
+    else fn(0, ctx);
+}
 #define API_BEGIN(ctx)                                         \
     if (!(ctx)) return SEZKP_CUDA_EINVAL;                      \
     try {                                                      \
@@ -104,8 +117,30 @@ int32_t sezkp_cuda_create(int device_id, sezkp_ctx** out) {
     return SEZKP_CUDA_OK;
 }
 
+int32_t sezkp_cuda_create_multi(const int* device_ids, int n_dev, sezkp_ctx** out) {
+    if (!out) return SEZKP_CUDA_EINVAL;
+    *out = nullptr;
+    try {
+        sezkp_group* g = group_create(device_ids, n_dev);
+        *out = g->ctx[0];
+    } catch (const SezkpError& e) {
+        g_create_error = e.what();
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return SEZKP_CUDA_ENOMEM;
+    }
+    return SEZKP_CUDA_OK;
+}
+int32_t sezkp_cuda_group_size(const sezkp_ctx* ctx) { return ctx ? group_world(ctx) : 0; }
+
 void sezkp_cuda_destroy(sezkp_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->group) {  // the caller holds ctx[0] of a group: tear the whole group down (it calls back here per member)
+        if (ctx->group->ctx[0] == ctx) group_destroy(ctx->group);
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ntt_free_tables(ctx);
@@ -265,44 +300,11 @@ int32_t sezkp_lde_from_evals_batch(sezkp_ctx* ctx, const uint64_t* evals, int lo
     API_END(ctx)
 }
 
-// LDE + commit pipeline (BASELINE config 4 / SURVEY K7): per column group iNTT -> coset LDE -> labeled leaves -> tree.
-// The extended columns live only in a scratch buffer that is reused group by group (never all resident): at blow-up 8 a
-// 2^24-row column is 1 GiB extended.  The leaf hash is NOT fused into the LDE's last pass: BLAKE3 is ALU-bound at ~32 ps
-// per leaf while the extra HBM round trip of the extended value costs 16 B / 6.5 TB/s = 2.5 ps, and the pass's tile
-// (strided rows) does not cover whole 1024-leaf chunks.
+// LDE + commit (BASELINE config 4, first half): see wide.cu.  On a context group the columns are sharded c % world.
 static void lde_commit_device(sezkp_ctx* ctx, const u64* evals_dev, const char* const* labels, int c, int log_n, int log_blow, u64 shift,
                               int chunk_log2, u8* roots_host) {
-    const size_t n = (size_t)1 << log_n, N = n << log_blow;
-    size_t group = ((size_t)2 << 30) / (N * 8);  // ~2 GiB of extended values per group
-    if (group < 1) group = 1;
-    if (group > (size_t)c) group = (size_t)c;
-    u64* coeffs = (u64*)ctx->scratch[4].ensure(group * n * 8);
-    u64* tmp = log_n > 10 ? (u64*)ctx->scratch[0].ensure(group * n * 8) : nullptr;
-    u64* inter = log_n > 10 ? (u64*)ctx->scratch[1].ensure(group * N * 8) : nullptr;
-    u64* ext = (u64*)ctx->scratch[5].ensure(group * N * 8);
     u8* d_roots = (u8*)ctx->scratch[10].ensure((size_t)c * 32 + 64);
-    for (size_t c0 = 0; c0 < (size_t)c; c0 += group) {
-        const size_t g = (c0 + group <= (size_t)c) ? group : (size_t)c - c0;
-        CUDA_CHECK(cudaMemcpyAsync(coeffs, evals_dev + c0 * n, g * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-        ntt_batch_device(ctx, coeffs, tmp, log_n, g, true);
-        coset_lde_device(ctx, coeffs, ext, inter, log_n, log_blow, shift, g);
-        Commit cm;
-        CommitOpts o;
-        o.dedup = false;  // extended values are high-entropy
-        o.roots_dev = d_roots + c0 * 32;
-        int cl = chunk_log2;
-        if (chunk_log2 == 10 && N >= ((size_t)1 << 20)) {  // roots only: 32-leaf sub-roots out of each 1024-leaf CTA (see stark.cu)
-            o.cta_log2 = 10;
-            cl = 5;
-        }
-        try {
-            commit_build(ctx, cm, ext, N, (int)g, cl, labels + c0, o);
-        } catch (...) {
-            cm.release(ctx);
-            throw;
-        }
-        cm.release(ctx);
-    }
+    lde_commit_columns(ctx, evals_dev, labels, c, log_n, log_blow, shift, chunk_log2, d_roots);
     CUDA_CHECK(cudaMemcpyAsync(roots_host, d_roots, (size_t)c * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
@@ -319,6 +321,28 @@ int32_t sezkp_lde_commit_batch(sezkp_ctx* ctx, const uint64_t* evals, const char
     REQUIRE(evals && labels && roots && c >= 1 && log_n >= 1 && log_n <= 29 && log_blow >= 0 && log_blow <= 4, "bad argument");
     const size_t count = (size_t)c << log_n;
     check_canonical(evals, count, "evals");
+    if (ctx->group) {  // columns sharded c % world: every GPU uploads and commits its own columns, roots are gathered on the host
+        const int world = group_world(ctx), max_local = (c + world - 1) / world;
+        std::vector<u8> all((size_t)world * max_local * 32, 0);
+        group_run(ctx->group, [&](int r, sezkp_ctx* cx) {
+            WideColumns wc;
+            try {
+                wide_columns_upload(cx, wc, evals, c, log_n, r, world);
+                if (wc.n_local) {
+                    std::vector<const char*> ll;
+                    for (int j = 0; j < wc.n_local; j++) ll.push_back(labels[r + j * world]);
+                    lde_commit_device(cx, wc.evals.as<u64>(), ll.data(), wc.n_local, log_n, log_blow, shift, chunk_log2,
+                                      &all[(size_t)r * max_local * 32]);
+                }
+            } catch (...) {
+                wc.release();
+                throw;
+            }
+            wc.release();
+        });
+        for (int k = 0; k < c; k++) std::memcpy(roots + 32 * (size_t)k, &all[((size_t)(k % world) * max_local + k / world) * 32], 32);
+        return SEZKP_CUDA_OK;
+    }
     u64* d = (u64*)ctx->scratch[2].ensure(count * 8);
     h2d(ctx, d, evals, count * 8);
     lde_commit_device(ctx, d, labels, c, log_n, log_blow, shift, chunk_log2, roots);
@@ -346,6 +370,73 @@ int32_t sezkp_deep_lde(sezkp_ctx* ctx, const uint64_t* base_evals, int log_n, in
     h2d(ctx, base, base_evals, n * 8);
     deep_lde_device(ctx, base, d_out, log_n, log_blow, shift, z);
     d2h(ctx, out, d_out, N * 8);
+    API_END(ctx)
+}
+
+/* ---- resident column sets + the config-4 pipeline (wide.cu) ---- */
+int32_t sezkp_columns_upload(sezkp_ctx* ctx, const uint64_t* evals, int c, int log_n, sezkp_columns** out) {
+    API_BEGIN(ctx)
+    REQUIRE(evals && out && c >= 1 && log_n >= 1 && log_n <= 29, "bad argument");
+    *out = nullptr;
+    check_canonical(evals, (size_t)c << log_n, "evals");
+    const int world = group_world(ctx);
+    std::unique_ptr<sezkp_columns> h(new sezkp_columns());
+    h->c = c;
+    h->log_n = log_n;
+    h->part.resize(world);
+    try {
+        on_all_gpus(ctx, [&](int r, sezkp_ctx* cx) { wide_columns_upload(cx, h->part[r], evals, c, log_n, r, world); });
+    } catch (...) {
+        sezkp_columns_free(ctx, h.release());
+        throw;
+    }
+    *out = h.release();
+    API_END(ctx)
+}
+int32_t sezkp_columns_synth(sezkp_ctx* ctx, uint64_t seed, int c, int log_n, sezkp_columns** out) {
+    API_BEGIN(ctx)
+    REQUIRE(out && c >= 1 && log_n >= 1 && log_n <= 29, "bad argument");
+    *out = nullptr;
+    const int world = group_world(ctx);
+    std::unique_ptr<sezkp_columns> h(new sezkp_columns());
+    h->c = c;
+    h->log_n = log_n;
+    h->part.resize(world);
+    try {
+        on_all_gpus(ctx, [&](int r, sezkp_ctx* cx) {
+            wide_columns_synth(cx, h->part[r], seed, c, log_n, r, world);
+            CUDA_CHECK(cudaStreamSynchronize(cx->stream));
+        });
+    } catch (...) {
+        sezkp_columns_free(ctx, h.release());
+        throw;
+    }
+    *out = h.release();
+    API_END(ctx)
+}
+void sezkp_columns_free(sezkp_ctx* ctx, sezkp_columns* cols) {
+    if (!cols) return;
+    if (ctx) {
+        for (size_t r = 0; r < cols->part.size(); r++) {
+            sezkp_ctx* cx = ctx->group ? ctx->group->ctx[r] : ctx;
+            cudaSetDevice(cx->device);
+            cudaStreamSynchronize(cx->stream);
+            cols->part[r].release();
+        }
+        cudaSetDevice(ctx->device);
+    }
+    delete cols;
+}
+int32_t sezkp_lde_commit_fri(sezkp_ctx* ctx, const sezkp_columns* cols, const char* const* labels, int log_blow, uint64_t shift,
+                             int chunk_log2, uint8_t* col_roots, uint8_t* fri_roots, uint64_t* final_value) {
+    API_BEGIN(ctx)
+    REQUIRE(cols && labels && col_roots && fri_roots && final_value, "bad argument");
+    REQUIRE((int)cols->part.size() == group_world(ctx), "column set was created on a different context");
+    for (int k = 0; k < cols->c; k++) REQUIRE(labels[k] != nullptr, "label %d is NULL", k);
+    on_all_gpus(ctx, [&](int r, sezkp_ctx* cx) {
+        wide_commit_fri_rank(cx, cols->part[r], labels, log_blow, shift, chunk_log2, r == 0 ? col_roots : nullptr,
+                             r == 0 ? fri_roots : nullptr, r == 0 ? final_value : nullptr, nullptr);
+    });
     API_END(ctx)
 }
 
@@ -566,6 +657,22 @@ int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, cons
                              size_t cap, size_t* len) {
     API_BEGIN(ctx)
     REQUIRE(manifest_root && len, "bad argument");
+    if (ctx->group && trace && 3 + 7 * (int)trace->tau >= ctx->group->world) {
+        // one proof over all GPUs of the group: columns c % world per GPU, FRI hashing split by chunk range, every exchange
+        // inside the library (group.cu); rank 0 serialises into the caller's buffer, the other ranks only count bytes
+        validate_trace(trace);
+        std::vector<size_t> lens(ctx->group->world, 0);
+        group_run(ctx->group, [&](int r, sezkp_ctx* cx) {
+            ShardInfo sh{r, cx->group->world, group_allgather_host, &cx->group->ranks[r]};
+            ProofSink sink(r == 0 ? proof_buf : nullptr, r == 0 ? cap : 0);
+            prove_v1_device(cx, trace, manifest_root, sink, &sh);
+            lens[r] = sink.len;
+        });
+        ProofSink proof(proof_buf, cap);
+        proof.len = lens[0];
+        deliver(proof, proof_buf, cap, len);
+        return SEZKP_CUDA_OK;
+    }
     ProofSink proof(proof_buf, cap);
     prove_v1_device(ctx, trace, manifest_root, proof);
     deliver(proof, proof_buf, cap, len);
@@ -598,10 +705,10 @@ int32_t sezkp_trace_upload(sezkp_ctx* ctx, const sezkp_trace_desc* trace, sezkp_
     validate_trace(trace);
     sezkp_trace_dev* t = new sezkp_trace_dev();
     try {
-        t->owner.upload(ctx, trace);
+        t->peers.resize(group_world(ctx) - 1);
+        on_all_gpus(ctx, [&](int r, sezkp_ctx* cx) { (r == 0 ? t->owner : t->peers[r - 1]).upload(cx, trace); });
     } catch (...) {
-        t->owner.buf.release();
-        delete t;
+        sezkp_trace_free(ctx, t);
         throw;
     }
     *out = t;
@@ -611,12 +718,30 @@ void sezkp_trace_free(sezkp_ctx* ctx, sezkp_trace_dev* t) {
     if (!t) return;
     if (ctx) cudaSetDevice(ctx->device);
     t->owner.buf.release();
+    for (size_t r = 0; r < t->peers.size(); r++) {
+        if (ctx && ctx->group) cudaSetDevice(ctx->group->ctx[r + 1]->device);
+        t->peers[r].buf.release();
+    }
+    if (ctx) cudaSetDevice(ctx->device);
     delete t;
 }
 int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* trace, const uint8_t manifest_root[32],
                                       uint8_t* proof_buf, size_t cap, size_t* len) {
     API_BEGIN(ctx)
     REQUIRE(trace && manifest_root && len, "bad argument");
+    if (ctx->group && (int)trace->peers.size() == ctx->group->world - 1 && 3 + 7 * (int)trace->owner.t.tau >= ctx->group->world) {
+        std::vector<size_t> lens(ctx->group->world, 0);
+        group_run(ctx->group, [&](int r, sezkp_ctx* cx) {
+            ShardInfo sh{r, cx->group->world, group_allgather_host, &cx->group->ranks[r]};
+            ProofSink sink(r == 0 ? proof_buf : nullptr, r == 0 ? cap : 0);
+            prove_v1_resident(cx, r == 0 ? trace->owner.t : trace->peers[r - 1].t, manifest_root, sink, &sh);
+            lens[r] = sink.len;
+        });
+        ProofSink proof(proof_buf, cap);
+        proof.len = lens[0];
+        deliver(proof, proof_buf, cap, len);
+        return SEZKP_CUDA_OK;
+    }
     ProofSink proof(proof_buf, cap);
     prove_v1_resident(ctx, trace->owner.t, manifest_root, proof);
     deliver(proof, proof_buf, cap, len);

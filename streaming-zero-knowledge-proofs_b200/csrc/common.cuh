@@ -93,6 +93,7 @@ struct PinnedBuf {
 };
 
 struct NttTables;  // ntt.cu
+struct sezkp_group;  // group.cuh
 
 // Size-keyed caching device allocator: repeated proofs reuse their buffers instead of paying
 // cudaMalloc / cudaFree (which synchronises the device) on every call.
@@ -168,7 +169,10 @@ struct sezkp_ctx {
     bool tab_cache_enabled = true;           // option "tab_cache"
     std::vector<u8> tab_cache_key;           // subtree tables in scratch[11] were built for exactly these (ColTab[], label templates)
     bool deep_fused = false;                // option "deep_fused": one-launch DEEP kernel (per-CTA inversion) also for large domains
+    std::map<const void*, size_t> func_smem;  // kernel -> dynamic shared memory already granted on this ctx's device
     u64 launches = 0;                       // kernels launched since last reset
+    sezkp_group* group = nullptr;           // non-null: member of a multi-GPU group (sezkp_cuda_create_multi); ctx[0] is the caller's handle
+    int group_rank = 0;
     sezkp_allgather_dev_fn allgather_dev = nullptr;  // optional device-side collective of the sharded prover
     void* allgather_dev_user = nullptr;
 };

@@ -1494,11 +1494,11 @@ void commit_begin(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int 
     }
     cm.upper = (u32*)ctx->pool.alloc((size_t)cols * (2 * cm.n_ch - 1) * 32);
     if (opt.dedup && ctx->dedup_enabled && !opt.fold_src) {
-        static bool configured = false;
+        size_t& configured = ctx->func_smem[(const void*)chunk_commit_dedup128_kernel];  // per context: the attribute is per device
         if (!configured) {
             CUDA_CHECK(cudaFuncSetAttribute(chunk_commit_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem)));
             CUDA_CHECK(cudaFuncSetAttribute(chunk_commit_dedup128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Dedup128Smem)));
-            configured = true;
+            configured = 1;
         }
         u32* memo = (u32*)ctx->scratch[8].ensure((size_t)MEMO_SLOTS * MEMO_WORDS * 4);
         CUDA_CHECK(cudaMemsetAsync(memo, 0, (size_t)MEMO_SLOTS * MEMO_WORDS * 4, ctx->stream));

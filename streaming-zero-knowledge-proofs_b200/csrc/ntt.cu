@@ -430,10 +430,12 @@ static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
     d.pitch = tile_pitch(d.b, d.logR);
     const size_t smem = (((size_t)d.pitch << d.logR) + (d.b > 5 ? ((size_t)1 << d.b) : 0)) * 8;
     pass_fn fn = kernel_for_bits(d.b, d.inv != 0);
-    static std::map<pass_fn, size_t> configured;  // max dynamic smem already granted per kernel
-    if (smem > 48 * 1024 && configured[fn] < smem) {
+    // max dynamic smem already granted per kernel — per context: the attribute is per device, and the contexts of a
+    // group run on concurrent threads
+    size_t& granted = ctx->func_smem[(const void*)fn];
+    if (smem > 48 * 1024 && granted < smem) {
         CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[fn] = smem;
+        granted = smem;
     }
     fn<<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(d);
     CUDA_CHECK(cudaGetLastError());

@@ -11,7 +11,6 @@
 #include "hash.cuh"
 #include "ntt.cuh"
 #include "stark.cuh"
-#include "transcript.hpp"
 
 namespace {
 
@@ -807,24 +806,6 @@ std::vector<std::string> column_labels(u32 tau) {  // v1/openings.rs:89-116
         for (u32 r = 0; r < tau; r++) out.push_back(std::string(g) + std::to_string(r));
     return out;
 }
-
-u64 le64(const u8* p) {
-    u64 v;
-    std::memcpy(&v, p, 8);
-    return v;
-}
-
-struct TranscriptAbsorb : HostAbsorb {
-    host::Transcript& tr;
-    explicit TranscriptAbsorb(host::Transcript& t) : tr(t) {}
-    void on_root(int, const u8* root) override { tr.absorb("fri_layer_root", root, 32); }  // v1/prover.rs:187, 219, 235
-    std::vector<u64> draw_betas(int n) override {                                           // v1/params.rs:103-113
-        auto by = tr.challenge("fri_betas", 8 * (size_t)n);
-        std::vector<u64> out(n);
-        for (int i = 0; i < n; i++) out[i] = le64(&by[8 * i]) % gl::P;
-        return out;
-    }
-};
 
 }  // namespace
 

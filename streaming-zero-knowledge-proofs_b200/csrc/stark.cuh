@@ -5,6 +5,8 @@
 
 #include "common.cuh"
 #include "hash.cuh"
+#include "gl.cuh"
+#include "transcript.hpp"
 
 struct DeviceTrace {  // device image of sezkp_trace_desc (+ block_start prefix sums)
     u32 tau;
@@ -62,6 +64,23 @@ struct HostAbsorb {  // transcript hooks of the FRI commit loop
     virtual void on_root(int layer, const u8* root) = 0;
     virtual std::vector<u64> draw_betas(int n) = 0;
     virtual ~HostAbsorb() {}
+};
+// Transcript hooks of the FRI loop as prove_v1 uses them (v1/prover.rs:187, 219, 235; v1/params.rs:103-113).
+inline u64 le64(const u8* p) {
+    u64 v;
+    std::memcpy(&v, p, 8);
+    return v;
+}
+struct TranscriptAbsorb : HostAbsorb {
+    host::Transcript& tr;
+    explicit TranscriptAbsorb(host::Transcript& t) : tr(t) {}
+    void on_root(int, const u8* root) override { tr.absorb("fri_layer_root", root, 32); }
+    std::vector<u64> draw_betas(int n) override {
+        auto by = tr.challenge("fri_betas", 8 * (size_t)n);
+        std::vector<u64> out(n);
+        for (int i = 0; i < n; i++) out[i] = le64(&by[8 * i]) % gl::P;
+        return out;
+    }
 };
 struct FriLayers {
     int log_N = 0;

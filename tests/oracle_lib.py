@@ -18,7 +18,7 @@ u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 
 def build():
     so = os.path.join(ODIR, "liboracle.so")
-    srcs = [os.path.join(ODIR, f) for f in ("capi.cpp", "stark.hpp", "blake3_ref.hpp", "gl.hpp")]
+    srcs = [os.path.join(ODIR, f) for f in ("capi.cpp", "stark.hpp", "wide.hpp", "blake3_ref.hpp", "gl.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ODIR, "-s"])
     return so
@@ -192,6 +192,42 @@ class Oracle:
         self._ck(self.lib.oracle_fri_commit(l0.ctypes.data_as(C.c_void_p), C.c_int(log_n), b.ctypes.data_as(C.c_void_p),
                                             roots.ctypes.data_as(C.c_void_p), C.byref(fin)))
         return roots, fin.value
+
+    # ---- config 4 (wide LDE + commit + FRI, oracle/wide.hpp) ----
+    def wide_column(self, c, log_n) -> np.ndarray:
+        out = np.empty(1 << log_n, np.uint64)
+        self._ck(self.lib.oracle_wide_column(C.c_uint64(c), C.c_int(log_n), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def lde_commit_root(self, evals, log_blow, shift, label) -> bytes:
+        a = np.ascontiguousarray(evals, np.uint64)
+        out = C.create_string_buffer(32)
+        self._ck(self.lib.oracle_lde_commit_root(a.ctypes.data_as(C.c_void_p), C.c_int(a.size.bit_length() - 1), C.c_int(log_blow),
+                                                 C.c_uint64(shift), label.encode(), out))
+        return out.raw
+
+    def wide_column_root(self, c, log_n, log_blow=3, shift=3) -> bytes:
+        out = C.create_string_buffer(32)
+        self._ck(self.lib.oracle_wide_column_root(C.c_uint64(c), C.c_int(log_n), C.c_int(log_blow), C.c_uint64(shift), out))
+        return out.raw
+
+    def wide_tail(self, evals, n_cols, log_n, col_roots, log_blow=3, shift=3):
+        """evals [n_cols][n] or None (generator columns) -> dict(alphas, z, betas, fri_roots, final)"""
+        lN = log_n + log_blow
+        roots = np.ascontiguousarray(col_roots, np.uint8).reshape(n_cols, 32)
+        al = np.empty(n_cols, np.uint64)
+        be = np.empty(lN, np.uint64)
+        fr = np.empty((lN + 1, 32), np.uint8)
+        z, fin = C.c_uint64(0), C.c_uint64(0)
+        ev = None
+        if evals is not None:
+            ev = np.ascontiguousarray(evals, np.uint64)
+            assert ev.shape == (n_cols, 1 << log_n)
+        self._ck(self.lib.oracle_wide_tail(ev.ctypes.data_as(C.c_void_p) if ev is not None else None, C.c_size_t(n_cols), C.c_int(log_n),
+                                           C.c_int(log_blow), C.c_uint64(shift), roots.ctypes.data_as(C.c_void_p),
+                                           al.ctypes.data_as(C.c_void_p), C.byref(z), be.ctypes.data_as(C.c_void_p),
+                                           fr.ctypes.data_as(C.c_void_p), C.byref(fin)))
+        return {"alphas": al, "z": z.value, "betas": be, "fri_roots": fr, "final": fin.value}
 
     # ---- prover / verifier ----
     def prove_v1(self, ct, manifest_root: bytes, faithful_cost=False, taps=False):

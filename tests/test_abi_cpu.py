@@ -40,6 +40,9 @@ def test_no_cpu_fallback_without_gpu():
     assert ei.value.code == -4  # ENODEV
     with pytest.raises(m.SezkpCudaError):
         m.StarkV1Cuda.prove(m.demo_block(16), bytes(32))
+    with pytest.raises(m.SezkpCudaError) as ei:
+        m.Context(devices=[0, 1])  # sezkp_cuda_create_multi
+    assert ei.value.code == -4
 
 
 def test_trace_desc_layout_matches_header():

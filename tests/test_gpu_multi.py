@@ -1,0 +1,108 @@
+"""Multi-GPU context groups (sezkp_cuda_create_multi): ONE process, one worker thread + context per GPU, every exchange
+inside the library.  Outputs must be byte-identical to the single-GPU path.  A device may be listed more than once, so
+the whole group logic (sharded upload, column sharding, FRI chunk sharding, opening exchange, peer sums) is exercised on a
+single GPU too; with >= 2 GPUs the same tests also run over real peers."""
+import numpy as np
+import pytest
+
+from conftest import pkg
+from oracle_lib import P
+
+pytestmark = pytest.mark.gpu
+
+
+def device_lists():
+    import torch
+    n = torch.cuda.device_count()
+    out = [[0, 0], [0, 0, 0]]
+    if n >= 2:
+        out.append([0, 1])
+    if n >= 4:
+        out.append([0, 1, 2, 3])
+    if n >= 8:
+        out.append(list(range(8)))
+    return out
+
+
+@pytest.fixture(scope="module")
+def single():
+    return pkg().Context()
+
+
+@pytest.fixture(scope="module", params=device_lists(), ids=lambda d: "gpus" + "".join(map(str, d)))
+def group(request):
+    g = pkg().Context(devices=request.param)
+    assert g.n_gpus == len(request.param)
+    yield g
+    g.close()
+
+
+@pytest.mark.parametrize("T,b,tau", [(1 << 10, 128, 1), (1 << 12, 512, 2), (1 << 14, 512, 8), (1 << 18, 512, 3)])
+def test_group_prove_is_byte_identical(single, group, T, b, tau):
+    """host-descriptor prove: sharded upload + all-gather of the compact trace, columns c % world, FRI hashing by chunk range
+    (T = 2^18 has sharded layers of 2^21 and 2^20 values), opening records exchanged between the rank threads"""
+    m = pkg()
+    ct = m.simulate(T, b, tau, seed=5)
+    root = m.manifest_root(ct)
+    want = single.prove_v1(ct, root)
+    assert group.prove_v1(ct, root) == want
+    ct.pack_ops()
+    assert group.prove_v1(ct, root) == want
+
+
+def test_group_prove_resident(single, group):
+    m = pkg()
+    ct = m.simulate(1 << 16, 512, 8, seed=6)
+    root = m.manifest_root(ct)
+    want = single.prove_v1(ct, root)
+    rt = group.upload_trace(ct)
+    for _ in range(2):
+        assert group.prove_v1_resident(rt, root) == want
+    rt.free()
+
+
+def test_group_lde_commit_and_wide_pipeline(single, group, oracle):
+    rng = np.random.default_rng(77)
+    c, log_n = 7, 12  # 7 columns over 2 / 3 GPUs: ragged column shares
+    ev = (rng.integers(0, 1 << 63, size=(c, 1 << log_n), dtype=np.uint64) * np.uint64(2) + np.uint64(1)) % np.uint64(P)
+    labels = [f"c_{k}" for k in range(c)]
+    want_roots = single.lde_commit(ev, labels, 3)
+    assert np.array_equal(group.lde_commit(ev, labels, 3), want_roots)
+    cu_s, cu_g = single.columns_upload(ev), group.columns_upload(ev)
+    a, b = single.lde_commit_fri(cu_s), group.lde_commit_fri(cu_g)
+    cu_s.free(), cu_g.free()
+    assert np.array_equal(a[0], want_roots)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    w = oracle.wide_tail(ev, c, log_n, want_roots)
+    assert np.array_equal(b[1], w["fri_roots"]) and b[2] == w["final"]
+
+
+def test_group_wide_pipeline_sharded_fri_layers(single, group):
+    """2^18 rows x blow-up 8: FRI layers of 2^21 and 2^20 values are hashed by chunk range across the group"""
+    cs_s, cs_g = single.columns_synth(5, 18), group.columns_synth(5, 18)
+    a, b = single.lde_commit_fri(cs_s), group.lde_commit_fri(cs_g)
+    cs_s.free(), cs_g.free()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+
+
+def test_group_fewer_columns_than_gpus(single, group):
+    cs_s, cs_g = single.columns_synth(1, 10), group.columns_synth(1, 10)
+    a, b = single.lde_commit_fri(cs_s), group.lde_commit_fri(cs_g)
+    cs_s.free(), cs_g.free()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+
+
+def test_group_error_on_one_call_leaves_group_usable(single, group):
+    m = pkg()
+    bad = m.simulate(1000, 100, 2)  # not a power of two
+    with pytest.raises(m.SezkpCudaError) as ei:
+        group.prove_v1(bad, bytes(32))
+    assert ei.value.code == -1
+    ct = m.simulate(1 << 10, 128, 2, seed=9)
+    root = m.manifest_root(ct)
+    assert group.prove_v1(ct, root) == single.prove_v1(ct, root)
+
+
+def test_group_plain_entry_points_run_on_first_gpu(group, oracle):
+    v = np.arange(1 << 12, dtype=np.uint64)
+    assert np.array_equal(group.ntt(v), oracle.ntt(v))

@@ -1,0 +1,144 @@
+"""GPU parity at the NAMED benchmark shapes (BASELINE.json configs / SURVEY.md §8d): the CUDA path against oracle digests
+computed offline by tests/golden/make_named_shape_digests.py (the oracle needs minutes at these sizes), plus the config-4
+pipeline against the live oracle at small sizes."""
+import numpy as np
+import pytest
+
+from conftest import load_fixture, pkg
+from oracle_lib import P, det_vec_fast
+
+pytestmark = pytest.mark.gpu
+GOLD = load_fixture("named_shape_digests.json")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return pkg().Context()
+
+
+def b3(oracle, a):
+    return oracle.blake3(np.ascontiguousarray(a, np.uint64).tobytes()).hex()
+
+
+# ----------------------------------------------------------------------------- config 2: 64 x 2^20, blow-up 4
+def test_config2_all_64_columns_vs_oracle_digests(ctx, oracle):
+    """sezkp-ffts/benches/ntt.rs:36-99 cases on config 2's shape: forward NTT, inverse NTT, evaluate_on_coset_pow2(., 22, 3)
+    of det_vec(2^20, 2024 + c) for all 64 columns, BLAKE3 per output column against the oracle."""
+    gold = GOLD["config2_64x2^20_det_vec_seed2024+c"]
+    cols = np.stack([det_vec_fast(1 << 20, 2024 + c) for c in range(64)])
+    for c in range(64):
+        assert b3(oracle, cols[c]) == gold[str(c)]["input"], f"det_vec column {c}"
+    fwd = ctx.ntt(cols)  # one batched call over the whole [64][2^20] array, like the bench
+    for c in range(64):
+        assert b3(oracle, fwd[c]) == gold[str(c)]["forward"], f"forward NTT column {c}"
+    assert np.array_equal(ctx.ntt(fwd, inverse=True), cols)  # criterion case (ii): inverse on (i)'s output
+    inv = ctx.ntt(cols, inverse=True)
+    for c in range(64):
+        assert b3(oracle, inv[c]) == gold[str(c)]["inverse_of_input"], f"inverse NTT column {c}"
+    del fwd, inv
+    for c0 in range(0, 64, 16):  # 16 columns x 2^22 x 8 B = 512 MB of output per call
+        ext = ctx.coset_lde(cols[c0:c0 + 16], 2, 3)
+        for j in range(16):
+            assert b3(oracle, ext[j]) == gold[str(c0 + j)]["coset_k22_shift3"], f"coset LDE column {c0 + j}"
+
+
+@pytest.mark.parametrize("k", [21, 22, 24])
+def test_three_pass_ntt_vs_oracle_digest(ctx, oracle, k):
+    """2^21 / 2^22 / 2^24 use the three-pass plan; forward and inverse against the oracle (not only a round trip)."""
+    gold = GOLD["ntt_det_vec_seed7"][f"2^{k}"]
+    v = det_vec_fast(1 << k, 7)
+    assert b3(oracle, v) == gold["input"]
+    assert b3(oracle, ctx.ntt(v)) == gold["forward"]
+    assert b3(oracle, ctx.ntt(v, inverse=True)) == gold["inverse"]
+
+
+def test_lde_2e22_x8_two_columns_vs_oracle_digest(ctx, oracle):
+    """the prover's own LDE shape (n = 2^22, blow-up 8, shift 3), interpolate + coset evaluation, two columns batched"""
+    gold = GOLD["lde_2^22_x8_det_vec_seed100+c"]
+    cols = np.stack([det_vec_fast(1 << 22, 100 + c) for c in range(2)])
+    ext = ctx.lde_from_evals(cols, 3, 3)
+    for c in range(2):
+        assert b3(oracle, cols[c]) == gold[str(c)]["input"]
+        assert b3(oracle, ext[c]) == gold[str(c)]["lde_x8_shift3"], f"column {c}"
+
+
+# ----------------------------------------------------------------------------- config 1: README quick-start
+def test_quickstart_T2e15_proof_vs_oracle(ctx, oracle):
+    """sezkp-cli simulate --t 32768 --b 512 --tau 8 shape: proof bytes == live oracle == stored digest"""
+    m = pkg()
+    gold = GOLD["quickstart_T2^15_b512_tau8_seed42"]
+    ct = m.simulate(1 << 15, 512, 8, seed=42)
+    root = m.manifest_root(ct)
+    assert root.hex() == gold["manifest_root"]
+    proof = ctx.prove_v1(ct, root)
+    assert len(proof) == gold["proof_len"] and oracle.blake3(proof).hex() == gold["proof_blake3"]
+    assert proof == oracle.prove_v1(ct, root)
+
+
+# ----------------------------------------------------------------------------- config 4: wide LDE + commit + FRI
+def test_wide_generator_matches_oracle(ctx, oracle):
+    m = pkg()
+    cs = ctx.columns_synth(5, 10)
+    # the generator is checked through the pipeline below; here: uploaded oracle columns give the same roots as synthesised ones
+    ev = np.stack([oracle.wide_column(c, 10) for c in range(5)])
+    cu = ctx.columns_upload(ev)
+    a, b = ctx.lde_commit_fri(cs), ctx.lde_commit_fri(cu)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    cs.free(), cu.free()
+    assert m is not None
+
+
+@pytest.mark.parametrize("c,log_n", [(1, 4), (3, 7), (5, 10), (4, 11), (5, 14), (2, 16)])
+def test_wide_pipeline_vs_live_oracle(ctx, oracle, c, log_n):
+    """arbitrary columns and labels: column roots, FRI roots and final value of sezkp_lde_commit_fri == oracle/wide.hpp"""
+    rng = np.random.default_rng(100 * c + log_n)
+    ev = (rng.integers(0, 1 << 63, size=(c, 1 << log_n), dtype=np.uint64) * np.uint64(2) + np.uint64(1)) % np.uint64(P)
+    labels = [f"col/{k}-x" * (1 + k % 2) for k in range(c)]
+    cu = ctx.columns_upload(ev)
+    cr, fr, fin = ctx.lde_commit_fri(cu, labels)
+    cu.free()
+    want_roots = np.frombuffer(b"".join(oracle.lde_commit_root(ev[k], 3, 3, labels[k]) for k in range(c)), np.uint8).reshape(c, 32)
+    assert np.array_equal(cr, want_roots)
+    w = oracle.wide_tail(ev, c, log_n, want_roots)
+    assert np.array_equal(fr, w["fri_roots"]) and fin == w["final"]
+
+
+def check_wide_golden(ctx, key, n_cols_run):
+    g = GOLD[key]
+    log_n = g["log_n"]
+    cs = ctx.columns_synth(n_cols_run, log_n)
+    cr, fr, fin = ctx.lde_commit_fri(cs)
+    cs.free()
+    for k, want in g["column_roots"].items():
+        if int(k) < n_cols_run:
+            assert cr[int(k)].tobytes().hex() == want, f"column root {k}"
+    return cr, fr, fin, g
+
+
+def test_wide_2e20_vs_oracle_digest(ctx):
+    """0x5EED generator, 2^20 rows x blow-up 8: 8-column pipeline (roots, FRI roots, final) against the oracle"""
+    cr, fr, fin, g = check_wide_golden(ctx, "wide_0x5EED_2^20", 8)
+    p = g["pipeline"]
+    assert [r.tobytes().hex() for r in fr] == p["fri_roots"] and fin == p["final_value"]
+    # the same columns inside a wider set keep their roots (column c depends on (c, i) only): 256 columns, as config 4 names
+    cr256, _, _, _ = check_wide_golden(ctx, "wide_0x5EED_2^20", 256)
+    assert np.array_equal(cr256[:8], cr)
+
+
+def test_wide_2e24_vs_oracle_digest(ctx):
+    """config 4's named row count: 2^24 rows, N = 2^27.  8-column pipeline against the oracle (column roots, FRI roots, final)"""
+    if "wide_0x5EED_2^24" not in GOLD:
+        pytest.skip("golden digests at 2^24 not generated")
+    _, fr, fin, g = check_wide_golden(ctx, "wide_0x5EED_2^24", 8)
+    p = g["pipeline"]
+    assert [r.tobytes().hex() for r in fr] == p["fri_roots"] and fin == p["final_value"]
+
+
+def test_wide_named_shape_256_x_2e24_reproduces_oracle_roots(ctx):
+    """the full named shape, 256 columns x 2^24 rows on one GPU: the first 8 column roots equal the oracle's"""
+    if "wide_0x5EED_2^24" not in GOLD:
+        pytest.skip("golden digests at 2^24 not generated")
+    import torch
+    if torch.cuda.mem_get_info()[1] < 60 * (1 << 30):
+        pytest.skip("needs 60 GB of HBM")
+    check_wide_golden(ctx, "wide_0x5EED_2^24", 256)
