@@ -33,6 +33,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "streaming-zero-knowledge-proofs_b200"
+REAL_STDOUT = None
 METRIC = "stark_v1_prove_trace_rows_per_s"
 UNIT = "rows/s"
 
@@ -45,6 +46,11 @@ def workload():
     log_t = env_int("SEZKP_BENCH_LOG_T", 22)
     return {"workload": f"STARK v1 prove, simulated trace T=2^{log_t}, b=512, tau=8 (59 columns, blow-up 8, 30 queries)",
             "log_T": log_t, "b": 512, "tau": 8, "l2": "inputs_exceed_l2 (2 GB of committed columns per step)"}
+
+
+def full_config(n_gpus):
+    """the `config` object of the JSON line: identical for both arms (the driver compares them)"""
+    return dict(workload(), parallelism=f"independent proofs x{n_gpus}" if n_gpus > 1 else "single GPU")
 
 
 class ClockSampler(threading.Thread):
@@ -131,7 +137,14 @@ def run_reference(args, rank):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic", "config": workload(),
+        "dtype": "u64", "data": "synthetic",
+        # `config` names the workload both arms are quoted on (the contract: the reference arm runs "on your arm's config",
+        # each step a bounded sample of it); what the sample actually was is stated in `sample_config` and `cpu_baseline`
+        "config": full_config(args.gpus),
+        "sample_config": {"log_T": log_t, "b": 512, "tau": 8, "proofs_per_step": cores, "cores": cores,
+                          "note": f"each step = {cores} independent oracle proofs at T=2^{log_t} (one per host core), NOT T=2^22: "
+                                  "one oracle proof at T=2^22 takes ~28 min on one core (tests/golden/prove_digests.json: 1680 s, "
+                                  "2.5e3 rows/s/core, i.e. slower per row than this sample), so the sample flatters the CPU arm"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "single_thread_value": (1 << log_t) / single},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -165,13 +178,79 @@ def timed(torch, fn, steps):
     return s.elapsed_time(e) / steps  # ms
 
 
+def det_vec(n, seed):
+    """The input generator of the reference's criterion bench (sezkp-ffts/benches/ntt.rs:21-34), vectorised: an LCG mod 2^32
+    in closed form by affine doubling, xor i * 0x9E3779B97F4A7C15, mod p."""
+    A, Cc, p = 1664525, 1013904223, 0xFFFFFFFF00000001
+    a0 = (A * seed + Cc) & 0xFFFFFFFFFFFFFFFF
+    x = np.empty(n, np.uint64)
+    x[0] = ((a0 * A + Cc) & 0xFFFFFFFFFFFFFFFF) % (1 << 32)
+    filled, mulk, addk = 1, A, Cc
+    while filled < n:
+        take = min(filled, n - filled)
+        x[filled:filled + take] = (x[:take] * np.uint64(mulk) + np.uint64(addk)) & np.uint64(0xFFFFFFFF)
+        addk = (addk * mulk + addk) & 0xFFFFFFFF
+        mulk = (mulk * mulk) & 0xFFFFFFFF
+        filled += take
+    with np.errstate(over="ignore"):
+        i = np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    return (x ^ i) % np.uint64(p)
+
+
+def _cpu_micro_worker(job):
+    """one oracle micro case in a worker process (cpu_baseline leg): returns seconds"""
+    kind, k, cols, seed = job
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    orc = oracle_lib.load()
+    if kind == "blake3":
+        v = det_vec(1 << k, seed)
+        t0 = time.perf_counter()
+        orc.streaming_layer_root(v)  # 2^k leaf hashes + 2^k - 1 parent combiners
+        return time.perf_counter() - t0
+    v = np.stack([det_vec(1 << k, seed + c) for c in range(cols)])
+    t0 = time.perf_counter()
+    if kind == "ntt_forward":
+        orc.ntt(v)
+    elif kind == "ntt_inverse":
+        orc.ntt(v, inverse=True)
+    else:
+        orc.coset_eval(v, k + 2, 3)
+    return time.perf_counter() - t0
+
+
+def cpu_micro_baselines():
+    """BASELINE.md §3 micro baselines: the three criterion cases of sezkp-ffts/benches/ntt.rs:36-99 (2^16, 2^18, seed 2024,
+    shift 3, blow-up 4) and config 2's 2^20, plus BLAKE3 leaf + parent hashing of 2^20 leaves — oracle port, 1 core and all
+    cores (one column / one tree per core; the reference itself is single-threaded).  Bounded to ~20 s of CPU work."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    out = {"cores_all": cores, "kind": "port (oracle/, u128 % p arithmetic like the reference's Fp64::mul_raw)"}
+    with mp.get_context("fork").Pool(cores) as pool:
+        for kind in ("ntt_forward", "ntt_inverse", "coset_lde_x4"):
+            for k in (16, 18, 20):
+                n = 1 << k
+                bytes_per_col = 16 * n if kind.startswith("ntt") else 8 * n * 5
+                t1 = _cpu_micro_worker((kind, k, 1, 2024))
+                tall = max(pool.map(_cpu_micro_worker, [(kind, k, 1, 2024 + c) for c in range(cores)]))
+                out[f"{kind}_2^{k}"] = {"one_core": {"ms_per_column": t1 * 1e3, "elements_per_s": n / t1, "GBps": bytes_per_col / t1 / 1e9},
+                                        "all_cores": {"columns": cores, "ms": tall * 1e3, "elements_per_s": cores * n / tall,
+                                                      "GBps": cores * bytes_per_col / tall / 1e9}}
+        k = 20
+        t1 = _cpu_micro_worker(("blake3", k, 1, 1))
+        tall = max(pool.map(_cpu_micro_worker, [("blake3", k, 1, 1 + c) for c in range(cores)]))
+        comp = 2 * (1 << k) - 1
+        out["blake3_leaf_plus_parent_2^20_leaves"] = {"one_core": {"compressions_per_s": comp / t1},
+                                                      "all_cores": {"trees": cores, "compressions_per_s": cores * comp / tall}}
+    return out
+
+
 def micro_bench(torch, ctx, hbm_peak):
     """Config 2 (BASELINE.json configs[1]): 64 columns x 2^20, det_vec(seed 2024+c); forward NTT, inverse NTT, coset LDE x4."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     cols, k, lb = 64, 20, 2
     n = 1 << k
-    rng = np.random.default_rng(2024)
-    host = (rng.integers(0, 1 << 63, size=(cols, n), dtype=np.uint64) % np.uint64(0xFFFFFFFF00000001))
+    host = np.stack([det_vec(n, 2024 + c) for c in range(cols)])
     d = torch.from_numpy(host.view(np.int64)).cuda()
     out = torch.empty((cols, n << lb), dtype=torch.int64, device="cuda")
     res = {}
@@ -195,45 +274,81 @@ def micro_bench(torch, ctx, hbm_peak):
     return res
 
 
-def lde_commit_bench(torch, dist, ctx, rank, world, hbm_peak, steps):
-    """BASELINE configs[3] shape family (LDE + labeled BLAKE3 column commit), columns sharded c % world, roots all-gathered
-    with NCCL.  Default 64 columns x 2^22 rows, blow-up 8 (SEZKP_W_COLS / SEZKP_W_LOG_N select e.g. the full 256 x 2^24)."""
-    cols, k, lb = env_int("SEZKP_W_COLS", 64), env_int("SEZKP_W_LOG_N", 22), 3
-    n = 1 << k
-    mine = list(range(rank, cols, world))
-    g = torch.Generator(device="cuda")
-    g.manual_seed(0x5EED + rank)
-    ev = torch.randint(0, (1 << 62), (max(len(mine), 1), n), dtype=torch.int64, device="cuda", generator=g)  # < 2^62 < p: canonical
-    labels = [f"c_{c}" for c in mine]
-
-    def step():
-        roots = ctx.lde_commit(ev, labels, lb, 3, dev=True, log_n=k) if mine else np.zeros((0, 32), np.uint8)
-        if world > 1:  # C1: all-gather of 32-byte column roots (padded to the per-rank maximum)
-            pad = torch.zeros(((cols + world - 1) // world) * 32, dtype=torch.uint8, device="cuda")
-            pad[: roots.size] = torch.from_numpy(roots.reshape(-1)).cuda()
-            out = [torch.empty_like(pad) for _ in range(world)]
-            dist.all_gather(out, pad)
-        return roots
-
-    step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) * 1e3 / steps
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    alg = cols * (8 * n * (1 + (1 << lb)) + 8 * (n << lb))  # LDE (read n, write B*n) + commit (read B*n)
-    del ev
-    return {"workload": f"{cols} columns x 2^{k} rows, blow-up 8: iNTT + coset LDE + labeled BLAKE3 commit, columns sharded over {world} GPU(s)",
-            "ms_per_step": ms, "rows_per_s": n / (ms / 1e3), "algorithmic_GB": alg / 1e9, "GBps": alg / ms / 1e6,
+def wide_bench(m, devices, hbm_peak, steps):
+    """BASELINE configs[3] / SURVEY 8d config 4 as named: 256 columns x 2^24 rows (SEZKP_W_COLS / SEZKP_W_LOG_N), blow-up 8:
+    per column iNTT + coset LDE + labeled BLAKE3 commit, then alphas -> combination -> DEEP LDE -> FRI fold-and-commit.
+    ONE process, one multi-GPU context (sezkp_cuda_create_multi): column c on GPU c % N, every exchange inside the library
+    over NVLink peer access (C1 column roots, C3 peer-sum kernel, C2 FRI subtree roots).  Columns are synthesised on the
+    device (SURVEY's 0x5EED generator) and resident before the timed region."""
+    cols, k, lb = env_int("SEZKP_W_COLS", 256), env_int("SEZKP_W_LOG_N", 24), 3
+    n, world = 1 << k, len(devices)
+    g = m.Context(devices=devices) if world > 1 else m.Context(devices[0])
+    try:
+        cs = g.columns_synth(cols, k)
+        cr, fr, fin = g.lde_commit_fri(cs)  # warm-up (tables, pools)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cr, fr, fin = g.lde_commit_fri(cs)
+        wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+        tm = g.timings()
+        cs.free()
+    finally:
+        g.close()
+    ms = tm.get("device_ms_max_over_gpus", wall_ms)
+    golden = None
+    gp = os.path.join(ROOT, "tests", "golden", "named_shape_digests.json")
+    key = f"wide_0x5EED_2^{k}"
+    if os.path.exists(gp) and key in json.load(open(gp)):
+        want = json.load(open(gp))[key]["column_roots"]
+        golden = all(cr[int(c)].tobytes().hex() == h for c, h in want.items() if int(c) < cols)
+    N = n << lb
+    lde_bytes = cols * 8 * n * (1 + (1 << lb))          # SURVEY 8d: LDE from evaluations, 8 n (1 + B) per column
+    commit_bytes = cols * 8 * N                          # column commit from values, root only: 8 N per column
+    fri_bytes = 24 * N + 8 * n * (1 + (1 << lb))         # DEEP LDE of the one combination vector + FRI (~24 N)
+    alg = lde_bytes + commit_bytes + fri_bytes
+    comp = cols * (2 * N - 1) + 2 * (2 * N - 1)
+    return {"workload": f"{cols} columns x 2^{k} rows, blow-up 8: iNTT + coset LDE + labeled BLAKE3 commit + alphas + combination + DEEP LDE "
+                        f"+ FRI ({k + lb + 1} layers), columns sharded c % {world} over {world} GPU(s), one process (context group)",
+            "n_gpus": world, "ms_per_step": ms, "wall_ms_per_step": wall_ms, "rows_per_s": n / (ms / 1e3),
+            "column_rows_per_s": cols * n / (ms / 1e3), "algorithmic_GB": alg / 1e9, "GBps": alg / ms / 1e6,
             "GBps_per_gpu": alg / ms / 1e6 / world, "frac_of_hbm_peak_per_gpu": alg / ms / 1e6 / world / hbm_peak,
-            "leaf_compressions_per_s": cols * (2 * (n << lb) - 1) / (ms / 1e3)}
+            "compressions_per_s": comp / (ms / 1e3), "compressions_per_s_per_gpu": comp / (ms / 1e3) / world,
+            "frac_of_alu_pipe_bound_per_gpu": comp / (ms / 1e3) / world / (148 * 64 * 1.965e9 / 455),
+            "phases_ms_gpu0": tm, "first_columns_match_oracle_digests": golden,
+            "timing": "CUDA events on every GPU's stream inside the library, max over GPUs (wall clock of the blocking call next to it)"}
+
+
+def group_prove_bench(torch, m, devices, ct, root, proof_buf, want_proof, steps):
+    """ONE proof (the headline workload) sharded over the GPUs of one multi-GPU context: host pinned input -> proof bytes,
+    and the same with the compact trace resident on every GPU.  No torchrun, no callbacks: a single sezkp_stark_v1_prove."""
+    g = m.Context(devices=devices)
+    try:
+        g.set_option("tab_cache", 0)
+        for _ in range(2):
+            p = g.prove_v1(ct, root, proof_buf)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            p = g.prove_v1(ct, root, proof_buf, view=True)
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+        same = bytes(p) == want_proof
+        e2e_ph = g.timings()
+        rt = g.upload_trace(ct)
+        for _ in range(2):
+            g.prove_v1_resident(rt, root, proof_buf)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            p = g.prove_v1_resident(rt, root, proof_buf, view=True)
+        res_ms = (time.perf_counter() - t0) * 1e3 / steps
+        same = same and bytes(p) == want_proof
+        res_ph = g.timings()
+        rt.free()
+    finally:
+        g.close()
+    T = ct.n_rows
+    return {"n_gpus": len(devices), "api": "sezkp_cuda_create_multi + sezkp_stark_v1_prove (one process, exchanges inside the library)",
+            "e2e_ms_per_proof": e2e_ms, "e2e_rows_per_s": T / (e2e_ms / 1e3), "resident_ms_per_proof": res_ms,
+            "resident_rows_per_s": T / (res_ms / 1e3), "identical_to_single_gpu_proof": bool(same),
+            "e2e_phases_ms_gpu0": e2e_ph, "resident_phases_ms_gpu0": res_ph}
 
 
 def jsonl_stream_bench(torch, ctx, m, steps):
@@ -291,6 +406,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # native libraries (NCCL_DEBUG=INFO, CUDA) write to fd 1: point fd 1 at stderr for the whole run and keep the real
+    # stdout for the single JSON line
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -298,8 +419,12 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("SEZKP_NCCL_DEBUG", "NONE")  # keep stdout to the one JSON line
+        # NCCL_DEBUG is left as the caller set it (the driver reads the communicator lines); see REAL_STDOUT below for how
+        # stdout still carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_pg = dist.new_group(backend="gloo")  # host-only barriers (an NCCL barrier would park a spinning kernel on every GPU)
+    else:
+        host_pg = None
     m = importlib.import_module(PKG)
     ctx = m.Context(local)
     stream = torch.cuda.Stream()  # the library launches on torch's current stream so torch events bracket its work
@@ -348,6 +473,18 @@ def main():
     phases = ctx.timings()
     ms = max_over_ranks(ms)
     value = world * T / (ms / 1e3)
+
+    # ---- worst-case step: the same proof with the value-aware column commit switched off (one compression per tree node,
+    #      what a trace whose columns defeat every structure class costs); identical proof bytes ----
+    ctx.set_option("dedup", 0)
+    ctx.set_option("tabled", 0)
+    for _ in range(2):
+        p_worst = ctx.prove_v1_resident(rt, root, proof_buf)
+    wc_ms = max_over_ranks(timed(torch, lambda: ctx.prove_v1_resident(rt, root, proof_buf, view=True), max(3, args.steps // 2)))
+    worst_case = {"ms_per_step": wc_ms, "rows_per_s": world * T / (wc_ms / 1e3), "identical_proof": bool(p_worst == proof),
+                  "note": "dedup=0, tabled=0: plain chunk_commit kernel for the 59 trace columns"}
+    ctx.set_option("dedup", 2)
+    ctx.set_option("tabled", 1)
 
     # ---- end-to-end arm: host (pinned) buffers through the public API ----
     for _ in range(min(args.warmup, 2)):
@@ -476,8 +613,26 @@ def main():
                                               "(dedup); plain = one compression per node; all three give identical roots"}}
         micro = None if args.no_micro else micro_bench(torch, ctx, hbm_peak)
         jsonl_stream = None if args.no_micro else jsonl_stream_bench(torch, ctx, m, 2)
-    # BASELINE configs[3] family last: ~0.7 s of sustained hashing per step, after which the board sits at its power cap
-    lde_commit = None if args.no_micro else lde_commit_bench(torch, dist, ctx, rank, world, hbm_peak, max(2, min(args.steps, 3)))
+    # ---- single-process multi-GPU legs (sezkp_cuda_create_multi): rank 0 alone drives ALL GPUs of the job through one
+    #      context group; the other ranks release their GPU memory and wait at a host-side barrier ----
+    ctx.close()
+    ctx = None
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(group=host_pg)
+    wide = group_prove = None
+    if rank == 0:
+        devices = list(range(world))
+        if world > 1:
+            group_prove = group_prove_bench(torch, m, devices, ct, root, proof_buf, proof, args.steps)
+        # BASELINE configs[3] last: seconds of sustained hashing per step, after which the boards sit at their power cap
+        if not args.no_micro:
+            wide = wide_bench(m, devices, hbm_peak, max(1, min(args.steps, 2)))
+    if world > 1:
+        dist.barrier(group=host_pg)
     if rank == 0:
 
         sampler.stop_flag = True  # the GPU is idle from here on
@@ -492,7 +647,9 @@ def main():
         t0 = time.perf_counter()
         cproof = orc.prove_v1(cct, croot)
         cdt = time.perf_counter() - t0
+        ctx = m.Context(local)
         parity = ctx.prove_v1(cct, croot) == cproof  # same bytes on the same input (checker role of the oracle)
+        ctx.close()
         # the reference's actual cost profile: its layer-0 FRI paths re-run the whole DEEP-LDE stream once per Merkle level
         # (v1/fri_stream.rs:273-309) — timed with the oracle's faithful-cost mode at a size that finishes in seconds
         log_f = env_int("SEZKP_CPU_FAITHFUL_LOG_T", 8)
@@ -504,6 +661,7 @@ def main():
         faithful = {"value": (1 << log_f) / fdt, "unit": UNIT, "log_T": log_f, "seconds": fdt,
                     "identical_to_compute_once": bool(fproof == orc.prove_v1(fct, froot)),
                     "note": "30 queries x 2 paths x log2(8n) full recomputations of the LDE stream, like the reference"}
+        micro_cpu = None if args.no_micro else cpu_micro_baselines()
         cpu_baseline = {"value": (1 << log_c) / cdt, "unit": UNIT, "cores": 1, "kind": "port", "faithful_cost": faithful,
                         "sample": f"one oracle prove_v1 at T=2^{log_c}, b=512, tau=8 ({cdt:.1f} s); reference is single-threaded",
                         "gpu_proof_identical": bool(parity)}
@@ -511,19 +669,23 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 (Goldilocks field) / u32 (BLAKE3)", "data": "synthetic",
-            "config": dict(wl, parallelism=f"independent proofs x{world}" if world > 1 else "single GPU"),
+            "config": full_config(world),
             "clocks": sampler.summary(),
             "e2e": {"value": world * T / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "api": "sezkp_stark_v1_prove (host pinned buffers)"},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "phases_ms": phases, "e2e_phases_ms": e2e_phases, "proof_bytes": len(proof), "micro": micro, "lde_commit": lde_commit, "jsonl_stream": jsonl_stream, "sharded_single_proof": sharded,
+            "phases_ms": phases, "e2e_phases_ms": e2e_phases, "proof_bytes": len(proof), "worst_case_step": worst_case, "micro": micro,
+            "micro_cpu": micro_cpu, "lde_commit_fri": wide, "jsonl_stream": jsonl_stream, "sharded_single_proof": group_prove,
+            "sharded_single_proof_nccl_callbacks": sharded,
         }
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        REAL_STDOUT.write(json.dumps(out) + "\n")
+        REAL_STDOUT.flush()
 
 
 if __name__ == "__main__":

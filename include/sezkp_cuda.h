@@ -57,6 +57,7 @@ int32_t sezkp_cuda_create(int device_id, sezkp_ctx** out);   /* device_id < 0: c
  * A device id may be listed more than once (its ranks then share that GPU): useful for testing on a single GPU. */
 int32_t sezkp_cuda_create_multi(const int* device_ids, int n_dev, sezkp_ctx** out);
 int32_t sezkp_cuda_group_size(const sezkp_ctx* ctx);         /* GPUs behind this ctx (1 for sezkp_cuda_create)       */
+int32_t sezkp_cuda_device_count(void);                       /* usable CUDA devices in this process (0: none)        */
 void sezkp_cuda_destroy(sezkp_ctx* ctx);
 const char* sezkp_cuda_last_error(const sezkp_ctx* ctx);     /* ctx may be NULL: error of the last failed create   */
 /* use_own != 0: (re)create a private non-blocking stream; else adopt the caller's cudaStream_t (NULL = legacy default

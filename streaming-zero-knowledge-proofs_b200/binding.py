@@ -28,7 +28,7 @@ EXPORTS = [
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
     "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_stark_v1_proof_bound", "sezkp_trace_upload", "sezkp_trace_free",
     "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded", "sezkp_stark_v1_prove_resident_sharded",
-    "sezkp_cuda_set_allgather_dev", "sezkp_cuda_create_multi", "sezkp_cuda_group_size", "sezkp_columns_upload", "sezkp_columns_synth",
+    "sezkp_cuda_set_allgather_dev", "sezkp_cuda_create_multi", "sezkp_cuda_group_size", "sezkp_cuda_device_count", "sezkp_columns_upload", "sezkp_columns_synth",
     "sezkp_columns_free", "sezkp_lde_commit_fri", "sezkp_jsonl_parse", "sezkp_jsonl_free", "sezkp_jsonl_last_error", "sezkp_stark_v1_ingest_jsonl", "sezkp_stark_v1_prove_jsonl_file",
 ]
 

@@ -134,6 +134,14 @@ int32_t sezkp_cuda_create_multi(const int* device_ids, int n_dev, sezkp_ctx** ou
     return SEZKP_CUDA_OK;
 }
 int32_t sezkp_cuda_group_size(const sezkp_ctx* ctx) { return ctx ? group_world(ctx) : 0; }
+int32_t sezkp_cuda_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
 
 void sezkp_cuda_destroy(sezkp_ctx* ctx) {
     if (!ctx) return;
@@ -192,6 +200,9 @@ int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value) {
         if (value == 1 || value == 2) ctx->dedup_variant = (int)value;
     } else if (std::strcmp(name, "tabled") == 0) {
         ctx->tabled_enabled = value != 0;
+    } else if (std::strcmp(name, "ntt_gen") == 0) {
+        REQUIRE(value == 1 || value == 2, "ntt_gen must be 1 or 2");
+        ctx->ntt_gen = (int)value;
     } else if (std::strcmp(name, "deep_fused") == 0) {
         ctx->deep_fused = value != 0;
     } else if (std::strcmp(name, "tab_cache") == 0) {
@@ -437,6 +448,11 @@ int32_t sezkp_lde_commit_fri(sezkp_ctx* ctx, const sezkp_columns* cols, const ch
         wide_commit_fri_rank(cx, cols->part[r], labels, log_blow, shift, chunk_log2, r == 0 ? col_roots : nullptr,
                              r == 0 ? fri_roots : nullptr, r == 0 ? final_value : nullptr, nullptr);
     });
+    double dev_max = 0;  // every GPU timed its own part with CUDA events on its stream: report the maximum
+    for (int r = 0; r < group_world(ctx); r++)
+        for (auto& kv : (ctx->group ? ctx->group->ctx[r] : ctx)->timings)
+            if (kv.first == "device_ms" && kv.second > dev_max) dev_max = kv.second;
+    ctx->timings.push_back({"device_ms_max_over_gpus", dev_max});
     API_END(ctx)
 }
 

@@ -229,15 +229,159 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const PassDesc
     }
 }
 
+// Second-generation pass kernel (two-step passes, b >= 6): global loads go straight into the registers of the thread
+// that runs the first register DFT on them, and the second register DFT's results go straight from registers to HBM.
+// The shared-memory tile is touched once (written after step 1, read by step 2) instead of three times, and two of the
+// three block barriers disappear.  Why this works without any shuffle: in the first-generation kernel the thread that
+// copied rows {r2 + B*t} of column c into the tile was already the thread that ran step 1 on exactly those rows, and the
+// thread that ran step 2 for (c, k1) was the one that stored rows {k1 + A*k2} — both round trips were thread-private.
+//   columns contiguous in HBM (strided passes):  task = (c fastest, r2 / k1 slowest)  -> a warp touches 32/R rows x R*8 B
+//   rows contiguous in HBM (last pass / single pass): task = (r2 or k1 fastest)      -> a warp touches B*8 (A*8) contiguous B
+// The inter-step twiddles w_{2^b}^(r2*k1) sit in shared memory as a [A][B] matrix so that both task mappings read them
+// without bank conflicts (a flat power table indexed r2*k1 is a stride-k1 access when r2 runs across the lanes).
+template <int K1, int K2, bool INV>
+__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass2_kernel(const PassDesc d) {
+    extern __shared__ u64 smem[];
+    constexpr int A = 1 << K1, B = 1 << K2, b = K1 + K2, rows = 1 << b;
+    static_assert(K2 > 0, "two-step passes only");
+    const int pitch = d.pitch, logR = d.logR, R = 1 << logR;
+    u64* tile = smem;
+    u64* Ws = smem + (size_t)R * pitch;  // [A][B]: Ws[k1*B + r2] = w^(r2*k1)
+    const u32 eps = gl::lazy::k_eps32;
+    const int tid = threadIdx.x;
+
+    const u32 tile_id = blockIdx.x;
+    const u32 ct = tile_id % d.col_tiles;
+    const u32 rest = tile_id / d.col_tiles;
+    const u32 u = rest % d.U;
+    const u64 v = rest / d.U;
+    const u64 C0 = (u64)ct << logR;
+    const u64* in_base = d.in + u * d.in_u_stride + (v >> d.in_v_shift) * d.in_v_stride;
+    u64* out_base = d.out + u * d.out_u_stride + v * d.out_v_stride;
+
+    for (int i = tid; i < rows; i += NTT_THREADS) Ws[i] = d.W[(i >> K2) * (i & (B - 1))];
+
+    // ---- step 1: A-point DFTs over r1 of rows B*r1 + r2, operands straight from HBM ----
+    const int tasks1 = B << logR;
+    for (int g0 = 0; g0 < tasks1; g0 += NTT_THREADS) {
+        const int g = g0 + tid;
+        const bool live = g < tasks1;
+        int c, r2;
+        if (d.load_rows_fast) {
+            r2 = g & (B - 1);
+            c = g >> K2;
+        } else {
+            c = g & (R - 1);
+            r2 = g >> logR;
+        }
+        const u64 C = C0 + c;
+        u64 x[A];
+        if (live && C < d.total_cols) {
+            const u64* src = in_base + (C & ((1ULL << d.in_clog) - 1)) * d.in_cs_lo + (C >> d.in_clog) * d.in_cs_hi + (u64)r2 * d.in_row_stride;
+            const u64 rs = d.in_row_stride << K2;  // rows r2 + B*t
+#pragma unroll
+            for (int t = 0; t < A; t++) x[t] = src[(u64)t * rs];
+            if (d.use_pre) {
+                const u32 j = (u32)((d.coset_from_col ? C : v) & ((1u << d.coset_log) - 1));
+                const u64* ga = d.GA + (size_t)j * d.ga_pitch + r2;
+                if (d.use_gb) {
+                    const u64 gbc = d.GB[(size_t)j * d.gb_pitch + C];
+#pragma unroll
+                    for (int t = 0; t < A; t++) x[t] = gl::lazy::mulc(x[t], gl::lazy::mulc(ga[t << K2], gbc, eps), eps);
+                } else {
+#pragma unroll
+                    for (int t = 0; t < A; t++) x[t] = gl::lazy::mulc(x[t], ga[t << K2], eps);
+                }
+            } else if (d.canon_in) {
+#pragma unroll
+                for (int t = 0; t < A; t++) x[t] = gl::lazy::canon2(x[t]);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < A; t++) x[t] = 0;
+        }
+        if (g0 == 0) __syncthreads();  // Ws complete (the global loads above are already in flight)
+        if (live) {
+            gl::lazy::dft_pow2<K1, INV>(x, eps);
+            u64* col = tile + c * pitch + r2;
+            const u64* wrow = Ws + r2;
+#pragma unroll
+            for (int k = 0; k < A; k++) {
+                const u64 y = x[gl::lazy::brev_bits(k, K1)];
+                col[k * (B + 1)] = k == 0 ? gl::lazy::canon2(y) : gl::lazy::mulc(y, wrow[k << K2], eps);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- step 2: B-point DFTs over r2, results straight to HBM (inter-pass twiddle, scale, canonical) ----
+    const int tasks2 = A << logR;
+    for (int g = tid; g < tasks2; g += NTT_THREADS) {
+        int c, k1;
+        if (d.store_rows_fast) {
+            k1 = g & (A - 1);
+            c = g >> K1;
+        } else {
+            c = g & (R - 1);
+            k1 = g >> logR;
+        }
+        const u64 C = C0 + c;
+        if (C >= d.total_cols) continue;
+        const u64* col = tile + c * pitch + k1 * (B + 1);
+        u64 x[B];
+#pragma unroll
+        for (int t = 0; t < B; t++) x[t] = col[t];
+        gl::lazy::dft_pow2<K2, INV>(x, eps);
+        u64* dst = out_base + (C & ((1ULL << d.out_clog) - 1)) * d.out_cs_lo + (C >> d.out_clog) * d.out_cs_hi + (u64)k1 * d.out_row_stride;
+        const u64 rs = d.out_row_stride << K1;  // rows k1 + A*k2
+        if (d.use_tw) {
+            if (d.tw_full) {
+                const u64* twf = d.tw_full + C + (u64)k1 * d.tw_pitch;
+                const u64 tp = d.tw_pitch << K1;
+                constexpr int G = B < 8 ? B : 8;  // twiddle loads in flight per thread (registers: x[] already holds 2*B)
+#pragma unroll
+                for (int k0 = 0; k0 < B; k0 += G) {
+                    u64 w[G];
+#pragma unroll
+                    for (int q = 0; q < G; q++) w[q] = twf[(u64)(k0 + q) * tp];
+#pragma unroll
+                    for (int q = 0; q < G; q++) {
+                        u64 y = gl::lazy::mulc(x[gl::lazy::brev_bits(k0 + q, K2)], w[q], eps);
+                        if (d.use_scale) y = gl::lazy::mulc(y, d.scale, eps);
+                        dst[(u64)(k0 + q) * rs] = y;
+                    }
+                }
+            } else {
+                const u64 Cs = C * d.tw_stride;
+#pragma unroll 4
+                for (int k2 = 0; k2 < B; k2++) {
+                    const u64 E = (u64)(k1 + (k2 << K1)) * Cs;
+                    const u64 w = gl::lazy::mulc(d.tw_lo[E & ((1ULL << d.tw_lb) - 1)], d.tw_hi[E >> d.tw_lb], eps);
+                    u64 y = gl::lazy::mulc(x[gl::lazy::brev_bits(k2, K2)], w, eps);
+                    if (d.use_scale) y = gl::lazy::mulc(y, d.scale, eps);
+                    dst[(u64)k2 * rs] = y;
+                }
+            }
+        } else if (d.use_scale) {
+#pragma unroll
+            for (int k2 = 0; k2 < B; k2++) dst[(u64)k2 * rs] = gl::lazy::mulc(x[gl::lazy::brev_bits(k2, K2)], d.scale, eps);
+        } else {
+#pragma unroll
+            for (int k2 = 0; k2 < B; k2++) dst[(u64)k2 * rs] = gl::lazy::canon2(x[gl::lazy::brev_bits(k2, K2)]);
+        }
+    }
+}
+
 // Full inter-pass twiddle matrix T[k][J] = w^(k*J*stride) (k < rows, J < pitch): same shape as the data block, so the
 // store loop reads it with the data's own coalescing; it stays in L2 across the columns of a batch.
+// `scale` (N^-1 of an inverse transform, else 1) is folded into the first pass's matrix, so the last pass of an inverse
+// NTT canonicalises instead of multiplying every element once more.
 __global__ void tw_fill_kernel(u64* __restrict__ out, u64 count, u64 pitch, u64 stride, const u64* __restrict__ lo,
-                               const u64* __restrict__ hi, int lb) {
+                               const u64* __restrict__ hi, int lb, u64 scale) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const u64 k = i / pitch, J = i - k * pitch;
     const u64 E = k * J * stride;
-    out[i] = gl::mul(lo[E & ((1ULL << lb) - 1)], hi[E >> lb]);
+    out[i] = gl::mul(gl::mul(lo[E & ((1ULL << lb) - 1)], hi[E >> lb]), scale);
 }
 
 typedef void (*pass_fn)(const PassDesc);
@@ -250,7 +394,18 @@ void split_bits(int b, int& K1, int& K2) {
     K1 = k1[b];
     K2 = b - K1;
 }
-pass_fn kernel_for_bits(int b, bool inv) {
+template <int K1, int K2>
+pass_fn get_fn2(bool inv) { return inv ? ntt_pass2_kernel<K1, K2, true> : ntt_pass2_kernel<K1, K2, false>; }
+// second-generation kernel (fused global I/O) for the two-step widths; `gen` 1 selects the first-generation kernel (A/B runs)
+pass_fn kernel_for_bits(int b, bool inv, int gen) {
+    if (gen >= 2) switch (b) {
+        case 6: return get_fn2<3, 3>(inv);
+        case 7: return get_fn2<4, 3>(inv);
+        case 8: return get_fn2<4, 4>(inv);
+        case 9: return get_fn2<5, 4>(inv);
+        case 10: return get_fn2<5, 5>(inv);
+        default: break;
+    }
     switch (b) {
         case 1: return get_fn<1, 0>(inv);
         case 2: return get_fn<2, 0>(inv);
@@ -289,6 +444,7 @@ struct NttTables {
     u64* tw_full[3] = {nullptr, nullptr, nullptr};  // per non-last pass, built on first use when the transform is small enough
     int tw_lb = 0;
     u64 scale = 1;  // N^-1 for inverse
+    bool tw0_scaled = false;  // tw_full[0] already carries `scale`
     // coset tables, keyed by (logB, shift)
     struct Coset {
         u64* GA = nullptr;
@@ -429,7 +585,7 @@ static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
     REQUIRE(tiles > 0 && tiles < (1ULL << 31), "NTT grid too large (%llu tiles)", (unsigned long long)tiles);
     d.pitch = tile_pitch(d.b, d.logR);
     const size_t smem = (((size_t)d.pitch << d.logR) + (d.b > 5 ? ((size_t)1 << d.b) : 0)) * 8;
-    pass_fn fn = kernel_for_bits(d.b, d.inv != 0);
+    pass_fn fn = kernel_for_bits(d.b, d.inv != 0, ctx->ntt_gen);
     // max dynamic smem already granted per kernel — per context: the attribute is per device, and the contexts of a
     // group run on concurrent threads
     size_t& granted = ctx->func_smem[(const void*)fn];
@@ -442,7 +598,7 @@ static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
     ctx->launches++;
 }
 
-constexpr int FULL_TW_MAX_LOG = 23;  // full twiddle matrices up to 2^23 entries (64 MiB) per pass
+constexpr int FULL_TW_MAX_LOG = 24;  // full twiddle matrices up to 2^24 entries (128 MiB) per pass
 static void attach_full_twiddles(sezkp_ctx* ctx, NttTables* t, PassDesc& d, int p, u64 rows, u64 Sp, u64 stride) {
     const u64 count = rows * Sp;
     if (count > (1ULL << FULL_TW_MAX_LOG)) return;
@@ -452,9 +608,12 @@ static void attach_full_twiddles(sezkp_ctx* ctx, NttTables* t, PassDesc& d, int 
             cudaGetLastError();
             return;  // fall back to the two-level tables
         }
-        tw_fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(buf, count, Sp, stride, t->tw_lo, t->tw_hi, t->tw_lb);
+        const bool fold = t->inverse && p == 0;
+        tw_fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(buf, count, Sp, stride, t->tw_lo, t->tw_hi, t->tw_lb,
+                                                                                fold ? t->scale : 1);
         ctx->launches++;
         t->tw_full[p] = buf;
+        if (fold) t->tw0_scaled = true;
     }
     d.tw_full = t->tw_full[p];
     d.tw_pitch = Sp;
@@ -548,7 +707,7 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
                 d.out_u_stride = N1;    // k_2 * N_1
             }
             d.load_rows_fast = 1;
-            d.use_scale = inverse;
+            d.use_scale = inverse && !t->tw0_scaled;
             d.scale = t->scale;
         }
         launch_pass(ctx, d, cols);

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cstring>
 
+#include "group.cuh"
 #include "stark.cuh"
 
 namespace {
@@ -239,7 +240,72 @@ void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof) {
     t.mv = st->d_mv;
     t.write_flag = st->d_wflag;
     t.write_sym = st->d_wsym;
-    prove_v1_resident(ctx, t, st->manifest_root, proof, nullptr);
+    if (ctx->group && 3 + 7 * (int)st->tau >= ctx->group->world) {
+        // Context group: the trace was ingested on this GPU only (the host parser is the bound of this path); replicate it to
+        // the peers over NVLink and let every GPU prove its share (columns c % world, FRI hashing by chunk range).
+        sezkp_group* g = ctx->group;
+        const int world = g->world;
+        struct Peer {
+            DevBuf buf;
+            DeviceTrace t;
+        };
+        std::vector<Peer> peers(world - 1);
+        const size_t row_off = (off + 255) & ~(size_t)255;
+        const size_t o_imv = row_off, o_mv = o_imv + ((n + 15) & ~(size_t)15), o_wf = o_mv + n * tau, o_ws = o_wf + n * tau;
+        const size_t total = o_ws + n * tau * 2;
+        const double t_rep0 = now_ms();
+        try {
+            for (int r = 1; r < world; r++) {
+                sezkp_ctx* px = g->ctx[r];
+                Peer& p = peers[r - 1];
+                CUDA_CHECK(cudaSetDevice(px->device));
+                u8* base = (u8*)p.buf.ensure(total);
+                CUDA_CHECK(cudaSetDevice(ctx->device));
+                auto cp = [&](size_t o, const void* src, size_t bytes) {
+                    CUDA_CHECK(cudaMemcpyPeerAsync(base + o, px->device, src, ctx->device, bytes, ctx->stream));
+                };
+                cp(0, meta, off);
+                cp(o_imv, st->d_input_mv, n);
+                cp(o_mv, st->d_mv, n * tau);
+                cp(o_wf, st->d_wflag, n * tau);
+                cp(o_ws, st->d_wsym, n * tau * 2);
+                p.t = t;
+                p.t.block_start = (const u64*)(base + o_start);
+                p.t.block_len = (const u64*)(base + o_len);
+                p.t.win_left = (const int64_t*)(base + o_wl);
+                p.t.win_right = (const int64_t*)(base + o_wr);
+                p.t.head_in_off = (const u32*)(base + o_io);
+                p.t.head_out_off = (const u32*)(base + o_oo);
+                p.t.input_mv = (const int8_t*)(base + o_imv);
+                p.t.mv = (const int8_t*)(base + o_mv);
+                p.t.write_flag = (const u8*)(base + o_wf);
+                p.t.write_sym = (const uint16_t*)(base + o_ws);
+            }
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            const double rep_ms = now_ms() - t_rep0;
+            group_run(g, [&](int r, sezkp_ctx* cx) {
+                ShardInfo sh{r, world, group_allgather_host, &g->ranks[r]};
+                ProofSink sink(r == 0 ? proof.buf : nullptr, r == 0 ? proof.cap : 0);
+                prove_v1_resident(cx, r == 0 ? t : peers[r - 1].t, st->manifest_root, sink, &sh);
+                if (r == 0) proof.len = sink.len;
+            });
+            ctx->timings.insert(ctx->timings.begin(), {"stream_replicate_ms", rep_ms});
+        } catch (...) {
+            for (int r = 1; r < world; r++) {
+                cudaSetDevice(g->ctx[r]->device);
+                peers[r - 1].buf.release();
+            }
+            cudaSetDevice(ctx->device);
+            throw;
+        }
+        for (int r = 1; r < world; r++) {
+            cudaSetDevice(g->ctx[r]->device);
+            peers[r - 1].buf.release();
+        }
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+    } else {
+        prove_v1_resident(ctx, t, st->manifest_root, proof, nullptr);
+    }
     const double hidden = st->copy_ms > 0 ? 1.0 - (exposed_ms + st->stall_ms) / st->copy_ms : 0.0;
     ctx->timings.insert(ctx->timings.begin(), {"stream_copy_hidden_frac", hidden < 0 ? 0.0 : hidden});
     ctx->timings.insert(ctx->timings.begin(), {"stream_copy_exposed_ms", exposed_ms + st->stall_ms});

@@ -157,6 +157,17 @@ void wide_commit_fri_rank(sezkp_ctx* ctx, const WideColumns& wc, const char* con
     const u64 n = 1ULL << L, N = 1ULL << log_N;
     const int n_local = wc.n_local, max_local = (c + world - 1) / world;
     ctx->timings.clear();
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // device-side duration of this rank's part (reported next to the host laps)
+    CUDA_CHECK(cudaEventCreate(&ev0));
+    CUDA_CHECK(cudaEventCreate(&ev1));
+    struct EvGuard {
+        cudaEvent_t a, b;
+        ~EvGuard() {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    } ev_guard{ev0, ev1};
+    CUDA_CHECK(cudaEventRecord(ev0, ctx->stream));
     double t0 = wide_now_ms();
     const double t_begin = t0;
     auto lap = [&](const char* name) {
@@ -267,5 +278,10 @@ void wide_commit_fri_rank(sezkp_ctx* ctx, const WideColumns& wc, const char* con
         throw;
     }
     fl.release(ctx);
+    CUDA_CHECK(cudaEventRecord(ev1, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(ev1));
+    float dev_ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&dev_ms, ev0, ev1));
+    ctx->timings.push_back({"device_ms", (double)dev_ms});
     ctx->timings.push_back({"total", wide_now_ms() - t_begin});
 }

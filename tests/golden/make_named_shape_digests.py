@@ -11,6 +11,8 @@ the oracle needs minutes for.  Sections (run all, or name some on the command li
   wide20      config 4 generator (0x5EED splitmix, labels c_{c}) at 2^20 rows x blow-up 8: roots of columns 0..7 and 255,
               and the whole pipeline (alphas, z, FRI roots, final value) for 8 columns
   wide24      the same at the named row count 2^24 (N = 2^27): roots of columns 0..7, pipeline for 8 columns
+  wide24_full config 4 exactly as named: all 256 column roots and the pipeline over 256 columns x 2^24 rows (hours of CPU;
+              not in the default list)
 Usage: make_named_shape_digests.py [section ...]   (SEZKP_GOLDEN_PROCS = worker processes, default all cores)"""
 import importlib
 import json
@@ -105,6 +107,10 @@ def main():
         if "wide20" in want:
             out["wide_0x5EED_2^20"] = wide(pool, 20, list(range(8)) + [255], 8)
             print("wide20", out["wide_0x5EED_2^20"]["oracle_seconds"], "s", flush=True)
+            save()
+        if "wide24_full" in want:
+            out["wide_0x5EED_2^24_256cols"] = wide(pool, 24, list(range(256)), 256)
+            print("wide24_full", out["wide_0x5EED_2^24_256cols"]["oracle_seconds"], "s", flush=True)
             save()
         if "wide24" in want:
             out["wide_0x5EED_2^24"] = wide(pool, 24, list(range(8)), 8)

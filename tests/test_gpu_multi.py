@@ -106,3 +106,26 @@ def test_group_error_on_one_call_leaves_group_usable(single, group):
 def test_group_plain_entry_points_run_on_first_gpu(group, oracle):
     v = np.arange(1 << 12, dtype=np.uint64)
     assert np.array_equal(group.ntt(v), oracle.ntt(v))
+
+
+def test_group_streaming_and_jsonl(single, group, tmp_path):
+    """ProvingBackendStream + the native JSONL front-end on a context group: rows are ingested on the first GPU, replicated
+    to the peers over NVLink at finish, and every GPU proves its share — same bytes as the one-shot single-GPU proof."""
+    m = pkg()
+    ct = m.simulate(1 << 14, 512, 4, seed=11)
+    root = m.manifest_root(ct)
+    want = single.prove_v1(ct, root)
+
+    def pieces():
+        for k in range(0, ct.n_blocks, 5):
+            e = min(ct.n_blocks, k + 5)
+            r = slice(k * 512, e * 512)
+            yield m.CompactTrace(tau=ct.tau, block_len=ct.block_len[k:e], win_left=ct.win_left[k:e], win_right=ct.win_right[k:e],
+                                 head_in_off=ct.head_in_off[k:e], head_out_off=ct.head_out_off[k:e], input_mv=ct.input_mv[r],
+                                 mv=ct.mv[r], write_flag=ct.write_flag[r], write_sym=ct.write_sym[r])
+
+    assert group.prove_v1_stream(pieces(), root) == want
+    path = str(tmp_path / "blocks.jsonl")
+    m.io_jsonl.write_jsonl(path, ct)
+    assert group.prove_v1_jsonl_file(path, root, ct.n_rows, ct.tau, threads=4) == want
+    assert "stream_replicate_ms" in group.timings()
