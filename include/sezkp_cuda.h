@@ -236,6 +236,11 @@ int32_t sezkp_jsonl_parse(const char* text, size_t len, int n_threads, sezkp_jso
                           const sezkp_block_scalars** scalars);
 void sezkp_jsonl_free(sezkp_jsonl_trace* t);
 const char* sezkp_jsonl_last_error(void);                     /* thread-local                                       */
+/* The inverse (what the reference CLI's export-jsonl writes, crates/sezkp-cli/src/main.rs): one serde_json BlockSummary
+ * per line, field order of sezkp-core/src/types.rs:116-151, formatted on n_threads host threads (<= 0: all cores).
+ * scalars may be NULL (version 1, block ids from 1, step ranges from the block lengths).  No ctx and no GPU needed. */
+int32_t sezkp_jsonl_write_file(const char* path, const sezkp_trace_desc* trace, const sezkp_block_scalars* scalars, int n_threads,
+                               uint64_t* bytes_written);
 int32_t sezkp_stark_v1_ingest_jsonl(sezkp_ctx* ctx, sezkp_stream* st, const char* text, size_t len, int n_threads,
                                     uint64_t* n_blocks, uint64_t* n_rows);
 int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const uint8_t manifest_root[32], int n_threads,

@@ -29,7 +29,7 @@ EXPORTS = [
     "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_stark_v1_proof_bound", "sezkp_trace_upload", "sezkp_trace_free",
     "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded", "sezkp_stark_v1_prove_resident_sharded",
     "sezkp_cuda_set_allgather_dev", "sezkp_cuda_create_multi", "sezkp_cuda_group_size", "sezkp_cuda_device_count", "sezkp_columns_upload", "sezkp_columns_synth",
-    "sezkp_columns_free", "sezkp_lde_commit_fri", "sezkp_jsonl_parse", "sezkp_jsonl_free", "sezkp_jsonl_last_error", "sezkp_stark_v1_ingest_jsonl", "sezkp_stark_v1_prove_jsonl_file",
+    "sezkp_columns_free", "sezkp_lde_commit_fri", "sezkp_jsonl_parse", "sezkp_jsonl_write_file", "sezkp_jsonl_free", "sezkp_jsonl_last_error", "sezkp_stark_v1_ingest_jsonl", "sezkp_stark_v1_prove_jsonl_file",
 ]
 
 ERR_NAMES = {0: "OK", -1: "EINVAL", -2: "ENOMEM", -3: "ECUDA", -4: "ENODEV", -5: "ERANGE", -6: "ESTATE", -7: "ECOMM"}
@@ -445,6 +445,23 @@ def parse_jsonl(text: bytes, threads: int = 0) -> CompactTrace:
             in_head_in=rec["in_head_in"].copy(), in_head_out=rec["in_head_out"].copy())
     finally:
         lib.sezkp_jsonl_free(h)
+
+
+def write_jsonl_native(path: str, ct: CompactTrace, threads: int = 0) -> int:
+    """Native multi-threaded JSONL writer (sezkp_jsonl_write_file): same bytes as io_jsonl.write_jsonl, ~100x faster."""
+    lib = load_library()
+    d = ct.as_desc(packed=False)
+    sc = None
+    if ct.version is not None:
+        rec = np.zeros(ct.n_blocks, BLOCK_SCALARS_DTYPE)
+        for name in ("step_lo", "step_hi", "in_head_in", "in_head_out", "block_id", "version", "ctrl_in", "ctrl_out"):
+            rec[name] = getattr(ct, name)
+        sc = rec
+    n = C.c_uint64(0)
+    rc = lib.sezkp_jsonl_write_file(path.encode(), C.byref(d), _p(sc) if sc is not None else None, C.c_int(threads), C.byref(n))
+    if rc != 0:
+        raise SezkpCudaError(rc, lib.sezkp_jsonl_last_error().decode())
+    return int(n.value)
 
 
 def proof_size_bound(n_rows: int, tau: int) -> int:

@@ -93,8 +93,29 @@ __device__ __forceinline__ void g_fn(u32& a, u32& b, u32& bl, u32& c, u32& d, u3
     g_fn<((M) & 2) != 0, ((M) & 4) != 0, ((M) & 8) != 0>(s2, s7, l7, s8, s13, m[i12], m[i13], k);                  \
     g_fn<((M) & 2) != 0, ((M) & 4) != 0, ((M) & 8) != 0>(s3, s4, l4, s9, s14, m[i14], m[i15], k);
 
+// Compile-time G with zero message words: the three column steps of an unlabeled leaf's first round that do not touch
+// the value (columns 1-3: state words are IV / counter / block_len / flags, message words m2..m7 are zero) are constants.
+struct GConst {
+    u32 a, b, c, d;
+};
+constexpr u32 c_rotr(u32 x, int r) { return (x >> r) | (x << (32 - r)); }
+constexpr GConst g_const(u32 a, u32 b, u32 c, u32 d) {
+    a = a + b;
+    d = c_rotr(d ^ a, 16);
+    c = c + d;
+    b = c_rotr(b ^ c, 12);
+    a = a + b;
+    d = c_rotr(d ^ a, 8);
+    c = c + d;
+    b = c_rotr(b ^ c, 7);
+    return GConst{a, b, c, d};
+}
+
 // One-block hash: out[8] = BLAKE3(message of block_len bytes held zero-padded in m[16]).
-template <u32 SCHED = B3_SCHED>
+// LEAF8: the message is an unlabeled 8-byte leaf (m[2..15] = 0, block_len = 8): round 0 runs one column step instead of
+// four, the other three are folded at compile time (the run-time-1 multiplier of B3_ADD would otherwise hide them from the
+// compiler's constant propagation).
+template <u32 SCHED = B3_SCHED, bool LEAF8 = false>
 __device__ __forceinline__ void hash_block(const u32 (&m)[16], u32 block_len, u32 (&out)[8]) {
     u32 s0 = B3_IV0, s1 = B3_IV1, s2 = B3_IV2, s3 = B3_IV3, s4 = B3_IV4, s5 = B3_IV5, s6 = B3_IV6, s7 = B3_IV7;
     u32 s8 = B3_IV0, s9 = B3_IV1, s10 = B3_IV2, s11 = B3_IV3, s12 = 0, s13 = 0, s14 = block_len, s15 = B3_FLAGS_ONE_BLOCK;
@@ -102,7 +123,20 @@ __device__ __forceinline__ void hash_block(const u32 (&m)[16], u32 block_len, u3
     const Consts k = {k_one, k_pow20, k_pow25};
     constexpr u32 M0 = SCHED & 15, M1 = (SCHED >> 4) & 15, M2 = (SCHED >> 8) & 15, M3 = (SCHED >> 12) & 15, M4 = (SCHED >> 16) & 15,
                   M5 = (SCHED >> 20) & 15, M6 = (SCHED >> 24) & 15;
-    B3_ROUND(false, M0, m, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    if (LEAF8 && (M0 & 3) == 0) {
+        constexpr GConst c1 = g_const(B3_IV1, B3_IV5, B3_IV1, 0), c2 = g_const(B3_IV2, B3_IV6, B3_IV2, 8),
+                         c3 = g_const(B3_IV3, B3_IV7, B3_IV3, B3_FLAGS_ONE_BLOCK);
+        g_fn<false, false, false>(s0, s4, l4, s8, s12, m[0], m[1], k);
+        s1 = c1.a; s5 = c1.b; s9 = c1.c; s13 = c1.d;
+        s2 = c2.a; s6 = c2.b; s10 = c2.c; s14 = c2.d;
+        s3 = c3.a; s7 = c3.b; s11 = c3.c; s15 = c3.d;
+        g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s0, s5, l5, s10, s15, m[8], m[9], k);
+        g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s1, s6, l6, s11, s12, m[10], m[11], k);
+        g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s2, s7, l7, s8, s13, m[12], m[13], k);
+        g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s3, s4, l4, s9, s14, m[14], m[15], k);
+    } else {
+        B3_ROUND(false, M0, m, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    }
     B3_ROUND((M0 & 8) != 0, M1, m, 2, 6, 3, 10, 7, 0, 4, 13, 1, 11, 12, 5, 9, 14, 15, 8)
     B3_ROUND((M1 & 8) != 0, M2, m, 3, 4, 10, 12, 13, 2, 7, 14, 6, 5, 9, 0, 11, 15, 8, 1)
     B3_ROUND((M2 & 8) != 0, M3, m, 10, 7, 12, 9, 14, 3, 13, 15, 4, 0, 11, 2, 5, 8, 1, 6)
@@ -119,7 +153,7 @@ __device__ __forceinline__ void hash_block(const u32 (&m)[16], u32 block_len, u3
 // Unlabeled leaf of one canonical field element.
 __device__ __forceinline__ void leaf(u64 v, u32 (&out)[8]) {
     u32 m[16] = {(u32)v, (u32)(v >> 32), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    hash_block(m, 8, out);
+    hash_block<B3_SCHED, true>(m, 8, out);
 }
 // Parent of two digests.
 __device__ __forceinline__ void parent(const u32 (&l)[8], const u32 (&r)[8], u32 (&out)[8]) {

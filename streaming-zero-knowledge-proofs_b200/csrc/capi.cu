@@ -842,6 +842,30 @@ int32_t sezkp_jsonl_parse(const char* text, size_t len, int n_threads, sezkp_jso
     return SEZKP_CUDA_OK;
 }
 void sezkp_jsonl_free(sezkp_jsonl_trace* t) { delete t; }
+int32_t sezkp_jsonl_write_file(const char* path, const sezkp_trace_desc* trace, const sezkp_block_scalars* scalars, int n_threads,
+                               uint64_t* bytes_written) {
+    if (!path || !trace) {
+        g_jsonl_error = "bad argument";
+        return SEZKP_CUDA_EINVAL;
+    }
+    try {
+        if (!trace->block_len || !trace->win_left || !trace->win_right || !trace->head_in_off || !trace->head_out_off || !trace->input_mv ||
+            !trace->mv || !trace->write_flag || !trace->write_sym || trace->tau < 1)
+            throw std::runtime_error("trace descriptor has NULL arrays");
+        uint64_t sum = 0;
+        for (uint64_t k = 0; k < trace->n_blocks; k++) sum += trace->block_len[k];
+        if (sum != trace->n_rows) throw std::runtime_error("n_rows != sum(block_len)");
+        const size_t n = jsonl::write_file(path, *trace, scalars, jsonl_threads(n_threads));
+        if (bytes_written) *bytes_written = n;
+    } catch (const std::bad_alloc&) {
+        g_jsonl_error = "host allocation failed";
+        return SEZKP_CUDA_ENOMEM;
+    } catch (const std::exception& e) {
+        g_jsonl_error = e.what();
+        return SEZKP_CUDA_EINVAL;
+    }
+    return SEZKP_CUDA_OK;
+}
 
 // parse on the host threads and ingest the workers' outputs one after the other (file order), without concatenating them
 static void jsonl_parse_and_ingest(sezkp_ctx* ctx, sezkp_stream*& st, const uint8_t* manifest_root, uint64_t expected_rows,

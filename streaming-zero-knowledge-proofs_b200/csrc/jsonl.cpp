@@ -637,4 +637,113 @@ void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_
     out.n_lines = lines;
 }
 
+// ---- writer: the inverse of the parser, the text serde_json::to_string emits for a BlockSummary (field order of
+//      crates/sezkp-core/src/types.rs:116-151; what the reference CLI's `export-jsonl` writes, one block per line) ----
+namespace {
+inline void put_str(std::string& o, const char* s) { o.append(s); }
+inline void put_int(std::string& o, long long v) {
+    char buf[24];
+    int n = 0;
+    unsigned long long u = v < 0 ? 0ULL - (unsigned long long)v : (unsigned long long)v;
+    do {
+        buf[n++] = (char)('0' + u % 10);
+        u /= 10;
+    } while (u);
+    if (v < 0) o.push_back('-');
+    while (n) o.push_back(buf[--n]);
+}
+void format_block(std::string& o, const sezkp_trace_desc& d, const sezkp_block_scalars* sc, uint64_t k, uint64_t row0, const std::string& tags) {
+    const uint64_t n = d.block_len[k], tau = d.tau;
+    put_str(o, "{\"version\":");
+    put_int(o, sc ? sc[k].version : 1);
+    put_str(o, ",\"block_id\":");
+    put_int(o, sc ? sc[k].block_id : (long long)(k + 1));
+    put_str(o, ",\"step_lo\":");
+    put_int(o, sc ? (long long)sc[k].step_lo : (long long)(row0 + 1));
+    put_str(o, ",\"step_hi\":");
+    put_int(o, sc ? (long long)sc[k].step_hi : (long long)(row0 + n));
+    put_str(o, ",\"ctrl_in\":");
+    put_int(o, sc ? sc[k].ctrl_in : 0);
+    put_str(o, ",\"ctrl_out\":");
+    put_int(o, sc ? sc[k].ctrl_out : 0);
+    put_str(o, ",\"in_head_in\":");
+    put_int(o, sc ? sc[k].in_head_in : 0);
+    put_str(o, ",\"in_head_out\":");
+    put_int(o, sc ? sc[k].in_head_out : 0);
+    put_str(o, ",\"windows\":[");
+    for (uint64_t r = 0; r < tau; r++) {
+        put_str(o, r ? ",{\"left\":" : "{\"left\":");
+        put_int(o, d.win_left[k * tau + r]);
+        put_str(o, ",\"right\":");
+        put_int(o, d.win_right[k * tau + r]);
+        o.push_back('}');
+    }
+    put_str(o, "],\"head_in_offsets\":[");
+    for (uint64_t r = 0; r < tau; r++) {
+        if (r) o.push_back(',');
+        put_int(o, d.head_in_off[k * tau + r]);
+    }
+    put_str(o, "],\"head_out_offsets\":[");
+    for (uint64_t r = 0; r < tau; r++) {
+        if (r) o.push_back(',');
+        put_int(o, d.head_out_off[k * tau + r]);
+    }
+    put_str(o, "],\"movement_log\":{\"steps\":[");
+    for (uint64_t j = 0; j < n; j++) {
+        const uint64_t i = row0 + j;
+        put_str(o, j ? ",{\"input_mv\":" : "{\"input_mv\":");
+        put_int(o, d.input_mv[i]);
+        put_str(o, ",\"tapes\":[");
+        for (uint64_t r = 0; r < tau; r++) {
+            put_str(o, r ? ",{\"write\":" : "{\"write\":");
+            if (d.write_flag[i * tau + r]) put_int(o, d.write_sym[i * tau + r]);
+            else put_str(o, "null");
+            put_str(o, ",\"mv\":");
+            put_int(o, d.mv[i * tau + r]);
+            o.push_back('}');
+        }
+        put_str(o, "]}");
+    }
+    put_str(o, "]},\"pre_tags\":");
+    o.append(tags);
+    put_str(o, ",\"post_tags\":");
+    o.append(tags);
+    put_str(o, "}\n");
+}
+}  // namespace
+
+size_t write_file(const char* path, const sezkp_trace_desc& d, const sezkp_block_scalars* scalars, int n_threads) {
+    if (d.flags != 0) throw std::runtime_error("jsonl writer: packed descriptors are not supported");
+    FILE* f = std::fopen(path, "wb");
+    if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+    std::string tags = "[";
+    for (uint32_t r = 0; r < d.tau; r++) tags += r ? ",[0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0]" : "[0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0]";
+    tags += "]";
+    std::vector<uint64_t> start(d.n_blocks + 1, 0);
+    for (uint64_t k = 0; k < d.n_blocks; k++) start[k + 1] = start[k] + d.block_len[k];
+    if (n_threads < 1) n_threads = 1;
+    const uint64_t batch = 256 * (uint64_t)n_threads;  // blocks formatted per round (bounded memory: ~100 KB of text per block)
+    std::vector<std::string> bufs(n_threads);
+    size_t total = 0;
+    bool ok = true;
+    for (uint64_t k0 = 0; k0 < d.n_blocks && ok; k0 += batch) {
+        const uint64_t k1 = std::min<uint64_t>(d.n_blocks, k0 + batch), per = (k1 - k0 + n_threads - 1) / n_threads;
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([&, t] {
+                std::string& o = bufs[t];
+                o.clear();
+                for (uint64_t k = k0 + t * per; k < std::min(k1, k0 + (t + 1) * per); k++) format_block(o, d, scalars, k, start[k], tags);
+            });
+        for (auto& x : th) x.join();
+        for (int t = 0; t < n_threads && ok; t++) {
+            ok = std::fwrite(bufs[t].data(), 1, bufs[t].size(), f) == bufs[t].size();
+            total += bufs[t].size();
+        }
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) throw std::runtime_error(std::string("write error on ") + path);
+    return total;
+}
+
 }  // namespace jsonl

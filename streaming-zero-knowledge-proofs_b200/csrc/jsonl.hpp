@@ -32,4 +32,8 @@ void parse(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_
 size_t parse_parts(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_t first_line_no, std::vector<Trace>& parts,
                    uint32_t& tau_out);
 
+// Writer (inverse of the parser): one serde-JSON BlockSummary per line, formatted on n_threads host threads; `scalars` may be
+// null (version 1, block ids from 1, step ranges from the block lengths).  Returns the bytes written.
+size_t write_file(const char* path, const sezkp_trace_desc& d, const sezkp_block_scalars* scalars, int n_threads);
+
 }  // namespace jsonl

@@ -2,6 +2,7 @@
 (`stream_block_summaries_jsonl`, crates/sezkp-core/src/io_jsonl.rs:27-88): same blocks, same order, blank lines
 skipped, malformed lines rejected with their line number.  Host logic only — no GPU, no compute calls."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -122,3 +123,20 @@ def test_errors_in_a_multi_worker_parse_report_the_first_bad_line(tmp_path):
     with pytest.raises(m.SezkpCudaError) as ei:
         m.binding.parse_jsonl(("\n".join(mixed) + "\n").encode(), 8)
     assert "tau" in str(ei.value) or "tapes" in str(ei.value), str(ei.value)
+
+
+def test_native_writer_matches_python_writer_and_round_trips(tmp_path):
+    """sezkp_jsonl_write_file (the export-jsonl direction) emits byte-for-byte what io_jsonl.write_jsonl does, also for ragged
+    blocks and non-power-of-two traces, and the native parser reads it back."""
+    import filecmp
+    from importlib import import_module
+    m = pkg()
+    b = import_module("streaming-zero-knowledge-proofs_b200.binding")
+    for T, blk, tau, threads in ((1 << 12, 512, 3, 4), (1000, 300, 2, 3), (64, 64, 1, 1), (5000, 7, 8, 16)):
+        ct = m.simulate(T, blk, tau, seed=T)
+        pa, pb = str(tmp_path / "a.jsonl"), str(tmp_path / "b.jsonl")
+        m.io_jsonl.write_jsonl(pa, ct)
+        n = b.write_jsonl_native(pb, ct, threads)
+        assert n == os.path.getsize(pa) and filecmp.cmp(pa, pb, shallow=False)
+        back = b.parse_jsonl(open(pb, "rb").read(), threads)
+        assert np.array_equal(back.mv, ct.mv) and np.array_equal(back.write_sym, ct.write_sym) and np.array_equal(back.block_len, ct.block_len)
