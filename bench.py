@@ -362,7 +362,7 @@ def jsonl_stream_bench(torch, ctx, m, steps):
     root = m.manifest_root(ct)
     d = tempfile.mkdtemp(prefix="sezkp_jsonl_")
     path = os.path.join(d, "blocks.jsonl")
-    m.io_jsonl.write_jsonl(path, ct)
+    importlib.import_module(PKG + ".binding").write_jsonl_native(path, ct)  # sezkp_jsonl_write_file: same bytes as io_jsonl.write_jsonl
     size = os.path.getsize(path)
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:

@@ -201,7 +201,7 @@ int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value) {
     } else if (std::strcmp(name, "tabled") == 0) {
         ctx->tabled_enabled = value != 0;
     } else if (std::strcmp(name, "ntt_gen") == 0) {
-        REQUIRE(value == 1 || value == 2, "ntt_gen must be 1 or 2");
+        REQUIRE(value >= 1 && value <= 4, "ntt_gen must be 1..4");
         ctx->ntt_gen = (int)value;
     } else if (std::strcmp(name, "deep_fused") == 0) {
         ctx->deep_fused = value != 0;

@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass_kernel(const PassDesc
 //   rows contiguous in HBM (last pass / single pass): task = (r2 or k1 fastest)      -> a warp touches B*8 (A*8) contiguous B
 // The inter-step twiddles w_{2^b}^(r2*k1) sit in shared memory as a [A][B] matrix so that both task mappings read them
 // without bank conflicts (a flat power table indexed r2*k1 is a stride-k1 access when r2 runs across the lanes).
-template <int K1, int K2, bool INV>
-__global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass2_kernel(const PassDesc d) {
+template <int K1, int K2, bool INV, int MINB, int THREADS>
+__global__ void __launch_bounds__(THREADS, MINB) ntt_pass2_kernel(const PassDesc d) {
     extern __shared__ u64 smem[];
     constexpr int A = 1 << K1, B = 1 << K2, b = K1 + K2, rows = 1 << b;
     static_assert(K2 > 0, "two-step passes only");
@@ -259,11 +259,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass2_kernel(const PassDes
     const u64* in_base = d.in + u * d.in_u_stride + (v >> d.in_v_shift) * d.in_v_stride;
     u64* out_base = d.out + u * d.out_u_stride + v * d.out_v_stride;
 
-    for (int i = tid; i < rows; i += NTT_THREADS) Ws[i] = d.W[(i >> K2) * (i & (B - 1))];
+    for (int i = tid; i < rows; i += THREADS) Ws[i] = d.W[(i >> K2) * (i & (B - 1))];
 
     // ---- step 1: A-point DFTs over r1 of rows B*r1 + r2, operands straight from HBM ----
     const int tasks1 = B << logR;
-    for (int g0 = 0; g0 < tasks1; g0 += NTT_THREADS) {
+    for (int g0 = 0; g0 < tasks1; g0 += THREADS) {
         const int g = g0 + tid;
         const bool live = g < tasks1;
         int c, r2;
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass2_kernel(const PassDes
     __syncthreads();
     // ---- step 2: B-point DFTs over r2, results straight to HBM (inter-pass twiddle, scale, canonical) ----
     const int tasks2 = A << logR;
-    for (int g = tid; g < tasks2; g += NTT_THREADS) {
+    for (int g = tid; g < tasks2; g += THREADS) {
         int c, k1;
         if (d.store_rows_fast) {
             k1 = g & (A - 1);
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass2_kernel(const PassDes
             if (d.tw_full) {
                 const u64* twf = d.tw_full + C + (u64)k1 * d.tw_pitch;
                 const u64 tp = d.tw_pitch << K1;
-                constexpr int G = B < 8 ? B : 8;  // twiddle loads in flight per thread (registers: x[] already holds 2*B)
+                constexpr int G = MINB >= 3 ? 4 : 8;  // twiddle loads in flight per thread (registers: x[] already holds 2*B)
 #pragma unroll
                 for (int k0 = 0; k0 < B; k0 += G) {
                     u64 w[G];
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 3) ntt_pass2_kernel(const PassDes
                 }
             } else {
                 const u64 Cs = C * d.tw_stride;
-#pragma unroll 4
+#pragma unroll  // full unroll: a run-time index into x[] would move the whole array to local memory
                 for (int k2 = 0; k2 < B; k2++) {
                     const u64 E = (u64)(k1 + (k2 << K1)) * Cs;
                     const u64 w = gl::lazy::mulc(d.tw_lo[E & ((1ULL << d.tw_lb) - 1)], d.tw_hi[E >> d.tw_lb], eps);
@@ -394,16 +394,16 @@ void split_bits(int b, int& K1, int& K2) {
     K1 = k1[b];
     K2 = b - K1;
 }
-template <int K1, int K2>
-pass_fn get_fn2(bool inv) { return inv ? ntt_pass2_kernel<K1, K2, true> : ntt_pass2_kernel<K1, K2, false>; }
+template <int K1, int K2, int MINB, int THREADS = NTT_THREADS>
+pass_fn get_fn2(bool inv) { return inv ? ntt_pass2_kernel<K1, K2, true, MINB, THREADS> : ntt_pass2_kernel<K1, K2, false, MINB, THREADS>; }
 // second-generation kernel (fused global I/O) for the two-step widths; `gen` 1 selects the first-generation kernel (A/B runs)
 pass_fn kernel_for_bits(int b, bool inv, int gen) {
     if (gen >= 2) switch (b) {
-        case 6: return get_fn2<3, 3>(inv);
-        case 7: return get_fn2<4, 3>(inv);
-        case 8: return get_fn2<4, 4>(inv);
-        case 9: return get_fn2<5, 4>(inv);
-        case 10: return get_fn2<5, 5>(inv);
+        case 6: return get_fn2<3, 3, 3>(inv);
+        case 7: return get_fn2<4, 3, 3>(inv);
+        case 8: return get_fn2<4, 4, 3>(inv);
+        case 9: return gen == 4 ? get_fn2<5, 4, 4, 128>(inv) : gen == 3 ? get_fn2<5, 4, 2>(inv) : get_fn2<5, 4, 3>(inv);
+        case 10: return gen == 4 ? get_fn2<5, 5, 4, 128>(inv) : gen == 3 ? get_fn2<5, 5, 2>(inv) : get_fn2<5, 5, 3>(inv);
         default: break;
     }
     switch (b) {
@@ -572,8 +572,11 @@ void ntt_free_tables(sezkp_ctx* ctx) {
 /* ------------------------------------------------------------------------------------------ */
 /* pass construction + launch                                                                  */
 /* ------------------------------------------------------------------------------------------ */
-static int pick_logR(int b, u64 avail_cols, int min_logR) {
-    int lr = TILE_LOG_ELEMS - b;
+// gen 4 runs the widest passes (b >= 9: 32-point register DFTs, 64 data registers per thread) with 128-thread CTAs on
+// 4096-element tiles: 128 registers per thread without spills and four independent CTAs per SM
+static int pass_threads(const sezkp_ctx* ctx, int b) { return ctx->ntt_gen == 4 && b >= 9 ? 128 : NTT_THREADS; }
+static int pick_logR(const sezkp_ctx* ctx, int b, u64 avail_cols, int min_logR) {
+    int lr = TILE_LOG_ELEMS - (pass_threads(ctx, b) == 128 ? 1 : 0) - b;
     if (lr > MAX_LOG_R) lr = MAX_LOG_R;
     while (lr > 0 && (1ULL << lr) > avail_cols) lr--;
     if (lr < min_logR) lr = min_logR;
@@ -593,7 +596,7 @@ static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
         CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         granted = smem;
     }
-    fn<<<(unsigned)tiles, NTT_THREADS, smem, ctx->stream>>>(d);
+    fn<<<(unsigned)tiles, pass_threads(ctx, d.b), smem, ctx->stream>>>(d);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -644,7 +647,7 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
         base_desc(d, t, L);
         d.in = data;
         d.out = data;
-        d.logR = pick_logR(L, cols, 0);
+        d.logR = pick_logR(ctx, L, cols, 0);
         d.col_tiles = (u32)((cols + (1ULL << d.logR) - 1) >> d.logR);
         d.total_cols = cols;
         d.in_row_stride = 1;
@@ -672,7 +675,7 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
         if (!last) {  // case A
             d.in = (m == 3 && p == 1) ? data : data;
             d.out = (m == 2) ? tmp : (p == 0 ? data : tmp);
-            d.logR = pick_logR(b, Sp, 0);
+            d.logR = pick_logR(ctx, b, Sp, 0);
             d.col_tiles = (u32)(Sp >> d.logR);
             d.total_cols = Sp;
             d.U = (u32)(N / Mp);
@@ -692,7 +695,7 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
             const u64 N1 = 1ULL << plan[0], S1 = N / N1;
             d.in = tmp;
             d.out = data;
-            d.logR = pick_logR(b, N1, 0);
+            d.logR = pick_logR(ctx, b, N1, 0);
             d.col_tiles = (u32)(N1 >> d.logR);
             d.total_cols = N1;
             d.in_row_stride = 1;
@@ -732,7 +735,7 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
         d.in = coeffs;
         d.out = out;
         d.total_cols = cols * B;
-        d.logR = pick_logR(L, d.total_cols, 0);
+        d.logR = pick_logR(ctx, L, d.total_cols, 0);
         d.col_tiles = (u32)((d.total_cols + (1ULL << d.logR) - 1) >> d.logR);
         d.in_row_stride = 1;
         d.in_clog = logB;
@@ -765,7 +768,7 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
         if (!last) {  // case A / A'
             d.in = (p == 0) ? coeffs : inter;
             d.out = inter;
-            d.logR = pick_logR(b, Sp, 0);
+            d.logR = pick_logR(ctx, b, Sp, 0);
             d.col_tiles = (u32)(Sp >> d.logR);
             d.total_cols = Sp;
             d.U = (u32)(n / Mp);
@@ -797,7 +800,7 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
             d.in = inter;
             d.out = out;
             d.total_cols = N1 * B;
-            d.logR = pick_logR(b, d.total_cols, logB);
+            d.logR = pick_logR(ctx, b, d.total_cols, logB);
             d.col_tiles = (u32)(d.total_cols >> d.logR);
             d.in_row_stride = 1;
             d.in_clog = logB;

@@ -19,12 +19,19 @@ namespace {
 /* ------------------------------------------------------------------------------------------ */
 // One warp per (block, tape): running head position (post-move, relative to 0 at block entry).  Lanes take
 // consecutive rows, so the prefix sum is a warp scan plus a carry and the stores are coalesced.
-__global__ void __launch_bounds__(256) head_scan_kernel(DeviceTrace t, u64* __restrict__ cols, u64 blk0, u64 blk1) {
+// f.col_mod > 1 (one proof sharded over several GPUs): only the columns c with c % col_mod == col_rem are produced for every
+// row — the columns this rank commits — plus ALL columns for the rows [full_lo, full_hi) and the row `halo`: the row slice
+// this rank composes (row i of the composition reads rows i and i + 1 mod n).
+__global__ void __launch_bounds__(256) head_scan_kernel(DeviceTrace t, u64* __restrict__ cols, u64 blk0, u64 blk1, const ExpandFilter f) {
     const u64 id = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u32 lane = threadIdx.x & 31;
     if (id >= (blk1 - blk0) * t.tau) return;
     const u64 k = blk0 + id / t.tau;
     const u32 r = (u32)(id % t.tau);
+    if (f.col_mod > 1 && (3 + 3 * t.tau + r) % f.col_mod != f.col_rem) {  // not an own column: only blocks that touch the row slice
+        const u64 s0 = t.block_start[k], s1 = s0 + t.block_len[k];
+        if (!((s0 < f.full_hi && s1 > f.full_lo) || (f.halo >= s0 && f.halo < s1))) return;
+    }
     const u64 start = t.block_start[k], len = t.block_len[k];
     u64* head = cols + (3 + 3ULL * t.tau + r) * t.n_rows + start;  // group order: mv, wflag, wsym, head, ...
     const signed char* mv = (const signed char*)(t.ops ? (const int8_t*)t.ops : t.mv) + start * t.tau + r;
@@ -44,9 +51,11 @@ __global__ void __launch_bounds__(256) head_scan_kernel(DeviceTrace t, u64* __re
     }
 }
 // One thread per row: everything except head.
-__global__ void expand_rows_kernel(DeviceTrace t, u64* __restrict__ cols, u64 row0, u64 row1) {
+__global__ void expand_rows_kernel(DeviceTrace t, u64* __restrict__ cols, u64 row0, u64 row1, const ExpandFilter f) {
     const u64 i = row0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= row1) return;
+    const bool all_cols = f.col_mod <= 1 || (i >= f.full_lo && i < f.full_hi) || i == f.halo;
+    auto own = [&](u32 c) { return all_cols || c % f.col_mod == f.col_rem; };
     // block containing row i: largest k with block_start[k] <= i (blocks of length 0 are skipped by the search)
     u64 lo = 0, hi = t.n_blocks;
     while (hi - lo > 1) {
@@ -58,9 +67,9 @@ __global__ void expand_rows_kernel(DeviceTrace t, u64* __restrict__ cols, u64 ro
     const u64 start = t.block_start[k], len = t.block_len[k];
     const u64 n = t.n_rows;
     const u32 tau = t.tau;
-    cols[0 * n + i] = gl::from_i64((int64_t)t.input_mv[i]);
-    cols[1 * n + i] = (i == start) ? 1 : 0;
-    cols[2 * n + i] = (i + 1 == start + len) ? 1 : 0;
+    if (own(0)) cols[0 * n + i] = gl::from_i64((int64_t)t.input_mv[i]);
+    if (own(1)) cols[1 * n + i] = (i == start) ? 1 : 0;
+    if (own(2)) cols[2 * n + i] = (i + 1 == start + len) ? 1 : 0;
     for (u32 r = 0; r < tau; r++) {
         const u64 p = i * tau + r;
         int wf, mvv;
@@ -75,14 +84,14 @@ __global__ void expand_rows_kernel(DeviceTrace t, u64* __restrict__ cols, u64 ro
             mvv = (int)t.mv[p];
             sym = (u64)t.write_sym[p];
         }
-        cols[(3 + 0ULL * tau + r) * n + i] = gl::from_i64((int64_t)mvv);
-        cols[(3 + 1ULL * tau + r) * n + i] = (u64)wf;
-        cols[(3 + 2ULL * tau + r) * n + i] = wf ? sym : 0;
+        if (own(3 + 0 * tau + r)) cols[(3 + 0ULL * tau + r) * n + i] = gl::from_i64((int64_t)mvv);
+        if (own(3 + 1 * tau + r)) cols[(3 + 1ULL * tau + r) * n + i] = (u64)wf;
+        if (own(3 + 2 * tau + r)) cols[(3 + 2ULL * tau + r) * n + i] = wf ? sym : 0;
         const int64_t diff = t.win_right[k * tau + r] - t.win_left[k * tau + r];
         const u64 ad = diff < 0 ? (u64)0 - (u64)diff : (u64)diff;
-        cols[(3 + 4ULL * tau + r) * n + i] = gl::from_u64(ad + 1);
-        cols[(3 + 5ULL * tau + r) * n + i] = (u64)t.head_in_off[k * tau + r];
-        cols[(3 + 6ULL * tau + r) * n + i] = (u64)t.head_out_off[k * tau + r];
+        if (own(3 + 4 * tau + r)) cols[(3 + 4ULL * tau + r) * n + i] = gl::from_u64(ad + 1);
+        if (own(3 + 5 * tau + r)) cols[(3 + 5ULL * tau + r) * n + i] = (u64)t.head_in_off[k * tau + r];
+        if (own(3 + 6 * tau + r)) cols[(3 + 6ULL * tau + r) * n + i] = (u64)t.head_out_off[k * tau + r];
     }
 }
 
@@ -101,10 +110,10 @@ struct ComposeParams {
 // once per row: 6 multiplications per tape + 13 per row instead of 19 per tape + a 22-bit power per row.  All sums are
 // lazy representatives (gl::lazy); only values whose BITS matter (range terms) are canonical.
 __global__ void __launch_bounds__(128) compose_kernel(const u64* __restrict__ cols, u64 n, u32 tau, ComposeParams cp,
-                                                      const u64* __restrict__ w_lo, u64* __restrict__ out) {
+                                                      const u64* __restrict__ w_lo, u64* __restrict__ out, u64 row0, u64 row1) {
     namespace L = gl::lazy;
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const u64 i = row0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row1) return;
     const u64 ip1 = (i + 1 == n) ? 0 : i + 1;
     const u64 is_first = cols[1 * n + i], is_last = cols[2 * n + i];
     u64 s_bool = 0, s_mv = 0, s_hu = 0, s_hr = 0, s_sr = 0, s_bf = 0, s_bl = 0;
@@ -462,14 +471,14 @@ void DeviceTraceOwner::upload(sezkp_ctx* ctx, const sezkp_trace_desc* d) {
 }
 
 // rows [row0,row1) of every non-head column and the head columns of blocks [blk0,blk1)
-void expand_columns_range(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols, u64 row0, u64 row1, u64 blk0, u64 blk1) {
+void expand_columns_range(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols, u64 row0, u64 row1, u64 blk0, u64 blk1, const ExpandFilter& f) {
     if (blk1 > blk0) {
-        head_scan_kernel<<<blocks_for((blk1 - blk0) * t.tau * 32, 256), 256, 0, ctx->stream>>>(t, cols, blk0, blk1);
+        head_scan_kernel<<<blocks_for((blk1 - blk0) * t.tau * 32, 256), 256, 0, ctx->stream>>>(t, cols, blk0, blk1, f);
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
     }
     if (row1 > row0) {
-        expand_rows_kernel<<<blocks_for(row1 - row0, 256), 256, 0, ctx->stream>>>(t, cols, row0, row1);
+        expand_rows_kernel<<<blocks_for(row1 - row0, 256), 256, 0, ctx->stream>>>(t, cols, row0, row1, f);
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
     }
@@ -497,7 +506,8 @@ static const u64* power_table_device(sezkp_ctx* ctx, int L, int lo_bits) {
 }
 
 void compose_device(sezkp_ctx* ctx, const u64* cols, u64 n, u32 tau, const u64 alphas8[8], const u64* mask, size_t mask_deg,
-                    u64* out) {
+                    u64* out, u64 row0, u64 row1) {
+    if (row1 > n) row1 = n;  // default arguments: the whole base domain
     REQUIRE(mask_deg <= 8, "mask degree %zu > 8 unsupported", mask_deg);
     ComposeParams cp{};
     for (int i = 0; i < 8; i++) {
@@ -520,7 +530,8 @@ void compose_device(sezkp_ctx* ctx, const u64* cols, u64 n, u32 tau, const u64 a
         x = gl::mul(x, w_lo_step);
     }
     const u64* w_lo = power_table_device(ctx, L, cp.lo_bits);
-    compose_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(cols, n, tau, cp, w_lo, out);
+    if (row1 <= row0) return;
+    compose_kernel<<<blocks_for(row1 - row0, 128), 128, 0, ctx->stream>>>(cols, n, tau, cp, w_lo, out, row0, row1);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -930,8 +941,22 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
 
     // A. compact trace -> committed columns
     u64* cols = (u64*)ctx->scratch[3].ensure((size_t)n_cols * n * 8);
+    // One proof over several GPUs with a device-side collective: this rank expands only what it needs — its own columns
+    // (c % world == rank) for every row, and all columns for the row slice [n*rank/world, n*(rank+1)/world) whose composition
+    // values it computes; the slices of base_vals are all-gathered (8n bytes in total) instead of every rank composing all
+    // rows from all 59 columns.
+    const bool row_sliced = !plan && world > 1 && ctx->allgather_dev && n % (u64)world == 0 && n / (u64)world >= 1024;
+    const u64 slice_lo = row_sliced ? n / (u64)world * (u64)rank : 0, slice_hi = row_sliced ? slice_lo + n / (u64)world : n;
     if (!plan) {
-        expand_columns_device(ctx, trace, cols);
+        ExpandFilter f;
+        if (row_sliced) {
+            f.col_mod = (u32)world;
+            f.col_rem = (u32)rank;
+            f.full_lo = slice_lo;
+            f.full_hi = slice_hi < n ? slice_hi + 1 : n;
+            f.halo = slice_hi < n ? ~0ULL : 0;  // the last slice wraps around to row 0
+        }
+        expand_columns_range(ctx, trace, cols, 0, n, 0, trace.n_blocks, f);
         lap("expand_columns");
     }
 
@@ -1005,7 +1030,14 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
 
         // F. composition -> iNTT -> coset LDE -> DEEP (v1/prover.rs:142-178, v1/lde.rs:42-97)
         u64* base_vals = (u64*)ctx->scratch[4].ensure(n * 8);
-        compose_device(ctx, cols, n, tau, alphas, mask, 4, base_vals);
+        compose_device(ctx, cols, n, tau, alphas, mask, 4, base_vals, slice_lo, slice_hi);
+        if (row_sliced) {
+            const size_t bytes = (size_t)(slice_hi - slice_lo) * 8;
+            u8* stage = (u8*)ctx->scratch[6].ensure(bytes);
+            CUDA_CHECK(cudaMemcpyAsync(stage, base_vals + slice_lo, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            const int32_t rc = ctx->allgather_dev(ctx->allgather_dev_user, stage, bytes, base_vals, (void*)ctx->stream);
+            if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "device allgather callback failed with status %d", rc);
+        }
         lap("compose");
         fl.values = (u64*)ctx->pool.alloc(2 * N * 8);  // the DEEP-LDE lands where FRI layer 0 lives: no 8N-byte copy
         u64* lde = fl.values;

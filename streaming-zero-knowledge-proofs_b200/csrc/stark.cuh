@@ -44,7 +44,7 @@ struct SlabPlan {  // pipelined upload: per slab the rows, the blocks that end i
 void validate_trace(const sezkp_trace_desc* d);
 void expand_columns_device(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols_dev);
 void compose_device(sezkp_ctx* ctx, const u64* cols_dev, u64 n, u32 tau, const u64 alphas8[8], const u64* mask, size_t mask_deg,
-                    u64* out_dev);
+                    u64* out_dev, u64 row0 = 0, u64 row1 = ~0ULL);  // rows [row0, row1) only (row i reads rows i and i+1 mod n)
 bool z_on_coset(u64 z, u64 shift, int log_N);
 void deep_lde_device(sezkp_ctx* ctx, u64* base_vals_dev /* destroyed */, u64* out_dev, int L, int logB, u64 shift, u64 z);
 
@@ -101,7 +101,13 @@ struct ShardInfo {  // column sharding across the GPUs of one box (one process p
 };
 void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], ProofSink& proof_out,
                        const ShardInfo* shard = nullptr, const SlabPlan* plan = nullptr);
-void expand_columns_range(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols_dev, u64 row0, u64 row1, u64 blk0, u64 blk1);
+struct ExpandFilter {  // which (column, row) cells an expansion produces; the default produces everything
+    u32 col_mod = 0, col_rem = 0;           // col_mod > 1: columns c % col_mod == col_rem for every row ...
+    u64 full_lo = 0, full_hi = 0, halo = ~0ULL;  // ... plus all columns for rows [full_lo, full_hi) and row `halo`
+};
+// rows [row0,row1) of the non-head columns and the head columns of blocks [blk0,blk1)
+void expand_columns_range(sezkp_ctx* ctx, const DeviceTrace& t, u64* cols_dev, u64 row0, u64 row1, u64 blk0, u64 blk1,
+                          const ExpandFilter& f = ExpandFilter());
 void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 manifest_root[32], ProofSink& proof_out,
                      const ShardInfo* shard = nullptr);
 
