@@ -147,6 +147,18 @@ int32_t sezkp_lde_commit_fri(sezkp_ctx* ctx, const sezkp_columns* cols, const ch
 int32_t sezkp_column_open(sezkp_ctx* ctx, const sezkp_tree* tree, const uint32_t* col_idx, const uint64_t* row_idx, size_t k,
                           uint64_t* values, uint8_t* chunk_roots, uint8_t* path_in_chunk, uint8_t* path_to_chunk,
                           int* depth_in, int* depth_out);
+/* Batched verification of openings: verify_chunked_open (v1/merkle.rs:243-280; ColumnCommit / OnDemandOpenings proofs, as
+ * checked by verify_v1 v1/verify.rs:60-196) and MerkleTree::verify (v1/merkle.rs:111-126; FRI layer paths, v1/fri.rs:130-222)
+ * for k openings in one launch.  Per opening i: the leaf of values[i] — labeled with labels[col_idx[i]], or unlabeled when
+ * labels is NULL — is walked up path_in_chunk[i] (depth_in siblings, position index_in_chunk[i]); if chunk_roots is given the
+ * result must equal chunk_roots[i]; then up path_to_chunk[i] (depth_out siblings, position chunk_index[i]) to
+ * col_roots[col_idx[i]].  ok[i] = 1 iff every comparison holds (and values[i] is canonical).  col_idx may be NULL when c == 1;
+ * a plain Merkle path is depth_out = 0, chunk_roots = NULL.  The reference's verifier itself stays on the CPU. */
+int32_t sezkp_verify_openings(sezkp_ctx* ctx, const uint8_t* col_roots /* [c][32] */, const char* const* labels_or_null, int c,
+                              const uint32_t* col_idx, const uint64_t* values, const uint64_t* index_in_chunk,
+                              const uint64_t* chunk_index, const uint8_t* chunk_roots /* [k][32] or NULL */,
+                              const uint8_t* path_in_chunk /* [k][depth_in][32] */, int depth_in,
+                              const uint8_t* path_to_chunk /* [k][depth_out][32] */, int depth_out, size_t k, uint8_t* ok /* [k] */);
 void sezkp_tree_free(sezkp_ctx* ctx, sezkp_tree* tree);
 
 /* ------------------------------------------------------------------ FRI ------ */

@@ -24,7 +24,7 @@ EXPORTS = [
     "sezkp_ntt_batch", "sezkp_ntt_batch_dev", "sezkp_coset_lde_batch", "sezkp_coset_lde_batch_dev",
     "sezkp_lde_from_evals_batch", "sezkp_lde_from_evals_batch_dev", "sezkp_deep_lde", "sezkp_deep_lde_dev",
     "sezkp_leaf_hash", "sezkp_merkle_root", "sezkp_column_commit_batch", "sezkp_column_commit_batch_dev",
-    "sezkp_lde_commit_batch", "sezkp_lde_commit_batch_dev", "sezkp_column_open", "sezkp_tree_free", "sezkp_fri_commit", "sezkp_fri_commit_dev", "sezkp_fri_open", "sezkp_fri_free",
+    "sezkp_lde_commit_batch", "sezkp_lde_commit_batch_dev", "sezkp_column_open", "sezkp_verify_openings", "sezkp_tree_free", "sezkp_fri_commit", "sezkp_fri_commit_dev", "sezkp_fri_open", "sezkp_fri_free",
     "sezkp_trace_columns", "sezkp_compose_base", "sezkp_stark_v1_prove", "sezkp_stark_v1_begin", "sezkp_stark_v1_ingest",
     "sezkp_stark_v1_finish", "sezkp_stark_v1_abort", "sezkp_stark_v1_proof_bound", "sezkp_trace_upload", "sezkp_trace_free",
     "sezkp_stark_v1_prove_resident", "sezkp_stark_v1_prove_sharded", "sezkp_stark_v1_prove_resident_sharded",
@@ -230,6 +230,29 @@ class Context:
         fn = self.lib.sezkp_column_commit_batch_dev if dev else self.lib.sezkp_column_commit_batch
         self._ck(fn(self.h, ptr, arr, C.c_int(c), C.c_size_t(n), C.c_int(chunk_log2), _p(roots), C.byref(tree) if keep else None))
         return (roots, ColumnTree(self, tree)) if keep else roots
+
+    def verify_openings(self, col_roots, labels: Optional[Sequence[str]], col_idx, values, idx_in, chunk_idx=None, chunk_roots=None,
+                        path_in=None, path_to=None) -> np.ndarray:
+        """Batched verify_chunked_open / MerkleTree::verify: -> bool array [k].  path_in [k][din][32], path_to [k][dout][32]."""
+        roots = np.ascontiguousarray(col_roots, np.uint8).reshape(-1, 32)
+        c = roots.shape[0]
+        v = np.ascontiguousarray(values, np.uint64)
+        k = v.size
+        ci = np.ascontiguousarray(col_idx, np.uint32) if col_idx is not None else None
+        ii = np.ascontiguousarray(idx_in, np.uint64)
+        io = np.ascontiguousarray(chunk_idx, np.uint64) if chunk_idx is not None else None
+        cr = np.ascontiguousarray(chunk_roots, np.uint8).reshape(k, 32) if chunk_roots is not None else None
+        pi = np.ascontiguousarray(path_in, np.uint8).reshape(k, -1, 32) if path_in is not None and np.size(path_in) else None
+        pt = np.ascontiguousarray(path_to, np.uint8).reshape(k, -1, 32) if path_to is not None and np.size(path_to) else None
+        din = pi.shape[1] if pi is not None else 0
+        dout = pt.shape[1] if pt is not None else 0
+        arr = (C.c_char_p * c)(*[l.encode() for l in labels]) if labels is not None else None
+        ok = np.zeros(k, np.uint8)
+        self._ck(self.lib.sezkp_verify_openings(self.h, _p(roots), arr, C.c_int(c), _p(ci) if ci is not None else None, _p(v), _p(ii),
+                                                _p(io) if io is not None else None, _p(cr) if cr is not None else None,
+                                                _p(pi) if pi is not None else None, C.c_int(din), _p(pt) if pt is not None else None,
+                                                C.c_int(dout), C.c_size_t(k), _p(ok)))
+        return ok.astype(bool)
 
     def lde_commit(self, evals, labels: Sequence[str], log_blow: int, shift: int = 3, chunk_log2=10, dev=False, log_n=None) -> np.ndarray:
         """iNTT -> coset LDE -> labeled leaf hash -> root per column (extended columns never all resident)."""

@@ -553,6 +553,21 @@ int32_t sezkp_column_open(sezkp_ctx* ctx, const sezkp_tree* tree, const uint32_t
     }
     API_END(ctx)
 }
+int32_t sezkp_verify_openings(sezkp_ctx* ctx, const uint8_t* col_roots, const char* const* labels_or_null, int c, const uint32_t* col_idx,
+                              const uint64_t* values, const uint64_t* index_in_chunk, const uint64_t* chunk_index,
+                              const uint8_t* chunk_roots, const uint8_t* path_in_chunk, int depth_in, const uint8_t* path_to_chunk,
+                              int depth_out, size_t k, uint8_t* ok) {
+    API_BEGIN(ctx)
+    REQUIRE(col_roots && c >= 1 && depth_in >= 0 && depth_in <= 64 && depth_out >= 0 && depth_out <= 64, "bad argument");
+    if (k) {
+        REQUIRE(values && index_in_chunk && ok && (path_in_chunk || depth_in == 0) && (depth_out == 0 || (path_to_chunk && chunk_index)),
+                "bad argument");
+        REQUIRE(col_idx || c == 1, "col_idx is required with more than one column");
+        verify_paths_device(ctx, col_roots, labels_or_null, c, col_idx, values, index_in_chunk, chunk_index, chunk_roots, path_in_chunk,
+                            depth_in, path_to_chunk, depth_out, k, ok);
+    }
+    API_END(ctx)
+}
 void sezkp_tree_free(sezkp_ctx* ctx, sezkp_tree* tree) {
     if (!tree) return;
     if (!ctx) return;

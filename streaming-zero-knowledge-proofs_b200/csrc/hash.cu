@@ -1711,3 +1711,107 @@ void merkle_root_device(sezkp_ctx* ctx, u32* level, u32* tmp, size_t n, u8* root
     CUDA_CHECK(cudaMemcpyAsync(root_host, a, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* batched path verification (a15: MerkleTree::verify v1/merkle.rs:111-126, verify_chunked_open :243-280) */
+/* ------------------------------------------------------------------------------------------ */
+namespace {
+struct VerifyArgs {
+    const u32* col_roots;              // [c][8]
+    const b3::LabelTemplate* tpl;      // [c] or null (unlabeled leaves)
+    const u32* col_idx;                // [k] or null (column 0)
+    const u64* values;                 // [k]
+    const u64* idx_in;                 // [k]
+    const u64* idx_out;                // [k] (unused when dout == 0)
+    const u32* chunk_roots;            // [k][8] or null: no intermediate check
+    const u32* path_in;                // [k][din][8]
+    const u32* path_to;                // [k][dout][8]
+    int din, dout;
+    size_t k;
+    u8* ok;                            // [k]
+};
+__device__ __forceinline__ void walk_up(u32 (&cur)[8], u64 idx, const u32* __restrict__ sibs, int depth) {
+    for (int l = 0; l < depth; l++) {
+        u32 s[8], o[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) s[w] = sibs[l * 8 + w];
+        if ((idx & 1) == 0) b3::parent(cur, s, o);
+        else b3::parent(s, cur, o);
+#pragma unroll
+        for (int w = 0; w < 8; w++) cur[w] = o[w];
+        idx >>= 1;
+    }
+}
+__global__ void __launch_bounds__(128) verify_paths_kernel(const VerifyArgs a) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.k) return;
+    const u32 col = a.col_idx ? a.col_idx[i] : 0;
+    const u64 v = a.values[i];
+    u32 cur[8];
+    if (a.tpl) {
+        const b3::LabelTemplate t = a.tpl[col];
+        B3_DISPATCH_LABELED(t, { b3::leaf_labeled_w<B3W>(t, v, cur); })
+    } else b3::leaf(v, cur);
+    walk_up(cur, a.idx_in[i], a.path_in + i * (size_t)a.din * 8, a.din);
+    bool good = v < gl::P;  // a non-canonical value can never be an honest opening
+    if (a.chunk_roots) {
+#pragma unroll
+        for (int w = 0; w < 8; w++) good = good && cur[w] == a.chunk_roots[i * 8 + w];
+    }
+    if (a.dout) walk_up(cur, a.idx_out[i], a.path_to + i * (size_t)a.dout * 8, a.dout);
+#pragma unroll
+    for (int w = 0; w < 8; w++) good = good && cur[w] == a.col_roots[(size_t)col * 8 + w];
+    a.ok[i] = good ? 1 : 0;
+}
+}  // namespace
+
+void verify_paths_device(sezkp_ctx* ctx, const u8* col_roots, const char* const* labels, int c, const u32* col_idx, const u64* values,
+                         const u64* idx_in, const u64* idx_out, const u8* chunk_roots, const u8* path_in, int din, const u8* path_to,
+                         int dout, size_t k, u8* ok_host) {
+    if (k == 0) return;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_roots = 0, o_tpl = al(o_roots + (size_t)c * 32), o_col = al(o_tpl + (labels ? sizeof(b3::LabelTemplate) * c : 0)),
+                 o_val = al(o_col + (col_idx ? k * 4 : 0)), o_ii = al(o_val + k * 8), o_io = al(o_ii + k * 8),
+                 o_cr = al(o_io + (dout ? k * 8 : 0)), o_pi = al(o_cr + (chunk_roots ? k * 32 : 0)),
+                 o_pt = al(o_pi + k * (size_t)din * 32), o_ok = al(o_pt + k * (size_t)dout * 32), total = al(o_ok + k);
+    u8* h = (u8*)ctx->pinned[1].ensure(total);
+    u8* d = (u8*)ctx->scratch[7].ensure(total);
+    std::memcpy(h + o_roots, col_roots, (size_t)c * 32);
+    if (labels)
+        for (int j = 0; j < c; j++) {
+            REQUIRE(labels[j] != nullptr, "label %d is NULL", j);
+            const b3::LabelTemplate t = make_label_template(labels[j]);
+            std::memcpy(h + o_tpl + sizeof t * j, &t, sizeof t);
+        }
+    if (col_idx) {
+        for (size_t i = 0; i < k; i++) REQUIRE(col_idx[i] < (u32)c, "opening %zu: column index out of range", i);
+        std::memcpy(h + o_col, col_idx, k * 4);
+    }
+    std::memcpy(h + o_val, values, k * 8);
+    std::memcpy(h + o_ii, idx_in, k * 8);
+    if (dout) std::memcpy(h + o_io, idx_out, k * 8);
+    if (chunk_roots) std::memcpy(h + o_cr, chunk_roots, k * 32);
+    if (din) std::memcpy(h + o_pi, path_in, k * (size_t)din * 32);
+    if (dout) std::memcpy(h + o_pt, path_to, k * (size_t)dout * 32);
+    CUDA_CHECK(cudaMemcpyAsync(d, h, o_ok, cudaMemcpyHostToDevice, ctx->stream));
+    VerifyArgs a;
+    a.col_roots = (const u32*)(d + o_roots);
+    a.tpl = labels ? (const b3::LabelTemplate*)(d + o_tpl) : nullptr;
+    a.col_idx = col_idx ? (const u32*)(d + o_col) : nullptr;
+    a.values = (const u64*)(d + o_val);
+    a.idx_in = (const u64*)(d + o_ii);
+    a.idx_out = (const u64*)(d + o_io);
+    a.chunk_roots = chunk_roots ? (const u32*)(d + o_cr) : nullptr;
+    a.path_in = (const u32*)(d + o_pi);
+    a.path_to = (const u32*)(d + o_pt);
+    a.din = din;
+    a.dout = dout;
+    a.k = k;
+    a.ok = d + o_ok;
+    verify_paths_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(a);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
+    CUDA_CHECK(cudaMemcpyAsync(h + o_ok, d + o_ok, k, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(ok_host, h + o_ok, k);
+}

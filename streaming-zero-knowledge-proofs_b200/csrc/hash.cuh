@@ -95,3 +95,7 @@ void commit_open(sezkp_ctx* ctx, const Commit& cm, const u32* col_idx, const u64
 // Plain helpers
 void leaf_hash_device(sezkp_ctx* ctx, const u64* vals_dev, size_t n, const char* label_or_null, u32* out_dev);
 void merkle_root_device(sezkp_ctx* ctx, u32* level_dev /* n digests, destroyed */, u32* tmp_dev, size_t n, u8* root_host);
+// Batched Merkle path verification (MerkleTree::verify / verify_chunked_open): see sezkp_verify_openings in the C header.
+void verify_paths_device(sezkp_ctx* ctx, const u8* col_roots, const char* const* labels_or_null, int c, const u32* col_idx_or_null,
+                         const u64* values, const u64* idx_in, const u64* idx_out, const u8* chunk_roots_or_null, const u8* path_in, int din,
+                         const u8* path_to, int dout, size_t k, u8* ok_host);

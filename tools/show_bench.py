@@ -19,13 +19,17 @@ if d.get("micro"):
 print("cpu", d["cpu_baseline"]["value"], d["cpu_baseline"].get("gpu_proof_identical"), "clocks", d["clocks"])
 if d.get("sharded_single_proof"):
     sh = d["sharded_single_proof"]
-    print("sharded", round(sh["ms_per_proof"], 2), "ms/proof", f"{sh['rows_per_s']:.4g} rows/s", "identical", sh["identical_on_all_ranks"], {k: round(v, 2) for k, v in sh["phases_ms_rank0"].items()})
-    if sh.get("resident"):
-        r = sh["resident"]
-        print("sharded resident", round(r["ms_per_proof"], 2), "ms/proof", r["identical_to_e2e_proof"], {k: round(v, 2) for k, v in r["phases_ms_rank0"].items()})
-if d.get("lde_commit"):
-    lc = d["lde_commit"]
-    print("lde_commit", round(lc["ms_per_step"], 2), "ms", round(lc["GBps"], 1), "GB/s alg", round(lc["frac_of_hbm_peak_per_gpu"], 4), "of HBM peak/GPU", f"{lc['leaf_compressions_per_s']:.3g} compressions/s")
+    print("group prove", sh["n_gpus"], "GPUs: e2e", round(sh["e2e_ms_per_proof"], 2), "ms, resident", round(sh["resident_ms_per_proof"], 2), "ms, identical",
+          sh["identical_to_single_gpu_proof"], {k: round(v, 2) for k, v in sh["resident_phases_ms_gpu0"].items()})
+if d.get("sharded_single_proof_nccl_callbacks"):
+    sh = d["sharded_single_proof_nccl_callbacks"]
+    print("nccl-callback prove", round(sh["ms_per_proof"], 2), "ms e2e,", round(sh["resident"]["ms_per_proof"], 2), "ms resident, identical", sh["identical_on_all_ranks"])
+if d.get("worst_case_step"):
+    print("worst case step", round(d["worst_case_step"]["ms_per_step"], 2), "ms, identical", d["worst_case_step"]["identical_proof"])
+if d.get("lde_commit_fri"):
+    lc = d["lde_commit_fri"]
+    print("lde_commit_fri", lc["n_gpus"], "GPUs:", round(lc["ms_per_step"], 1), "ms", round(lc["GBps_per_gpu"], 1), "GB/s/GPU alg", f"{lc['compressions_per_s_per_gpu']:.3g} compr/s/GPU",
+          "oracle roots", lc["first_columns_match_oracle_digests"], {k: round(v, 1) for k, v in lc["phases_ms_gpu0"].items()})
 if d.get("jsonl_stream"):
     j = d["jsonl_stream"]
     print("jsonl_stream", f"{j['rows_per_s']:.4g} rows/s", round(j["ms_per_step"], 1), "ms", round(j["file_MBps"]), "MB/s", j["parser_threads"], "threads",
