@@ -206,6 +206,97 @@ def simulate(T: int, b: int, tau: int, seed: int = 42) -> CompactTrace:
     return partition(input_mv, mv, wflag, wsym, b)
 
 
+# ---- exact reproduction of `sezkp-cli simulate` (reference crates/sezkp-trace/src/generator.rs:38-73) -------------------
+# rand 0.9.2: StdRng = ChaCha12, seed_from_u64(42) expands the seed with PCG32 (rand_core), BlockRng hands out the words of
+# four ChaCha blocks at a time; random_range(0..=2) (i32) and random_range(0u16..=15) draw one u32 and take the high half of
+# sample * range (a second draw only when the low half exceeds 2^32 - range: Canon's single-extra-sample correction);
+# random_bool(0.4) compares one u64 (two words, low first) with floor(0.4 * 2^64).
+def _chacha12_words(key, first_block: int, n_blocks: int) -> np.ndarray:
+    """ChaCha12 keystream words of blocks [first_block, first_block + n_blocks), 16 u32 each, vectorised over blocks."""
+    M = np.uint64(0xFFFFFFFF)
+    ctr = np.arange(first_block, first_block + n_blocks, dtype=np.uint64)
+    init = [np.full(n_blocks, c, np.uint64) for c in (0x61707865, 0x3320646E, 0x79622D32, 0x6B206574)]
+    init += [np.full(n_blocks, k, np.uint64) for k in key]
+    init += [ctr & M, ctr >> np.uint64(32), np.zeros(n_blocks, np.uint64), np.zeros(n_blocks, np.uint64)]
+    w = [x.copy() for x in init]
+
+    def rotl(x, r):
+        return ((x << np.uint64(r)) | (x >> np.uint64(32 - r))) & M
+
+    def qr(a, b, c, d):
+        w[a] = (w[a] + w[b]) & M; w[d] = rotl(w[d] ^ w[a], 16)
+        w[c] = (w[c] + w[d]) & M; w[b] = rotl(w[b] ^ w[c], 12)
+        w[a] = (w[a] + w[b]) & M; w[d] = rotl(w[d] ^ w[a], 8)
+        w[c] = (w[c] + w[d]) & M; w[b] = rotl(w[b] ^ w[c], 7)
+
+    for _ in range(6):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    out = np.stack([(w[i] + init[i]) & M for i in range(16)], axis=1)
+    return out.reshape(-1)
+
+
+def _std_rng_seed(state: int):
+    """rand_core SeedableRng::seed_from_u64: eight PCG32 outputs = the 32-byte ChaCha key (little-endian words)."""
+    key = []
+    for _ in range(8):
+        state = (state * 6364136223846793005 + 11634580027462260723) & 0xFFFFFFFFFFFFFFFF
+        xs = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+        rot = state >> 59
+        key.append(((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF)
+    return key
+
+
+def simulate_exact(T: int, b: int, tau: int) -> CompactTrace:
+    """Byte-identical inputs to `sezkp-cli simulate --t T --b b --tau tau` (generate_trace + partition_trace); checked
+    against the reference's shipped blocks.cbor (tests/golden/fixture_root_T64.json).  The draw sequence is data dependent
+    (a symbol is drawn only when the write coin comes up), so the consumer is a scalar loop over a vectorised keystream:
+    about 1e5 steps/s — use `simulate` (splitmix, same distribution) for the large benchmark traces."""
+    if T <= 0 or b <= 0 or not (1 <= tau <= 255):
+        raise ValueError("T and b must be positive, 1 <= tau <= 255")
+    key = _std_rng_seed(42)
+    P_INT = int(0.4 * 2.0 ** 64)  # Bernoulli::new(0.4).p_int
+    input_mv = np.empty(T, np.int8)
+    mv = np.empty((T, tau), np.int8)
+    wflag = np.zeros((T, tau), np.uint8)
+    wsym = np.zeros((T, tau), np.uint16)
+    # BlockRng buffer: 64 words (4 blocks) per refill; next_u64 at index 63 pairs the last word (low) with the first word of
+    # the next buffer (high) — i.e. the stream is consumed strictly word by word, so one flat stream is equivalent
+    words, pos, next_block = [], 0, 0
+
+    def need(k):
+        nonlocal words, pos, next_block
+        if pos + k > len(words):
+            blocks = max(4096, (k + 15) // 16)
+            words = words[pos:] + _chacha12_words(key, next_block, blocks).tolist()
+            pos = 0
+            next_block += blocks
+
+    def u32():
+        nonlocal pos
+        v = words[pos]
+        pos += 1
+        return v
+
+    def rng_range(r):
+        m = u32() * r
+        hi, lo = m >> 32, m & 0xFFFFFFFF
+        if lo > ((-r) & 0xFFFFFFFF):
+            hi += 1 if lo + ((u32() * r) >> 32) > 0xFFFFFFFF else 0
+        return hi
+
+    for i in range(T):
+        need(2 + 6 * tau)
+        input_mv[i] = rng_range(3) - 1
+        for r in range(tau):
+            lo = u32()
+            if (lo | (u32() << 32)) < P_INT:
+                wflag[i, r] = 1
+                wsym[i, r] = rng_range(16)
+            mv[i, r] = rng_range(3) - 1
+    return partition(input_mv, mv, wflag, wsym, b)
+
+
 def partition(input_mv, mv, wflag, wsym, b: int) -> CompactTrace:
     """reference partition_trace (partition.rs:43-150) on flat step arrays."""
     T, tau = mv.shape

@@ -103,3 +103,30 @@ def test_artifact_envelope_matches_reference_fixture_shape(tmp_path):
     assert isinstance(obj["proof_bytes"], list) and all(isinstance(x, int) for x in obj["proof_bytes"][:8])  # Vec<u8> without serde_bytes
     assert list(obj["meta"].keys()) == ["domain_n", "proto", "tau"]  # serde_json map: alphabetical
     assert len(obj["manifest_root"]) == 32
+
+
+def test_simulate_exact_reproduces_the_reference_fixture():
+    """f4: `sezkp-cli simulate` inputs (rand 0.9.2 StdRng = ChaCha12, seed_from_u64(42), generator.rs:38-73) and
+    partition_trace (partition.rs:61-147) reproduced exactly: every field of the reference's shipped blocks.cbor (T=64, b=8,
+    tau=2) and its manifest root."""
+    from conftest import load_fixture
+    m = pkg()
+    fx = load_fixture("fixture_root_T64.json")
+    ct = m.simulate_exact(64, 8, 2)
+    assert ct.n_blocks == len(fx["blocks"])
+    row = 0
+    for k, bk in enumerate(fx["blocks"]):
+        steps = bk["movement_log"]["steps"]
+        assert int(ct.block_len[k]) == len(steps)
+        assert (int(ct.version[k]), int(ct.block_id[k]), int(ct.step_lo[k]), int(ct.step_hi[k])) == (bk["version"], bk["block_id"], bk["step_lo"], bk["step_hi"])
+        assert (int(ct.ctrl_in[k]), int(ct.ctrl_out[k]), int(ct.in_head_in[k]), int(ct.in_head_out[k])) == (bk["ctrl_in"], bk["ctrl_out"], bk["in_head_in"], bk["in_head_out"])
+        assert [int(x) for x in ct.win_left[k]] == [w["left"] for w in bk["windows"]]
+        assert [int(x) for x in ct.win_right[k]] == [w["right"] for w in bk["windows"]]
+        assert [int(x) for x in ct.head_in_off[k]] == bk["head_in_offsets"] and [int(x) for x in ct.head_out_off[k]] == bk["head_out_offsets"]
+        for j, s in enumerate(steps):
+            assert int(ct.input_mv[row + j]) == s["input_mv"]
+            for r, tp in enumerate(s["tapes"]):
+                assert int(ct.mv[row + j, r]) == tp["mv"]
+                assert bool(ct.write_flag[row + j, r]) == (tp["write"] is not None) and int(ct.write_sym[row + j, r]) == (tp["write"] or 0)
+        row += len(steps)
+    assert m.manifest_root(ct).hex() == fx["manifest"]["root"]

@@ -75,6 +75,21 @@ def test_quickstart_T2e15_proof_vs_oracle(ctx, oracle):
     assert proof == oracle.prove_v1(ct, root)
 
 
+def test_quickstart_exact_simulate_inputs_proof_vs_oracle(ctx, oracle):
+    """config 1 on inputs byte-identical to `sezkp-cli simulate --t 32768 --b 512 --tau 8` (ChaCha12 StdRng reproduced by
+    simulate_exact, pinned on the reference's shipped blocks.cbor): proof == stored oracle digest, and the oracle's verifier
+    gives the same verdict on the GPU proof as on its own."""
+    m = pkg()
+    gold = load_fixture("quickstart_exact.json")["quickstart_exact_T2^15_b512_tau8"]
+    ct = m.simulate_exact(1 << 15, 512, 8)
+    root = m.manifest_root(ct)
+    assert root.hex() == gold["manifest_root"]
+    proof = ctx.prove_v1(ct, root)
+    assert len(proof) == gold["proof_len"] and oracle.blake3(proof).hex() == gold["proof_blake3"]
+    ok, _ = oracle.verify_v1(proof, ct)
+    assert ok == gold["oracle_verify_accepts"]
+
+
 # ----------------------------------------------------------------------------- config 4: wide LDE + commit + FRI
 def test_wide_generator_matches_oracle(ctx, oracle):
     m = pkg()
