@@ -192,9 +192,7 @@ int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx) {
     API_END(ctx)
 }
 
-int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value) {
-    API_BEGIN(ctx)
-    REQUIRE(name != nullptr, "bad argument");
+static void set_option_one(sezkp_ctx* ctx, const char* name, int64_t value) {
     if (std::strcmp(name, "dedup") == 0) {
         ctx->dedup_enabled = value != 0;
         if (value == 1 || value == 2) ctx->dedup_variant = (int)value;
@@ -203,13 +201,19 @@ int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value) {
     } else if (std::strcmp(name, "ntt_gen") == 0) {
         REQUIRE(value >= 1 && value <= 4, "ntt_gen must be 1..4");
         ctx->ntt_gen = (int)value;
+    } else if (std::strcmp(name, "lde_fuse") == 0) {
+        ctx->lde_fuse = value != 0;
     } else if (std::strcmp(name, "deep_fused") == 0) {
         ctx->deep_fused = value != 0;
     } else if (std::strcmp(name, "tab_cache") == 0) {
         ctx->tab_cache_enabled = value != 0;
         ctx->tab_cache_key.clear();
-    }
-    else sezkp_fail(SEZKP_CUDA_EINVAL, "unknown option '%s'", name);
+    } else sezkp_fail(SEZKP_CUDA_EINVAL, "unknown option '%s'", name);
+}
+int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value) {
+    API_BEGIN(ctx)
+    REQUIRE(name != nullptr, "bad argument");
+    for (int r = 0; r < group_world(ctx); r++) set_option_one(ctx->group ? ctx->group->ctx[r] : ctx, name, value);  // every GPU of a group
     API_END(ctx)
 }
 

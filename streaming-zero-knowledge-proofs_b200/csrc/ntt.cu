@@ -9,6 +9,7 @@
 // A coset LDE with blow-up B is B independent size-n NTTs of the coefficients scaled by powers of
 // g_j = shift*w_N^j (j < B), whose outputs interleave: out[j + B*i] = NTT_n(c_t * g_j^t)[i].
 // All values in HBM are canonical residues; results are therefore bit-identical to the reference.
+#include "blake3.cuh"
 #include "common.cuh"
 #include "gl.cuh"
 #include "ntt.cuh"
@@ -51,6 +52,10 @@ struct PassDesc {
     const u64* GB;
     int use_pre, use_gb, coset_from_col, coset_log;
     u32 ga_pitch, gb_pitch;
+    // fused leaf hashing (K7, last LDE pass only): the pass writes 32-leaf labeled sub-roots instead of the values
+    const b3::LabelTemplate* fuse_tpl;  // [batch columns]
+    u32* fuse_upper;                    // level 0 of column v's retained tree at fuse_upper + v * fuse_col_words
+    u64 fuse_col_words;
 };
 
 // Tile layout: element (column c, row r) lives at c*pitch + pos(r), pos(r) = r + (r >> K2) — one word of skew per
@@ -371,6 +376,106 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass2_kernel(const PassDesc
     }
 }
 
+// K7 (north_star item 3): the last pass of a coset LDE fused with the labeled leaf hash and the first five tree levels, so
+// the extended column never travels to HBM: steps 1 and 2 are those of ntt_pass2_kernel, but step 2 puts its canonical
+// outputs back into the shared-memory tile in OUTPUT order — a tile row is R consecutive leaves of the extended column —
+// and every thread then owns one aligned group of 32 leaves: 32 leaf compressions + 31 parent compressions as a
+// streaming reduction with a five-entry stack, no communication, one 32-byte sub-root stored per thread.  The tile always
+// holds 8192 leaves = 256 groups = one per thread.  Requires R >= 32 (pass width <= 8 bits), i.e. three-pass plans.
+template <int K1, int K2>
+__global__ void __launch_bounds__(NTT_THREADS, 2) lde_hash_pass_kernel(const PassDesc d) {
+    extern __shared__ u64 smem[];
+    constexpr int A = 1 << K1, B = 1 << K2, b = K1 + K2, rows = 1 << b, THREADS = NTT_THREADS;
+    constexpr int PER = (1 << TILE_LOG_ELEMS) / THREADS;  // 32 values per thread in every phase
+    constexpr int NIT1 = PER / A, NIT2 = PER / B;
+    const int pitch = d.pitch, logR = d.logR, R = 1 << logR;
+    u64* tile = smem;
+    u64* Ws = smem + (size_t)R * pitch;
+    const u32 eps = gl::lazy::k_eps32;
+    const int tid = threadIdx.x;
+    const u32 tile_id = blockIdx.x;
+    const u32 ct = tile_id % d.col_tiles;
+    const u32 rest = tile_id / d.col_tiles;
+    const u32 u = rest % d.U;
+    const u64 v = rest / d.U;
+    const u64 C0 = (u64)ct << logR;
+    const u64* in_base = d.in + u * d.in_u_stride + (v >> d.in_v_shift) * d.in_v_stride;
+    for (int i = tid; i < rows; i += THREADS) Ws[i] = d.W[(i >> K2) * (i & (B - 1))];
+    // ---- step 1 (rows are contiguous in HBM: r2 runs across the lanes) ----
+#pragma unroll
+    for (int it = 0; it < NIT1; it++) {
+        const int g = tid + it * THREADS;
+        const int r2 = g & (B - 1), c = g >> K2;
+        const u64 C = C0 + c;
+        const u64* src = in_base + (C & ((1ULL << d.in_clog) - 1)) * d.in_cs_lo + (C >> d.in_clog) * d.in_cs_hi + (u64)r2 * d.in_row_stride;
+        const u64 rs = d.in_row_stride << K2;
+        u64 x[A];
+#pragma unroll
+        for (int t = 0; t < A; t++) x[t] = src[(u64)t * rs];
+        if (it == 0) __syncthreads();  // Ws complete
+        gl::lazy::dft_pow2<K1, false>(x, eps);
+        u64* col = tile + c * pitch + r2;
+        const u64* wrow = Ws + r2;
+#pragma unroll
+        for (int k = 0; k < A; k++) {
+            const u64 y = x[gl::lazy::brev_bits(k, K1)];
+            col[k * (B + 1)] = k == 0 ? gl::lazy::canon2(y) : gl::lazy::mulc(y, wrow[k << K2], eps);
+        }
+    }
+    __syncthreads();
+    // ---- step 2: all inputs into registers first (the tile is about to be overwritten in output order) ----
+    u64 xs[PER];
+#pragma unroll
+    for (int it = 0; it < NIT2; it++) {
+        const int g = tid + it * THREADS;
+        const int c = g & (R - 1), k1 = g >> logR;
+        const u64* col = tile + c * pitch + k1 * (B + 1);
+#pragma unroll
+        for (int t = 0; t < B; t++) xs[it * B + t] = col[t];
+    }
+    __syncthreads();
+    const int opitch = R + 1;  // output-order tile: leaf (row k, column c) at k * (R + 1) + c
+#pragma unroll
+    for (int it = 0; it < NIT2; it++) {
+        const int g = tid + it * THREADS;
+        const int c = g & (R - 1), k1 = g >> logR;
+        u64 x[B];
+#pragma unroll
+        for (int t = 0; t < B; t++) x[t] = xs[it * B + t];
+        gl::lazy::dft_pow2<K2, false>(x, eps);
+#pragma unroll
+        for (int k2 = 0; k2 < B; k2++) tile[(k1 + (k2 << K1)) * opitch + c] = gl::lazy::canon2(x[gl::lazy::brev_bits(k2, K2)]);
+    }
+    __syncthreads();
+    // ---- step 3: one aligned group of 32 leaves per thread -> labeled leaves -> five tree levels -> sub-root ----
+    const int parts = R >> 5;  // groups per tile row
+    const int row = tid / parts, part = tid - row * parts;
+    const u64* leaves = tile + row * opitch + part * 32;
+    const b3::LabelTemplate tpl = d.fuse_tpl[v];
+    u32 stack[5][8];
+    u32 cur[8];
+    B3_DISPATCH_LABELED(tpl, {
+        for (int i = 0; i < 32; i++) {
+            b3::leaf_labeled_w<B3W>(tpl, leaves[i], cur);
+            int lvl = 0;
+            for (int idx = i; idx & 1; idx >>= 1, lvl++) {
+                u32 o[8];
+                b3::parent(stack[lvl], cur, o);
+#pragma unroll
+                for (int w = 0; w < 8; w++) cur[w] = o[w];
+            }
+            if (lvl < 5) {
+#pragma unroll
+                for (int w = 0; w < 8; w++) stack[lvl][w] = cur[w];
+            }
+        }
+    })
+    const u64 leaf0 = u * d.out_u_stride + (C0 + (u64)part * 32) + (u64)row * d.out_row_stride;  // first leaf of the group in column v
+    u32* dst = d.fuse_upper + v * d.fuse_col_words + (leaf0 >> 5) * 8;
+    *(uint4*)dst = make_uint4(cur[0], cur[1], cur[2], cur[3]);
+    *(uint4*)(dst + 4) = make_uint4(cur[4], cur[5], cur[6], cur[7]);
+}
+
 // Full inter-pass twiddle matrix T[k][J] = w^(k*J*stride) (k < rows, J < pitch): same shape as the data block, so the
 // store loop reads it with the data's own coalescing; it stays in L2 across the columns of a batch.
 // `scale` (N^-1 of an inverse transform, else 1) is folded into the first pass's matrix, so the last pass of an inverse
@@ -589,6 +694,10 @@ static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
     d.pitch = tile_pitch(d.b, d.logR);
     const size_t smem = (((size_t)d.pitch << d.logR) + (d.b > 5 ? ((size_t)1 << d.b) : 0)) * 8;
     pass_fn fn = kernel_for_bits(d.b, d.inv != 0, ctx->ntt_gen);
+    if (d.fuse_upper) {  // K7: last LDE pass + labeled leaf hash + five tree levels
+        REQUIRE(!d.inv && (d.b == 7 || d.b == 8) && d.b + d.logR == TILE_LOG_ELEMS && d.logR >= 5, "internal: fused LDE/hash pass shape");
+        fn = d.b == 8 ? (pass_fn)lde_hash_pass_kernel<4, 4> : (pass_fn)lde_hash_pass_kernel<4, 3>;
+    }
     // max dynamic smem already granted per kernel — per context: the attribute is per device, and the contexts of a
     // group run on concurrent threads
     size_t& granted = ctx->func_smem[(const void*)fn];
@@ -596,7 +705,7 @@ static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
         CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         granted = smem;
     }
-    fn<<<(unsigned)tiles, pass_threads(ctx, d.b), smem, ctx->stream>>>(d);
+    fn<<<(unsigned)tiles, d.fuse_upper ? NTT_THREADS : pass_threads(ctx, d.b), smem, ctx->stream>>>(d);
     CUDA_CHECK(cudaGetLastError());
     ctx->launches++;
 }
@@ -719,7 +828,13 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
 }
 
 // Coset LDE: coeffs [cols][n] -> out [cols][B*n]; inter must hold cols*B*n elements when log n > MAX_PASS_BITS.
-void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, int L, int logB, u64 shift, u64 cols) {
+bool lde_hash_fusable(int L, int logB) {  // the last pass must be 7 or 8 bits wide with at least 32 tile columns
+    if (L <= 2 * MAX_PASS_BITS) return false;
+    const std::vector<int> plan = make_plan(L);
+    const int b = plan.back();
+    return (b == 7 || b == 8) && ((u64)1 << (plan[0] + logB)) >= ((u64)1 << (TILE_LOG_ELEMS - b)) && TILE_LOG_ELEMS - b >= 5 && logB <= TILE_LOG_ELEMS - b;
+}
+void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, int L, int logB, u64 shift, u64 cols, const LdeHashFuse* fuse) {
     REQUIRE(L >= 1 && L <= 3 * MAX_PASS_BITS, "log_n %d out of range", L);
     REQUIRE(logB >= 0 && logB <= 4 && L + logB <= 32, "log_blow %d out of range", logB);
     REQUIRE(shift != 0 && shift < gl::P, "coset shift must be a non-zero canonical field element");
@@ -816,6 +931,12 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
                 d.out_u_stride = N1 * B;
             }
             d.load_rows_fast = 1;
+            if (fuse) {
+                REQUIRE(lde_hash_fusable(L, logB), "internal: LDE of 2^%d x 2^%d cannot be fused with the leaf hash", L, logB);
+                d.fuse_tpl = (const b3::LabelTemplate*)fuse->templates;
+                d.fuse_upper = fuse->upper;
+                d.fuse_col_words = fuse->col_words;
+            }
             launch_pass(ctx, d, cols);
         }
         S = Sp;

@@ -120,11 +120,30 @@ void lde_commit_columns(sezkp_ctx* ctx, const u64* evals_dev, const char* const*
     u64* coeffs = (u64*)ctx->scratch[4].ensure(group * n * 8);
     u64* tmp = log_n > 10 ? (u64*)ctx->scratch[0].ensure(group * n * 8) : nullptr;
     u64* inter = log_n > 10 ? (u64*)ctx->scratch[1].ensure(group * N * 8) : nullptr;
-    u64* ext = (u64*)ctx->scratch[5].ensure(group * N * 8);
+    // K7 (option "lde_fuse"): the LDE's last pass hashes its outputs and writes 32-leaf sub-roots; the extended values never
+    // reach HBM.  Same roots either way.
+    const bool fuse = ctx->lde_fuse && chunk_log2 == 10 && lde_hash_fusable(log_n, log_blow);
+    u64* ext = fuse ? nullptr : (u64*)ctx->scratch[5].ensure(group * N * 8);
     for (size_t c0 = 0; c0 < (size_t)c; c0 += group) {
         const size_t g = (c0 + group <= (size_t)c) ? group : (size_t)c - c0;
         CUDA_CHECK(cudaMemcpyAsync(coeffs, evals_dev + c0 * n, g * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         ntt_batch_device(ctx, coeffs, tmp, log_n, g, true);
+        if (fuse) {
+            Commit cm;
+            CommitOpts o;
+            o.roots_dev = d_roots + c0 * 32;
+            try {
+                commit_begin(ctx, cm, nullptr, N, (int)g, 5, labels + c0, o);
+                LdeHashFuse f{cm.templates, cm.upper, (2 * cm.n_ch - 1) * 8};
+                coset_lde_device(ctx, coeffs, nullptr, inter, log_n, log_blow, shift, g, &f);
+                commit_finish(ctx, cm, o);
+            } catch (...) {
+                cm.release(ctx);
+                throw;
+            }
+            cm.release(ctx);
+            continue;
+        }
         coset_lde_device(ctx, coeffs, ext, inter, log_n, log_blow, shift, g);
         Commit cm;
         CommitOpts o;

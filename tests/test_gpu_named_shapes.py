@@ -157,3 +157,39 @@ def test_wide_named_shape_256_x_2e24_reproduces_oracle_roots(ctx):
     if torch.cuda.mem_get_info()[1] < 60 * (1 << 30):
         pytest.skip("needs 60 GB of HBM")
     check_wide_golden(ctx, "wide_0x5EED_2^24", 256)
+
+
+# ----------------------------------------------------------------------------- K7: LDE fused with the leaf hash
+@pytest.mark.parametrize("log_n,c", [(21, 3), (22, 2), (23, 1)])
+def test_lde_fused_leaf_hash_gives_the_same_roots(log_n, c):
+    """option lde_fuse: the last LDE pass hashes its outputs (labeled leaves + 5 tree levels) instead of writing them;
+    three-pass plans with last-pass widths 7 and 8 (2^21: 7/7/7, 2^22: 8/7/7, 2^23: 8/8/7)"""
+    m = pkg()
+    ctx = m.Context()
+    try:
+        ev = np.stack([det_vec_fast(1 << log_n, 900 + k) for k in range(c)])
+        labels = [f"c_{k}" if k else "a-rather-long-label-of-31-bytes.." for k in range(c)]
+        want = ctx.lde_commit(ev, labels, 3)
+        ctx.set_option("lde_fuse", 1)
+        got = ctx.lde_commit(ev, labels, 3)
+        got2 = ctx.lde_commit(ev, labels, 2)  # blow-up 4: 32 tile columns = 8 k1 values x 4 cosets
+        ctx.set_option("lde_fuse", 0)
+        assert np.array_equal(got, want)
+        assert np.array_equal(got2, ctx.lde_commit(ev, labels, 2))
+    finally:
+        ctx.close()
+
+
+def test_lde_fused_wide_2e24_vs_oracle_digest():
+    """the fused pipeline at config 4's row count against the oracle's column roots and FRI roots"""
+    if "wide_0x5EED_2^24" not in GOLD:
+        pytest.skip("golden digests at 2^24 not generated")
+    m = pkg()
+    ctx = m.Context()
+    try:
+        ctx.set_option("lde_fuse", 1)
+        _, fr, fin, g = check_wide_golden(ctx, "wide_0x5EED_2^24", 8)
+        p = g["pipeline"]
+        assert [r.tobytes().hex() for r in fr] == p["fri_roots"] and fin == p["final_value"]
+    finally:
+        ctx.close()
