@@ -75,7 +75,7 @@ int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx);
  * subtree tables for structured columns; "deep_fused" (default 0): one-launch DEEP kernel also for large domains; "tab_cache" (default 1): keep the
  * subtree tables across proofs while their parameters and labels are unchanged; "ntt_gen" (default 3): NTT pass-kernel
  * generation (1 = round-1 kernel with three shared-memory round trips, 2-4 = global loads/stores fused into the register
- * DFTs, differing in register budget / CTA size; A/B measurements); "lde_fuse" (default 0): fuse the last pass of the LDE
+ * DFTs, differing in register budget / CTA size; A/B measurements); "lde_fuse" (default 1): fuse the last pass of the LDE
  * with the labeled leaf hash in sezkp_lde_commit_batch / sezkp_lde_commit_fri (north_star item 3; same roots) */
 int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value);
 /* number of kernels launched by this ctx since creation / since the last reset */

@@ -169,7 +169,7 @@ struct sezkp_ctx {
     bool tab_cache_enabled = true;           // option "tab_cache"
     std::vector<u8> tab_cache_key;           // subtree tables in scratch[11] were built for exactly these (ColTab[], label templates)
     int ntt_gen = 3;                        // option "ntt_gen": pass-kernel generation (1 = round-1 kernel; 2-4 = fused global I/O, see ntt.cu kernel_for_bits)
-    bool lde_fuse = false;                  // option "lde_fuse" (K7): fuse the LDE's last pass with the labeled leaf hash in lde_commit / lde_commit_fri
+    bool lde_fuse = true;                   // option "lde_fuse" (K7): fuse the LDE's last pass with the labeled leaf hash in lde_commit / lde_commit_fri
     bool deep_fused = false;                // option "deep_fused": one-launch DEEP kernel (per-CTA inversion) also for large domains
     std::map<const void*, size_t> func_smem;  // kernel -> dynamic shared memory already granted on this ctx's device
     u64 launches = 0;                       // kernels launched since last reset

@@ -551,7 +551,13 @@ void deep_lde_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, 
     ntt_batch_device(ctx, base_vals, tmp, L, 1, true);
     u64* inter = (u64*)ctx->scratch[1].ensure(N * 8);
     coset_lde_device(ctx, base_vals, out, inter, L, logB, shift, 1);
-    const u64 w = gl::root_2exp((unsigned)(L + logB));
+    deep_quotient_device(ctx, out, L + logB, shift, z);
+}
+
+// y[i] *= (shift * w^i - z)^-1 for i < 2^log_dom, w = the primitive 2^log_dom-th root (v1/lde.rs:76-93, batched inversion)
+void deep_quotient_device(sezkp_ctx* ctx, u64* out, int log_dom, u64 shift, u64 z) {
+    const u64 N = 1ULL << log_dom;
+    const u64 w = gl::root_2exp((unsigned)log_dom);
     DeepParams dp;
     dp.shift = shift;
     dp.z = z;
@@ -561,8 +567,8 @@ void deep_lde_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, 
     for (int l = 0; l < 32; l++) dp.w_lane[l] = gl::pow(w, (u64)l);
     // shift * w^(cta * elements per CTA), cached per (log N, shift)
     const u64 n_cta = blocks_for(N, DEEP_THREADS * DEEP_PER_THREAD);
-    const auto key = std::make_pair(L + logB, shift);  // n_cta is a function of log N, so the entry's length is implied
-    if (!ctx->deep_tables.count(key) && ctx->deep_tables.size() >= 16) {  // callers that vary `shift`: bounded cache
+    const auto key = std::make_pair(log_dom, shift);  // n_cta is a function of log N, so the entry's length is implied
+    if (!ctx->deep_tables.count(key) && ctx->deep_tables.size() >= 32) {  // callers that vary `shift`: bounded cache
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         for (auto& kv : ctx->deep_tables) cudaFree(kv.second);
         ctx->deep_tables.clear();
@@ -591,6 +597,53 @@ void deep_lde_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, 
         CUDA_CHECK(cudaGetLastError());
         ctx->launches++;
     }
+}
+
+namespace {
+// out[j + B*i] = gathered[j*n + i]: the coset-major result of the sharded LDE back into the reference's natural order
+__global__ void __launch_bounds__(256) coset_interleave_kernel(const u64* __restrict__ gathered, u64 n, int logB, u64* __restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int B = 1 << logB;
+    for (int j = 0; j < B; j++) out[((u64)i << logB) + j] = gathered[(u64)j * n + i];
+}
+}  // namespace
+
+// The same DEEP-LDE with the B cosets of the extension domain split over the ranks of a sharded proof: the evaluation domain
+// shift*<w_N> is the union of the cosets g_j*<w_n>, g_j = shift*w_N^j, and out[j + B*i] = f(g_j w_n^i) / (g_j w_n^i - z) — a
+// plain coset evaluation of size n with shift g_j followed by the quotient on that coset.  Rank r evaluates cosets
+// [r*B/world, (r+1)*B/world), the coset-major pieces are all-gathered on the device and interleaved locally.  Values are
+// the unique canonical results, so the output is bit-identical to deep_lde_device's.  Needs world | B.
+void deep_lde_sharded_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, int logB, u64 shift, u64 z, int rank, int world) {
+    REQUIRE(z < gl::P && shift < gl::P && shift != 0, "shift / z must be canonical, shift non-zero");
+    REQUIRE(!z_on_coset(z, shift, L + logB), "OOD point z lies on the evaluation coset");
+    const int B = 1 << logB, per = B / world;
+    REQUIRE(world >= 1 && per >= 1 && per * world == B && ctx->allgather_dev, "internal: coset sharding needs world | blow-up and a device collective");
+    const u64 n = 1ULL << L;
+    u64* tmp = (u64*)ctx->scratch[0].ensure(n * 8);
+    ntt_batch_device(ctx, base_vals, tmp, L, 1, true);
+    u64* inter = (u64*)ctx->scratch[1].ensure(n * 8);
+    u64* mine = (u64*)ctx->pool.alloc((size_t)per * n * 8);
+    u64* gathered = (u64*)ctx->pool.alloc((size_t)B * n * 8);
+    try {
+        const u64 wN = gl::root_2exp((unsigned)(L + logB));
+        for (int q = 0; q < per; q++) {
+            const u64 gj = gl::mul(shift, gl::pow(wN, (u64)(rank * per + q)));
+            coset_lde_device(ctx, base_vals, mine + (u64)q * n, inter, L, 0, gj, 1);
+            deep_quotient_device(ctx, mine + (u64)q * n, L, gj, z);
+        }
+        const int32_t rc = ctx->allgather_dev(ctx->allgather_dev_user, mine, (size_t)per * n * 8, gathered, (void*)ctx->stream);
+        if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "device allgather callback failed with status %d", rc);
+        coset_interleave_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(gathered, n, logB, out);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+    } catch (...) {
+        ctx->pool.free(mine);
+        ctx->pool.free(gathered);
+        throw;
+    }
+    ctx->pool.free(mine);
+    ctx->pool.free(gathered);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1041,7 +1094,9 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         lap("compose");
         fl.values = (u64*)ctx->pool.alloc(2 * N * 8);  // the DEEP-LDE lands where FRI layer 0 lives: no 8N-byte copy
         u64* lde = fl.values;
-        deep_lde_device(ctx, base_vals, lde, L, logB, shift, z);
+        // sharded proof with a device collective: each rank evaluates 8/world cosets of the extension domain (needs world | 8)
+        if (row_sliced && (1 << logB) % world == 0) deep_lde_sharded_device(ctx, base_vals, lde, L, logB, shift, z, rank, world);
+        else deep_lde_device(ctx, base_vals, lde, L, logB, shift, z);
         lap("deep_lde");
 
         // G. FRI fold + commit; root0 is absorbed before the betas are drawn (v1/prover.rs:184-243)

@@ -47,6 +47,9 @@ void compose_device(sezkp_ctx* ctx, const u64* cols_dev, u64 n, u32 tau, const u
                     u64* out_dev, u64 row0 = 0, u64 row1 = ~0ULL);  // rows [row0, row1) only (row i reads rows i and i+1 mod n)
 bool z_on_coset(u64 z, u64 shift, int log_N);
 void deep_lde_device(sezkp_ctx* ctx, u64* base_vals_dev /* destroyed */, u64* out_dev, int L, int logB, u64 shift, u64 z);
+void deep_quotient_device(sezkp_ctx* ctx, u64* y_dev, int log_dom, u64 shift, u64 z);
+void deep_lde_sharded_device(sezkp_ctx* ctx, u64* base_vals_dev /* destroyed */, u64* out_dev, int L, int logB, u64 shift, u64 z, int rank,
+                             int world);
 
 // Where the serialised proof goes: straight into the caller's buffer (no intermediate copy).  Bytes beyond the
 // capacity are counted but not written, so a NULL / short buffer still yields the required length.

@@ -161,7 +161,7 @@ def test_wide_named_shape_256_x_2e24_reproduces_oracle_roots(ctx):
 
 # ----------------------------------------------------------------------------- K7: LDE fused with the leaf hash
 @pytest.mark.parametrize("log_n,c", [(21, 3), (22, 2), (23, 1)])
-def test_lde_fused_leaf_hash_gives_the_same_roots(log_n, c):
+def test_lde_fused_leaf_hash_gives_the_same_roots(oracle, log_n, c):
     """option lde_fuse: the last LDE pass hashes its outputs (labeled leaves + 5 tree levels) instead of writing them;
     three-pass plans with last-pass widths 7 and 8 (2^21: 7/7/7, 2^22: 8/7/7, 2^23: 8/8/7)"""
     m = pkg()
@@ -169,25 +169,27 @@ def test_lde_fused_leaf_hash_gives_the_same_roots(log_n, c):
     try:
         ev = np.stack([det_vec_fast(1 << log_n, 900 + k) for k in range(c)])
         labels = [f"c_{k}" if k else "a-rather-long-label-of-31-bytes.." for k in range(c)]
+        ctx.set_option("lde_fuse", 0)  # separate leaf-hash kernel over the stored extended columns
         want = ctx.lde_commit(ev, labels, 3)
-        ctx.set_option("lde_fuse", 1)
+        want2 = ctx.lde_commit(ev, labels, 2)
+        ctx.set_option("lde_fuse", 1)  # the default
         got = ctx.lde_commit(ev, labels, 3)
         got2 = ctx.lde_commit(ev, labels, 2)  # blow-up 4: 32 tile columns = 8 k1 values x 4 cosets
-        ctx.set_option("lde_fuse", 0)
-        assert np.array_equal(got, want)
-        assert np.array_equal(got2, ctx.lde_commit(ev, labels, 2))
+        assert np.array_equal(got, want) and np.array_equal(got2, want2)
+        if log_n == 21:  # live oracle at 2^24 leaves (~15 s)
+            assert oracle.lde_commit_root(ev[0], 3, 3, labels[0]) == got[0].tobytes()
     finally:
         ctx.close()
 
 
-def test_lde_fused_wide_2e24_vs_oracle_digest():
-    """the fused pipeline at config 4's row count against the oracle's column roots and FRI roots"""
+def test_lde_unfused_wide_2e24_vs_oracle_digest():
+    """the unfused pipeline (lde_fuse = 0) at config 4's row count against the oracle's column roots and FRI roots"""
     if "wide_0x5EED_2^24" not in GOLD:
         pytest.skip("golden digests at 2^24 not generated")
     m = pkg()
     ctx = m.Context()
     try:
-        ctx.set_option("lde_fuse", 1)
+        ctx.set_option("lde_fuse", 0)  # the unfused path against the same digests (the default, fused, path is checked above)
         _, fr, fin, g = check_wide_golden(ctx, "wide_0x5EED_2^24", 8)
         p = g["pipeline"]
         assert [r.tobytes().hex() for r in fr] == p["fri_roots"] and fin == p["final_value"]
