@@ -570,7 +570,7 @@ def main():
         compressions = 2 * N - 1
         alu_bound = 148 * 64 * 1.965e9 / 455
         traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
-        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
         if os.path.exists(tpath) and wl["log_T"] == 22:
             traffic = json.load(open(tpath)).get("chunk_commit_kernel_fri_layer0_dram_bytes_per_launch")
         # second kernel family of the step: the value-aware commit of the 59 trace columns (subtree tables)

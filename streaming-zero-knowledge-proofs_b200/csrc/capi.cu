@@ -886,36 +886,55 @@ int32_t sezkp_jsonl_write_file(const char* path, const sezkp_trace_desc* trace, 
     return SEZKP_CUDA_OK;
 }
 
-// parse on the host threads and ingest the workers' outputs one after the other (file order), without concatenating them
-static void jsonl_parse_and_ingest(sezkp_ctx* ctx, sezkp_stream*& st, const uint8_t* manifest_root, uint64_t expected_rows,
-                                   const char* text, size_t len, int n_threads, size_t first_line, size_t* lines, uint64_t* blocks,
-                                   uint64_t* rows, double* parse_ms) {
+// One piece of JSONL text parsed on the host threads: the workers' outputs in file order (not concatenated).
+struct ParsedPiece {
     std::vector<jsonl::Trace> parts;
-    u32 tau = st ? stream_tau(st) : 0;
+    size_t lines = 0;
+    u32 tau = 0;
+    double parse_ms = 0;
+    std::string error;      // non-empty: parsing failed (reported by the consumer, in file order)
+    bool oom = false;
+};
+static void jsonl_parse_piece(const char* text, size_t len, int n_threads, u32 tau_hint, size_t first_line, ParsedPiece& out) {
     const auto t0 = std::chrono::steady_clock::now();
     try {
-        const size_t nl = jsonl::parse_parts(text, len, jsonl_threads(n_threads), tau, first_line, parts, tau);
-        if (lines) *lines = nl;
+        out.tau = tau_hint;
+        out.lines = jsonl::parse_parts(text, len, jsonl_threads(n_threads), tau_hint, first_line, out.parts, out.tau);
     } catch (const std::bad_alloc&) {
-        throw;
+        out.oom = true;
     } catch (const std::exception& e) {
-        sezkp_fail(SEZKP_CUDA_EINVAL, "%s", e.what());
+        out.error = e.what();
     }
-    if (parse_ms) *parse_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    for (auto& t : parts) {
+    out.parse_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+static void jsonl_ingest_piece(sezkp_ctx* ctx, sezkp_stream*& st, const uint8_t* manifest_root, uint64_t expected_rows, ParsedPiece& pc,
+                               uint64_t* blocks, uint64_t* rows) {
+    if (pc.oom) throw std::bad_alloc();
+    if (!pc.error.empty()) sezkp_fail(SEZKP_CUDA_EINVAL, "%s", pc.error.c_str());
+    for (auto& t : pc.parts) {
         if (t.block_len.empty()) continue;
         if (!st) {
             REQUIRE(manifest_root != nullptr, "internal: stream not started");
-            st = stream_begin(ctx, tau, manifest_root, expected_rows);
+            st = stream_begin(ctx, pc.tau, manifest_root, expected_rows);
         }
         sezkp_trace_desc d;
-        t.tau = tau;
+        t.tau = pc.tau;
         t.fill_desc(d);
         stream_ingest(ctx, st, &d);
         if (blocks) *blocks += t.block_len.size();
         if (rows) *rows += t.input_mv.size();
         t = jsonl::Trace();
     }
+}
+// parse, then ingest (the one-shot text entry point)
+static void jsonl_parse_and_ingest(sezkp_ctx* ctx, sezkp_stream*& st, const uint8_t* manifest_root, uint64_t expected_rows,
+                                   const char* text, size_t len, int n_threads, size_t first_line, size_t* lines, uint64_t* blocks,
+                                   uint64_t* rows, double* parse_ms) {
+    ParsedPiece pc;
+    jsonl_parse_piece(text, len, n_threads, st ? stream_tau(st) : 0, first_line, pc);
+    if (lines) *lines = pc.lines;
+    if (parse_ms) *parse_ms += pc.parse_ms;
+    jsonl_ingest_piece(ctx, st, manifest_root, expected_rows, pc, blocks, rows);
 }
 int32_t sezkp_stark_v1_ingest_jsonl(sezkp_ctx* ctx, sezkp_stream* st, const char* text, size_t len, int n_threads,
                                     uint64_t* n_blocks, uint64_t* n_rows) {
@@ -934,7 +953,7 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
     API_BEGIN(ctx)
     REQUIRE(path && manifest_root && proof_buf && len, "bad argument");
     REQUIRE(expected_rows <= (1ULL << 29), "expected_rows too large");
-    if (chunk_bytes == 0) chunk_bytes = (size_t)16 << 20;
+    if (chunk_bytes == 0) chunk_bytes = (size_t)64 << 20;
     FILE* f = std::fopen(path, "rb");
     if (!f) sezkp_fail(SEZKP_CUDA_EINVAL, "cannot open %s", path);
     sezkp_stream* st = nullptr;
@@ -966,6 +985,10 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
         total_bytes += got;
     };
     std::thread reader;
+    // state the parser thread writes: declared outside the try block so that it outlives the thread on every unwind path
+    // (the handler joins `reader` before these go out of scope)
+    ParsedPiece pc[2];
+    std::vector<std::pair<size_t, size_t>> pieces;  // (offset, length) of the mapped file's pieces, cut at newlines
     void* map = MAP_FAILED;
     size_t map_len = 0;
     try {
@@ -980,9 +1003,10 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
             read_ms += ms_now() - t0;
         }
         if (map != MAP_FAILED) {
+            // Two-stage pipeline over pieces of the mapped file: while this thread packs piece k into the pinned staging ring
+            // (stream_ingest: memcpy + H2D submission), the parser threads already work on piece k + 1.
             const char* text = (const char*)map;
-            size_t pos = 0;
-            while (pos < map_len) {
+            for (size_t pos = 0; pos < map_len;) {
                 size_t use = std::min(chunk_bytes, map_len - pos);
                 if (pos + use < map_len) {  // cut at the last newline of the piece (or extend to the next one)
                     size_t e = use;
@@ -993,11 +1017,32 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
                     }
                     use = e;
                 }
-                size_t nl = 0;
-                jsonl_parse_and_ingest(ctx, st, manifest_root, expected_rows, text + pos, use, n_threads, line_no, &nl, nullptr, nullptr, &parse_ms);
-                line_no += nl;
+                pieces.push_back({pos, use});
                 pos += use;
             }
+            int cur = 0;
+            u32 tau_known = 0;
+            auto launch = [&](size_t k, ParsedPiece& dst) {
+                dst = ParsedPiece();
+                const size_t first_line = line_no;
+                const u32 tau_hint = tau_known;
+                reader = std::thread([&dst, &pieces, text, k, n_threads, tau_hint, first_line] {
+                    jsonl_parse_piece(text + pieces[k].first, pieces[k].second, n_threads, tau_hint, first_line, dst);
+                });
+            };
+            if (!pieces.empty()) launch(0, pc[0]);
+            for (size_t k = 0; k < pieces.size(); k++) {
+                reader.join();  // piece k is parsed
+                ParsedPiece& p = pc[cur];
+                parse_ms += p.parse_ms;
+                line_no += p.lines;
+                const bool ok = p.error.empty() && !p.oom;
+                if (ok && p.tau) tau_known = p.tau;
+                if (ok && k + 1 < pieces.size()) launch(k + 1, pc[cur ^ 1]);  // parse the next piece while this one is ingested
+                jsonl_ingest_piece(ctx, st, manifest_root, expected_rows, p, nullptr, nullptr);
+                cur ^= 1;
+            }
+            if (reader.joinable()) reader.join();
             total_bytes = map_len;
         } else {
         int cur = 0;
