@@ -1,30 +1,48 @@
 // Multi-GPU context group (see group.cuh).
 #include "group.cuh"
 
+#include <chrono>
 #include <cstring>
 
 void GroupBarrier::reset(int w) {
     std::lock_guard<std::mutex> lk(mu);
     world = w;
-    count = 0;
-    failed = false;
+    count.store(0);
+    failed.store(false);
 }
 void GroupBarrier::wait() {
-    std::unique_lock<std::mutex> lk(mu);
-    if (failed) sezkp_fail(SEZKP_CUDA_ECOMM, "another GPU of the group failed");
-    const u64 my = gen;
-    if (++count == world) {
-        count = 0;
-        gen++;
+    if (failed.load(std::memory_order_acquire)) sezkp_fail(SEZKP_CUDA_ECOMM, "another GPU of the group failed");
+    const u64 my = gen.load(std::memory_order_acquire);
+    if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == world) {  // last arrival releases the others
+        count.store(0, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(mu);  // pairs with the sleepers' predicate check
+            gen.store(my + 1, std::memory_order_release);
+        }
         cv.notify_all();
         return;
     }
-    cv.wait(lk, [&] { return gen != my || failed; });
-    if (gen == my) sezkp_fail(SEZKP_CUDA_ECOMM, "another GPU of the group failed");
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int spins = 0;; spins++) {
+        if (gen.load(std::memory_order_acquire) != my) return;
+        if (failed.load(std::memory_order_acquire)) break;
+        if ((spins & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(50)) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return gen.load(std::memory_order_acquire) != my || failed.load(std::memory_order_acquire); });
+            if (gen.load(std::memory_order_acquire) != my) return;
+            break;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    sezkp_fail(SEZKP_CUDA_ECOMM, "another GPU of the group failed");
 }
 void GroupBarrier::fail() {
-    std::lock_guard<std::mutex> lk(mu);
-    failed = true;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        failed.store(true, std::memory_order_release);
+    }
     cv.notify_all();
 }
 

@@ -8,6 +8,7 @@
 //     peer-pointer exchange for kernels that read the other GPUs' HBM directly (wide.cu);
 //   * an error on one rank fails the group barrier, so the other ranks unwind instead of waiting for ever.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -15,12 +16,17 @@
 
 #include "common.cuh"
 
+// Sense-reversing barrier of the rank threads.  The waits inside a collective are microseconds long (the ranks run in
+// lockstep), and a mutex + condition-variable wake-up costs tens of microseconds per rank — with 8 ranks and a dozen
+// collectives per proof that was ~0.6 ms of a 5 ms proof.  So waiters spin on an atomic generation counter first and only
+// fall back to the condition variable after ~50 us (a rank that is still busy hashing its share).
 struct GroupBarrier {
     std::mutex mu;
     std::condition_variable cv;
-    int world = 1, count = 0;
-    u64 gen = 0;
-    bool failed = false;
+    int world = 1;
+    std::atomic<int> count{0};
+    std::atomic<u64> gen{0};
+    std::atomic<bool> failed{false};
     void reset(int w);
     void wait();  // throws SezkpError(ECOMM) once the barrier has been failed
     void fail();

@@ -372,6 +372,27 @@ __global__ void __launch_bounds__(1024) fri_tail_fold_kernel(u64* __restrict__ b
     }
 }
 
+// Scatter of a packed all-gather of FRI subtree roots: recv is [world][total_words]; inside a rank's block, layer i occupies
+// own_words[i] words at off_words[i] and belongs at upper[i] + rank * own_words[i] (equal chunk ranges per rank).
+struct GatherScatter {
+    static constexpr int MAX = 12;
+    u32* upper[MAX];
+    u32 own_words[MAX], off_words[MAX];
+    u32 total_words;
+    int n, world;
+    const u32* recv;
+};
+__global__ void __launch_bounds__(256) gather_scatter_kernel(const GatherScatter gs) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte quad per thread (digests are 32 B: everything is aligned)
+    const u64 quads_per_rank = gs.total_words / 4;
+    if (q >= quads_per_rank * gs.world) return;
+    const u32 r = (u32)(q / quads_per_rank), w = (u32)(q % quads_per_rank) * 4;
+    int i = 0;
+    while (i + 1 < gs.n && w >= gs.off_words[i + 1]) i++;
+    const uint4 v = *(const uint4*)(gs.recv + (u64)r * gs.total_words + w);
+    *(uint4*)(gs.upper[i] + (u64)r * gs.own_words[i] + (w - gs.off_words[i])) = v;
+}
+
 inline unsigned blocks_for(u64 n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
 double now_ms() {
@@ -694,15 +715,40 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     auto gather_chunk_roots = [&](Commit* const* cms, int cnt) {
         bool even = ctx->allgather_dev != nullptr;
         for (int i = 0; i < cnt; i++) even = even && (cms[i]->n_ch / CG) % (u64)world == 0;
-        if (even) {  // device-side: own range -> staging -> all-gather straight into level 0 of `upper` (rank-major = chunk order)
+        if (even && cnt == 1) {  // device-side: own range -> staging -> all-gather straight into level 0 of `upper` (rank-major = chunk order)
+            const u64 lo = own_lo(cms[0]->n_ch), hi = own_hi(cms[0]->n_ch);
+            const size_t bytes = (size_t)(hi - lo) * 32;
+            u8* stage = (u8*)ctx->scratch[6].ensure(bytes);
+            CUDA_CHECK(cudaMemcpyAsync(stage, cms[0]->upper + lo * 8, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+            const int32_t rc = ctx->allgather_dev(ctx->allgather_dev_user, stage, bytes, cms[0]->upper, (void*)ctx->stream);
+            if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "device allgather callback failed with status %d", rc);
+            return;
+        }
+        if (even) {  // several layers: ONE collective — pack the own ranges, all-gather, scatter with one small kernel
+            REQUIRE(cnt <= GatherScatter::MAX, "internal: too many sharded FRI layers");
+            GatherScatter gs{};
+            gs.n = cnt;
+            gs.world = world;
+            size_t total = 0;
             for (int i = 0; i < cnt; i++) {
-                const u64 lo = own_lo(cms[i]->n_ch), hi = own_hi(cms[i]->n_ch);
-                const size_t bytes = (size_t)(hi - lo) * 32;
-                u8* stage = (u8*)ctx->scratch[6].ensure(bytes);
-                CUDA_CHECK(cudaMemcpyAsync(stage, cms[i]->upper + lo * 8, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-                const int32_t rc = ctx->allgather_dev(ctx->allgather_dev_user, stage, bytes, cms[i]->upper, (void*)ctx->stream);
-                if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "device allgather callback failed with status %d", rc);
+                gs.upper[i] = cms[i]->upper;
+                gs.own_words[i] = (u32)((own_hi(cms[i]->n_ch) - own_lo(cms[i]->n_ch)) * 8);
+                gs.off_words[i] = (u32)(total / 4);
+                total += (size_t)gs.own_words[i] * 4;
             }
+            gs.total_words = (u32)(total / 4);
+            u8* stage = (u8*)ctx->scratch[6].ensure(total * (size_t)(world + 1));
+            for (int i = 0; i < cnt; i++)
+                CUDA_CHECK(cudaMemcpyAsync(stage + (size_t)gs.off_words[i] * 4, cms[i]->upper + own_lo(cms[i]->n_ch) * 8, (size_t)gs.own_words[i] * 4,
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
+            u8* recv = stage + total;
+            const int32_t rc = ctx->allgather_dev(ctx->allgather_dev_user, stage, total, recv, (void*)ctx->stream);
+            if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "device allgather callback failed with status %d", rc);
+            gs.recv = (const u32*)recv;
+            const u64 words = (u64)gs.total_words * world;
+            gather_scatter_kernel<<<blocks_for(words / 4, 256), 256, 0, ctx->stream>>>(gs);
+            CUDA_CHECK(cudaGetLastError());
+            ctx->launches++;
             return;
         }
         size_t per_rank = 0;
