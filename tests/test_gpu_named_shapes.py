@@ -156,7 +156,11 @@ def test_wide_named_shape_256_x_2e24_reproduces_oracle_roots(ctx):
     import torch
     if torch.cuda.mem_get_info()[1] < 60 * (1 << 30):
         pytest.skip("needs 60 GB of HBM")
-    check_wide_golden(ctx, "wide_0x5EED_2^24", 256)
+    cr, fr, fin, _ = check_wide_golden(ctx, "wide_0x5EED_2^24", 256)
+    full = GOLD.get("wide_0x5EED_2^24_256cols")
+    if full is not None:  # config 4 exactly as named, every output against the oracle (make_named_shape_digests.py wide24_full)
+        assert [cr[c].tobytes().hex() for c in range(256)] == [full["column_roots"][str(c)] for c in range(256)]
+        assert [r.tobytes().hex() for r in fr] == full["pipeline"]["fri_roots"] and fin == full["pipeline"]["final_value"]
 
 
 # ----------------------------------------------------------------------------- K7: LDE fused with the leaf hash
