@@ -129,3 +129,44 @@ def test_group_streaming_and_jsonl(single, group, tmp_path):
     m.io_jsonl.write_jsonl(path, ct)
     assert group.prove_v1_jsonl_file(path, root, ct.n_rows, ct.tau, threads=4) == want
     assert "stream_replicate_ms" in group.timings()
+
+
+def test_new_api_error_paths(single):
+    """bad arguments of the round-2 entry points come back as status codes; the context stays usable"""
+    import ctypes as C
+    m = pkg()
+    lib = m.load_library()
+    # device list problems
+    with pytest.raises(m.SezkpCudaError):
+        m.Context(devices=[0, 4096])
+    with pytest.raises(m.SezkpCudaError):
+        m.Context(devices=[])
+    # non-canonical column values are rejected on upload
+    bad = np.full((1, 16), P, np.uint64)
+    with pytest.raises(m.SezkpCudaError) as ei:
+        single.columns_upload(bad)
+    assert ei.value.code == -1
+    # a column set belongs to the context (group size) that created it
+    cs = single.columns_synth(2, 8)
+    g = m.Context(devices=[0, 0])
+    try:
+        with pytest.raises(m.SezkpCudaError) as ei:
+            g.lde_commit_fri(cs)
+        assert ei.value.code == -1
+        # shift must be a non-zero canonical field element
+        cg = g.columns_synth(2, 8)
+        with pytest.raises(m.SezkpCudaError):
+            g.lde_commit_fri(cg, shift=0)
+        a = g.lde_commit_fri(cg)  # the group is still usable after the failed call
+        b = single.lde_commit_fri(cs)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+        cg.free()
+    finally:
+        cs.free()
+        g.close()
+    # verify_openings: k = 0 is fine, a column index out of range is EINVAL
+    assert single.verify_openings(np.zeros((1, 32), np.uint8), None, None, np.zeros(0, np.uint64), np.zeros(0, np.uint64)).size == 0
+    with pytest.raises(m.SezkpCudaError) as ei:
+        single.verify_openings(np.zeros((2, 32), np.uint8), ["a", "b"], np.array([2], np.uint32), np.zeros(1, np.uint64), np.zeros(1, np.uint64))
+    assert ei.value.code == -1
+    assert lib.sezkp_cuda_device_count() >= 1
