@@ -21,6 +21,22 @@ constexpr int MAX_PASS_BITS = 10;
 constexpr int TILE_LOG_ELEMS = 13;  // 8192 elements = 64 KiB per tile
 constexpr int MAX_LOG_R = 6;
 
+// Bounds-checked build (`make dbg` -> libsezkp_cuda_dbg.so, run by tests/test_gpu_named_shapes.py::test_bounds_checked_build):
+// every global address a pass kernel forms is checked against the extent of the buffer it belongs to.  compute-sanitizer is
+// closed on this pool, so this is the memory-safety evidence for the addressing of the pass descriptors.
+#ifdef SEZKP_BOUNDS_CHECK
+#define NTT_CHECK(off, ext, what)                                                                                          \
+    do {                                                                                                                   \
+        if ((u64)(off) >= (u64)(ext)) {                                                                                    \
+            printf("NTT bounds violation: %s offset %llu >= extent %llu (block %u, thread %u, b=%d logR=%d)\n", what,      \
+                   (unsigned long long)(off), (unsigned long long)(ext), blockIdx.x, threadIdx.x, d.b, d.logR);            \
+            __trap();                                                                                                      \
+        }                                                                                                                  \
+    } while (0)
+#else
+#define NTT_CHECK(off, ext, what) ((void)0)
+#endif
+
 struct PassDesc {
     const u64* in;
     u64* out;
@@ -52,6 +68,8 @@ struct PassDesc {
     const u64* GB;
     int use_pre, use_gb, coset_from_col, coset_log;
     u32 ga_pitch, gb_pitch;
+    // buffer extents in elements (bounds-checked build only: make dbg, -DSEZKP_BOUNDS_CHECK)
+    u64 in_extent, out_extent, tw_extent, fuse_extent;
     // fused leaf hashing (K7, last LDE pass only): the pass writes 32-leaf labeled sub-roots instead of the values
     const b3::LabelTemplate* fuse_tpl;  // [batch columns]
     u32* fuse_upper;                    // level 0 of column v's retained tree at fuse_upper + v * fuse_col_words
@@ -284,6 +302,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass2_kernel(const PassDesc
         if (live && C < d.total_cols) {
             const u64* src = in_base + (C & ((1ULL << d.in_clog) - 1)) * d.in_cs_lo + (C >> d.in_clog) * d.in_cs_hi + (u64)r2 * d.in_row_stride;
             const u64 rs = d.in_row_stride << K2;  // rows r2 + B*t
+            NTT_CHECK((u64)(src - d.in) + (u64)(A - 1) * rs, d.in_extent, "pass load");
 #pragma unroll
             for (int t = 0; t < A; t++) x[t] = src[(u64)t * rs];
             if (d.use_pre) {
@@ -338,10 +357,12 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass2_kernel(const PassDesc
         gl::lazy::dft_pow2<K2, INV>(x, eps);
         u64* dst = out_base + (C & ((1ULL << d.out_clog) - 1)) * d.out_cs_lo + (C >> d.out_clog) * d.out_cs_hi + (u64)k1 * d.out_row_stride;
         const u64 rs = d.out_row_stride << K1;  // rows k1 + A*k2
+        NTT_CHECK((u64)(dst - d.out) + (u64)(B - 1) * rs, d.out_extent, "pass store");
         if (d.use_tw) {
             if (d.tw_full) {
                 const u64* twf = d.tw_full + C + (u64)k1 * d.tw_pitch;
                 const u64 tp = d.tw_pitch << K1;
+                NTT_CHECK((u64)(twf - d.tw_full) + (u64)(B - 1) * tp, d.tw_extent, "twiddle matrix");
                 constexpr int G = MINB >= 3 ? 4 : 8;  // twiddle loads in flight per thread (registers: x[] already holds 2*B)
 #pragma unroll
                 for (int k0 = 0; k0 < B; k0 += G) {
@@ -410,6 +431,7 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) lde_hash_pass_kernel(const Pas
         const u64* src = in_base + (C & ((1ULL << d.in_clog) - 1)) * d.in_cs_lo + (C >> d.in_clog) * d.in_cs_hi + (u64)r2 * d.in_row_stride;
         const u64 rs = d.in_row_stride << K2;
         u64 x[A];
+        NTT_CHECK((u64)(src - d.in) + (u64)(A - 1) * rs, d.in_extent, "fused pass load");
 #pragma unroll
         for (int t = 0; t < A; t++) x[t] = src[(u64)t * rs];
         if (it == 0) __syncthreads();  // Ws complete
@@ -472,6 +494,8 @@ __global__ void __launch_bounds__(NTT_THREADS, 2) lde_hash_pass_kernel(const Pas
     })
     const u64 leaf0 = u * d.out_u_stride + (C0 + (u64)part * 32) + (u64)row * d.out_row_stride;  // first leaf of the group in column v
     u32* dst = d.fuse_upper + v * d.fuse_col_words + (leaf0 >> 5) * 8;
+    NTT_CHECK((u64)(dst - d.fuse_upper) + 7, d.fuse_extent, "sub-root store");
+    NTT_CHECK((leaf0 >> 5), (d.fuse_col_words + 8) / 16, "sub-root index within the column's level 0");
     *(uint4*)dst = make_uint4(cur[0], cur[1], cur[2], cur[3]);
     *(uint4*)(dst + 4) = make_uint4(cur[4], cur[5], cur[6], cur[7]);
 }
@@ -713,6 +737,7 @@ static void launch_pass(sezkp_ctx* ctx, PassDesc& d, u64 V) {
 constexpr int FULL_TW_MAX_LOG = 24;  // full twiddle matrices up to 2^24 entries (128 MiB) per pass
 static void attach_full_twiddles(sezkp_ctx* ctx, NttTables* t, PassDesc& d, int p, u64 rows, u64 Sp, u64 stride) {
     const u64 count = rows * Sp;
+    d.tw_extent = count;
     if (count > (1ULL << FULL_TW_MAX_LOG)) return;
     if (!t->tw_full[p]) {
         u64* buf = nullptr;
@@ -756,6 +781,7 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
         base_desc(d, t, L);
         d.in = data;
         d.out = data;
+        d.in_extent = d.out_extent = cols * N;
         d.logR = pick_logR(ctx, L, cols, 0);
         d.col_tiles = (u32)((cols + (1ULL << d.logR) - 1) >> d.logR);
         d.total_cols = cols;
@@ -822,6 +848,7 @@ void ntt_batch_device(sezkp_ctx* ctx, u64* data, u64* tmp, int L, u64 cols, bool
             d.use_scale = inverse && !t->tw0_scaled;
             d.scale = t->scale;
         }
+        d.in_extent = d.out_extent = cols * N;
         launch_pass(ctx, d, cols);
         S = Sp;
     }
@@ -849,6 +876,8 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
         base_desc(d, t, L);
         d.in = coeffs;
         d.out = out;
+        d.in_extent = cols * n;
+        d.out_extent = cols * B * n;
         d.total_cols = cols * B;
         d.logR = pick_logR(ctx, L, d.total_cols, 0);
         d.col_tiles = (u32)((d.total_cols + (1ULL << d.logR) - 1) >> d.logR);
@@ -883,6 +912,8 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
         if (!last) {  // case A / A'
             d.in = (p == 0) ? coeffs : inter;
             d.out = inter;
+            d.in_extent = (p == 0) ? cols * n : cols * B * n;
+            d.out_extent = cols * B * n;
             d.logR = pick_logR(ctx, b, Sp, 0);
             d.col_tiles = (u32)(Sp >> d.logR);
             d.total_cols = Sp;
@@ -914,6 +945,7 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
             const u64 N1 = 1ULL << plan[0], S1 = n / N1;
             d.in = inter;
             d.out = out;
+            d.in_extent = d.out_extent = cols * B * n;
             d.total_cols = N1 * B;
             d.logR = pick_logR(ctx, b, d.total_cols, logB);
             d.col_tiles = (u32)(d.total_cols >> d.logR);
@@ -936,6 +968,7 @@ void coset_lde_device(sezkp_ctx* ctx, const u64* coeffs, u64* out, u64* inter, i
                 d.fuse_tpl = (const b3::LabelTemplate*)fuse->templates;
                 d.fuse_upper = fuse->upper;
                 d.fuse_col_words = fuse->col_words;
+                d.fuse_extent = cols * fuse->col_words;
             }
             launch_pass(ctx, d, cols);
         }
