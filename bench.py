@@ -298,9 +298,15 @@ def wide_bench(m, devices, hbm_peak, steps):
     golden = None
     gp = os.path.join(ROOT, "tests", "golden", "named_shape_digests.json")
     key = f"wide_0x5EED_2^{k}"
+    golden_all = None
     if os.path.exists(gp) and key in json.load(open(gp)):
-        want = json.load(open(gp))[key]["column_roots"]
+        gold = json.load(open(gp))
+        want = gold[key]["column_roots"]
         golden = all(cr[int(c)].tobytes().hex() == h for c, h in want.items() if int(c) < cols)
+        full = gold.get(f"{key}_{cols}cols")  # the oracle's run of exactly this shape (all column roots, FRI roots, final value)
+        if full is not None:
+            golden_all = (all(cr[c].tobytes().hex() == full["column_roots"][str(c)] for c in range(cols))
+                          and [r.tobytes().hex() for r in fr] == full["pipeline"]["fri_roots"] and fin == full["pipeline"]["final_value"])
     N = n << lb
     lde_bytes = cols * 8 * n * (1 + (1 << lb))          # LDE from evaluations, 8 n (1 + B) per column
     commit_bytes = cols * 8 * N                          # column commit from values, root only: 8 N per column
@@ -315,6 +321,7 @@ def wide_bench(m, devices, hbm_peak, steps):
             "compressions_per_s": comp / (ms / 1e3), "compressions_per_s_per_gpu": comp / (ms / 1e3) / world,
             "frac_of_alu_pipe_bound_per_gpu": comp / (ms / 1e3) / world / (148 * 64 * 1.965e9 / 455),
             "phases_ms_gpu0": tm, "first_columns_match_oracle_digests": golden,
+            "all_outputs_match_oracle_digests": golden_all,
             "timing": "CUDA events on every GPU's stream inside the library, max over GPUs (wall clock of the blocking call next to it)"}
 
 
