@@ -109,8 +109,9 @@ void wide_columns_upload(sezkp_ctx* ctx, WideColumns& wc, const u64* evals_host,
 }
 
 // LDE + commit of `c` resident columns: per column group iNTT -> coset LDE -> labeled leaves -> tree.  Roots go to
-// d_roots (device, [c][32]).  The leaf hash is a separate kernel from the LDE's last pass — see DESIGN.md §4.4 for the
-// measurement behind that choice.
+// d_roots (device, [c][32]).  By default (option "lde_fuse", three-pass sizes) the LDE's last pass hashes its own outputs
+// (lde_hash_pass_kernel, ntt.cu) and the extended columns never reach HBM; otherwise they go through a scratch buffer that
+// is reused group by group and are hashed by the chunk kernel.  DESIGN.md §4.4 has the A/B measurement.
 void lde_commit_columns(sezkp_ctx* ctx, const u64* evals_dev, const char* const* labels, int c, int log_n, int log_blow, u64 shift,
                         int chunk_log2, u8* d_roots) {
     const size_t n = (size_t)1 << log_n, N = n << log_blow;
