@@ -76,7 +76,9 @@ int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx);
  * subtree tables across proofs while their parameters and labels are unchanged; "ntt_gen" (default 3): NTT pass-kernel
  * generation (1 = round-1 kernel with three shared-memory round trips, 2-4 = global loads/stores fused into the register
  * DFTs, differing in register budget / CTA size; A/B measurements); "lde_fuse" (default 1): fuse the last pass of the LDE
- * with the labeled leaf hash in sezkp_lde_commit_batch / sezkp_lde_commit_fri (north_star item 3; same roots) */
+ * with the labeled leaf hash in sezkp_lde_commit_batch / sezkp_lde_commit_fri (north_star item 3; same roots); "phase_sync"
+ * (default 1): how sezkp_cuda_get_timings clocks the prover's phases — 1 = host clock with a stream synchronisation at every
+ * phase boundary, 0 = CUDA events read back at the end of the proof */
 int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value);
 /* number of kernels launched by this ctx since creation / since the last reset */
 uint64_t sezkp_cuda_launch_count(sezkp_ctx* ctx, int reset);

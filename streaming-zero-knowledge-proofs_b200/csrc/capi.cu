@@ -163,6 +163,7 @@ void sezkp_cuda_destroy(sezkp_ctx* ctx) {
     ctx->pool.live.clear();
     ctx->pool.trim();
     for (auto e : ctx->slab_events) cudaEventDestroy(e);
+    for (auto e : ctx->phase_events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -203,6 +204,8 @@ static void set_option_one(sezkp_ctx* ctx, const char* name, int64_t value) {
         ctx->ntt_gen = (int)value;
     } else if (std::strcmp(name, "lde_fuse") == 0) {
         ctx->lde_fuse = value != 0;
+    } else if (std::strcmp(name, "phase_sync") == 0) {
+        ctx->phase_sync = value != 0;
     } else if (std::strcmp(name, "deep_fused") == 0) {
         ctx->deep_fused = value != 0;
     } else if (std::strcmp(name, "tab_cache") == 0) {

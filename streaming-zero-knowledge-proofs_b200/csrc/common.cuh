@@ -151,6 +151,7 @@ struct sezkp_ctx {
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;          // side stream for slab uploads (created on first use)
     std::vector<cudaEvent_t> slab_events;
+    std::vector<cudaEvent_t> phase_events;      // phase clock of the prover (timing events, created on first use)
     std::string last_error;
     std::map<u64, NttTables*> ntt_tables;  // key: (log_n, inverse, coset params)
     std::map<std::pair<int, u64>, u64*> deep_tables;  // (log N, shift) -> device table of the first coset point of every DEEP CTA (capped)
@@ -170,6 +171,7 @@ struct sezkp_ctx {
     std::vector<u8> tab_cache_key;           // subtree tables in scratch[11] were built for exactly these (ColTab[], label templates)
     int ntt_gen = 3;                        // option "ntt_gen": pass-kernel generation (1 = round-1 kernel; 2-4 = fused global I/O, see ntt.cu kernel_for_bits)
     bool lde_fuse = true;                   // option "lde_fuse" (K7): fuse the LDE's last pass with the labeled leaf hash in lde_commit / lde_commit_fri
+    bool phase_sync = true;                 // option "phase_sync" (default 1): phase clock = host time with a stream synchronisation per phase; 0 = CUDA events read back at the end (no added syncs, but measured 0.3-0.4 ms SLOWER end to end on the slab-pipelined path, tools/e2e_ab.py)
     bool deep_fused = false;                // option "deep_fused": one-launch DEEP kernel (per-CTA inversion) also for large domains
     std::map<const void*, size_t> func_smem;  // kernel -> dynamic shared memory already granted on this ctx's device
     u64 launches = 0;                       // kernels launched since last reset

@@ -1025,12 +1025,45 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
     ctx->timings.clear();
     double t0 = now_ms();
     const double t_begin = t0;
-    auto lap = [&](const char* name) {
-        cudaStreamSynchronize(ctx->stream);
+    // Phase clock.  The device phases (expand .. fri_commit) are bracketed by CUDA events on the prover's stream and read
+    // back once at the end: no synchronisation is added for the sake of timing (three of the old per-phase
+    // cudaStreamSynchronize calls drained the stream where the algorithm needs no host round trip).  A phase's interval
+    // contains the host work that precedes its first launch (transcript, table look-ups), so the phases add up to the
+    // device timeline.  openings / serialize are host-side phases and use the host clock.
+    std::vector<const char*> ev_names;
+    int n_ev = 0;
+    auto mark = [&](const char* name) {
+        if (ctx->phase_sync) {  // option "phase_sync": the old clock — drain the stream at every phase boundary, host time
+            if (!name) return;
+            cudaStreamSynchronize(ctx->stream);
+            const double t1 = now_ms();
+            ctx->timings.push_back({name, t1 - t0});
+            t0 = t1;
+            return;
+        }
+        if ((int)ctx->phase_events.size() <= n_ev) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreate(&e));
+            ctx->phase_events.push_back(e);
+        }
+        CUDA_CHECK(cudaEventRecord(ctx->phase_events[n_ev++], ctx->stream));
+        if (name) ev_names.push_back(name);
+    };
+    auto flush_marks = [&]() {  // all marked work is complete (the caller has just synchronised the stream)
+        if (ctx->phase_sync) return;
+        for (int i = 1; i < n_ev; i++) {
+            float ms = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->phase_events[i - 1], ctx->phase_events[i]));
+            ctx->timings.push_back({ev_names[i - 1], (double)ms});
+        }
+        t0 = now_ms();
+    };
+    auto lap = [&](const char* name) {  // host-clock phase (the stream is idle when these are taken)
         double t1 = now_ms();
         ctx->timings.push_back({name, t1 - t0});
         t0 = t1;
     };
+    mark(nullptr);
     const u64 n = trace.n_rows;
     const u32 tau = trace.tau;
     const int L = ilog2(n), logB = 3, log_N = L + logB;  // BLOWUP = 8 (v1/params.rs:28)
@@ -1056,7 +1089,7 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             f.halo = slice_hi < n ? ~0ULL : 0;  // the last slice wraps around to row 0
         }
         expand_columns_range(ctx, trace, cols, 0, n, 0, trace.n_blocks, f);
-        lap("expand_columns");
+        mark("expand_columns");
     }
 
     // B. transcript prelude (v1/prover.rs:67-70)
@@ -1106,7 +1139,7 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
                     std::memcpy(&col_roots[32 * c], &all[((size_t)(c % world) * max_local + c / world) * 32], 32);
             }
         }
-        lap("column_commit");
+        mark("column_commit");
         tr.absorb_u64("n_cols", (u64)n_cols);
         for (int c = 0; c < n_cols; c++) tr.absorb("col_root", &col_roots[32 * c], 32);
 
@@ -1137,20 +1170,22 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             const int32_t rc = ctx->allgather_dev(ctx->allgather_dev_user, stage, bytes, base_vals, (void*)ctx->stream);
             if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "device allgather callback failed with status %d", rc);
         }
-        lap("compose");
+        mark("compose");
         fl.values = (u64*)ctx->pool.alloc(2 * N * 8);  // the DEEP-LDE lands where FRI layer 0 lives: no 8N-byte copy
         u64* lde = fl.values;
         // sharded proof with a device collective: each rank evaluates 8/world cosets of the extension domain (needs world | 8)
         if (row_sliced && (1 << logB) % world == 0) deep_lde_sharded_device(ctx, base_vals, lde, L, logB, shift, z, rank, world);
         else deep_lde_device(ctx, base_vals, lde, L, logB, shift, z);
-        lap("deep_lde");
+        mark("deep_lde");
 
         // G. FRI fold + commit; root0 is absorbed before the betas are drawn (v1/prover.rs:184-243)
         std::vector<u8> fri_roots((size_t)(log_N + 1) * 32);
         u64 final_value = 0;
         TranscriptAbsorb ab(tr);
         fri_commit_device(ctx, fl, lde, log_N, nullptr, fri_roots.data(), &final_value, &ab, shard);
-        lap("fri_commit");
+        mark("fri_commit");
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // fri_commit_device ended with a synchronising copy: this returns at once
+        flush_marks();
 
         // H. AIR row queries and column openings (v1/prover.rs:248-292)
         std::vector<u64> rows(NUM_QUERIES);
@@ -1202,7 +1237,9 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         fri_open_requests(fl, fri_idx.data(), NUM_QUERIES, f_pos.data(), reqs, (u32)fri_base);
         u64* req_val;  // results stay in the context's pinned staging buffer until the proof is serialised
         u8 *req_cr, *all_paths;
+        const double t_open0 = now_ms();
         open_batch_staged(ctx, reqs, fri_base + fri_digests, &req_val, &req_cr, &all_paths);
+        const double t_open1 = now_ms();
         std::vector<u64> col_val(k_open, 0);
         std::vector<u8> col_cr(k_open * 32, 0);
         for (size_t i = 0; i < n_col_reqs; i++) {
@@ -1239,6 +1276,10 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         const u64* f_val = req_val + n_col_reqs;
         const u8* f_paths = all_paths + fri_base * 32;
         lap("openings");
+        // sub-phases of `openings` (not part of the sum): request upload + one open_kernel launch + result download / the
+        // exchange of the opening records between the ranks of a sharded proof
+        ctx->timings.push_back({"openings.launch_and_copy", t_open1 - t_open0});
+        ctx->timings.push_back({"openings.exchange", now_ms() - t_open1});
 
         // J. ProofV1 in declaration order (v1/proof.rs:80-98)
         Writer w(proof_out);  // straight into the caller's buffer
