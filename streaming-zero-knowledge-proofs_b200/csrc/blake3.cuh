@@ -111,12 +111,28 @@ constexpr GConst g_const(u32 a, u32 b, u32 c, u32 d) {
     return GConst{a, b, c, d};
 }
 
-// One-block hash: out[8] = BLAKE3(message of block_len bytes held zero-padded in m[16]).
-// LEAF8: the message is an unlabeled 8-byte leaf (m[2..15] = 0, block_len = 8): round 0 runs one column step instead of
-// four, the other three are folded at compile time (the run-time-1 multiplier of B3_ADD would otherwise hide them from the
-// compiler's constant propagation).
-template <u32 SCHED = B3_SCHED, bool LEAF8 = false>
-__device__ __forceinline__ void hash_block(const u32 (&m)[16], u32 block_len, u32 (&out)[8]) {
+// G with message words on the host / at compile time (label templates precompute the value-independent part of round 0).
+constexpr void g_plain(u32& a, u32& b, u32& c, u32& d, u32 mx, u32 my) {
+    a = a + b + mx;
+    d = c_rotr(d ^ a, 16);
+    c = c + d;
+    b = c_rotr(b ^ c, 12);
+    a = a + b + my;
+    d = c_rotr(d ^ a, 8);
+    c = c + d;
+    b = c_rotr(b ^ c, 7);
+}
+
+// One-block hash: out[8] = BLAKE3(message of block_len bytes held zero-padded in m[16]).  MODE selects how much of round 0
+// is already known:
+//   0  nothing;
+//   1  unlabeled 8-byte leaf (m[2..15] = 0, block_len = 8): round 0 runs one column step instead of four, the other three
+//      are folded at compile time (the run-time-1 multiplier of B3_ADD would otherwise hide them from constant propagation);
+//   2  labeled leaf: column step 0 (message words m0, m1 = "col_leaf", state words IV) comes precomputed in pre[0..3];
+//   3  labeled leaf whose value starts at word >= 4: column step 1 (m2 = label length, m3 = label bytes) in pre[4..7] too.
+template <u32 SCHED = B3_SCHED, int MODE = 0>
+__device__ __forceinline__ void hash_block(const u32 (&m)[16], u32 block_len, u32 (&out)[8], const u32* pre = nullptr) {
+    constexpr bool LEAF8 = MODE == 1;
     u32 s0 = B3_IV0, s1 = B3_IV1, s2 = B3_IV2, s3 = B3_IV3, s4 = B3_IV4, s5 = B3_IV5, s6 = B3_IV6, s7 = B3_IV7;
     u32 s8 = B3_IV0, s9 = B3_IV1, s10 = B3_IV2, s11 = B3_IV3, s12 = 0, s13 = 0, s14 = block_len, s15 = B3_FLAGS_ONE_BLOCK;
     u32 l4 = 0, l5 = 0, l6 = 0, l7 = 0;
@@ -130,6 +146,19 @@ __device__ __forceinline__ void hash_block(const u32 (&m)[16], u32 block_len, u3
         s1 = c1.a; s5 = c1.b; s9 = c1.c; s13 = c1.d;
         s2 = c2.a; s6 = c2.b; s10 = c2.c; s14 = c2.d;
         s3 = c3.a; s7 = c3.b; s11 = c3.c; s15 = c3.d;
+        g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s0, s5, l5, s10, s15, m[8], m[9], k);
+        g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s1, s6, l6, s11, s12, m[10], m[11], k);
+        g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s2, s7, l7, s8, s13, m[12], m[13], k);
+        g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s3, s4, l4, s9, s14, m[14], m[15], k);
+    } else if (MODE >= 2 && (M0 & 3) == 0) {
+        s0 = pre[0]; s4 = pre[1]; s8 = pre[2]; s12 = pre[3];
+        if (MODE == 3) {
+            s1 = pre[4]; s5 = pre[5]; s9 = pre[6]; s13 = pre[7];
+        } else {
+            g_fn<false, false, false>(s1, s5, l5, s9, s13, m[2], m[3], k);
+        }
+        g_fn<false, false, false>(s2, s6, l6, s10, s14, m[4], m[5], k);
+        g_fn<false, false, false>(s3, s7, l7, s11, s15, m[6], m[7], k);
         g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s0, s5, l5, s10, s15, m[8], m[9], k);
         g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s1, s6, l6, s11, s12, m[10], m[11], k);
         g_fn<false, (M0 & 4) != 0, (M0 & 8) != 0>(s2, s7, l7, s8, s13, m[12], m[13], k);
@@ -153,7 +182,7 @@ __device__ __forceinline__ void hash_block(const u32 (&m)[16], u32 block_len, u3
 // Unlabeled leaf of one canonical field element.
 __device__ __forceinline__ void leaf(u64 v, u32 (&out)[8]) {
     u32 m[16] = {(u32)v, (u32)(v >> 32), 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    hash_block<B3_SCHED, true>(m, 8, out);
+    hash_block<B3_SCHED, 1>(m, 8, out);
 }
 // Parent of two digests.
 __device__ __forceinline__ void parent(const u32 (&l)[8], const u32 (&r)[8], u32 (&out)[8]) {
@@ -172,7 +201,18 @@ struct LabelTemplate {
     u32 words[16];
     u32 off;        // byte offset of the value
     u32 block_len;  // 20 + L
+    u32 pre[8];     // round 0 after the value-independent column steps: {s0,s4,s8,s12} after G(m0,m1) and {s1,s5,s9,s13}
+                    // after G(m2,m3); the second quadruple is only used when the value starts at word >= 4 (off >= 16)
 };
+// fills t.pre from t.words (host side, when the template is built)
+inline void label_template_precompute(LabelTemplate& t) {
+    u32 a = B3_IV0, b = B3_IV4, c = B3_IV0, d = 0;
+    g_plain(a, b, c, d, t.words[0], t.words[1]);
+    t.pre[0] = a; t.pre[1] = b; t.pre[2] = c; t.pre[3] = d;
+    a = B3_IV1; b = B3_IV5; c = B3_IV1; d = 0;
+    g_plain(a, b, c, d, t.words[2], t.words[3]);
+    t.pre[4] = a; t.pre[5] = b; t.pre[6] = c; t.pre[7] = d;
+}
 // W = word index of the first value byte (static so that the 16 message words stay in registers).
 template <int W>
 __device__ __forceinline__ void leaf_labeled_w(const LabelTemplate& t, u64 v, u32 (&out)[8]) {
@@ -184,7 +224,7 @@ __device__ __forceinline__ void leaf_labeled_w(const LabelTemplate& t, u64 v, u3
     m[W] |= lo << sh;
     if (W + 1 < 16) m[W + 1] |= __funnelshift_l(lo, hi, sh);
     if (W + 2 < 16) m[W + 2] |= __funnelshift_l(hi, 0u, sh);
-    hash_block(m, t.block_len, out);
+    hash_block<B3_SCHED, (W >= 4 ? 3 : 2)>(m, t.block_len, out, t.pre);
 }
 // Runs BODY with a compile-time W matching the (block-uniform) template; BODY uses LEAF(v, out).
 #define B3_DISPATCH_LABELED(t, BODY)                                       \

@@ -164,6 +164,7 @@ void sezkp_cuda_destroy(sezkp_ctx* ctx) {
     ctx->pool.trim();
     for (auto e : ctx->slab_events) cudaEventDestroy(e);
     for (auto e : ctx->phase_events) cudaEventDestroy(e);
+    delete ctx->open_reqs;
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

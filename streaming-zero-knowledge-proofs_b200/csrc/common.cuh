@@ -93,6 +93,7 @@ struct PinnedBuf {
 };
 
 struct NttTables;  // ntt.cu
+struct OpenReq;    // hash.cuh
 struct sezkp_group;  // group.cuh
 
 // Size-keyed caching device allocator: repeated proofs reuse their buffers instead of paying
@@ -158,6 +159,8 @@ struct sezkp_ctx {
     std::map<int, u64*> power_tables;      // log_n -> device table of the low powers of w_n (composition mask)
     DevPool pool;
     DevBuf scratch[12];                      // reusable work buffers (per purpose, see users)
+    std::vector<OpenReq>* open_reqs = nullptr;  // request list of the prover's single opening launch, reused across proofs
+    std::vector<u8> host_stage[2];            // grow-only pageable staging (opening-record exchange of the sharded prover)
     PinnedBuf pinned[2];                     // host staging: [0] opening requests / results
     PinnedBuf stream_stage[3];               // staging ring of the streaming ingest, kept across streams (cudaHostAlloc of ~100 MB costs ~50 ms)
     bool stream_stage_busy = false;          // one stream at a time borrows the ring; a second concurrent stream allocates its own

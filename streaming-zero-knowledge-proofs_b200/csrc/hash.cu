@@ -1236,6 +1236,7 @@ b3::LabelTemplate make_label_template(const char* label) {
     std::memcpy(t.words, bytes, 64);
     t.off = (u32)(12 + L);
     t.block_len = (u32)(20 + L);
+    b3::label_template_precompute(t);
     return t;
 }
 

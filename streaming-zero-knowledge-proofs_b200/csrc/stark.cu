@@ -1222,7 +1222,9 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             for (int i = 0; i < NUM_QUERIES; i++) fri_idx[i] = le64(&by[8 * i]) % N;
         }
         const int din = cm.cl, dout = ilog2(cm.n_ch), cdepth = din + dout;
-        std::vector<OpenReq> reqs;
+        if (!ctx->open_reqs) ctx->open_reqs = new std::vector<OpenReq>();
+        std::vector<OpenReq>& reqs = *ctx->open_reqs;  // reused across proofs (see host_stage)
+        reqs.clear();
         reqs.reserve(k_open + (size_t)NUM_QUERIES * log_N * 2);
         // column openings: only the locally committed columns; slots of the other ranks are filled by the exchange
         std::vector<u32> req_slot;  // request index -> opening slot
@@ -1253,7 +1255,13 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             size_t max_own = 0;
             for (auto& v : owned) max_own = v.size() > max_own ? v.size() : max_own;
             const size_t bytes = max_own * rec;
-            std::vector<u8> mine(bytes, 0), all((size_t)world * bytes);
+            // grow-only staging kept in the context: a fresh 1.7 MB vector per proof is an mmap + page faults + munmap, and with
+            // eight rank threads of one process doing that at the same moment the kernel's address-space lock serialised them
+            // (0.48 ms of a 4.5 ms proof at N = 8)
+            std::vector<u8>& mine = ctx->host_stage[0];
+            std::vector<u8>& all = ctx->host_stage[1];
+            if (mine.size() < bytes) mine.resize(bytes);
+            if (all.size() < (size_t)world * bytes) all.resize((size_t)world * bytes);
             for (size_t j = 0; j < owned[rank].size(); j++) {
                 const size_t o = owned[rank][j];
                 std::memcpy(&mine[j * rec], &col_val[o], 8);
