@@ -348,6 +348,7 @@ def group_prove_bench(torch, m, devices, ct, root, proof_buf, want_proof, steps)
         res_ms = (time.perf_counter() - t0) * 1e3 / steps
         same = same and bytes(p) == want_proof
         res_ph = g.timings()
+        res_all = [g.timings_gpu(r) for r in range(len(devices))]
         rt.free()
     finally:
         g.close()
@@ -355,7 +356,7 @@ def group_prove_bench(torch, m, devices, ct, root, proof_buf, want_proof, steps)
     return {"n_gpus": len(devices), "api": "sezkp_cuda_create_multi + sezkp_stark_v1_prove (one process, exchanges inside the library)",
             "e2e_ms_per_proof": e2e_ms, "e2e_rows_per_s": T / (e2e_ms / 1e3), "resident_ms_per_proof": res_ms,
             "resident_rows_per_s": T / (res_ms / 1e3), "identical_to_single_gpu_proof": bool(same),
-            "e2e_phases_ms_gpu0": e2e_ph, "resident_phases_ms_gpu0": res_ph}
+            "e2e_phases_ms_gpu0": e2e_ph, "resident_phases_ms_gpu0": res_ph, "resident_phases_ms_per_gpu": res_all}
 
 
 def jsonl_stream_bench(torch, ctx, m, steps):

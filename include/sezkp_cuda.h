@@ -84,6 +84,8 @@ int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value);
 uint64_t sezkp_cuda_launch_count(sezkp_ctx* ctx, int reset);
 /* JSON object {"phase": ms, ...} of the last sezkp_stark_v1_prove on this ctx */
 int32_t sezkp_cuda_get_timings(sezkp_ctx* ctx, char* json_buf, size_t cap);
+/* the same for GPU `rank` of a multi-GPU context (rank 0 = sezkp_cuda_get_timings) */
+int32_t sezkp_cuda_get_timings_gpu(sezkp_ctx* ctx, int rank, char* json_buf, size_t cap);
 
 /* ------------------------------------------------------------ NTT / LDE ------ */
 /* forward_ntt_in_place / inverse_ntt_in_place per column (sezkp-ffts/src/ntt.rs:79-111, 117-155):

@@ -20,7 +20,7 @@ P = 0xFFFFFFFF00000001
 
 EXPORTS = [
     "sezkp_cuda_abi_version", "sezkp_cuda_create", "sezkp_cuda_destroy", "sezkp_cuda_last_error", "sezkp_cuda_set_stream",
-    "sezkp_cuda_synchronize", "sezkp_cuda_set_option", "sezkp_cuda_launch_count", "sezkp_cuda_get_timings",
+    "sezkp_cuda_synchronize", "sezkp_cuda_set_option", "sezkp_cuda_launch_count", "sezkp_cuda_get_timings", "sezkp_cuda_get_timings_gpu",
     "sezkp_ntt_batch", "sezkp_ntt_batch_dev", "sezkp_coset_lde_batch", "sezkp_coset_lde_batch_dev",
     "sezkp_lde_from_evals_batch", "sezkp_lde_from_evals_batch_dev", "sezkp_deep_lde", "sezkp_deep_lde_dev",
     "sezkp_leaf_hash", "sezkp_merkle_root", "sezkp_column_commit_batch", "sezkp_column_commit_batch_dev",
@@ -149,6 +149,11 @@ class Context:
     def timings(self) -> dict:
         buf = C.create_string_buffer(4096)
         self._ck(self.lib.sezkp_cuda_get_timings(self.h, buf, C.c_size_t(4096)))
+        return json.loads(buf.value.decode())
+
+    def timings_gpu(self, rank: int) -> dict:
+        buf = C.create_string_buffer(4096)
+        self._ck(self.lib.sezkp_cuda_get_timings_gpu(self.h, C.c_int(rank), buf, C.c_size_t(4096)))
         return json.loads(buf.value.decode())
 
     # ---- NTT / LDE (host buffers) ----

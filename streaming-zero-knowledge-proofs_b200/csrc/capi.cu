@@ -228,15 +228,26 @@ uint64_t sezkp_cuda_launch_count(sezkp_ctx* ctx, int reset) {
     return v;
 }
 
-int32_t sezkp_cuda_get_timings(sezkp_ctx* ctx, char* json_buf, size_t cap) {
-    API_BEGIN(ctx)
+static std::string timings_json(const sezkp_ctx* c) {
     std::string s = "{";
-    for (size_t i = 0; i < ctx->timings.size(); i++) {
+    for (size_t i = 0; i < c->timings.size(); i++) {
         char t[128];
-        snprintf(t, sizeof t, "%s\"%s\": %.4f", i ? ", " : "", ctx->timings[i].first.c_str(), ctx->timings[i].second);
+        snprintf(t, sizeof t, "%s\"%s\": %.4f", i ? ", " : "", c->timings[i].first.c_str(), c->timings[i].second);
         s += t;
     }
-    s += "}";
+    return s + "}";
+}
+int32_t sezkp_cuda_get_timings_gpu(sezkp_ctx* ctx, int rank, char* json_buf, size_t cap) {
+    API_BEGIN(ctx)
+    REQUIRE(rank >= 0 && rank < group_world(ctx), "rank out of range");
+    const std::string s = timings_json(ctx->group ? ctx->group->ctx[rank] : ctx);
+    if (!json_buf || cap < s.size() + 1) sezkp_fail(SEZKP_CUDA_ERANGE, "timings buffer too small (need %zu)", s.size() + 1);
+    std::memcpy(json_buf, s.c_str(), s.size() + 1);
+    API_END(ctx)
+}
+int32_t sezkp_cuda_get_timings(sezkp_ctx* ctx, char* json_buf, size_t cap) {
+    API_BEGIN(ctx)
+    std::string s = timings_json(ctx);
     if (!json_buf || cap < s.size() + 1) sezkp_fail(SEZKP_CUDA_ERANGE, "timings buffer too small (need %zu)", s.size() + 1);
     std::memcpy(json_buf, s.c_str(), s.size() + 1);
     API_END(ctx)
@@ -702,7 +713,7 @@ int32_t sezkp_stark_v1_prove(sezkp_ctx* ctx, const sezkp_trace_desc* trace, cons
         validate_trace(trace);
         std::vector<size_t> lens(ctx->group->world, 0);
         group_run(ctx->group, [&](int r, sezkp_ctx* cx) {
-            ShardInfo sh{r, cx->group->world, group_allgather_host, &cx->group->ranks[r]};
+            ShardInfo sh{r, cx->group->world, group_allgather_host, &cx->group->ranks[r], group_gather_root_host};
             ProofSink sink(r == 0 ? proof_buf : nullptr, r == 0 ? cap : 0);
             prove_v1_device(cx, trace, manifest_root, sink, &sh);
             lens[r] = sink.len;
@@ -771,7 +782,7 @@ int32_t sezkp_stark_v1_prove_resident(sezkp_ctx* ctx, const sezkp_trace_dev* tra
     if (ctx->group && (int)trace->peers.size() == ctx->group->world - 1 && 3 + 7 * (int)trace->owner.t.tau >= ctx->group->world) {
         std::vector<size_t> lens(ctx->group->world, 0);
         group_run(ctx->group, [&](int r, sezkp_ctx* cx) {
-            ShardInfo sh{r, cx->group->world, group_allgather_host, &cx->group->ranks[r]};
+            ShardInfo sh{r, cx->group->world, group_allgather_host, &cx->group->ranks[r], group_gather_root_host};
             ProofSink sink(r == 0 ? proof_buf : nullptr, r == 0 ? cap : 0);
             prove_v1_resident(cx, r == 0 ? trace->owner.t : trace->peers[r - 1].t, manifest_root, sink, &sh);
             lens[r] = sink.len;

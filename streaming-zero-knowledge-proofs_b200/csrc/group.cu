@@ -118,6 +118,7 @@ sezkp_group* group_create(const int* device_ids, int n_dev) {
         }
         g->ranks.resize(n_dev);
         g->send.assign(n_dev, nullptr);
+        g->root_slots.assign(n_dev, nullptr);
         g->rc.assign(n_dev, 0);
         g->err.assign(n_dev, "");
         g->ev_ready.assign(n_dev, nullptr);
@@ -188,6 +189,19 @@ int32_t group_allgather_host(void* user, const void* send, size_t bytes, void* r
         g->bar.wait();
         for (int s = 0; s < g->world; s++) std::memcpy((u8*)recv_all + (size_t)s * bytes, g->send[s], bytes);
         g->bar.wait();  // nobody reuses its send buffer before every rank has copied it
+    } catch (const SezkpError&) {
+        return -1;
+    }
+    return 0;
+}
+
+int32_t group_gather_root_host(void* user, const void* send, const void** all_ptrs) {
+    GroupRank* gr = (GroupRank*)user;
+    sezkp_group* g = gr->g;
+    try {
+        g->root_slots[gr->rank] = send;  // a slot array of its own: the buffers stay published after the barrier
+        g->bar.wait();
+        for (int s = 0; s < g->world; s++) all_ptrs[s] = g->root_slots[s];
     } catch (const SezkpError&) {
         return -1;
     }

@@ -56,6 +56,7 @@ struct sezkp_group {
     GroupBarrier bar;
     // exchange slots (valid between two barrier phases of one collective)
     std::vector<const void*> send;
+    std::vector<const void*> root_slots;  // group_gather_root_host
     std::vector<cudaEvent_t> ev_ready, ev_done;
 };
 
@@ -69,6 +70,9 @@ void group_run(sezkp_group* g, const std::function<void(int, sezkp_ctx*)>& fn);
 // (sezkp_allgather_fn / sezkp_allgather_dev_fn, include/sezkp_cuda.h); `user` is a GroupRank*.
 int32_t group_allgather_host(void* user, const void* send, size_t bytes, void* recv_all);
 int32_t group_allgather_dev(void* user, const void* send_dev, size_t bytes, void* recv_all_dev, void* cuda_stream);
+// Gather to rank 0 without copies (ShardInfo::gather_root): every rank publishes its buffer, one barrier, all_ptrs[s] = rank
+// s's buffer.  The buffers must outlive the group call.
+int32_t group_gather_root_host(void* user, const void* send, const void** all_ptrs);
 // Peer-pointer exchange: publishes `mine` (device memory of this rank, complete on `stream`), returns every rank's pointer
 // in all[world] and makes `stream` wait until each of them is complete.  Pair with group_release_peers(), which keeps every
 // rank from reusing its buffer before all peers' kernels that read it have finished.

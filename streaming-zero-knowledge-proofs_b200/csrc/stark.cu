@@ -1248,6 +1248,9 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             col_val[req_slot[i]] = req_val[i];
             std::memcpy(&col_cr[(size_t)req_slot[i] * 32], &req_cr[i * 32], 32);
         }
+        // per-opening record pointers (value 8 B | chunk root 32 B | path cdepth * 32 B); unsharded: assembled views below
+        std::vector<const u8*> rec_ptr;
+        bool deliver = true;  // this rank serialises the proof
         if (world > 1) {  // gather the opening records (value, chunk root, path): every rank sends only the ones it owns
             const size_t rec = 8 + 32 + (size_t)cdepth * 32;
             std::vector<std::vector<u32>> owned(world);
@@ -1255,28 +1258,34 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             size_t max_own = 0;
             for (auto& v : owned) max_own = v.size() > max_own ? v.size() : max_own;
             const size_t bytes = max_own * rec;
-            // grow-only staging kept in the context: a fresh 1.7 MB vector per proof is an mmap + page faults + munmap, and with
-            // eight rank threads of one process doing that at the same moment the kernel's address-space lock serialised them
-            // (0.48 ms of a 4.5 ms proof at N = 8)
+            // grow-only staging kept in the context (a fresh 1.7 MB vector per proof and rank thread is an mmap + page faults +
+            // munmap under the process-wide address-space lock)
             std::vector<u8>& mine = ctx->host_stage[0];
-            std::vector<u8>& all = ctx->host_stage[1];
             if (mine.size() < bytes) mine.resize(bytes);
-            if (all.size() < (size_t)world * bytes) all.resize((size_t)world * bytes);
             for (size_t j = 0; j < owned[rank].size(); j++) {
                 const size_t o = owned[rank][j];
                 std::memcpy(&mine[j * rec], &col_val[o], 8);
                 std::memcpy(&mine[j * rec + 8], &col_cr[o * 32], 32);
                 std::memcpy(&mine[j * rec + 40], &all_paths[o * (size_t)cdepth * 32], (size_t)cdepth * 32);
             }
-            exchange(mine.data(), bytes, all.data());
-            for (int r = 0; r < world; r++)
-                for (size_t j = 0; j < owned[r].size(); j++) {
-                    const size_t o = owned[r][j];
-                    const u8* src = &all[(size_t)r * bytes + j * rec];
-                    std::memcpy(&col_val[o], src, 8);
-                    std::memcpy(&col_cr[o * 32], src + 8, 32);
-                    std::memcpy(&all_paths[o * (size_t)cdepth * 32], src + 40, (size_t)cdepth * 32);
+            if (shard->gather_root) {  // context group: one rendezvous, rank 0 reads the peers' records in place
+                std::vector<const void*> peers(world);
+                const int32_t rc = shard->gather_root(shard->user, mine.data(), peers.data());
+                if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "opening-record rendezvous failed with status %d", rc);
+                deliver = rank == 0;
+                if (deliver) {
+                    rec_ptr.resize(k_open);
+                    for (int r = 0; r < world; r++)
+                        for (size_t j = 0; j < owned[r].size(); j++) rec_ptr[owned[r][j]] = (const u8*)peers[r] + j * rec;
                 }
+            } else {  // one process per GPU: all-gather through the host callback, every rank assembles the whole proof
+                std::vector<u8>& all = ctx->host_stage[1];
+                if (all.size() < (size_t)world * bytes) all.resize((size_t)world * bytes);
+                exchange(mine.data(), bytes, all.data());
+                rec_ptr.resize(k_open);
+                for (int r = 0; r < world; r++)
+                    for (size_t j = 0; j < owned[r].size(); j++) rec_ptr[owned[r][j]] = &all[(size_t)r * bytes + j * rec];
+            }
         }
         const u64* o_val = col_val.data();
         const u8* o_cr = col_cr.data();
@@ -1290,6 +1299,14 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         ctx->timings.push_back({"openings.exchange", now_ms() - t_open1});
 
         // J. ProofV1 in declaration order (v1/proof.rs:80-98)
+        if (!deliver) {  // context group: only rank 0 writes the proof; this rank's records stay published in its staging buffer
+            proof_out.len = 0;
+            ctx->timings.push_back({"serialize", 0.0});
+            ctx->timings.push_back({"total", now_ms() - t_begin});
+            cm.release(ctx);
+            fl.release(ctx);
+            return;
+        }
         Writer w(proof_out);  // straight into the caller's buffer
         w.u64le(N);
         w.u64le(tau);
@@ -1301,13 +1318,23 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         }
         auto put_opening = [&](size_t o) {
             const u64 row = o_row[o];
-            w.raw(&o_val[o], 8);
+            const u8 *pv, *pc, *pp;
+            if (!rec_ptr.empty()) {  // sharded: the record sits in its owner's staging buffer
+                pv = rec_ptr[o];
+                pc = pv + 8;
+                pp = pv + 40;
+            } else {
+                pv = (const u8*)&o_val[o];
+                pc = &o_cr[o * 32];
+                pp = &o_paths[o * (size_t)cdepth * 32];
+            }
+            w.raw(pv, 8);
             w.u64le(row);
             w.u64le(row >> din);
             w.u64le(row & ((1ULL << din) - 1));
-            w.raw(&o_cr[o * 32], 32);
-            w.digest_vec(&o_paths[o * (size_t)cdepth * 32], din);
-            w.digest_vec(&o_paths[(o * (size_t)cdepth + din) * 32], dout);
+            w.raw(pc, 32);
+            w.digest_vec(pp, din);
+            w.digest_vec(pp + (size_t)din * 32, dout);
         };
         w.u64le(NUM_QUERIES);
         for (int qi = 0; qi < NUM_QUERIES; qi++) {

@@ -97,10 +97,14 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0_dev, int
                        u64* final_value, HostAbsorb* absorb_or_null, const ShardInfo* shard = nullptr);
 void fri_open_requests(const FriLayers& fl, const u64* idx0, size_t k, u64* positions, std::vector<OpenReq>& reqs, u32 base_off);
 void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_t k, u64* positions, u64* values, u8* paths);
-struct ShardInfo {  // column sharding across the GPUs of one box (one process per GPU)
+struct ShardInfo {  // column sharding across the GPUs of one box
     int rank, world;
     sezkp_allgather_fn allgather;
     void* user;
+    // Optional (context groups: the ranks are threads of one process and only rank 0 delivers the proof): publish `send` and
+    // rendezvous once; rank 0 then reads the peers' buffers in place through all_ptrs[world] — no copies, no second barrier.
+    // `send` must stay valid until the whole group call has returned (context-owned staging).
+    int32_t (*gather_root)(void* user, const void* send, const void** all_ptrs) = nullptr;
 };
 void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manifest_root[32], ProofSink& proof_out,
                        const ShardInfo* shard = nullptr, const SlabPlan* plan = nullptr);

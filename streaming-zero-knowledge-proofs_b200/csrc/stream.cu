@@ -284,7 +284,7 @@ void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof) {
             CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
             const double rep_ms = now_ms() - t_rep0;
             group_run(g, [&](int r, sezkp_ctx* cx) {
-                ShardInfo sh{r, world, group_allgather_host, &g->ranks[r]};
+                ShardInfo sh{r, world, group_allgather_host, &g->ranks[r], group_gather_root_host};
                 ProofSink sink(r == 0 ? proof.buf : nullptr, r == 0 ? proof.cap : 0);
                 prove_v1_resident(cx, r == 0 ? t : peers[r - 1].t, st->manifest_root, sink, &sh);
                 if (r == 0) proof.len = sink.len;
