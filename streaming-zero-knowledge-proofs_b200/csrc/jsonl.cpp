@@ -16,6 +16,9 @@
 #include <cstring>
 #include <stdexcept>
 #include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace jsonl {
 
@@ -297,6 +300,159 @@ inline bool fast_step(Cursor& c, Trace& t, uint32_t& tau) {
     return true;
 }
 
+// Bulk fast path for the steps array (the bytes that make up 97 % of a line): as many consecutive steps as are written
+// exactly the way serde_json writes them — `{"input_mv":-1,"tapes":[{"write":null,"mv":1},...tau ops...]}` separated by
+// single commas — are parsed with fixed-width loads and compares, no per-byte bounds checks (every tape op starts with
+// at least SLACK readable bytes ahead, longer than the longest op this path accepts) and raw stores into arrays grown
+// once per call.  Returns the number of steps taken; the cursor is left right behind the last one (at ',' or ']').
+// Anything else — whitespace, other key order, large numbers, the last bytes of a line — is left to parse_step, which
+// also produces the error messages.
+inline uint64_t ld8(const char* p) {
+    uint64_t v;
+    std::memcpy(&v, p, 8);
+    return v;
+}
+inline uint32_t ld4(const char* p) {
+    uint32_t v;
+    std::memcpy(&v, p, 4);
+    return v;
+}
+constexpr uint64_t lit8(const char (&s)[9]) {
+    uint64_t v = 0;
+    for (int i = 7; i >= 0; i--) v = (v << 8) | (uint8_t)s[i];
+    return v;
+}
+constexpr uint32_t lit4(const char (&s)[5]) {
+    uint32_t v = 0;
+    for (int i = 3; i >= 0; i--) v = (v << 8) | (uint8_t)s[i];
+    return v;
+}
+// unsigned decimal of 1..5 digits without a leading zero, not followed by a digit, '.', 'e' or 'E'
+inline bool fast_uint(const char*& q, uint32_t& out) {
+    uint32_t d = (uint32_t)(uint8_t)q[0] - '0';
+    if (d > 9) return false;
+    const char* p = q + 1;
+    uint32_t v = d, e = (uint32_t)(uint8_t)*p - '0';
+    if (e <= 9) {
+        if (d == 0) return false;
+        int digits = 1;
+        do {
+            v = v * 10 + e;
+            p++;
+            e = (uint32_t)(uint8_t)*p - '0';
+        } while (e <= 9 && ++digits < 5);
+        if (e <= 9) return false;
+    }
+    if (*p == '.' || *p == 'e' || *p == 'E') return false;
+    out = v;
+    q = p;
+    return true;
+}
+size_t fast_steps(Cursor& c, Trace& t, uint32_t tau) {
+    constexpr ptrdiff_t SLACK = 40;  // > 9 + 5 + 6 + 4 + 1 bytes of the longest accepted tape op + the separators after it
+    const char* q = c.p;
+    const char* const end = c.end;
+    const size_t min_step = 25 + (size_t)tau * 19;
+    if ((size_t)(end - q) < min_step) return 0;
+    const size_t cap_steps = (size_t)(end - q) / min_step + 1;
+    const size_t rows0 = t.input_mv.size(), cells0 = t.mv.size();
+    t.input_mv.resize(rows0 + cap_steps);
+    t.mv.resize(cells0 + cap_steps * tau);
+    t.write_flag.resize(cells0 + cap_steps * tau);
+    t.write_sym.resize(cells0 + cap_steps * tau);
+    int8_t* pi = t.input_mv.data() + rows0;
+    int8_t* pm = t.mv.data() + cells0;
+    uint8_t* pf = t.write_flag.data() + cells0;
+    uint16_t* ps = t.write_sym.data() + cells0;
+    size_t done = 0;
+    for (;;) {
+        const char* s = q;
+        if (done) {
+            if (*s != ',') break;
+            s++;
+        }
+        if (end - s < SLACK) break;
+        // {"input_mv":
+        if (ld8(s) != lit8("{\"input_") || ld4(s + 8) != lit4("mv\":")) break;
+        s += 12;
+        bool neg = *s == '-';
+        s += neg;
+        uint32_t v;
+        if (!fast_uint(s, v) || v > 127u + neg) break;
+        const int8_t in_mv = (int8_t)(neg ? -(int32_t)v : (int32_t)v);
+        // ,"tapes":[
+        if (ld8(s) != lit8(",\"tapes\"") || s[8] != ':' || s[9] != '[') break;
+        s += 10;
+        uint32_t r = 0;
+        for (; r < tau; r++) {
+            if (end - s < SLACK) break;
+            if (r) {
+                if (*s != ',') break;
+                s++;
+            }
+            // {"write":
+            if (ld8(s) != lit8("{\"write\"") || s[8] != ':') break;
+            s += 9;
+            constexpr uint64_t MV6 = lit8(",\"mv\":\0\0"), M6 = 0xFFFFFFFFFFFFull;
+#if defined(__SSE2__)
+            {   // common shapes — write = null | D | DD, mv = D | -D — without data-dependent branches (null or number, one
+                // or two digits and the sign are coin flips in real traces): the closing brace is found with one 16-byte
+                // compare, every field position follows from it, and only the next op's address depends on the search.
+                const unsigned mask = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)s), _mm_set1_epi8('}')));
+                const unsigned pos = (unsigned)__builtin_ctz(mask | 0x10000u);  // s[pos] == '}' (16: none in range)
+                if (pos >= 8 && pos < 16) {
+                    const uint32_t dm = (uint32_t)(uint8_t)s[pos - 1] - '0';
+                    const uint32_t ng = s[pos - 2] == '-';
+                    const uint32_t wlen = pos - 7 - ng;  // bytes of the write field
+                    const uint32_t d0 = (uint32_t)(uint8_t)s[0] - '0', d1 = (uint32_t)(uint8_t)s[1] - '0';
+                    const uint32_t isnull = (wlen == 4) & (ld4(s) == lit4("null"));
+                    const uint32_t one = (wlen == 1) & (d0 <= 9), two = (wlen == 2) & (d0 - 1 <= 8) & (d1 <= 9);
+                    if (((ld8(s + wlen) & M6) == MV6) & (dm <= 9) & (isnull | one | two)) {
+                        pf[r] = (uint8_t)(isnull ^ 1);
+                        ps[r] = (uint16_t)(two ? d0 * 10 + d1 : one ? d0 : 0u);
+                        pm[r] = (int8_t)(ng ? -(int32_t)dm : (int32_t)dm);
+                        s += pos + 1;
+                        continue;
+                    }
+                }
+            }
+#endif
+            if (ld4(s) == lit4("null")) {
+                s += 4;
+                pf[r] = 0;
+                ps[r] = 0;
+            } else {
+                if (!fast_uint(s, v) || v > 65535) break;
+                pf[r] = 1;
+                ps[r] = (uint16_t)v;
+            }
+            // ,"mv":
+            if ((ld8(s) & M6) != MV6) break;
+            s += 6;
+            neg = *s == '-';
+            s += neg;
+            if (!fast_uint(s, v) || v > 127u + neg) break;
+            if (*s != '}') break;
+            s++;
+            pm[r] = (int8_t)(neg ? -(int32_t)v : (int32_t)v);
+        }
+        if (r != tau || end - s < 2 || s[0] != ']' || s[1] != '}') break;
+        q = s + 2;
+        pi[done] = in_mv;
+        pm += tau;
+        pf += tau;
+        ps += tau;
+        done++;
+        if (done == cap_steps) break;
+    }
+    t.input_mv.resize(rows0 + done);
+    t.mv.resize(cells0 + done * tau);
+    t.write_flag.resize(cells0 + done * tau);
+    t.write_sym.resize(cells0 + done * tau);
+    c.p = q;
+    return done;
+}
+
 void parse_step(Cursor& c, Trace& t, uint32_t& tau) {
     if (fast_step(c, t, tau)) return;
     bool have_in = false, have_tapes = false;
@@ -440,8 +596,12 @@ void parse_block(Cursor& c, Trace& t, uint32_t& tau) {
                             c.expect('[');
                             if (!c.accept(']')) {
                                 do {
-                                    parse_step(c, t, tau);
-                                    n_steps++;
+                                    const size_t k = tau ? fast_steps(c, t, tau) : 0;
+                                    n_steps += k;
+                                    if (k == 0) {
+                                        parse_step(c, t, tau);
+                                        n_steps++;
+                                    }
                                 } while (c.accept(','));
                                 c.expect(']');
                             }

@@ -140,3 +140,45 @@ def test_native_writer_matches_python_writer_and_round_trips(tmp_path):
         assert n == os.path.getsize(pa) and filecmp.cmp(pa, pb, shallow=False)
         back = b.parse_jsonl(open(pb, "rb").read(), threads)
         assert np.array_equal(back.mv, ct.mv) and np.array_equal(back.write_sym, ct.write_sym) and np.array_equal(back.block_len, ct.block_len)
+
+
+def test_bulk_fast_path_boundaries(tmp_path):
+    """The bulk steps path (fast_steps in csrc/jsonl.cpp) accepts only serde-exact bytes with 1-2 digit symbols and one-digit
+    moves in its branch-free form; everything else inside an otherwise exact line must fall through to the slower forms and
+    still give the same arrays or the same errors: 3-5 digit symbols, |mv| up to 128, "-0", whitespace in the middle of the
+    steps array, a steps array that ends the line (no slack bytes behind the last op), leading zeros, floats."""
+    m = pkg()
+    ct = m.simulate(256, 64, 3, seed=11)
+    lines = jsonl_bytes(m, ct, tmp_path).decode().splitlines()
+    docs = [json.loads(l) for l in lines]
+    rows = [s for d in docs for s in d["movement_log"]["steps"]]
+    # unusual but valid numbers, spread over many steps
+    edits = {5: (0, 65535, -128), 6: (1, 100, 127), 70: (2, 9999, -1), 71: (0, 12345, 0), 130: (1, 15, 100), 255: (2, 65535, -128)}
+    for i, (r, sym, mv) in edits.items():
+        rows[i]["tapes"][r] = {"write": sym, "mv": mv}
+    text = "\n".join(json.dumps(d, separators=(",", ":")) for d in docs) + "\n"
+    assert '"write":65535,"mv":-128' in text
+    ref = m.blocks_to_compact(docs)
+    same(m.binding.parse_jsonl(text.encode(), 1), ref)
+    # "-0" is a valid integer; whitespace after a comma in the middle of the steps array; both must parse to the same arrays
+    t2 = text.replace('"mv":0}', '"mv":-0}', 3).replace('},{"input_mv"', '}, {"input_mv"', 2).replace('},{"write"', '} ,{"write"', 2)
+    assert t2 != text
+    same(m.binding.parse_jsonl(t2.encode(), 1), ref)
+    # movement_log as the LAST key: the steps array is followed by "]}}" only, so the last ops have no slack bytes behind them
+    tail = []
+    for d in docs:
+        d2 = {k: v for k, v in d.items() if k != "movement_log"}
+        d2["movement_log"] = d["movement_log"]
+        tail.append(json.dumps(d2, separators=(",", ":")))
+    assert all(l.endswith("]}}") for l in tail)
+    same(m.binding.parse_jsonl(("\n".join(tail)).encode(), 1), ref)
+    # malformed numbers inside exact bytes are still rejected, with the reference's line number
+    for old, new, needle in (('"mv":1}', '"mv":01}', "leading zero"), ('"mv":1}', '"mv":1.0}', "float"), ('"mv":1}', '"mv":128}', "out of range"),
+                             ('"write":null', '"write":nul', None), ('"write":null', '"write":65536', "out of range"),
+                             ('"input_mv":', '"input_mv":-129,"x":', "out of range")):
+        ls = text.splitlines()
+        assert old in ls[1]
+        ls[1] = ls[1].replace(old, new, 1)
+        with pytest.raises(m.SezkpCudaError) as ei:
+            m.binding.parse_jsonl(("\n".join(ls) + "\n").encode(), 1)
+        assert "line 2" in str(ei.value) and (needle is None or needle in str(ei.value)), str(ei.value)
