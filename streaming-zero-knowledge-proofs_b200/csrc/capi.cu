@@ -910,11 +910,12 @@ struct ParsedPiece {
     std::string error;      // non-empty: parsing failed (reported by the consumer, in file order)
     bool oom = false;
 };
-static void jsonl_parse_piece(const char* text, size_t len, int n_threads, u32 tau_hint, size_t first_line, ParsedPiece& out) {
+static void jsonl_parse_piece(const char* text, size_t len, int n_threads, u32 tau_hint, size_t first_line, ParsedPiece& out,
+                              jsonl::WorkerPool* pool = nullptr) {
     const auto t0 = std::chrono::steady_clock::now();
     try {
         out.tau = tau_hint;
-        out.lines = jsonl::parse_parts(text, len, jsonl_threads(n_threads), tau_hint, first_line, out.parts, out.tau);
+        out.lines = jsonl::parse_parts(text, len, jsonl_threads(n_threads), tau_hint, first_line, out.parts, out.tau, pool);
     } catch (const std::bad_alloc&) {
         out.oom = true;
     } catch (const std::exception& e) {
@@ -1003,6 +1004,7 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
     // state the parser thread writes: declared outside the try block so that it outlives the thread on every unwind path
     // (the handler joins `reader` before these go out of scope)
     ParsedPiece pc[2];
+    std::unique_ptr<jsonl::WorkerPool> pool;  // used by `reader`: must outlive it on every unwind path as well
     std::vector<std::pair<size_t, size_t>> pieces;  // (offset, length) of the mapped file's pieces, cut at newlines
     void* map = MAP_FAILED;
     size_t map_len = 0;
@@ -1014,7 +1016,7 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
             const double t0 = ms_now();
             map_len = (size_t)sb.st_size;
             map = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fileno(f), 0);
-            if (map != MAP_FAILED) madvise(map, map_len, MADV_SEQUENTIAL | MADV_WILLNEED);
+            if (map != MAP_FAILED) madvise(map, map_len, MADV_WILLNEED);  // the parser threads read disjoint ranges concurrently: no SEQUENTIAL hint
             read_ms += ms_now() - t0;
         }
         if (map != MAP_FAILED) {
@@ -1037,12 +1039,15 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
             }
             int cur = 0;
             u32 tau_known = 0;
+            // parser threads live for the whole file (one pool, not 32 thread creations per piece)
+            if (pieces.size() > 1 && jsonl_threads(n_threads) > 1) pool.reset(new jsonl::WorkerPool(jsonl_threads(n_threads)));
+            jsonl::WorkerPool* const pl = pool.get();
             auto launch = [&](size_t k, ParsedPiece& dst) {
                 dst = ParsedPiece();
                 const size_t first_line = line_no;
                 const u32 tau_hint = tau_known;
-                reader = std::thread([&dst, &pieces, text, k, n_threads, tau_hint, first_line] {
-                    jsonl_parse_piece(text + pieces[k].first, pieces[k].second, n_threads, tau_hint, first_line, dst);
+                reader = std::thread([&dst, &pieces, text, k, n_threads, tau_hint, first_line, pl] {
+                    jsonl_parse_piece(text + pieces[k].first, pieces[k].second, n_threads, tau_hint, first_line, dst, pl);
                 });
             };
             if (!pieces.empty()) launch(0, pc[0]);

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -670,8 +672,69 @@ void Trace::fill_desc(sezkp_trace_desc& d) const {
 // [len*i/T, len*(i+1)/T), finds its first line start itself, and counts the newlines of its range on the way.
 // tau_hint = 0: every worker takes tau from its first block and the parts are checked against each other.
 // first_line_no is only used in error messages.  Returns the number of lines seen (blank ones included).
+struct WorkerPool::Impl {
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::vector<std::thread> th;
+    const std::function<void(int)>* fn = nullptr;
+    int tasks = 0, next = 0, pending = 0;
+    uint64_t gen = 0;
+    bool quit = false;
+    // take tasks until none is left; called with the lock held, returns with it held
+    void drain(std::unique_lock<std::mutex>& lk) {
+        while (next < tasks) {
+            const int i = next++;
+            const std::function<void(int)>* f = fn;
+            lk.unlock();
+            (*f)(i);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_all();
+        }
+    }
+    void worker() {
+        std::unique_lock<std::mutex> lk(mu);
+        uint64_t seen = 0;
+        for (;;) {
+            cv_job.wait(lk, [&] { return quit || gen != seen; });
+            if (quit) return;
+            seen = gen;
+            drain(lk);
+        }
+    }
+};
+WorkerPool::WorkerPool(int n_threads) : p_(new Impl()), n_(std::max(1, std::min(n_threads, 256))) {
+    try {
+        for (int i = 1; i < n_; i++) p_->th.emplace_back([this] { p_->worker(); });  // the caller of run() is the n-th worker
+    } catch (...) {
+        n_ = (int)p_->th.size() + 1;  // fewer threads than asked for: still correct
+    }
+}
+WorkerPool::~WorkerPool() {
+    {
+        std::lock_guard<std::mutex> lk(p_->mu);
+        p_->quit = true;
+    }
+    p_->cv_job.notify_all();
+    for (auto& t : p_->th) t.join();
+    delete p_;
+}
+void WorkerPool::run(int tasks, const std::function<void(int)>& fn) {
+    if (tasks <= 0) return;
+    std::unique_lock<std::mutex> lk(p_->mu);
+    p_->fn = &fn;
+    p_->tasks = tasks;
+    p_->next = 0;
+    p_->pending = tasks;
+    p_->gen++;
+    p_->cv_job.notify_all();
+    p_->drain(lk);
+    p_->cv_done.wait(lk, [&] { return p_->pending == 0; });
+    p_->fn = nullptr;
+    p_->tasks = p_->next = 0;
+}
+
 size_t parse_parts(const char* text, size_t len, int n_threads, uint32_t tau_hint, size_t first_line_no, std::vector<Trace>& parts,
-                   uint32_t& tau_out) {
+                   uint32_t& tau_out, WorkerPool* pool) {
     const char* const end = text + len;
     int T = std::max(1, std::min(n_threads, 256));
     if (len < ((size_t)T << 16)) T = (int)std::max<size_t>(1, len >> 16);  // at least 64 KiB of text per worker
@@ -725,6 +788,8 @@ size_t parse_parts(const char* text, size_t len, int n_threads, uint32_t tau_hin
     };
     if (T == 1) {
         work(0);
+    } else if (pool) {
+        pool->run(T, work);
     } else {
         std::vector<std::thread> th;
         for (int ti = 0; ti < T; ti++) th.emplace_back(work, ti);

@@ -525,7 +525,7 @@ def test_jsonl_stream_prove_matches_one_shot(ctx, tmp_path):
     assert "stream_h2d_copy_ms" in tm and "stream_copy_hidden_frac" in tm
 
 
-@pytest.mark.parametrize("T,b,tau,chunk,threads", [(4096, 64, 3, 0, 0), (1 << 15, 512, 8, 300_000, 4), (1 << 13, 37 * 0 + 256, 2, 70_000, 1)])
+@pytest.mark.parametrize("T,b,tau,chunk,threads", [(4096, 64, 3, 0, 0), (1 << 15, 512, 8, 300_000, 4), (1 << 13, 37 * 0 + 256, 2, 70_000, 1), (1 << 15, 512, 8, 1_000_000, 8)])
 def test_native_jsonl_file_prove_matches_one_shot(ctx, tmp_path, T, b, tau, chunk, threads):
     """f2, native front-end: .jsonl file -> multi-threaded parser -> pinned staging ring -> same proof bytes as the
     one-shot prove, for files cut into many chunks (chunk boundaries fall mid-line) and for a single chunk."""
