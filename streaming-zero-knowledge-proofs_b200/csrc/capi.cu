@@ -939,7 +939,7 @@ static void jsonl_ingest_piece(sezkp_ctx* ctx, sezkp_stream*& st, const uint8_t*
         stream_ingest(ctx, st, &d);
         if (blocks) *blocks += t.block_len.size();
         if (rows) *rows += t.input_mv.size();
-        t = jsonl::Trace();
+        t.clear_keep_capacity();  // the next piece parsed into this slot reuses the arrays
     }
 }
 // parse, then ingest (the one-shot text entry point)
@@ -1043,7 +1043,11 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
             if (pieces.size() > 1 && jsonl_threads(n_threads) > 1) pool.reset(new jsonl::WorkerPool(jsonl_threads(n_threads)));
             jsonl::WorkerPool* const pl = pool.get();
             auto launch = [&](size_t k, ParsedPiece& dst) {
-                dst = ParsedPiece();
+                {  // fresh state, but the workers' output arrays of two pieces ago are kept for reuse
+                    std::vector<jsonl::Trace> keep = std::move(dst.parts);
+                    dst = ParsedPiece();
+                    dst.parts = std::move(keep);
+                }
                 const size_t first_line = line_no;
                 const u32 tau_hint = tau_known;
                 reader = std::thread([&dst, &pieces, text, k, n_threads, tau_hint, first_line, pl] {

@@ -651,6 +651,20 @@ void append(Trace& dst, const Trace& src) {
 
 }  // namespace
 
+void Trace::clear_keep_capacity() {
+    tau = 0;
+    n_lines = 0;
+    block_len.clear();
+    win_left.clear();
+    win_right.clear();
+    head_in_off.clear();
+    head_out_off.clear();
+    input_mv.clear();
+    mv.clear();
+    write_flag.clear();
+    write_sym.clear();
+    manifest.clear();
+}
 void Trace::fill_desc(sezkp_trace_desc& d) const {
     d.tau = tau;
     d.flags = 0;
@@ -738,7 +752,8 @@ size_t parse_parts(const char* text, size_t len, int n_threads, uint32_t tau_hin
     const char* const end = text + len;
     int T = std::max(1, std::min(n_threads, 256));
     if (len < ((size_t)T << 16)) T = (int)std::max<size_t>(1, len >> 16);  // at least 64 KiB of text per worker
-    parts.assign((size_t)T, Trace());
+    parts.resize((size_t)T);  // elements a caller left in place are reused (their arrays keep their capacity)
+    for (auto& t : parts) t.clear_keep_capacity();
     struct Result {
         const char* err_line = nullptr;
         std::string err;

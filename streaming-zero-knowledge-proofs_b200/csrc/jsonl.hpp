@@ -23,6 +23,7 @@ struct Trace {
     std::vector<Manifest> manifest;
     size_t n_lines = 0;  // newline-terminated (or final unterminated) lines seen, blank ones included
     void fill_desc(sezkp_trace_desc& d) const;
+    void clear_keep_capacity();  // empty, but the arrays keep their memory (pieces of one file reuse them: no fresh pages per piece)
 };
 
 // Persistent parser threads for callers that parse many pieces of one file (prove_jsonl_file: a 13 GB file is ~200 pieces;

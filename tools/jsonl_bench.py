@@ -1,0 +1,19 @@
+"""Streaming-JSONL leg of bench.py alone, at one or more sizes: tools/jsonl_bench.py [log_T ...] (default 19 22).
+Prints one JSON object per size (same fields as bench.py's `jsonl_stream`, plus every stream timing)."""
+import importlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import torch  # noqa: E402
+
+m = importlib.import_module(bench.PKG)
+ctx = m.Context(0)
+for lt in [int(a) for a in sys.argv[1:]] or [19, 22]:
+    os.environ["SEZKP_JSONL_LOG_T"] = str(lt)
+    out = bench.jsonl_stream_bench(torch, ctx, m, 3)
+    out["timings"] = {k: v for k, v in ctx.timings().items() if k.startswith(("jsonl", "stream"))}
+    print(json.dumps(out), flush=True)
