@@ -182,3 +182,27 @@ def test_bulk_fast_path_boundaries(tmp_path):
         with pytest.raises(m.SezkpCudaError) as ei:
             m.binding.parse_jsonl(("\n".join(ls) + "\n").encode(), 1)
         assert "line 2" in str(ei.value) and (needle is None or needle in str(ei.value)), str(ei.value)
+
+
+def test_parser_under_sanitizers(tmp_path):
+    """tools/jsonl_fuzz.cpp: the parser compiled with -fsanitize=address,undefined parses ~7000 truncated / corrupted variants
+    of a small file from exact-size heap buffers; any out-of-bounds read of the fixed-width fast path aborts the run."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    m = pkg()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, m.__name__, "csrc")
+    exe = str(tmp_path / "jsonl_fuzz")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                         "-I", csrc, os.path.join(root, "tools", "jsonl_fuzz.cpp"), os.path.join(csrc, "jsonl.cpp"), "-o", exe],
+                        capture_output=True, text=True)
+    if cc.returncode != 0 and ("asan" in cc.stderr or "sanitize" in cc.stderr):
+        pytest.skip("sanitizer runtime not installed")
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    ct = m.simulate(4096, 512, 8, seed=5)
+    path = str(tmp_path / "f.jsonl")
+    m.io_jsonl.write_jsonl(path, ct)
+    run = subprocess.run([exe, path], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and "parsed ok" in run.stdout, (run.stdout + run.stderr)[-3000:]
