@@ -350,8 +350,75 @@ inline bool fast_uint(const char*& q, uint32_t& out) {
     q = p;
     return true;
 }
+// One tape op behind its `{"write":` in the less common shapes (3-5 digit symbols, multi-digit moves); s has FAST_SLACK
+// readable bytes behind the op's first byte.  Out of line so that the common path of fast_tapes stays small.
+__attribute__((noinline)) const char* slow_tape(const char* s, int8_t* pm, uint8_t* pf, uint16_t* ps) {
+    constexpr uint64_t MV6 = lit8(",\"mv\":\0\0"), M6 = 0xFFFFFFFFFFFFull;
+    uint32_t v;
+    if (ld4(s) == lit4("null")) {
+        s += 4;
+        *pf = 0;
+        *ps = 0;
+    } else {
+        if (!fast_uint(s, v) || v > 65535) return nullptr;
+        *pf = 1;
+        *ps = (uint16_t)v;
+    }
+    if ((ld8(s) & M6) != MV6) return nullptr;
+    s += 6;
+    const bool neg = *s == '-';
+    s += neg;
+    if (!fast_uint(s, v) || v > 127u + neg) return nullptr;
+    if (*s != '}') return nullptr;
+    *pm = (int8_t)(neg ? -(int32_t)v : (int32_t)v);
+    return s + 1;
+}
+// The tau tape ops of one step (see fast_steps); returns the position behind the last op, or null when the bytes are not
+// in the exact serde form.  Kept out of line: the decode wants its dozen temporaries in registers, and inlined into
+// fast_steps the compiler spilled them.
+constexpr ptrdiff_t FAST_SLACK = 40;  // > 9 + 5 + 6 + 4 + 1 bytes of the longest accepted tape op + the separators after it
+__attribute__((noinline)) const char* fast_tapes(const char* s, const char* const end, const uint32_t tau, int8_t* pm, uint8_t* pf,
+                                                 uint16_t* ps) {
+    for (uint32_t r = 0; r < tau; r++) {
+        if (end - s < FAST_SLACK) return nullptr;
+        if (r) {
+            if (*s != ',') return nullptr;
+            s++;
+        }
+        // {"write":
+        if (ld8(s) != lit8("{\"write\"") || s[8] != ':') return nullptr;
+        s += 9;
+        constexpr uint64_t MV6 = lit8(",\"mv\":\0\0"), M6 = 0xFFFFFFFFFFFFull;
+#if defined(__SSE2__)
+        {   // common shapes — write = null | D | DD, mv = D | -D — without data-dependent branches (null or number, one
+            // or two digits and the sign are coin flips in real traces): the closing brace is found with one 16-byte
+            // compare, every field position follows from it, and only the next op's address depends on the search.
+            const unsigned mask = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)s), _mm_set1_epi8('}')));
+            const unsigned pos = (unsigned)__builtin_ctz(mask | 0x10000u);  // s[pos] == '}' (16: none in range)
+            if (pos >= 8 && pos < 16) {
+                const uint32_t dm = (uint32_t)(uint8_t)s[pos - 1] - '0';
+                const uint32_t ng = s[pos - 2] == '-';
+                const uint32_t wlen = pos - 7 - ng;  // bytes of the write field
+                const uint32_t d0 = (uint32_t)(uint8_t)s[0] - '0', d1 = (uint32_t)(uint8_t)s[1] - '0';
+                const uint32_t isnull = (wlen == 4) & (ld4(s) == lit4("null"));
+                const uint32_t one = (wlen == 1) & (d0 <= 9), two = (wlen == 2) & (d0 - 1 <= 8) & (d1 <= 9);
+                if (((ld8(s + wlen) & M6) == MV6) & (dm <= 9) & (isnull | one | two)) {
+                    pf[r] = (uint8_t)(isnull ^ 1);
+                    ps[r] = (uint16_t)((d0 + ((0u - two) & (9 * d0 + d1))) & (0u - (isnull ^ 1)));
+                    pm[r] = (int8_t)((int32_t)(dm ^ (0u - ng)) + (int32_t)ng);
+                    s += pos + 1;
+                    continue;
+                }
+            }
+        }
+#endif
+        s = slow_tape(s, pm + r, pf + r, ps + r);
+        if (!s) return nullptr;
+    }
+    return s;
+}
 size_t fast_steps(Cursor& c, Trace& t, uint32_t tau) {
-    constexpr ptrdiff_t SLACK = 40;  // > 9 + 5 + 6 + 4 + 1 bytes of the longest accepted tape op + the separators after it
+    constexpr ptrdiff_t SLACK = FAST_SLACK;
     const char* q = c.p;
     const char* const end = c.end;
     const size_t min_step = 25 + (size_t)tau * 19;
@@ -385,60 +452,8 @@ size_t fast_steps(Cursor& c, Trace& t, uint32_t tau) {
         // ,"tapes":[
         if (ld8(s) != lit8(",\"tapes\"") || s[8] != ':' || s[9] != '[') break;
         s += 10;
-        uint32_t r = 0;
-        for (; r < tau; r++) {
-            if (end - s < SLACK) break;
-            if (r) {
-                if (*s != ',') break;
-                s++;
-            }
-            // {"write":
-            if (ld8(s) != lit8("{\"write\"") || s[8] != ':') break;
-            s += 9;
-            constexpr uint64_t MV6 = lit8(",\"mv\":\0\0"), M6 = 0xFFFFFFFFFFFFull;
-#if defined(__SSE2__)
-            {   // common shapes — write = null | D | DD, mv = D | -D — without data-dependent branches (null or number, one
-                // or two digits and the sign are coin flips in real traces): the closing brace is found with one 16-byte
-                // compare, every field position follows from it, and only the next op's address depends on the search.
-                const unsigned mask = (unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128((const __m128i*)s), _mm_set1_epi8('}')));
-                const unsigned pos = (unsigned)__builtin_ctz(mask | 0x10000u);  // s[pos] == '}' (16: none in range)
-                if (pos >= 8 && pos < 16) {
-                    const uint32_t dm = (uint32_t)(uint8_t)s[pos - 1] - '0';
-                    const uint32_t ng = s[pos - 2] == '-';
-                    const uint32_t wlen = pos - 7 - ng;  // bytes of the write field
-                    const uint32_t d0 = (uint32_t)(uint8_t)s[0] - '0', d1 = (uint32_t)(uint8_t)s[1] - '0';
-                    const uint32_t isnull = (wlen == 4) & (ld4(s) == lit4("null"));
-                    const uint32_t one = (wlen == 1) & (d0 <= 9), two = (wlen == 2) & (d0 - 1 <= 8) & (d1 <= 9);
-                    if (((ld8(s + wlen) & M6) == MV6) & (dm <= 9) & (isnull | one | two)) {
-                        pf[r] = (uint8_t)(isnull ^ 1);
-                        ps[r] = (uint16_t)(two ? d0 * 10 + d1 : one ? d0 : 0u);
-                        pm[r] = (int8_t)(ng ? -(int32_t)dm : (int32_t)dm);
-                        s += pos + 1;
-                        continue;
-                    }
-                }
-            }
-#endif
-            if (ld4(s) == lit4("null")) {
-                s += 4;
-                pf[r] = 0;
-                ps[r] = 0;
-            } else {
-                if (!fast_uint(s, v) || v > 65535) break;
-                pf[r] = 1;
-                ps[r] = (uint16_t)v;
-            }
-            // ,"mv":
-            if ((ld8(s) & M6) != MV6) break;
-            s += 6;
-            neg = *s == '-';
-            s += neg;
-            if (!fast_uint(s, v) || v > 127u + neg) break;
-            if (*s != '}') break;
-            s++;
-            pm[r] = (int8_t)(neg ? -(int32_t)v : (int32_t)v);
-        }
-        if (r != tau || end - s < 2 || s[0] != ']' || s[1] != '}') break;
+        s = fast_tapes(s, end, tau, pm, pf, ps);
+        if (!s || end - s < 2 || s[0] != ']' || s[1] != '}') break;
         q = s + 2;
         pi[done] = in_mv;
         pm += tau;
