@@ -360,11 +360,11 @@ def group_prove_bench(torch, m, devices, ct, root, proof_buf, want_proof, steps)
 
 
 def jsonl_stream_bench(torch, ctx, m, steps):
-    """BASELINE configs[4] family on one GPU (scaled: T = 2^SEZKP_JSONL_LOG_T rows, default 2^19 ~ 100 MB of JSONL):
+    """BASELINE configs[4] family on one GPU (scaled: T = 2^SEZKP_JSONL_LOG_T rows, default 2^21 ~ 415 MB of JSONL: several 64 MB pieces, so the parse / ingest pipeline and the copy overlap are exercised):
     .jsonl file -> native multi-threaded parser -> pinned staging ring -> H2D on a side stream -> prove.  The file is
     in the page cache; parsing is the bound, so the parser's rate and the hidden fraction of the copies are reported."""
     import tempfile
-    log_t = env_int("SEZKP_JSONL_LOG_T", 19)
+    log_t = env_int("SEZKP_JSONL_LOG_T", 21)
     T = 1 << log_t
     ct = m.simulate(T, 512, 8, seed=77)
     root = m.manifest_root(ct)
