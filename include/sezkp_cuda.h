@@ -78,7 +78,9 @@ int32_t sezkp_cuda_synchronize(sezkp_ctx* ctx);
  * DFTs, differing in register budget / CTA size; A/B measurements); "lde_fuse" (default 1): fuse the last pass of the LDE
  * with the labeled leaf hash in sezkp_lde_commit_batch / sezkp_lde_commit_fri (north_star item 3; same roots); "phase_sync"
  * (default 1): how sezkp_cuda_get_timings clocks the prover's phases — 1 = host clock with a stream synchronisation at every
- * phase boundary, 0 = CUDA events read back at the end of the proof */
+ * phase boundary, 0 = CUDA events read back at the end of the proof; "fri_coset" (default 1): one proof over a context group
+ * with peer access keeps the FRI layers coset-resident (local folds, each GPU materialises only its own hashing range;
+ * 0 = all-gather of layer 0 and replicated folds; same proof bytes) */
 int32_t sezkp_cuda_set_option(sezkp_ctx* ctx, const char* name, int64_t value);
 /* number of kernels launched by this ctx since creation / since the last reset */
 uint64_t sezkp_cuda_launch_count(sezkp_ctx* ctx, int reset);

@@ -209,6 +209,8 @@ static void set_option_one(sezkp_ctx* ctx, const char* name, int64_t value) {
         ctx->phase_sync = value != 0;
     } else if (std::strcmp(name, "deep_fused") == 0) {
         ctx->deep_fused = value != 0;
+    } else if (std::strcmp(name, "fri_coset") == 0) {
+        ctx->fri_coset = value != 0;
     } else if (std::strcmp(name, "tab_cache") == 0) {
         ctx->tab_cache_enabled = value != 0;
         ctx->tab_cache_key.clear();

@@ -175,6 +175,7 @@ struct sezkp_ctx {
     int ntt_gen = 3;                        // option "ntt_gen": pass-kernel generation (1 = round-1 kernel; 2-4 = fused global I/O, see ntt.cu kernel_for_bits)
     bool lde_fuse = true;                   // option "lde_fuse" (K7): fuse the LDE's last pass with the labeled leaf hash in lde_commit / lde_commit_fri
     bool phase_sync = true;                 // option "phase_sync" (default 1): phase clock = host time with a stream synchronisation per phase; 0 = CUDA events read back at the end (no added syncs, but measured 0.3-0.4 ms SLOWER end to end on the slab-pipelined path, tools/e2e_ab.py)
+    bool fri_coset = true;                  // option "fri_coset": coset-resident FRI layers for one proof over a context group (0: all-gather layer 0, replicated folds)
     bool deep_fused = false;                // option "deep_fused": one-launch DEEP kernel (per-CTA inversion) also for large domains
     std::map<const void*, size_t> func_smem;  // kernel -> dynamic shared memory already granted on this ctx's device
     u64 launches = 0;                       // kernels launched since last reset

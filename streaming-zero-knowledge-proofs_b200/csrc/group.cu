@@ -250,6 +250,9 @@ void group_publish_peers(GroupRank* gr, const void* mine, cudaStream_t stream, c
         all[s] = g->send[s];
         if (s != gr->rank) CUDA_CHECK(cudaStreamWaitEvent(stream, g->ev_ready[s], 0));
     }
+    // the slots (and the ready events) are shared with the other collectives: nobody may enter the next one — and overwrite
+    // its slot or re-record its event — before every rank has read all of them
+    g->bar.wait();
 }
 void group_release_peers(GroupRank* gr, cudaStream_t stream) {
     sezkp_group* g = gr->g;

@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "gl.cuh"
+#include "group.cuh"
 #include "hash.cuh"
 #include "ntt.cuh"
 #include "stark.cuh"
@@ -355,6 +356,55 @@ __global__ void fri_fold_kernel(const u64* __restrict__ in, u64 half, u64 beta, 
     if (i >= half) return;
     out[i] = gl::add(in[i], gl::mul(beta, in[i + half]));
 }
+// ---- coset-resident FRI layers (one proof over the GPUs of a context group, see fri_commit_device) ----
+// The extension domain is the union of the 8 cosets g_j<w_n>; rank r evaluated cosets [r*per, (r+1)*per) and keeps every
+// large FRI layer in that coset-major form: local[q][i] = layer[(r*per + q) + 8*i].  The fold pairs (k, k + len/2) have the
+// same residue mod 8, so folding needs no communication: it is the same fold on every local coset array.
+__global__ void __launch_bounds__(256) fri_fold_cosets_kernel(const u64* __restrict__ in, u64 m, u64 beta, u64* __restrict__ out) {
+    const u64 half = m >> 1;  // m = elements per coset of the input layer
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    const u64* src = in + (u64)blockIdx.y * m;
+    out[(u64)blockIdx.y * half + i] = gl::add(src[i], gl::mul(beta, src[i + half]));
+}
+// Hashing works on contiguous index ranges.  This kernel builds, for up to FRI_GATHER_MAX_JOBS layers at once, the natural-
+// order values of a range [8*i0, 8*(i0 + cnt)) from the eight coset arrays, reading the slices of the seven remote cosets
+// straight out of the peers' HBM (peer loads over NVLink, 2 KiB contiguous per coset and CTA) and writing 16 KiB of
+// consecutive outputs per CTA through a shared-memory transpose.  One launch replaces world*per peer copies + an interleave
+// pass per layer; only 1/world of every layer crosses NVLink per rank (the all-gather it replaces moved all of it).
+constexpr int FRI_GATHER_MAX_JOBS = 14, FRI_GATHER_MAX_WORLD = 8;  // log_N <= 32: at most 13 layers down to the first small one
+struct FriGatherJob {
+    u64 src_off;  // element offset of this layer's local array in every rank's buffer
+    u64 m;        // elements per coset (layer length / 8)
+    u64 i0, cnt;  // coset-index range; cnt is a multiple of 256
+    u64* dst;     // natural-order output: dst[8*(i - i0) + j]
+    u32 blk0;     // first CTA of this job
+};
+struct FriGatherJobs {
+    const u64* peer[FRI_GATHER_MAX_WORLD];
+    int per, n;
+    FriGatherJob j[FRI_GATHER_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) fri_gather_ranges_kernel(const FriGatherJobs jobs) {
+    __shared__ u64 s[8][257];
+    int k = 0;
+    while (k + 1 < jobs.n && blockIdx.x >= jobs.j[k + 1].blk0) k++;
+    const FriGatherJob& jb = jobs.j[k];
+    const u64 ib = (u64)(blockIdx.x - jb.blk0) * 256;
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {  // coset c = local coset c % per of rank c / per
+        const u64* src = jobs.peer[c / jobs.per] + jb.src_off + (u64)(c % jobs.per) * jb.m + jb.i0 + ib;
+        s[c][t] = src[t];
+    }
+    __syncthreads();
+    u64* dst = jb.dst + ib * 8;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const int o = t + 256 * w;
+        dst[o] = s[o & 7][o >> 3];
+    }
+}
 // All folds from a layer of 2*len0 values down to the single final value in one CTA (the layers are contiguous in
 // `buf`: layer of 2*len0 at buf, its fold of len0 behind it, and so on).  betas[k] folds the k-th of these layers.
 constexpr int FRI_TAIL_MAX_LAYERS = 16;
@@ -667,6 +717,33 @@ void deep_lde_sharded_device(sezkp_ctx* ctx, u64* base_vals, u64* out, int L, in
     ctx->pool.free(gathered);
 }
 
+// The rank's own cosets only, coset-major and left where they are: local[q][i] = f(g w_n^i) / (g w_n^i - z) with
+// g = shift * w_N^(rank*per + q).  This is layer 0 of the coset-resident FRI (fri_commit_device): no all-gather, no
+// interleave.  The caller owns the returned pool allocation (per * n elements).
+u64* deep_lde_coset_local_device(sezkp_ctx* ctx, u64* base_vals, int L, int logB, u64 shift, u64 z, int rank, int world) {
+    REQUIRE(z < gl::P && shift < gl::P && shift != 0, "shift / z must be canonical, shift non-zero");
+    REQUIRE(!z_on_coset(z, shift, L + logB), "OOD point z lies on the evaluation coset");
+    const int B = 1 << logB, per = B / world;
+    REQUIRE(world >= 1 && per >= 1 && per * world == B, "internal: coset sharding needs world | blow-up");
+    const u64 n = 1ULL << L;
+    u64* tmp = (u64*)ctx->scratch[0].ensure(n * 8);
+    ntt_batch_device(ctx, base_vals, tmp, L, 1, true);
+    u64* inter = (u64*)ctx->scratch[1].ensure(n * 8);
+    u64* mine = (u64*)ctx->pool.alloc((size_t)per * n * 8);
+    try {
+        const u64 wN = gl::root_2exp((unsigned)(L + logB));
+        for (int q = 0; q < per; q++) {
+            const u64 gj = gl::mul(shift, gl::pow(wN, (u64)(rank * per + q)));
+            coset_lde_device(ctx, base_vals, mine + (u64)q * n, inter, L, 0, gj, 1);
+            deep_quotient_device(ctx, mine + (u64)q * n, L, gj, z);
+        }
+    } catch (...) {
+        ctx->pool.free(mine);
+        throw;
+    }
+    return mine;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* FRI                                                                                         */
 /* ------------------------------------------------------------------------------------------ */
@@ -687,26 +764,75 @@ void FriLayers::release(sezkp_ctx* ctx) {
 // are reduced by every rank.  Folding is replicated (it is HBM-cheap and keeps every layer's values on every GPU, so
 // FRI openings need no exchange).  Two exchanges per proof: layer 0's subtree roots (its root gates the betas) and the
 // subtree roots of all other sharded layers together.  Outputs are byte-identical to the unsharded path.
+namespace {
+constexpr int FRI_FUSE_MIN_LOG = 20, FRI_TAIL_ONE_CTA_LOG = 14, FRI_SHARD_MIN_LOG = 20;
+// Large layers retain 32-leaf sub-roots instead of 1024-leaf chunk roots: a CTA still hashes 1024 leaves, but stops
+// when 32 nodes are left — below that a 256-thread CTA runs 5 levels with one partly filled warp — and the top of
+// all trees is reduced by upper_reduce with full CTAs.  Openings rebuild 32 leaves instead of 1024.
+constexpr int FRI_BIG_CL = 5, FRI_BIG_CTA_LOG = 10;
+// own chunk range of a sharded layer, in units of the CTA granularity (2^(BIG_CTA_LOG - BIG_CL) chunks)
+constexpr u64 FRI_CG = 1ULL << (FRI_BIG_CTA_LOG - FRI_BIG_CL);
+inline u64 fri_range_lo(u64 n_ch, int r, int world) { return ((n_ch / FRI_CG) * (u64)r / (u64)world) * FRI_CG; }
+}  // namespace
+
+int fri_range_owner(int log_N, int l, u64 row, int world) {
+    const int log_len = log_N - l;
+    if (world <= 1 || log_len < FRI_SHARD_MIN_LOG) return -1;
+    const u64 n_ch = (1ULL << log_len) >> FRI_BIG_CL, chunk = row >> FRI_BIG_CL;
+    int r = (int)(chunk * (u64)world / n_ch);  // exact for even splits; corrected below for ragged ones
+    while (r > 0 && chunk < fri_range_lo(n_ch, r, world)) r--;
+    while (r + 1 < world && chunk >= fri_range_lo(n_ch, r + 1, world)) r++;
+    return r;
+}
+
 void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log_N, const u64* betas, u8* roots_host,
-                       u64* final_value, HostAbsorb* absorb, const ShardInfo* shard) {
+                       u64* final_value, HostAbsorb* absorb, const ShardInfo* shard, const u64* coset_local0) {
     REQUIRE(log_N >= 1 && log_N <= 32, "log_N %d out of range", log_N);
     const u64 N = 1ULL << log_N;
     fl.log_N = log_N;
     // the caller may have produced layer 0 in place: fl.values pre-allocated (2N elements) and layer0 == fl.values
     if (!fl.values) fl.values = (u64*)ctx->pool.alloc(2 * N * 8);
     u8* d_roots = (u8*)ctx->scratch[10].ensure((size_t)(log_N + 1) * 32 + 64);
-    if (layer0 != fl.values) CUDA_CHECK(cudaMemcpyAsync(fl.values, layer0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    const bool coset = coset_local0 != nullptr;
+    if (!coset && layer0 != fl.values) CUDA_CHECK(cudaMemcpyAsync(fl.values, layer0, N * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     fl.commits.resize(log_N + 1);
     std::vector<u64> beta_store;
-    constexpr int FUSE_MIN_LOG = 20, TAIL_ONE_CTA_LOG = 14, SHARD_MIN_LOG = 20;
-    // Large layers retain 32-leaf sub-roots instead of 1024-leaf chunk roots: a CTA still hashes 1024 leaves, but stops
-    // when 32 nodes are left — below that a 256-thread CTA runs 5 levels with one partly filled warp — and the top of
-    // all trees is reduced by upper_reduce with full CTAs.  Openings rebuild 32 leaves instead of 1024.
-    constexpr int BIG_CL = 5, BIG_CTA_LOG = 10;
+    constexpr int FUSE_MIN_LOG = FRI_FUSE_MIN_LOG, TAIL_ONE_CTA_LOG = FRI_TAIL_ONE_CTA_LOG, SHARD_MIN_LOG = FRI_SHARD_MIN_LOG;
+    constexpr int BIG_CL = FRI_BIG_CL, BIG_CTA_LOG = FRI_BIG_CTA_LOG;
     const int world = shard ? shard->world : 1, rank = shard ? shard->rank : 0;
-    // own chunk range of a sharded layer, in units of the CTA granularity (2^(BIG_CTA_LOG - BIG_CL) chunks)
-    constexpr u64 CG = 1ULL << (BIG_CTA_LOG - BIG_CL);
-    auto range_lo = [&](u64 n_ch, int r) { return ((n_ch / CG) * (u64)r / (u64)world) * CG; };
+    constexpr u64 CG = FRI_CG;
+    auto range_lo = [&](u64 n_ch, int r) { return fri_range_lo(n_ch, r, world); };
+    // Coset-resident mode (see the kernels above): this rank holds cosets [rank*per, (rank+1)*per) of every large layer.
+    const int per = coset ? 8 / world : 0;
+    GroupRank* const gr = coset ? &ctx->group->ranks[ctx->group_rank] : nullptr;
+    if (coset)
+        REQUIRE(shard && world > 1 && world <= FRI_GATHER_MAX_WORLD && per * world == 8 && ctx->group && ctx->group->p2p &&
+                    ctx->group->world == world && log_N >= SHARD_MIN_LOG && log_N - (SHARD_MIN_LOG - 1) <= FRI_GATHER_MAX_JOBS,
+                "internal: coset-resident FRI needs a context group with peer access, world | 8 and a large layer 0");
+    u64* coset_loc = nullptr;  // local coset arrays of layers 1 .. first small layer
+    struct LocFree {
+        sezkp_ctx* c;
+        u64*& p;
+        ~LocFree() {
+            if (p) c->pool.free(p);
+        }
+    } loc_free{ctx, coset_loc};
+    // publish `mine_base` (this rank's coset arrays), then one launch that builds the jobs' natural-order ranges
+    auto gather_ranges = [&](const u64* mine_base, FriGatherJobs& jobs) {
+        const void* all[64];
+        group_publish_peers(gr, mine_base, ctx->stream, all);
+        for (int r = 0; r < world; r++) jobs.peer[r] = (const u64*)all[r];
+        jobs.per = per;
+        u32 blocks = 0;
+        for (int k = 0; k < jobs.n; k++) {
+            REQUIRE(jobs.j[k].cnt % 256 == 0 && jobs.j[k].cnt > 0, "internal: coset range not a multiple of 256");
+            jobs.j[k].blk0 = blocks;
+            blocks += (u32)(jobs.j[k].cnt / 256);
+        }
+        fri_gather_ranges_kernel<<<blocks, 256, 0, ctx->stream>>>(jobs);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+    };
     auto own_lo = [&](u64 n_ch) { return range_lo(n_ch, rank); };
     auto own_hi = [&](u64 n_ch) { return range_lo(n_ch, rank + 1); };
     auto max_own = [&](u64 n_ch) { return ((n_ch / CG + world - 1) / world + 1) * CG; };
@@ -786,6 +912,13 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
         if (world > 1 && log_N >= SHARD_MIN_LOG) {
             Commit& c0 = fl.commits[0];
             commit_begin(ctx, c0, fl.values, N, 1, BIG_CL, nullptr, o);
+            if (coset) {  // the own index range of layer 0 in natural order, pulled from the eight coset arrays
+                const u64 lo = own_lo(c0.n_ch) << BIG_CL, hi = own_hi(c0.n_ch) << BIG_CL;
+                FriGatherJobs jobs{};
+                jobs.n = 1;
+                jobs.j[0] = FriGatherJob{0, N >> 3, lo >> 3, (hi - lo) >> 3, fl.values + lo, 0};
+                gather_ranges(coset_local0, jobs);
+            }
             commit_chunks(ctx, c0, own_lo(c0.n_ch), own_hi(c0.n_ch), o);
             Commit* one[1] = {&c0};
             gather_chunk_roots(one, 1);
@@ -810,12 +943,52 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
     u64 off = N, len = N >> 1;
     int first_small = log_N + 1;
     std::vector<Commit*> sharded;
+    const int coset_ls = coset ? log_N - (SHARD_MIN_LOG - 1) : 0;  // first small layer: gathered whole, replicated from there on
+    if (coset) {
+        // every fold down to the first small layer on the local coset arrays (no communication), then ONE launch that
+        // builds this rank's range of every large layer and the whole first small layer from all ranks' arrays
+        std::vector<u64> loc_off(coset_ls + 1, 0);
+        u64 total = 0;
+        for (int l = 1; l <= coset_ls; l++) {
+            loc_off[l] = total;
+            total += (N >> l) / (u64)world;
+        }
+        coset_loc = (u64*)ctx->pool.alloc(total * 8);
+        const u64* src = coset_local0;
+        u64 m = N >> 3;  // elements per coset of the layer being folded
+        for (int l = 1; l <= coset_ls; l++) {
+            REQUIRE(betas[l - 1] < gl::P, "beta %d is not canonical", l - 1);
+            u64* dst = coset_loc + loc_off[l];
+            fri_fold_cosets_kernel<<<dim3(blocks_for(m >> 1, 256), (unsigned)per), 256, 0, ctx->stream>>>(src, m, betas[l - 1], dst);
+            CUDA_CHECK(cudaGetLastError());
+            ctx->launches++;
+            src = dst;
+            m >>= 1;
+        }
+        FriGatherJobs jobs{};
+        u64 o2 = N;
+        for (int l = 1; l <= coset_ls; l++) {
+            const u64 ln = N >> l, n_ch = ln >> BIG_CL;
+            const u64 lo = l < coset_ls ? own_lo(n_ch) << BIG_CL : 0, hi = l < coset_ls ? own_hi(n_ch) << BIG_CL : ln;
+            jobs.j[jobs.n++] = FriGatherJob{loc_off[l], ln >> 3, lo >> 3, (hi - lo) >> 3, fl.values + o2 + lo, 0};
+            o2 += ln;
+        }
+        gather_ranges(coset_loc, jobs);
+        // nobody frees or reuses its coset arrays (layer 0 included) before every peer's gather launches have finished
+        group_release_peers(gr, ctx->stream);
+    }
     for (int l = 1; l <= log_N; l++) {
         REQUIRE(betas[l - 1] < gl::P, "beta %d is not canonical", l - 1);
         CommitOpts o;
         const int log_len = log_N - l;
         if (log_len >= FUSE_MIN_LOG) {
-            if (world > 1 && log_len >= SHARD_MIN_LOG) {  // fold everywhere, hash the own chunk range
+            if (coset) {  // values of the own range are in place (gathered above): hash them
+                Commit& c = fl.commits[l];
+                o.cta_log2 = BIG_CTA_LOG;
+                commit_begin(ctx, c, fl.values + off, len, 1, BIG_CL, nullptr, o);
+                commit_chunks(ctx, c, own_lo(c.n_ch), own_hi(c.n_ch), o);
+                sharded.push_back(&c);
+            } else if (world > 1 && log_len >= SHARD_MIN_LOG) {  // fold everywhere, hash the own chunk range
                 fri_fold_kernel<<<blocks_for(len, 256), 256, 0, ctx->stream>>>(fl.values + (off - 2 * len), len, betas[l - 1], fl.values + off);
                 CUDA_CHECK(cudaGetLastError());
                 ctx->launches++;
@@ -834,7 +1007,9 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
         } else {
             if (first_small > log_N) first_small = l;
             commit_begin(ctx, fl.commits[l], fl.values + off, len, 1, 10, nullptr, o);
-            if (log_len >= TAIL_ONE_CTA_LOG) {
+            if (coset && l == coset_ls) {
+                // gathered whole from the coset arrays: nothing to fold
+            } else if (log_len >= TAIL_ONE_CTA_LOG) {
                 fri_fold_kernel<<<blocks_for(len, 256), 256, 0, ctx->stream>>>(fl.values + (off - 2 * len), len, betas[l - 1], fl.values + off);
                 CUDA_CHECK(cudaGetLastError());
                 ctx->launches++;
@@ -865,17 +1040,26 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
 
 // Requests for k query indices into layer 0 (two openings per layer per query), appended to `reqs`.
 // positions [k][log_N+1] is filled; request (q, l, s) gets path offset base_off + ((q*log_N + l)*2 + s)*log_N.
-void fri_open_requests(const FriLayers& fl, const u64* idx0, size_t k, u64* positions, std::vector<OpenReq>& reqs, u32 base_off) {
+void fri_open_requests(const FriLayers& fl, const u64* idx0, size_t k, u64* positions, std::vector<OpenReq>& reqs, u32 base_off,
+                       int keep_rank, int world, std::vector<int32_t>* req_index) {
     const int L = fl.log_N;
     const u64 N = 1ULL << L;
+    if (req_index) req_index->assign(k * (size_t)L * 2, -1);
     for (size_t q = 0; q < k; q++) {
         REQUIRE(idx0[q] < N, "FRI query %zu out of range", q);
         u64 idx = idx0[q];
         for (int l = 0; l < L; l++) {
             const u64 half = (N >> l) >> 1;
             positions[q * (L + 1) + l] = idx;
-            for (int s = 0; s < 2; s++)
-                reqs.push_back(make_open_req(fl.commits[l], 0, s ? (idx ^ half) : idx, base_off + (u32)(((q * L + l) * 2 + s) * L)));
+            for (int s = 0; s < 2; s++) {
+                const u64 row = s ? (idx ^ half) : idx;
+                if (keep_rank >= 0) {  // coset-resident layers: a large layer's values exist only on the owner of the row's range
+                    const int owner = fri_range_owner(L, l, row, world);
+                    if ((owner < 0 ? 0 : owner) != keep_rank) continue;
+                }
+                if (req_index) (*req_index)[(q * L + l) * 2 + s] = (int32_t)reqs.size();
+                reqs.push_back(make_open_req(fl.commits[l], 0, row, base_off + (u32)(((q * L + l) * 2 + s) * L)));
+            }
             idx %= half;  // v1/prover.rs:386-388, 430-434 (half >= 1)
         }
         positions[q * (L + 1) + L] = idx;
@@ -1105,6 +1289,7 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
     std::vector<u8> col_roots((size_t)n_cols * 32);
     Commit cm;
     FriLayers fl;
+    u64* coset_local = nullptr;  // coset-resident FRI: this rank's cosets of the DEEP-LDE (layer 0), pool-owned
     try {
         // column c is committed (and later opened) by rank c % world; local column j of rank r is global r + j*world
         const int n_local = (n_cols - rank + world - 1) / world, max_local = (n_cols + world - 1) / world;
@@ -1174,7 +1359,12 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         fl.values = (u64*)ctx->pool.alloc(2 * N * 8);  // the DEEP-LDE lands where FRI layer 0 lives: no 8N-byte copy
         u64* lde = fl.values;
         // sharded proof with a device collective: each rank evaluates 8/world cosets of the extension domain (needs world | 8)
-        if (row_sliced && (1 << logB) % world == 0) deep_lde_sharded_device(ctx, base_vals, lde, L, logB, shift, z, rank, world);
+        // Context group with peer access: the FRI layers stay coset-resident (each rank keeps its 8/world cosets, folds them
+        // locally and materialises only its own hashing range in natural order) — no all-gather of the 8N-byte layer 0.
+        const bool coset_fri = row_sliced && (1 << logB) % world == 0 && world <= 8 && ctx->fri_coset && ctx->group && ctx->group->p2p &&
+                               ctx->group->world == world && shard->gather_root && log_N >= FRI_SHARD_MIN_LOG;
+        if (coset_fri) coset_local = deep_lde_coset_local_device(ctx, base_vals, L, logB, shift, z, rank, world);
+        else if (row_sliced && (1 << logB) % world == 0) deep_lde_sharded_device(ctx, base_vals, lde, L, logB, shift, z, rank, world);
         else deep_lde_device(ctx, base_vals, lde, L, logB, shift, z);
         mark("deep_lde");
 
@@ -1182,7 +1372,11 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         std::vector<u8> fri_roots((size_t)(log_N + 1) * 32);
         u64 final_value = 0;
         TranscriptAbsorb ab(tr);
-        fri_commit_device(ctx, fl, lde, log_N, nullptr, fri_roots.data(), &final_value, &ab, shard);
+        fri_commit_device(ctx, fl, lde, log_N, nullptr, fri_roots.data(), &final_value, &ab, shard, coset_local);
+        if (coset_local) {  // fri_commit_device ended with a stream synchronisation and every peer has finished reading
+            ctx->pool.free(coset_local);
+            coset_local = nullptr;
+        }
         mark("fri_commit");
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // fri_commit_device ended with a synchronising copy: this returns at once
         flush_marks();
@@ -1236,7 +1430,10 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         const size_t n_col_reqs = reqs.size();
         const size_t fri_base = k_open * (size_t)cdepth, fri_digests = (size_t)NUM_QUERIES * log_N * 2 * log_N;
         std::vector<u64> f_pos((size_t)NUM_QUERIES * (log_N + 1));
-        fri_open_requests(fl, fri_idx.data(), NUM_QUERIES, f_pos.data(), reqs, (u32)fri_base);
+        // coset-resident FRI: a large layer's values exist only on the rank that owns the row's range; rank 0 serves the
+        // small (replicated) layers.  fri_req[slot] = this rank's request for FRI opening slot (q*log_N + l)*2 + s, or -1.
+        std::vector<int32_t> fri_req;
+        fri_open_requests(fl, fri_idx.data(), NUM_QUERIES, f_pos.data(), reqs, (u32)fri_base, coset_fri ? rank : -1, world, &fri_req);
         u64* req_val;  // results stay in the context's pinned staging buffer until the proof is serialised
         u8 *req_cr, *all_paths;
         const double t_open0 = now_ms();
@@ -1250,6 +1447,7 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         }
         // per-opening record pointers (value 8 B | chunk root 32 B | path cdepth * 32 B); unsharded: assembled views below
         std::vector<const u8*> rec_ptr;
+        std::vector<const u8*> fri_ptr;  // coset-resident FRI: record (value | path) of the openings served by peers, else null
         bool deliver = true;  // this rank serialises the proof
         if (world > 1) {  // gather the opening records (value, chunk root, path): every rank sends only the ones it owns
             const size_t rec = 8 + 32 + (size_t)cdepth * 32;
@@ -1258,10 +1456,24 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             size_t max_own = 0;
             for (auto& v : owned) max_own = v.size() > max_own ? v.size() : max_own;
             const size_t bytes = max_own * rec;
+            const size_t frec = 8 + (size_t)log_N * 32;  // FRI opening record: value | path slot
+            size_t my_fri = 0;
+            if (coset_fri && rank != 0)
+                for (int32_t ri : fri_req) my_fri += ri >= 0;
             // grow-only staging kept in the context (a fresh 1.7 MB vector per proof and rank thread is an mmap + page faults +
             // munmap under the process-wide address-space lock)
             std::vector<u8>& mine = ctx->host_stage[0];
-            if (mine.size() < bytes) mine.resize(bytes);
+            if (mine.size() < bytes + my_fri * frec) mine.resize(bytes + my_fri * frec);
+            if (my_fri) {  // this rank's FRI openings behind the column records, in slot order
+                size_t j = 0;
+                for (size_t slot = 0; slot < fri_req.size(); slot++) {
+                    if (fri_req[slot] < 0) continue;
+                    u8* dst = &mine[bytes + j * frec];
+                    std::memcpy(dst, &req_val[fri_req[slot]], 8);
+                    std::memcpy(dst + 8, &all_paths[(fri_base + slot * (size_t)log_N) * 32], (size_t)log_N * 32);
+                    j++;
+                }
+            }
             for (size_t j = 0; j < owned[rank].size(); j++) {
                 const size_t o = owned[rank][j];
                 std::memcpy(&mine[j * rec], &col_val[o], 8);
@@ -1277,6 +1489,21 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
                     rec_ptr.resize(k_open);
                     for (int r = 0; r < world; r++)
                         for (size_t j = 0; j < owned[r].size(); j++) rec_ptr[owned[r][j]] = (const u8*)peers[r] + j * rec;
+                    if (coset_fri) {  // where every peer-served FRI opening sits in that peer's staging (slot order per rank)
+                        fri_ptr.assign(fri_req.size(), nullptr);
+                        std::vector<size_t> cnt(world, 0);
+                        for (size_t q = 0; q < (size_t)NUM_QUERIES; q++) {
+                            u64 idx = fri_idx[q];
+                            for (int l = 0; l < log_N; l++) {
+                                const u64 half = (N >> l) >> 1;
+                                for (int sgn = 0; sgn < 2; sgn++) {
+                                    const int owner = fri_range_owner(log_N, l, sgn ? (idx ^ half) : idx, world);
+                                    if (owner > 0) fri_ptr[(q * log_N + l) * 2 + sgn] = (const u8*)peers[owner] + bytes + cnt[owner]++ * frec;
+                                }
+                                idx %= half;
+                            }
+                        }
+                    }
                 }
             } else {  // one process per GPU: all-gather through the host callback, every rank assembles the whole proof
                 std::vector<u8>& all = ctx->host_stage[1];
@@ -1290,7 +1517,6 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         const u64* o_val = col_val.data();
         const u8* o_cr = col_cr.data();
         const u8* o_paths = all_paths;
-        const u64* f_val = req_val + n_col_reqs;
         const u8* f_paths = all_paths + fri_base * 32;
         lap("openings");
         // sub-phases of `openings` (not part of the sum): request upload + one open_kernel launch + result download / the
@@ -1351,8 +1577,14 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
             for (int l = 0; l < log_N; l++) {
                 const int depth = log_N - l;
                 for (int s = 0; s < 2; s++) {
-                    w.raw(&f_val[((size_t)qi * log_N + l) * 2 + s], 8);
-                    w.digest_vec(&f_paths[(((size_t)qi * log_N + l) * 2 + s) * (size_t)log_N * 32], depth);
+                    const size_t slot = ((size_t)qi * log_N + l) * 2 + s;
+                    if (!fri_ptr.empty() && fri_ptr[slot]) {  // served by a peer: its record
+                        w.raw(fri_ptr[slot], 8);
+                        w.digest_vec(fri_ptr[slot] + 8, depth);
+                    } else {
+                        w.raw(&req_val[fri_req[slot]], 8);
+                        w.digest_vec(&f_paths[slot * (size_t)log_N * 32], depth);
+                    }
                 }
             }
         }
@@ -1361,6 +1593,7 @@ void prove_v1_resident(sezkp_ctx* ctx, const DeviceTrace& trace, const u8 manife
         lap("serialize");
         ctx->timings.push_back({"total", now_ms() - t_begin});
     } catch (...) {
+        if (coset_local) ctx->pool.free(coset_local);
         cm.release(ctx);
         fl.release(ctx);
         throw;

@@ -50,6 +50,7 @@ void deep_lde_device(sezkp_ctx* ctx, u64* base_vals_dev /* destroyed */, u64* ou
 void deep_quotient_device(sezkp_ctx* ctx, u64* y_dev, int log_dom, u64 shift, u64 z);
 void deep_lde_sharded_device(sezkp_ctx* ctx, u64* base_vals_dev /* destroyed */, u64* out_dev, int L, int logB, u64 shift, u64 z, int rank,
                              int world);
+u64* deep_lde_coset_local_device(sezkp_ctx* ctx, u64* base_vals_dev /* destroyed */, int L, int logB, u64 shift, u64 z, int rank, int world);
 
 // Where the serialised proof goes: straight into the caller's buffer (no intermediate copy).  Bytes beyond the
 // capacity are counted but not written, so a NULL / short buffer still yields the required length.
@@ -93,9 +94,18 @@ struct FriLayers {
 };
 struct ShardInfo;
 // shard != null: the hashing of the large layers is split by chunk range over the ranks (see stark.cu)
+// coset_local0 != null (context group with peer access, world | 8): coset-resident layers — layer 0 arrives as this rank's
+// cosets (deep_lde_coset_local_device), folding is local, only the own index range of every large layer is materialised in
+// natural order (fl.values holds that range at its natural position; the rest of a large layer is never written).
 void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0_dev, int log_N, const u64* betas_or_null, u8* roots_host,
-                       u64* final_value, HostAbsorb* absorb_or_null, const ShardInfo* shard = nullptr);
-void fri_open_requests(const FriLayers& fl, const u64* idx0, size_t k, u64* positions, std::vector<OpenReq>& reqs, u32 base_off);
+                       u64* final_value, HostAbsorb* absorb_or_null, const ShardInfo* shard = nullptr, const u64* coset_local0 = nullptr);
+// Rank that holds (and opens) index `row` of layer l under the chunk-range split of the large layers; -1: the layer is small
+// (replicated on every rank).
+int fri_range_owner(int log_N, int l, u64 row, int world);
+// keep_rank >= 0: only the requests this rank serves are appended (large layers: the range owner; small layers: rank 0);
+// req_index[(q*log_N + l)*2 + s] = index of the request in `reqs` or -1.
+void fri_open_requests(const FriLayers& fl, const u64* idx0, size_t k, u64* positions, std::vector<OpenReq>& reqs, u32 base_off,
+                       int keep_rank = -1, int world = 1, std::vector<int32_t>* req_index = nullptr);
 void fri_open_device(sezkp_ctx* ctx, const FriLayers& fl, const u64* idx0, size_t k, u64* positions, u64* values, u8* paths);
 struct ShardInfo {  // column sharding across the GPUs of one box
     int rank, world;

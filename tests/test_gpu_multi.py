@@ -170,3 +170,32 @@ def test_new_api_error_paths(single):
         single.verify_openings(np.zeros((2, 32), np.uint8), ["a", "b"], np.array([2], np.uint32), np.zeros(1, np.uint64), np.zeros(1, np.uint64))
     assert ei.value.code == -1
     assert lib.sezkp_cuda_device_count() >= 1
+
+
+@pytest.mark.parametrize("devs", [[0, 0], [0] * 4, [0] * 8], ids=lambda d: "ranks%d" % len(d))
+def test_coset_resident_fri_layers(single, devs):
+    """One proof over a context group: the DEEP-LDE stays split by coset, the large FRI layers are folded locally and only
+    each rank's hashing range is materialised (fri_gather_ranges_kernel reads the peers' coset arrays), FRI openings are
+    served by the range owners and gathered by rank 0.  Bytes must equal the single-GPU proof, with the mode on and off,
+    from host descriptors and from resident traces; 2^17 rows has one large layer (2^20), 2^19 rows three."""
+    import torch
+    m = pkg()
+    n = torch.cuda.device_count()
+    lists = [devs] + ([list(range(len(devs)))] if n >= len(devs) else [])
+    for dl in lists:
+        g = m.Context(devices=dl)
+        try:
+            for T, b, tau in [(1 << 17, 512, 2), (1 << 19, 512, 3)]:
+                ct = m.simulate(T, b, tau, seed=31)
+                root = m.manifest_root(ct)
+                want = single.prove_v1(ct, root)
+                assert g.prove_v1(ct, root) == want
+                rt = g.upload_trace(ct)
+                assert g.prove_v1_resident(rt, root) == want
+                g.set_option("fri_coset", 0)
+                assert g.prove_v1_resident(rt, root) == want
+                g.set_option("fri_coset", 1)
+                assert g.prove_v1_resident(rt, root) == want
+                rt.free()
+        finally:
+            g.close()
