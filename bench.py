@@ -325,12 +325,14 @@ def wide_bench(m, devices, hbm_peak, steps):
             "timing": "CUDA events on every GPU's stream inside the library, max over GPUs (wall clock of the blocking call next to it)"}
 
 
-def group_prove_bench(torch, m, devices, ct, root, proof_buf, want_proof, steps):
+def group_prove_bench(torch, m, devices, ct, root, proof_buf, want_proof, steps, options=None):
     """ONE proof (the headline workload) sharded over the GPUs of one multi-GPU context: host pinned input -> proof bytes,
     and the same with the compact trace resident on every GPU.  No torchrun, no callbacks: a single sezkp_stark_v1_prove."""
     g = m.Context(devices=devices)
     try:
         g.set_option("tab_cache", 0)
+        for k, v in (options or {}).items():
+            g.set_option(k, v)
         for _ in range(2):
             p = g.prove_v1(ct, root, proof_buf)
         t0 = time.perf_counter()

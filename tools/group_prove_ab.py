@@ -15,4 +15,8 @@ buf = torch.empty(b.proof_size_bound(ct.n_rows, ct.tau), dtype=torch.uint8, pin_
 one = m.Context(0)
 want = one.prove_v1(ct, root)
 one.close()
-print(json.dumps(bench.group_prove_bench(torch, m, devices, ct, root, buf, want, 10)))
+for coset in (1, 0, 1):  # A/B/A: coset-resident FRI layers vs all-gathered layer 0 + replicated folds
+    out = bench.group_prove_bench(torch, m, devices, ct, root, buf, want, 10, {"fri_coset": coset})
+    out["fri_coset"] = coset
+    out.pop("resident_phases_ms_per_gpu", None)
+    print(json.dumps(out), flush=True)
