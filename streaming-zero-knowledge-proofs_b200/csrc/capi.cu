@@ -926,23 +926,30 @@ static void jsonl_parse_piece(const char* text, size_t len, int n_threads, u32 t
     out.parse_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 static void jsonl_ingest_piece(sezkp_ctx* ctx, sezkp_stream*& st, const uint8_t* manifest_root, uint64_t expected_rows, ParsedPiece& pc,
-                               uint64_t* blocks, uint64_t* rows) {
+                               uint64_t* blocks, uint64_t* rows, const HostParallelFor* par = nullptr) {
     if (pc.oom) throw std::bad_alloc();
     if (!pc.error.empty()) sezkp_fail(SEZKP_CUDA_EINVAL, "%s", pc.error.c_str());
+    // all workers' outputs of the piece go in as ONE ingest (file order): validated together, packed into the staging ring
+    // on several threads when the caller provides them
+    std::vector<sezkp_trace_desc> descs;
+    descs.reserve(pc.parts.size());
     for (auto& t : pc.parts) {
         if (t.block_len.empty()) continue;
+        sezkp_trace_desc d;
+        t.tau = pc.tau;
+        t.fill_desc(d);
+        descs.push_back(d);
+        if (blocks) *blocks += t.block_len.size();
+        if (rows) *rows += t.input_mv.size();
+    }
+    if (!descs.empty()) {
         if (!st) {
             REQUIRE(manifest_root != nullptr, "internal: stream not started");
             st = stream_begin(ctx, pc.tau, manifest_root, expected_rows);
         }
-        sezkp_trace_desc d;
-        t.tau = pc.tau;
-        t.fill_desc(d);
-        stream_ingest(ctx, st, &d);
-        if (blocks) *blocks += t.block_len.size();
-        if (rows) *rows += t.input_mv.size();
-        t.clear_keep_capacity();  // the next piece parsed into this slot reuses the arrays
+        stream_ingest_parts(ctx, st, descs.data(), descs.size(), par);
     }
+    for (auto& t : pc.parts) t.clear_keep_capacity();  // the next piece parsed into these slots reuses the arrays
 }
 // parse, then ingest (the one-shot text entry point)
 static void jsonl_parse_and_ingest(sezkp_ctx* ctx, sezkp_stream*& st, const uint8_t* manifest_root, uint64_t expected_rows,
@@ -1007,6 +1014,7 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
     // (the handler joins `reader` before these go out of scope)
     ParsedPiece pc[2];
     std::unique_ptr<jsonl::WorkerPool> pool;  // used by `reader`: must outlive it on every unwind path as well
+    std::unique_ptr<jsonl::WorkerPool> copy_pool;
     std::vector<std::pair<size_t, size_t>> pieces;  // (offset, length) of the mapped file's pieces, cut at newlines
     void* map = MAP_FAILED;
     size_t map_len = 0;
@@ -1044,6 +1052,10 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
             // parser threads live for the whole file (one pool, not 32 thread creations per piece)
             if (pieces.size() > 1 && jsonl_threads(n_threads) > 1) pool.reset(new jsonl::WorkerPool(jsonl_threads(n_threads)));
             jsonl::WorkerPool* const pl = pool.get();
+            // a few more threads pack the parsed piece into the pinned ring while the parser threads work on the next one
+            if (pl) copy_pool.reset(new jsonl::WorkerPool(std::min(4, jsonl_threads(n_threads))));
+            HostParallelFor copy_par = [&](int tasks, const std::function<void(int)>& fn) { copy_pool->run(tasks, fn); };
+            const HostParallelFor* const cp = copy_pool ? &copy_par : nullptr;
             auto launch = [&](size_t k, ParsedPiece& dst) {
                 {  // fresh state, but the workers' output arrays of two pieces ago are kept for reuse
                     std::vector<jsonl::Trace> keep = std::move(dst.parts);
@@ -1065,7 +1077,7 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
                 const bool ok = p.error.empty() && !p.oom;
                 if (ok && p.tau) tau_known = p.tau;
                 if (ok && k + 1 < pieces.size()) launch(k + 1, pc[cur ^ 1]);  // parse the next piece while this one is ingested
-                jsonl_ingest_piece(ctx, st, manifest_root, expected_rows, p, nullptr, nullptr);
+                jsonl_ingest_piece(ctx, st, manifest_root, expected_rows, p, nullptr, nullptr, cp);
                 cur ^= 1;
             }
             if (reader.joinable()) reader.join();

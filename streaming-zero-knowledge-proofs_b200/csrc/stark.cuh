@@ -1,6 +1,7 @@
 // Internal interface of stark.cu.
 #pragma once
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "common.cuh"
@@ -132,6 +133,9 @@ void prove_v1_device(sezkp_ctx* ctx, const sezkp_trace_desc* desc, const u8 mani
 struct sezkp_stream;
 sezkp_stream* stream_begin(sezkp_ctx* ctx, u32 tau, const u8 manifest_root[32], u64 expected_rows);
 void stream_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* blocks);
+// run fn(0..tasks-1) on several host threads and return when all are done (fn does not throw)
+typedef std::function<void(int tasks, const std::function<void(int)>& fn)> HostParallelFor;
+void stream_ingest_parts(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* descs, size_t count, const HostParallelFor* par);
 void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof);
 void stream_free(sezkp_ctx* ctx, sezkp_stream* st);
 u32 stream_tau(const sezkp_stream* st);

@@ -147,34 +147,67 @@ sezkp_stream* stream_begin(sezkp_ctx* ctx, u32 tau, const u8 manifest_root[32], 
     return st;
 }
 
-void stream_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* b) {
-    REQUIRE(b && b->n_blocks >= 1 && b->tau == st->tau, "ingest: bad block descriptor (tau mismatch or empty)");
-    REQUIRE(b->flags == 0, "ingest: packed descriptors are not accepted by the streaming ingest");
-    REQUIRE(b->block_len && b->win_left && b->win_right && b->head_in_off && b->head_out_off && b->input_mv && b->mv && b->write_flag &&
-                b->write_sym,
-            "ingest: descriptor has NULL arrays");
+void stream_ingest(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* b) { stream_ingest_parts(ctx, st, b, 1, nullptr); }
+
+// `count` descriptors in block order, ingested as one: all are validated before the stream is touched, the per-block metadata
+// is appended, and the row arrays are packed into the pinned staging ring — with `par` on several host threads (one task per
+// descriptor and ring buffer segment): a single thread packs ~4 GB/s out of arrays other cores have just written, which made
+// this copy, not the JSON parser, the bound of the T = 2^26 JSONL path once the parser got faster.
+void stream_ingest_parts(sezkp_ctx* ctx, sezkp_stream* st, const sezkp_trace_desc* descs, size_t count, const HostParallelFor* par) {
+    REQUIRE(descs && count >= 1, "ingest: no descriptors");
     const size_t tau = st->tau;
-    // validate the whole descriptor before touching the stream: a rejected ingest must leave the handle as it was
+    // validate everything before touching the stream: a rejected ingest must leave the handle as it was
     u64 total = 0;
-    for (u64 k = 0; k < b->n_blocks; k++) {
-        REQUIRE(b->block_len[k] >= 1, "ingest: empty block");
-        total += b->block_len[k];
+    for (size_t p = 0; p < count; p++) {
+        const sezkp_trace_desc* b = &descs[p];
+        REQUIRE(b->n_blocks >= 1 && b->tau == st->tau, "ingest: bad block descriptor (tau mismatch or empty)");
+        REQUIRE(b->flags == 0, "ingest: packed descriptors are not accepted by the streaming ingest");
+        REQUIRE(b->block_len && b->win_left && b->win_right && b->head_in_off && b->head_out_off && b->input_mv && b->mv && b->write_flag &&
+                    b->write_sym,
+                "ingest: descriptor has NULL arrays");
+        u64 rows = 0;
+        for (u64 k = 0; k < b->n_blocks; k++) {
+            REQUIRE(b->block_len[k] >= 1, "ingest: empty block");
+            rows += b->block_len[k];
+        }
+        REQUIRE(rows == b->n_rows, "ingest: n_rows != sum(block_len)");
+        total += rows;
     }
-    REQUIRE(total == b->n_rows, "ingest: n_rows != sum(block_len)");
-    st->block_len.insert(st->block_len.end(), b->block_len, b->block_len + b->n_blocks);
-    st->win_left.insert(st->win_left.end(), b->win_left, b->win_left + b->n_blocks * tau);
-    st->win_right.insert(st->win_right.end(), b->win_right, b->win_right + b->n_blocks * tau);
-    st->in_off.insert(st->in_off.end(), b->head_in_off, b->head_in_off + b->n_blocks * tau);
-    st->out_off.insert(st->out_off.end(), b->head_out_off, b->head_out_off + b->n_blocks * tau);
-    size_t done = 0;
+    std::vector<u64> first(count + 1, 0);  // first row of every descriptor within this call
+    for (size_t p = 0; p < count; p++) {
+        const sezkp_trace_desc* b = &descs[p];
+        first[p + 1] = first[p] + b->n_rows;
+        st->block_len.insert(st->block_len.end(), b->block_len, b->block_len + b->n_blocks);
+        st->win_left.insert(st->win_left.end(), b->win_left, b->win_left + b->n_blocks * tau);
+        st->win_right.insert(st->win_right.end(), b->win_right, b->win_right + b->n_blocks * tau);
+        st->in_off.insert(st->in_off.end(), b->head_in_off, b->head_in_off + b->n_blocks * tau);
+        st->out_off.insert(st->out_off.end(), b->head_out_off, b->head_out_off + b->n_blocks * tau);
+    }
+    size_t done = 0, p0 = 0;
     while (done < total) {
         sezkp_stream::Stage& s = st->stage[st->cur];
         const size_t take = std::min((size_t)total - done, STAGE_ROWS - s.rows);
         u8* h = s.host;
-        std::memcpy(h + s.rows, b->input_mv + done, take);
-        std::memcpy(h + STAGE_ROWS + s.rows * tau, b->mv + done * tau, take * tau);
-        std::memcpy(h + STAGE_ROWS * (1 + tau) + s.rows * tau, b->write_flag + done * tau, take * tau);
-        std::memcpy(h + STAGE_ROWS * (1 + 2 * tau) + s.rows * tau * 2, b->write_sym + done * tau, take * tau * 2);
+        const size_t base = s.rows;
+        while (first[p0 + 1] <= done) p0++;
+        size_t p1 = p0;
+        while (p1 < count && first[p1] < done + take) p1++;
+        // descriptor p contributes its rows [max(first[p], done), min(first[p+1], done + take)) to this ring buffer
+        auto copy_part = [&](int i) {
+            const size_t p = p0 + (size_t)i;
+            const sezkp_trace_desc* b = &descs[p];
+            const size_t lo = std::max<size_t>(first[p], done), hi = std::min<size_t>(first[p + 1], done + take);
+            if (hi <= lo) return;
+            const size_t src = lo - first[p], dst = base + (lo - done), n = hi - lo;
+            std::memcpy(h + dst, b->input_mv + src, n);
+            std::memcpy(h + STAGE_ROWS + dst * tau, b->mv + src * tau, n * tau);
+            std::memcpy(h + STAGE_ROWS * (1 + tau) + dst * tau, b->write_flag + src * tau, n * tau);
+            std::memcpy(h + STAGE_ROWS * (1 + 2 * tau) + dst * tau * 2, b->write_sym + src * tau, n * tau * 2);
+        };
+        const int tasks = (int)(p1 - p0);
+        if (par && tasks > 1 && take * st->row_bytes() >= ((size_t)1 << 20)) (*par)(tasks, copy_part);
+        else
+            for (int i = 0; i < tasks; i++) copy_part(i);
         s.rows += take;
         done += take;
         if (s.rows == STAGE_ROWS) flush_stage(ctx, st);
