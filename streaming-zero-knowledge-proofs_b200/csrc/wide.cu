@@ -277,15 +277,24 @@ void wide_commit_fri_rank(sezkp_ctx* ctx, const WideColumns& wc, const char* con
 
     // 6. DEEP coset LDE straight into FRI layer-0 storage, then fold + commit
     FriLayers fl;
+    u64* coset_local = nullptr;
     try {
         fl.values = (u64*)ctx->pool.alloc(2 * N * 8);
-        deep_lde_device(ctx, base, fl.values, L, log_blow, shift, z);
+        // context group with peer access, blow-up 8: coset-resident FRI layers (stark.cu) — each GPU evaluates its 8/world
+        // cosets of the DEEP-LDE and folds them locally instead of every GPU computing the whole single-vector tail
+        const bool coset = world > 1 && grp && grp->p2p && log_blow == 3 && 8 % world == 0 && ctx->fri_coset && log_N >= 20;
+        if (coset) coset_local = deep_lde_coset_local_device(ctx, base, L, log_blow, shift, z, rank, world);
+        else deep_lde_device(ctx, base, fl.values, L, log_blow, shift, z);
         lap("deep_lde");
         std::vector<u8> fri_roots((size_t)(log_N + 1) * 32);
         u64 fin = 0;
         TranscriptAbsorb ab(tr);
         ShardInfo sh{rank, world, group_allgather_host, gr};
-        fri_commit_device(ctx, fl, fl.values, log_N, nullptr, fri_roots.data(), &fin, &ab, world > 1 ? &sh : nullptr);
+        fri_commit_device(ctx, fl, fl.values, log_N, nullptr, fri_roots.data(), &fin, &ab, world > 1 ? &sh : nullptr, coset_local);
+        if (coset_local) {
+            ctx->pool.free(coset_local);
+            coset_local = nullptr;
+        }
         lap("fri_commit");
         if (fri_roots_out) std::memcpy(fri_roots_out, fri_roots.data(), fri_roots.size());
         if (final_value) *final_value = fin;
@@ -294,6 +303,7 @@ void wide_commit_fri_rank(sezkp_ctx* ctx, const WideColumns& wc, const char* con
             taps->z = z;
         }
     } catch (...) {
+        if (coset_local) ctx->pool.free(coset_local);
         fl.release(ctx);
         throw;
     }

@@ -197,5 +197,14 @@ def test_coset_resident_fri_layers(single, devs):
                 g.set_option("fri_coset", 1)
                 assert g.prove_v1_resident(rt, root) == want
                 rt.free()
+            # the config-4 pipeline's single-vector tail (DEEP-LDE + FRI) uses the same coset-resident layers
+            cs_s, cs_g = single.columns_synth(9, 18), g.columns_synth(9, 18)
+            a, b = single.lde_commit_fri(cs_s), g.lde_commit_fri(cs_g)
+            g.set_option("fri_coset", 0)
+            c = g.lde_commit_fri(cs_g)
+            g.set_option("fri_coset", 1)
+            cs_s.free(), cs_g.free()
+            for x in (b, c):
+                assert np.array_equal(a[0], x[0]) and np.array_equal(a[1], x[1]) and a[2] == x[2]
         finally:
             g.close()
