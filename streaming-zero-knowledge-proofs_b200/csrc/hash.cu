@@ -1147,7 +1147,7 @@ __global__ void __launch_bounds__(HASH_THREADS, 5) upper_reduce_multi_kernel(con
     int j = 0;
     while (j + 1 < jobs.n && blockIdx.x >= jobs.cta0[j + 1]) j++;
     const UpperJob jb = jobs.j[j];
-    const u64 grp = blockIdx.x - jobs.cta0[j];
+    const u64 grp = jb.grp0 + (blockIdx.x - jobs.cta0[j]);
     const u32* src = jb.upper + ((2 * jb.n_ch - ((2 * jb.n_ch) >> jb.l0)) + (grp << jb.k)) * 8;
     const int cnt = 1 << jb.k;
     for (int i = threadIdx.x; i < cnt * 8; i += HASH_THREADS) s[(i & 7) * pitch + (i >> 3)] = src[i];
@@ -1603,6 +1603,7 @@ void commit_finish_multi(sezkp_ctx* ctx, Commit* cms, int count, u8* roots_dev) 
                 jb.l0 = l0;
                 jb.k = std::min(depth - l0, MAX_CL);
                 jb.root_out = roots_dev ? (u32*)(roots_dev + 32 * (size_t)(base + i)) : nullptr;
+                jb.grp0 = 0;
                 jobs.cta0[jobs.n] = ctas;
                 ctas += (u32)(cm.n_ch >> (l0 + jb.k));
                 jobs.n++;
@@ -1613,6 +1614,58 @@ void commit_finish_multi(sezkp_ctx* ctx, Commit* cms, int count, u8* roots_dev) 
             ctx->launches++;
         }
     }
+}
+
+void commit_finish_multi_range(sezkp_ctx* ctx, Commit* const* cms, int count, int rank, int world) {
+    REQUIRE(count <= UPPER_MAX_JOBS && world >= 1 && (world & (world - 1)) == 0 && rank >= 0 && rank < world, "internal: bad range finish");
+    const int wl = ilog2((u64)world);
+    for (int l0 = 0;; l0 += MAX_CL) {
+        UpperJobs jobs;
+        jobs.n = 0;
+        u32 ctas = 0;
+        for (int i = 0; i < count; i++) {
+            const Commit& cm = *cms[i];
+            REQUIRE(cm.cols == 1 && cm.n_ch % (u64)world == 0, "internal: range finish needs single columns and world | n_ch");
+            const int depth = ilog2(cm.n_ch) - wl;  // levels inside the own subtree
+            if (l0 >= depth) continue;
+            UpperJob& jb = jobs.j[jobs.n];
+            jb.upper = cm.upper;
+            jb.n_ch = cm.n_ch;
+            jb.l0 = l0;
+            jb.k = std::min(depth - l0, MAX_CL);
+            jb.root_out = nullptr;
+            const u64 groups = (cm.n_ch / (u64)world) >> (l0 + jb.k);  // of 2^k nodes at level l0, inside the own range
+            jb.grp0 = groups * (u64)rank;
+            jobs.cta0[jobs.n] = ctas;
+            ctas += (u32)groups;
+            jobs.n++;
+        }
+        if (jobs.n == 0) break;
+        upper_reduce_multi_kernel<<<ctas, HASH_THREADS, 0, ctx->stream>>>(jobs);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->launches++;
+    }
+}
+void commit_finish_multi_top(sezkp_ctx* ctx, Commit* const* cms, int count, int world, u8* const* roots_dev) {
+    REQUIRE(count <= UPPER_MAX_JOBS && world >= 1 && (world & (world - 1)) == 0, "internal: bad top finish");
+    const int wl = ilog2((u64)world);
+    UpperJobs jobs;
+    jobs.n = count;
+    for (int i = 0; i < count; i++) {
+        const Commit& cm = *cms[i];
+        REQUIRE(cm.cols == 1 && cm.n_ch % (u64)world == 0 && wl <= MAX_CL, "internal: top finish needs single columns and world | n_ch");
+        UpperJob& jb = jobs.j[i];
+        jb.upper = cm.upper;
+        jb.n_ch = cm.n_ch;
+        jb.l0 = ilog2(cm.n_ch) - wl;
+        jb.k = wl;  // one group of `world` nodes -> the root
+        jb.root_out = roots_dev && roots_dev[i] ? (u32*)roots_dev[i] : nullptr;
+        jb.grp0 = 0;
+        jobs.cta0[i] = (u32)i;
+    }
+    upper_reduce_multi_kernel<<<count, HASH_THREADS, 0, ctx->stream>>>(jobs);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->launches++;
 }
 
 void commit_build(sezkp_ctx* ctx, Commit& cm, const u64* values_dev, u64 n, int cols, int chunk_log2,

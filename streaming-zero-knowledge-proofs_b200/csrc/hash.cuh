@@ -57,6 +57,7 @@ struct UpperJob {
     u64 n_ch;
     int l0, k;
     u32* root_out;
+    u64 grp0;  // first group (of 2^k nodes at level l0) this job reduces; its CTA count is the number of groups
 };
 struct UpperJobs {
     UpperJob j[UPPER_MAX_JOBS];
@@ -64,6 +65,13 @@ struct UpperJobs {
     int n;
 };
 void commit_finish_multi(sezkp_ctx* ctx, Commit* cms, int count, u8* roots_dev);
+// Range-split finish of single-column commitments whose level-0 nodes were hashed by chunk range over `world` ranks (a power
+// of two dividing n_ch): _range reduces this rank's aligned range — a complete subtree — down to its ONE node at level
+// log2(n_ch / world); after the ranks have exchanged those nodes (32 bytes each), _top reduces the log2(world) levels above
+// them on every rank and writes root i to roots_dev[i] (device, may be null entries).  The levels below the exchanged one
+// exist only for the own range — which is where this rank's openings lie.
+void commit_finish_multi_range(sezkp_ctx* ctx, Commit* const* cms, int count, int rank, int world);
+void commit_finish_multi_top(sezkp_ctx* ctx, Commit* const* cms, int count, int world, u8* const* roots_dev);
 // Leaf hashes + chunk trees of `count` single-column unlabeled commitments (begin done, values final) in one launch.
 struct CommitJob {
     const u64* values;

@@ -904,6 +904,38 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
         }
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));  // `all` is a local
     };
+    // Coset-resident mode: a rank's chunk range is a complete subtree, and the openings of a large layer are served by the
+    // range owner — so instead of all-gathering the 32-leaf sub-roots of every layer (32 MB per GPU for layer 0 at T = 2^22,
+    // 512 MB at T = 2^26) and reducing the whole upper tree on every rank, each rank reduces its own subtree to ONE node, the
+    // ranks exchange those nodes (32 bytes per layer) and everybody reduces the log2(world) levels above them.
+    auto finish_ranges = [&](Commit* const* cms, int cnt, u8* const* roots_dev) {
+        for (int b0 = 0; b0 < cnt; b0 += GatherScatter::MAX) {
+            const int m = std::min(GatherScatter::MAX, cnt - b0);
+            commit_finish_multi_range(ctx, cms + b0, m, rank, world);
+            GatherScatter gs{};
+            gs.n = m;
+            gs.world = world;
+            const size_t total = (size_t)m * 32;
+            u8* stage = (u8*)ctx->scratch[6].ensure(total * (size_t)(world + 1));
+            for (int i = 0; i < m; i++) {
+                const Commit& c = *cms[b0 + i];
+                const int lr = ilog2(c.n_ch / (u64)world);  // level of the per-rank nodes
+                gs.upper[i] = c.upper + upper_off(c.n_ch, lr) * 8;
+                gs.own_words[i] = 8;
+                gs.off_words[i] = (u32)(8 * i);
+                CUDA_CHECK(cudaMemcpyAsync(stage + 32 * (size_t)i, gs.upper[i] + (size_t)rank * 8, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            gs.total_words = (u32)(total / 4);
+            u8* recv = stage + total;
+            const int32_t rc = ctx->allgather_dev(ctx->allgather_dev_user, stage, total, recv, (void*)ctx->stream);
+            if (rc != 0) sezkp_fail(SEZKP_CUDA_ECOMM, "device allgather callback failed with status %d", rc);
+            gs.recv = (const u32*)recv;
+            gather_scatter_kernel<<<blocks_for((u64)gs.total_words * world / 4, 256), 256, 0, ctx->stream>>>(gs);
+            CUDA_CHECK(cudaGetLastError());
+            ctx->launches++;
+            commit_finish_multi_top(ctx, cms + b0, m, world, roots_dev + b0);
+        }
+    };
     {
         CommitOpts o;
         o.roots_host = roots_host;
@@ -921,8 +953,15 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
             }
             commit_chunks(ctx, c0, own_lo(c0.n_ch), own_hi(c0.n_ch), o);
             Commit* one[1] = {&c0};
-            gather_chunk_roots(one, 1);
-            commit_finish(ctx, c0, o);
+            if (coset) {
+                u8* r0[1] = {d_roots};
+                finish_ranges(one, 1, r0);
+                CUDA_CHECK(cudaMemcpyAsync(roots_host, d_roots, 32, cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            } else {
+                gather_chunk_roots(one, 1);
+                commit_finish(ctx, c0, o);
+            }
         } else {
             commit_build(ctx, fl.commits[0], fl.values, N, 1, big0 ? BIG_CL : 10, nullptr, o);
         }
@@ -1029,8 +1068,15 @@ void fri_commit_device(sezkp_ctx* ctx, FriLayers& fl, const u64* layer0, int log
         len >>= 1;
     }
     if (first_small <= log_N) commit_chunks_multi(ctx, fl.commits.data() + first_small, log_N - first_small + 1);
-    if (!sharded.empty()) gather_chunk_roots(sharded.data(), (int)sharded.size());
-    commit_finish_multi(ctx, fl.commits.data() + 1, log_N, d_roots + 32);
+    if (coset) {  // large layers 1 .. first_small-1: own subtrees, one 32-byte node per layer and rank exchanged; then the small layers
+        std::vector<u8*> rd(sharded.size());
+        for (size_t i = 0; i < sharded.size(); i++) rd[i] = d_roots + 32 * (i + 1);
+        if (!sharded.empty()) finish_ranges(sharded.data(), (int)sharded.size(), rd.data());
+        commit_finish_multi(ctx, fl.commits.data() + first_small, log_N - first_small + 1, d_roots + 32 * (size_t)first_small);
+    } else {
+        if (!sharded.empty()) gather_chunk_roots(sharded.data(), (int)sharded.size());
+        commit_finish_multi(ctx, fl.commits.data() + 1, log_N, d_roots + 32);
+    }
     CUDA_CHECK(cudaMemcpyAsync(roots_host + 32, d_roots + 32, (size_t)log_N * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(final_value, fl.values + (2 * N - 2), 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
