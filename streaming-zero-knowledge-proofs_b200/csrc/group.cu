@@ -46,58 +46,77 @@ void GroupBarrier::fail() {
     cv.notify_all();
 }
 
+// one rank's share of a group job; errors are recorded, never thrown (a failing rank fails the barrier so that the others unwind)
+static void run_rank(sezkp_group* g, int rank, const std::function<void(int)>& job) {
+    int32_t rc = SEZKP_CUDA_OK;
+    std::string msg;
+    try {
+        CUDA_CHECK(cudaSetDevice(g->ctx[rank]->device));
+        job(rank);
+    } catch (const SezkpError& e) {
+        rc = e.code;
+        msg = e.what();
+    } catch (const std::bad_alloc&) {
+        rc = SEZKP_CUDA_ENOMEM;
+        msg = "host allocation failed";
+    } catch (const std::exception& e) {
+        rc = SEZKP_CUDA_ECUDA;
+        msg = e.what();
+    }
+    if (rc != SEZKP_CUDA_OK) {
+        cudaGetLastError();
+        g->bar.fail();
+    }
+    g->rc[rank] = rc;  // own slot; read by group_run after the completion hand-shake
+    g->err[rank] = msg;
+}
+
 static void worker_main(sezkp_group* g, int rank) {
     u64 seen = 0;
     for (;;) {
         std::function<void(int)> job;
+        // back-to-back calls (a prover loop): the next job usually arrives within microseconds of the last one — poll for it
+        // briefly before sleeping on the condition variable (a wake-up costs ~50 us per rank, a tenth of a sharded proof phase)
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int spins = 0; g->job_seq.load(std::memory_order_acquire) == seen && !g->quit_flag.load(std::memory_order_acquire); spins++) {
+            if ((spins & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
         {
             std::unique_lock<std::mutex> lk(g->mu);
-            g->cv_job.wait(lk, [&] { return g->quit || g->job_seq != seen; });
+            g->cv_job.wait(lk, [&] { return g->quit || g->job_seq.load(std::memory_order_acquire) != seen; });
             if (g->quit) return;
-            seen = g->job_seq;
+            seen = g->job_seq.load(std::memory_order_acquire);
             job = g->job;
         }
-        int32_t rc = SEZKP_CUDA_OK;
-        std::string msg;
-        try {
-            CUDA_CHECK(cudaSetDevice(g->ctx[rank]->device));
-            job(rank);
-        } catch (const SezkpError& e) {
-            rc = e.code;
-            msg = e.what();
-        } catch (const std::bad_alloc&) {
-            rc = SEZKP_CUDA_ENOMEM;
-            msg = "host allocation failed";
-        } catch (const std::exception& e) {
-            rc = SEZKP_CUDA_ECUDA;
-            msg = e.what();
-        }
-        if (rc != SEZKP_CUDA_OK) {
-            cudaGetLastError();
-            g->bar.fail();
-        }
+        run_rank(g, rank, job);
         {
             std::lock_guard<std::mutex> lk(g->mu);
-            g->rc[rank] = rc;
-            g->err[rank] = msg;
             if (--g->pending == 0) g->cv_done.notify_all();
         }
     }
 }
 
+// Rank 0's share runs on the calling thread (it is the longest: rank 0 serialises the proof), ranks 1.. on their workers: the
+// caller is not woken up at the end and one dispatch wake-up disappears.
 void group_run(sezkp_group* g, const std::function<void(int, sezkp_ctx*)>& fn) {
     g->bar.reset(g->world);
+    const std::function<void(int)> job = [g, &fn](int r) { fn(r, g->ctx[r]); };
     {
         std::lock_guard<std::mutex> lk(g->mu);
-        g->job = [g, &fn](int r) { fn(r, g->ctx[r]); };
-        g->pending = g->world;
-        g->job_seq++;
+        g->job = job;
+        g->pending = g->world - 1;
+        g->job_seq.fetch_add(1, std::memory_order_release);
     }
-    g->cv_job.notify_all();
+    if (g->world > 1) g->cv_job.notify_all();
+    run_rank(g, 0, job);
     {
         std::unique_lock<std::mutex> lk(g->mu);
         g->cv_done.wait(lk, [&] { return g->pending == 0; });
     }
+    cudaSetDevice(g->ctx[0]->device);
     int bad = -1;
     for (int r = 0; r < g->world; r++)
         if (g->rc[r] != SEZKP_CUDA_OK && (bad < 0 || (g->rc[bad] == SEZKP_CUDA_ECOMM && g->rc[r] != SEZKP_CUDA_ECOMM))) bad = r;
@@ -152,7 +171,7 @@ sezkp_group* group_create(const int* device_ids, int n_dev) {
             g->ctx[i]->allgather_dev_user = &g->ranks[i];
         }
         CUDA_CHECK(cudaSetDevice(device_ids[0]));
-        for (int i = 0; i < n_dev; i++) g->workers.emplace_back(worker_main, g, i);
+        for (int i = 1; i < n_dev; i++) g->workers.emplace_back(worker_main, g, i);  // rank 0 runs on the caller's thread
     } catch (...) {
         group_destroy(g);
         throw;
@@ -165,6 +184,7 @@ void group_destroy(sezkp_group* g) {
     {
         std::lock_guard<std::mutex> lk(g->mu);
         g->quit = true;
+        g->quit_flag.store(true, std::memory_order_release);
     }
     g->cv_job.notify_all();
     for (auto& t : g->workers)

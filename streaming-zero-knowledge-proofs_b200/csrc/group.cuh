@@ -1,7 +1,8 @@
 // Multi-GPU context group: ONE process drives the GPUs of a box (sezkp_cuda_create_multi), so the reference's
 // stateless single-process backend call (sezkp-core/src/backend.rs:41-61) can use all of them.
 //
-//   * one sezkp_ctx + one persistent worker thread per GPU (rank r = position in the device list);
+//   * one sezkp_ctx per GPU (rank r = position in the device list); rank 0's share of a call runs on the caller's thread,
+//     the other ranks on persistent worker threads;
 //   * the collectives of the sharded prover (stark.cu: column roots, FRI subtree roots, opening records, compact trace)
 //     are implemented inside the library: host all-gather = shared-memory exchange between the rank threads, device
 //     all-gather = cudaMemcpyPeerAsync pulls over NVLink ordered by CUDA events (no host synchronisation), and
@@ -48,9 +49,10 @@ struct sezkp_group {
     std::mutex mu;
     std::condition_variable cv_job, cv_done;
     std::function<void(int)> job;
-    u64 job_seq = 0;
+    std::atomic<u64> job_seq{0};
     int pending = 0;
     bool quit = false;
+    std::atomic<bool> quit_flag{false};  // the same, for the workers' lock-free polling
     std::vector<int32_t> rc;
     std::vector<std::string> err;
     GroupBarrier bar;
