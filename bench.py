@@ -396,7 +396,7 @@ def jsonl_stream_bench(torch, ctx, m, steps):
     return {"workload": f"streaming JSONL STARK prove, T=2^{log_t}, b=512, tau=8, {size / 1e6:.0f} MB file (page cache), 1 GPU",
             "rows_per_s": T / dt, "ms_per_step": dt * 1e3, "file_MBps": size / dt / 1e6, "parser_threads": threads,
             "proof_identical_to_one_shot": bool(ok),
-            "jsonl_parse_ms": tm.get("jsonl_parse_ms"), "jsonl_read_ms": tm.get("jsonl_read_ms"),
+            "jsonl_parse_ms": tm.get("jsonl_parse_ms"), "jsonl_pack_ms": tm.get("jsonl_pack_ms"), "jsonl_read_ms": tm.get("jsonl_read_ms"),
             "stream_h2d_copy_ms": tm.get("stream_h2d_copy_ms"), "stream_copy_hidden_frac": tm.get("stream_copy_hidden_frac"),
             "prove_ms_after_last_line": tm.get("total"),
             "python_reader_rows_per_s": (1 << 14) / py_dt,

@@ -983,7 +983,7 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
     if (!f) sezkp_fail(SEZKP_CUDA_EINVAL, "cannot open %s", path);
     sezkp_stream* st = nullptr;
     auto ms_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double read_ms = 0, parse_ms = 0;
+    double read_ms = 0, parse_ms = 0, pack_ms = 0;
     size_t total_bytes = 0, line_no = 1;
     // Two text buffers: while the parser threads work on one, a reader thread fills the other (fread of the next piece).
     // A piece is cut at its last newline; the tail is carried to the front of the next piece.
@@ -1014,7 +1014,6 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
     // (the handler joins `reader` before these go out of scope)
     ParsedPiece pc[2];
     std::unique_ptr<jsonl::WorkerPool> pool;  // used by `reader`: must outlive it on every unwind path as well
-    std::unique_ptr<jsonl::WorkerPool> copy_pool;
     std::vector<std::pair<size_t, size_t>> pieces;  // (offset, length) of the mapped file's pieces, cut at newlines
     void* map = MAP_FAILED;
     size_t map_len = 0;
@@ -1047,40 +1046,31 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
                 pieces.push_back({pos, use});
                 pos += use;
             }
-            int cur = 0;
             u32 tau_known = 0;
-            // parser threads live for the whole file (one pool, not 32 thread creations per piece)
-            if (pieces.size() > 1 && jsonl_threads(n_threads) > 1) pool.reset(new jsonl::WorkerPool(jsonl_threads(n_threads)));
+            // One pool of host threads for the whole file (not 32 thread creations per piece), used in two steps per piece:
+            // the workers parse their runs of lines, then the same threads pack what they have just produced — still hot in
+            // their caches — into the pinned staging ring.  (An earlier version packed piece k on this thread while the pool
+            // parsed piece k+1; with every core busy parsing, the packing threads only ran when the scheduler pre-empted a
+            // parser, and packing — 4 GB/s from one thread — had become the bound of the T = 2^26 path: 0.51 s of 0.60 s.)
+            if (jsonl_threads(n_threads) > 1) pool.reset(new jsonl::WorkerPool(jsonl_threads(n_threads)));
             jsonl::WorkerPool* const pl = pool.get();
-            // a few more threads pack the parsed piece into the pinned ring while the parser threads work on the next one
-            if (pl) copy_pool.reset(new jsonl::WorkerPool(std::min(4, jsonl_threads(n_threads))));
-            HostParallelFor copy_par = [&](int tasks, const std::function<void(int)>& fn) { copy_pool->run(tasks, fn); };
-            const HostParallelFor* const cp = copy_pool ? &copy_par : nullptr;
-            auto launch = [&](size_t k, ParsedPiece& dst) {
-                {  // fresh state, but the workers' output arrays of two pieces ago are kept for reuse
-                    std::vector<jsonl::Trace> keep = std::move(dst.parts);
-                    dst = ParsedPiece();
-                    dst.parts = std::move(keep);
-                }
-                const size_t first_line = line_no;
-                const u32 tau_hint = tau_known;
-                reader = std::thread([&dst, &pieces, text, k, n_threads, tau_hint, first_line, pl] {
-                    jsonl_parse_piece(text + pieces[k].first, pieces[k].second, n_threads, tau_hint, first_line, dst, pl);
-                });
-            };
-            if (!pieces.empty()) launch(0, pc[0]);
+            HostParallelFor pack_par = [&](int tasks, const std::function<void(int)>& fn) { pl->run(tasks, fn); };
+            const HostParallelFor* const cp = pl ? &pack_par : nullptr;
             for (size_t k = 0; k < pieces.size(); k++) {
-                reader.join();  // piece k is parsed
-                ParsedPiece& p = pc[cur];
+                ParsedPiece& p = pc[0];
+                {  // fresh state, but the workers' output arrays of the previous piece are kept for reuse
+                    std::vector<jsonl::Trace> keep = std::move(p.parts);
+                    p = ParsedPiece();
+                    p.parts = std::move(keep);
+                }
+                jsonl_parse_piece(text + pieces[k].first, pieces[k].second, n_threads, tau_known, line_no, p, pl);
                 parse_ms += p.parse_ms;
                 line_no += p.lines;
-                const bool ok = p.error.empty() && !p.oom;
-                if (ok && p.tau) tau_known = p.tau;
-                if (ok && k + 1 < pieces.size()) launch(k + 1, pc[cur ^ 1]);  // parse the next piece while this one is ingested
+                if (p.error.empty() && !p.oom && p.tau) tau_known = p.tau;
+                const double t_pack = ms_now();
                 jsonl_ingest_piece(ctx, st, manifest_root, expected_rows, p, nullptr, nullptr, cp);
-                cur ^= 1;
+                pack_ms += ms_now() - t_pack;
             }
-            if (reader.joinable()) reader.join();
             total_bytes = map_len;
         } else {
         int cur = 0;
@@ -1125,6 +1115,7 @@ int32_t sezkp_stark_v1_prove_jsonl_file(sezkp_ctx* ctx, const char* path, const 
         stream_free(ctx, st);
         st = nullptr;
         ctx->timings.insert(ctx->timings.begin(), {"jsonl_bytes", (double)total_bytes});
+        ctx->timings.insert(ctx->timings.begin(), {"jsonl_pack_ms", pack_ms});
         ctx->timings.insert(ctx->timings.begin(), {"jsonl_parse_ms", parse_ms});
         ctx->timings.insert(ctx->timings.begin(), {"jsonl_read_ms", read_ms});
     } catch (...) {
