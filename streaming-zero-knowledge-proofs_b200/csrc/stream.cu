@@ -278,8 +278,9 @@ void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof) {
         // the peers over NVLink and let every GPU prove its share (columns c % world, FRI hashing by chunk range).
         sezkp_group* g = ctx->group;
         const int world = g->world;
+        // The peers' copies live in their contexts' grow-only scratch slot 2 (the slot of the one-shot trace upload, idle
+        // during a resident prove): cudaMalloc + cudaFree of a 2.2 GB buffer on seven GPUs per call cost ~170 ms at T = 2^26.
         struct Peer {
-            DevBuf buf;
             DeviceTrace t;
         };
         std::vector<Peer> peers(world - 1);
@@ -292,7 +293,7 @@ void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof) {
                 sezkp_ctx* px = g->ctx[r];
                 Peer& p = peers[r - 1];
                 CUDA_CHECK(cudaSetDevice(px->device));
-                u8* base = (u8*)p.buf.ensure(total);
+                u8* base = (u8*)px->scratch[2].ensure(total);
                 CUDA_CHECK(cudaSetDevice(ctx->device));
                 auto cp = [&](size_t o, const void* src, size_t bytes) {
                     CUDA_CHECK(cudaMemcpyPeerAsync(base + o, px->device, src, ctx->device, bytes, ctx->stream));
@@ -324,16 +325,8 @@ void stream_finish(sezkp_ctx* ctx, sezkp_stream* st, ProofSink& proof) {
             });
             ctx->timings.insert(ctx->timings.begin(), {"stream_replicate_ms", rep_ms});
         } catch (...) {
-            for (int r = 1; r < world; r++) {
-                cudaSetDevice(g->ctx[r]->device);
-                peers[r - 1].buf.release();
-            }
             cudaSetDevice(ctx->device);
             throw;
-        }
-        for (int r = 1; r < world; r++) {
-            cudaSetDevice(g->ctx[r]->device);
-            peers[r - 1].buf.release();
         }
         CUDA_CHECK(cudaSetDevice(ctx->device));
     } else {
