@@ -1,6 +1,6 @@
 """Stress of the one-proof-over-a-context-group path: many proofs on groups of 2 / 4 / 8 ranks (one GPU listed several
 times, or real GPUs when present), coset-resident FRI on and off, host-descriptor and resident entry points; every proof is
-compared with the single-GPU bytes.  usage: coset_debug.py [iterations]"""
+compared with the single-GPU bytes.  usage: group_stress.py [iterations]"""
 import importlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
