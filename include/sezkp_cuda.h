@@ -249,9 +249,11 @@ void sezkp_stark_v1_abort(sezkp_ctx* ctx, sezkp_stream* st);
  *    (<= 0: all cores).  No ctx and no GPU needed.  *desc points into the handle; scalars (may be NULL) receives a
  *    pointer to n_blocks records.  Errors: EINVAL with sezkp_jsonl_last_error() = "jsonl line N: ...".
  *  - sezkp_stark_v1_ingest_jsonl: parse + ingest_block for every block of the text, in file order.
- *  - sezkp_stark_v1_prove_jsonl_file: the whole StreamingProver loop over a file read in chunk_bytes pieces
- *    (0: 16 MiB): reading the next piece and the H2D copies of the previous ones overlap the parsing.  tau comes from the first
- *    block.  sezkp_cuda_get_timings then also reports jsonl_read_ms, jsonl_parse_ms and jsonl_bytes. */
+ *  - sezkp_stark_v1_prove_jsonl_file: the whole StreamingProver loop over a file taken in chunk_bytes pieces
+ *    (0: 64 MiB).  Regular files are mapped: one pool of n_threads host threads parses a piece and then packs it into the
+ *    pinned staging ring, whose H2D copies run on a side stream behind the parsing of the next pieces; pipes and special
+ *    files are read with a double-buffered fread loop.  tau comes from the first block.  sezkp_cuda_get_timings then also
+ *    reports jsonl_read_ms, jsonl_parse_ms, jsonl_pack_ms and jsonl_bytes. */
 typedef struct sezkp_jsonl_trace sezkp_jsonl_trace;
 int32_t sezkp_jsonl_parse(const char* text, size_t len, int n_threads, sezkp_jsonl_trace** out, sezkp_trace_desc* desc,
                           const sezkp_block_scalars** scalars);
