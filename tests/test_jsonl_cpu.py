@@ -205,4 +205,13 @@ def test_parser_under_sanitizers(tmp_path):
     path = str(tmp_path / "f.jsonl")
     m.io_jsonl.write_jsonl(path, ct)
     run = subprocess.run([exe, path], capture_output=True, text=True, timeout=600)
-    assert run.returncode == 0 and "parsed ok" in run.stdout, (run.stdout + run.stderr)[-3000:]
+    assert run.returncode == 0 and "parsed ok" in run.stdout and "piecewise pool parse ok" in run.stdout, (run.stdout + run.stderr)[-3000:]
+    # the persistent worker pool + output arrays reused from piece to piece (the prover's file path) under ThreadSanitizer
+    exe_t = str(tmp_path / "jsonl_fuzz_tsan")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-fsanitize=thread", "-I", csrc, os.path.join(root, "tools", "jsonl_fuzz.cpp"),
+                         os.path.join(csrc, "jsonl.cpp"), "-o", exe_t], capture_output=True, text=True)
+    if cc.returncode != 0 and ("tsan" in cc.stderr or "sanitize" in cc.stderr):
+        return  # no TSan runtime: the ASan run above already covered the same code single-checked
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    run = subprocess.run([exe_t, path, "pool"], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and "piecewise pool parse ok" in run.stdout and "ThreadSanitizer" not in run.stderr, (run.stdout + run.stderr)[-3000:]
